@@ -1,0 +1,280 @@
+"""CPU oracle for the compressed-Whisper hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` leg may import this package, and only as the checker.  The product
+package (``openai_whisper_compression_b200``) never imports it and has no CPU fallback.
+
+Bit-exact fp32 / integer arithmetic lives in ``whisperq_oracle.c`` (built by
+``oracle/Makefile`` into ``oracle/_build/liboracle.so``); this module wraps it with numpy
+and adds the float64 restatements (log-mel, GEMM oracles).
+
+Parity status (see the header of whisperq_oracle.c and DESIGN.md):
+  * torch dynamic-int8 and log-mel: pinned against the live torch / HF implementations the
+    reference calls (model_utils.py:131-134, data_utils.py:56-58) via tests/golden/.
+  * bitsandbytes NF4 / LLM.int8, optimum-quanto qint8: PARITY UNPINNED (libraries absent, the
+    reference holds no golden vectors); restated from SURVEY.md Appendix A.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/whisperq_oracle.c with gcc (a few hundred ms)."""
+    src = os.path.join(_HERE, "whisperq_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "CC=gcc"])
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.orc_edit_distance.restype = ctypes.c_int64
+        _lib.orc_nf4_codebook.restype = ctypes.POINTER(ctypes.c_float)
+        _lib.orc_fp4_codebook.restype = ctypes.POINTER(ctypes.c_float)
+    return _lib
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+
+
+_QT = {"nf4": 0, "fp4": 1}
+
+NF4_CODE = np.array([lib().orc_nf4_codebook()[i] for i in range(16)], dtype=np.float32)
+FP4_CODE = np.array([lib().orc_fp4_codebook()[i] for i in range(16)], dtype=np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# bitsandbytes 4-bit
+# --------------------------------------------------------------------------------------
+def quantize_4bit(w: np.ndarray, blocksize: int = 64, quant_type: str = "nf4"
+                  ) -> Tuple[np.ndarray, np.ndarray]:
+    """bitsandbytes.functional.quantize_4bit: returns (packed uint8 [(n+1)//2, 1], absmax f32)."""
+    wf = _f32(w).reshape(-1)
+    n = wf.size
+    packed = np.zeros(((n + 1) // 2, 1), dtype=np.uint8)
+    absmax = np.zeros(((n + blocksize - 1) // blocksize,), dtype=np.float32)
+    lib().orc_quant_4bit(_p(wf), ctypes.c_int64(n), ctypes.c_int(blocksize),
+                         ctypes.c_int(_QT[quant_type]), _p(packed), _p(absmax))
+    return packed, absmax
+
+
+def dequantize_4bit(packed: np.ndarray, absmax: np.ndarray, shape: Sequence[int],
+                    blocksize: int = 64, quant_type: str = "nf4",
+                    dtype=np.float16) -> np.ndarray:
+    """bitsandbytes.functional.dequantize_4bit: code[nibble]*absmax (fp32) rounded to dtype."""
+    n = int(np.prod(shape))
+    out = np.empty((n,), dtype=np.float32)
+    packed = np.ascontiguousarray(packed, dtype=np.uint8)
+    absmax = _f32(absmax)
+    lib().orc_dequant_4bit(_p(packed), _p(absmax), ctypes.c_int64(n), ctypes.c_int(blocksize),
+                           ctypes.c_int(_QT[quant_type]), _p(out))
+    return out.astype(dtype).reshape(tuple(shape))
+
+
+def linear4bit_forward(x: np.ndarray, packed, absmax, shape, bias=None, blocksize=64,
+                       quant_type="nf4", compute_dtype=np.float16) -> np.ndarray:
+    """Linear4bit.forward: F.linear(x.to(cd), dequantize_4bit(W).to(cd), bias.to(cd)).
+
+    Returned in float64 (exact product of the rounded operands) -- the tolerance of the
+    comparison models the fp16 accumulate/round of the library GEMM."""
+    w = dequantize_4bit(packed, absmax, shape, blocksize, quant_type, compute_dtype)
+    xs = np.asarray(x).astype(compute_dtype).astype(np.float64)
+    y = xs.reshape(-1, shape[1]) @ w.astype(np.float64).T
+    if bias is not None:
+        y = y + np.asarray(bias).astype(compute_dtype).astype(np.float64)[None, :]
+    return y.reshape(tuple(np.asarray(x).shape[:-1]) + (shape[0],))
+
+
+# --------------------------------------------------------------------------------------
+# bitsandbytes LLM.int8
+# --------------------------------------------------------------------------------------
+def int8_vectorwise_quant(a: np.ndarray, threshold: float = 0.0):
+    """bitsandbytes.functional.int8_vectorwise_quant on fp16 input.
+
+    Returns (CA int8 [rows, cols], row_stats f32 [rows], outlier_cols int64 or None)."""
+    a16 = np.asarray(a).astype(np.float16)
+    af = _f32(a16).reshape(-1, a16.shape[-1])
+    rows, cols = af.shape
+    out = np.zeros((rows, cols), dtype=np.int8)
+    stats = np.zeros((rows,), dtype=np.float32)
+    flags = np.zeros((cols,), dtype=np.uint8)
+    lib().orc_bnb_int8_vectorwise_quant(_p(af), ctypes.c_int64(rows), ctypes.c_int64(cols),
+                                        ctypes.c_float(threshold), _p(out), _p(stats), _p(flags))
+    cols_idx = None
+    if threshold > 0.0 and flags.any():
+        cols_idx = np.nonzero(flags)[0].astype(np.int64)
+        if rows > 1:
+            lib().orc_bnb_zero_outlier_cols(_p(out), ctypes.c_int64(rows), ctypes.c_int64(cols),
+                                            _p(flags))
+    return out.reshape(a16.shape), stats, cols_idx
+
+
+def igemm_nt(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.int8)
+    b = np.ascontiguousarray(b, dtype=np.int8)
+    M, K = a.shape
+    N = b.shape[0]
+    c = np.zeros((M, N), dtype=np.int32)
+    lib().orc_igemm_nt(_p(a), _p(b), ctypes.c_int64(M), ctypes.c_int64(N), ctypes.c_int64(K), _p(c))
+    return c
+
+
+def int8_mm_dequant(c32, row_stats, col_stats, bias=None) -> np.ndarray:
+    c32 = np.ascontiguousarray(c32, dtype=np.int32)
+    M, N = c32.shape
+    out = np.empty((M, N), dtype=np.float32)
+    b = None if bias is None else _f32(bias)
+    lib().orc_bnb_mm_dequant(_p(c32), _p(_f32(row_stats)), _p(_f32(col_stats)), _p(b),
+                             ctypes.c_int64(M), ctypes.c_int64(N), _p(out))
+    return out.astype(np.float16)
+
+
+def int8_vectorwise_dequant(cb: np.ndarray, scb: np.ndarray) -> np.ndarray:
+    cb = np.ascontiguousarray(cb, dtype=np.int8)
+    N, K = cb.shape
+    out = np.empty((N, K), dtype=np.float32)
+    lib().orc_bnb_vectorwise_dequant(_p(cb), _p(_f32(scb)), ctypes.c_int64(N), ctypes.c_int64(K),
+                                     _p(out))
+    return out
+
+
+def linear8bitlt_forward(x: np.ndarray, CB: np.ndarray, SCB: np.ndarray, bias=None,
+                         threshold: float = 6.0):
+    """bitsandbytes MatMul8bitLt.forward (has_fp16_weights=False).
+
+    Returns (y fp16, y_outlier_part float64 or None).  Without outliers y is bit-exact; with
+    outliers y = fp16(fp32(y_int8_fp16) + subA @ subB) where the fp16 addmm's accumulation
+    order is unspecified, so callers compare with a 1-ulp(fp16)-scale tolerance."""
+    x16 = np.asarray(x).astype(np.float16)
+    A = x16.reshape(-1, x16.shape[-1])
+    CA, SCA, cols = int8_vectorwise_quant(A, threshold)
+    c32 = igemm_nt(CA, CB)
+    b16 = None if bias is None else np.asarray(bias).astype(np.float16)
+    y = int8_mm_dequant(c32, SCA, SCB, b16)
+    extra = None
+    if cols is not None and cols.size:
+        subA = A[:, cols].astype(np.float64)
+        subB = int8_vectorwise_dequant(CB[:, cols], SCB).astype(np.float16).astype(np.float64)
+        extra = subA @ subB.T
+        y = (y.astype(np.float32) + extra.astype(np.float32)).astype(np.float16)
+    return y.reshape(x16.shape[:-1] + (CB.shape[0],)), extra
+
+
+# --------------------------------------------------------------------------------------
+# optimum-quanto qint8
+# --------------------------------------------------------------------------------------
+def quanto_qint8(w: np.ndarray):
+    wf = _f32(w)
+    N, K = wf.shape
+    q = np.zeros((N, K), dtype=np.int8)
+    scale = np.zeros((N,), dtype=np.float32)
+    lib().orc_quanto_qint8(_p(wf), ctypes.c_int64(N), ctypes.c_int64(K), _p(q), _p(scale))
+    return q, scale.reshape(N, 1)
+
+
+def qlinear_forward(x: np.ndarray, q: np.ndarray, scale: np.ndarray, bias=None) -> np.ndarray:
+    """QLinear.forward (weights only): matmul(x, Wq.to(x.dtype).t()) * scale + bias, float64."""
+    xs = np.asarray(x).astype(np.float64)
+    y = xs.reshape(-1, q.shape[1]) @ q.astype(np.float64).T
+    y = y * np.asarray(scale).astype(np.float64).reshape(1, -1)
+    if bias is not None:
+        y = y + np.asarray(bias).astype(np.float64)[None, :]
+    return y.reshape(tuple(np.asarray(x).shape[:-1]) + (q.shape[0],))
+
+
+# --------------------------------------------------------------------------------------
+# torch dynamic int8
+# --------------------------------------------------------------------------------------
+def torch_weight_qint8(w: np.ndarray):
+    wf = _f32(w)
+    q = np.zeros(wf.shape, dtype=np.int8)
+    s = ctypes.c_float(0)
+    lib().orc_torch_weight_qint8(_p(wf), ctypes.c_int64(wf.size), _p(q), ctypes.byref(s))
+    return q, float(np.float32(s.value))
+
+
+def torch_act_quant(x: np.ndarray, reduce_range: bool = True):
+    xf = _f32(x)
+    q = np.zeros(xf.shape, dtype=np.uint8)
+    s = ctypes.c_float(0)
+    zp = ctypes.c_int32(0)
+    lib().orc_torch_act_quant(_p(xf), ctypes.c_int64(xf.size), ctypes.c_int(int(reduce_range)),
+                              _p(q), ctypes.byref(s), ctypes.byref(zp))
+    return q, float(np.float32(s.value)), int(zp.value)
+
+
+def igemm_u8s8_nt(a: np.ndarray, zp: int, b: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    b = np.ascontiguousarray(b, dtype=np.int8)
+    M, K = a.shape
+    N = b.shape[0]
+    c = np.zeros((M, N), dtype=np.int32)
+    lib().orc_igemm_u8s8_nt(_p(a), ctypes.c_int32(zp), _p(b), ctypes.c_int64(M), ctypes.c_int64(N),
+                            ctypes.c_int64(K), _p(c))
+    return c
+
+
+def torch_dynamic_linear(x: np.ndarray, wq: np.ndarray, w_scale: float, bias=None) -> np.ndarray:
+    """torch.ao.nn.quantized.dynamic.Linear.forward: per-tensor u8 activation (reduce_range),
+    u8 x s8 -> s32, y = acc * (s_x * s_w) + bias in fp32."""
+    xf = _f32(x)
+    xq, sx, zp = torch_act_quant(xf, True)
+    acc = igemm_u8s8_nt(xq.reshape(-1, xf.shape[-1]), zp, wq)
+    M, N = acc.shape
+    out = np.empty((M, N), dtype=np.float32)
+    b = None if bias is None else _f32(bias)
+    lib().orc_torch_requant(_p(acc), ctypes.c_float(sx), ctypes.c_float(w_scale), _p(b),
+                            ctypes.c_int64(M), ctypes.c_int64(N), _p(out))
+    return out.reshape(xf.shape[:-1] + (N,))
+
+
+# --------------------------------------------------------------------------------------
+# tallies
+# --------------------------------------------------------------------------------------
+def edit_distance(ref: Sequence[int], hyp: Sequence[int]) -> int:
+    r = np.ascontiguousarray(np.asarray(ref, dtype=np.int32))
+    h = np.ascontiguousarray(np.asarray(hyp, dtype=np.int32))
+    return int(lib().orc_edit_distance(_p(r), ctypes.c_int64(r.size), _p(h), ctypes.c_int64(h.size)))
+
+
+def _ids(tokens):
+    table = {}
+    return [table.setdefault(t, len(table)) for t in tokens], table
+
+
+def wer_cer_tally(references: Sequence[str], predictions: Sequence[str]) -> np.ndarray:
+    """int64[4] = {word errors, ref words, char errors, ref chars}; WER = 100*t[0]/t[1]
+    (evaluate.load('wer'/'cer') semantics, evaluation.py:110-116)."""
+    t = np.zeros(4, dtype=np.int64)
+    for ref, hyp in zip(references, predictions):
+        rw, hw = ref.split(), hyp.split()
+        vocab = {}
+        r = [vocab.setdefault(w, len(vocab)) for w in rw]
+        h = [vocab.setdefault(w, len(vocab)) for w in hw]
+        t[0] += edit_distance(r, h)
+        t[1] += len(rw)
+        t[2] += edit_distance([ord(c) for c in ref], [ord(c) for c in hyp])
+        t[3] += len(ref)
+    return t
+
+
+from .logmel import log_mel_spectrogram, mel_filter_bank_slaney  # noqa: E402,F401

@@ -1,0 +1,192 @@
+"""The oracle against the golden fixtures (tests/golden/, made by make_golden.py from the live
+torch / HF implementations the reference calls) and against its own algebraic invariants."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from tests.helpers import synth_audio
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_torch_dynamic_weight_codes_bit_exact(golden_dir, tag):
+    g = _load(golden_dir, f"torch_dynamic_{tag}.npz")
+    q, s = oracle.torch_weight_qint8(g["w"])
+    assert np.float32(s) == g["w_scale"]
+    assert int(g["w_zp"]) == 0
+    np.testing.assert_array_equal(q, g["w_int"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_torch_dynamic_activation_codes_bit_exact(golden_dir, tag):
+    g = _load(golden_dir, f"torch_dynamic_{tag}.npz")
+    q, s, zp = oracle.torch_act_quant(g["x"], True)
+    assert np.float32(s) == g["x_scale"]
+    assert zp == int(g["x_zp"])
+    np.testing.assert_array_equal(q, g["x_int"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_torch_dynamic_linear_output(golden_dir, tag):
+    g = _load(golden_dir, f"torch_dynamic_{tag}.npz")
+    y = oracle.torch_dynamic_linear(g["x"], g["w_int"], float(g["w_scale"]), g["bias"])
+    # integer part is exact; the fp32 requant differs from FBGEMM/oneDNN only in rounding order
+    np.testing.assert_allclose(y, g["y"], rtol=2e-6, atol=2e-6)
+
+
+def test_torch_dynamic_pruned_zeros_survive(golden_dir):
+    g = _load(golden_dir, "torch_dynamic_b.npz")
+    q, _ = oracle.torch_weight_qint8(g["w"])
+    assert (g["w"] == 0).mean() >= 0.5
+    assert np.all(q[g["w"] == 0] == 0)
+
+
+def test_prune_global_l1_golden(golden_dir):
+    """prune semantics the oracle assumes: exactly round(0.5*n) smallest |w| across both
+    tensors are zeroed, everything else untouched."""
+    g = _load(golden_dir, "prune_global_l1.npz")
+    w = np.concatenate([g["w0"].ravel(), g["w1"].ravel()])
+    p = np.concatenate([g["p0"].ravel(), g["p1"].ravel()])
+    k = int(round(0.5 * w.size))
+    assert (p == 0).sum() == k
+    thr = np.sort(np.abs(w))[k - 1]
+    assert np.all(np.abs(w[p == 0]) <= thr)
+    np.testing.assert_array_equal(p[p != 0], w[p != 0])
+
+
+@pytest.mark.parametrize("mels", [80, 128])
+def test_logmel_2s_matches_hf(golden_dir, mels):
+    g = _load(golden_dir, f"logmel_2s_{mels}.npz")
+    fb = oracle.mel_filter_bank_slaney(mels)
+    np.testing.assert_allclose(fb, g["mel_filters"], rtol=0, atol=1e-12)
+    for i, (n, seed) in enumerate(zip(g["lengths"], g["seeds"])):
+        out = oracle.log_mel_spectrogram(synth_audio(int(seed), int(n)), n_mels=mels, n_samples=32000)
+        assert out.shape == (1, mels, 200)
+        np.testing.assert_allclose(out[0], g["feats"][i], rtol=0, atol=2e-5)
+
+
+def test_logmel_30s_matches_hf(golden_dir):
+    g = _load(golden_dir, "logmel_30s_80.npz")
+    out = oracle.log_mel_spectrogram(synth_audio(int(g["audio_seed"])), n_mels=80)[0]
+    assert out.shape == (80, 3000)
+    np.testing.assert_allclose(out[:, g["frames"]], g["feats"], rtol=0, atol=2e-5)
+    assert abs(out.max() - float(g["fmax"])) < 2e-5
+    assert abs(out.sum() - float(g["fsum"])) < 0.5
+
+
+# ---------------------------------------------------------------------------------------------
+# self-derived known answers for the UNPINNED restatements (SURVEY.md section 8c "what we pin")
+# ---------------------------------------------------------------------------------------------
+def test_nf4_codebook_from_normal_quantiles():
+    """QLoRA create_normal_map(offset=0.9677083): regenerate the 16 NF4 values."""
+    from scipy.stats import norm
+    offset = 0.9677083
+    v1 = norm.ppf(np.linspace(offset, 0.5, 9)[:-1]).tolist()
+    v3 = (-norm.ppf(np.linspace(offset, 0.5, 8)[:-1])).tolist()
+    vals = np.array(sorted(v1 + [0.0] + v3), dtype=np.float64)
+    vals /= vals.max()
+    np.testing.assert_allclose(oracle.NF4_CODE, vals.astype(np.float32), rtol=0, atol=2e-7)
+
+
+def test_nf4_thresholds_are_midpoints_and_roundtrip():
+    code = oracle.NF4_CODE.astype(np.float64)
+    mids = (code[1:] + code[:-1]) / 2
+    # a value just above / below each midpoint lands in the upper / lower bin
+    blk = np.zeros(64, dtype=np.float32)
+    blk[0] = 1.0  # absmax = 1 -> normalised value == value
+    for i, m in enumerate(mids):
+        for delta, want in ((+1e-4, i + 1), (-1e-4, i)):
+            b = blk.copy()
+            b[1] = np.float32(m + delta)
+            packed, absmax = oracle.quantize_4bit(b)
+            assert absmax[0] == 1.0
+            assert (packed[0, 0] >> 4) == 15
+            assert (packed[0, 0] & 15) == want
+    # exact codebook values round-trip exactly
+    b = np.zeros(64, dtype=np.float32)
+    b[:16] = oracle.NF4_CODE
+    packed, absmax = oracle.quantize_4bit(b)
+    back = oracle.dequantize_4bit(packed, absmax, (64,), dtype=np.float32)
+    np.testing.assert_array_equal(back[:16], oracle.NF4_CODE)
+    assert np.all(back[16:] == 0)
+
+
+def test_nf4_zero_preserved_and_all_zero_block():
+    rng = np.random.RandomState(0)
+    w = (rng.randn(8, 128) * 0.02).astype(np.float16)
+    w[rng.rand(8, 128) < 0.5] = 0
+    w[3] = 0  # two all-zero blocks: absmax 0, 0*inf = NaN -> code 0, dequant -0.0 == 0
+    packed, absmax = oracle.quantize_4bit(w)
+    back = oracle.dequantize_4bit(packed, absmax, w.shape, dtype=np.float16)
+    assert np.all(back[w == 0] == 0)
+    assert absmax[6] == 0 and absmax[7] == 0
+    assert packed.shape == (8 * 128 // 2, 1) and absmax.shape == (16,)
+
+
+def test_nf4_ragged_and_empty():
+    w = np.linspace(-1, 1, 70).astype(np.float32)  # 64 + 6, odd count handled below
+    packed, absmax = oracle.quantize_4bit(w)
+    assert packed.shape == (35, 1) and absmax.shape == (2,)
+    w = np.linspace(-1, 1, 67).astype(np.float32)
+    packed, absmax = oracle.quantize_4bit(w)
+    assert packed.shape == (34, 1) and (packed[33, 0] & 15) == 7
+    packed, absmax = oracle.quantize_4bit(np.zeros((0,), np.float32))
+    assert packed.shape == (0, 1) and absmax.shape == (0,)
+
+
+def test_bnb_int8_rowmax_is_127_and_outliers():
+    rng = np.random.RandomState(1)
+    a = rng.randn(16, 96).astype(np.float16)
+    ca, stats, cols = oracle.int8_vectorwise_quant(a, 0.0)
+    assert cols is None
+    assert np.all(np.abs(ca).max(1) == 127)
+    np.testing.assert_array_equal(stats, np.abs(a.astype(np.float32)).max(1))
+    a[2, 5] = 7.5
+    a[9, 40] = -6.0  # |a| >= threshold is an outlier (not <)
+    ca, stats, cols = oracle.int8_vectorwise_quant(a, 6.0)
+    np.testing.assert_array_equal(cols, [5, 40])
+    assert np.all(ca[:, 5] == 0) and np.all(ca[:, 40] == 0)
+    assert stats[2] < 6.0 and stats[9] < 6.0
+
+
+def test_bnb_linear8bit_matches_fp_reference():
+    rng = np.random.RandomState(2)
+    W = (rng.randn(48, 64) * 0.05).astype(np.float16)
+    x = rng.randn(7, 64).astype(np.float16)
+    x[1, 3] = 9.0
+    bias = (rng.randn(48) * 0.1).astype(np.float16)
+    CB, SCB, _ = oracle.int8_vectorwise_quant(W, 0.0)
+    y, extra = oracle.linear8bitlt_forward(x, CB, SCB, bias, 6.0)
+    assert extra is not None
+    ref = x.astype(np.float64) @ W.astype(np.float64).T + bias.astype(np.float64)
+    assert np.abs(y.astype(np.float64) - ref).max() < 0.05
+
+
+def test_quanto_qint8_invariants():
+    rng = np.random.RandomState(3)
+    W = (rng.randn(32, 80) * 0.02).astype(np.float32)
+    W[rng.rand(32, 80) < 0.5] = 0
+    W[7] = 0
+    q, scale = oracle.quanto_qint8(W)
+    assert np.all(q[W == 0] == 0)
+    assert scale[7, 0] == 0 and np.all(q[7] == 0)
+    rows = [i for i in range(32) if i != 7]
+    assert np.all(np.abs(q[rows]).max(1) == 127)
+    np.testing.assert_array_equal(scale[:, 0], np.abs(W).max(1) / np.float32(127))
+    deq = q.astype(np.float32) * scale
+    assert np.abs(deq - W).max() <= scale.max() * 0.5 + 1e-9
+
+
+def test_edit_distance_and_tally():
+    assert oracle.edit_distance([1, 2, 3], [1, 2, 3]) == 0
+    assert oracle.edit_distance([1, 2, 3], []) == 3
+    assert oracle.edit_distance([], [4]) == 1
+    assert oracle.edit_distance([1, 2, 3, 4], [1, 3, 4, 5]) == 2
+    t = oracle.wer_cer_tally(["the cat sat", "a b"], ["the cat sat down", "a c"])
+    assert list(t[:2]) == [2, 5]
+    assert t[3] == len("the cat sat") + len("a b")
