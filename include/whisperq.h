@@ -1,0 +1,160 @@
+/*
+ * whisperq.h -- C ABI of libwhisperq.so, the B200 (sm_100a) implementation of the
+ * compressed-Whisper hot path (quantized / pruned linear layers + log-mel frontend).
+ *
+ * The reference (juligoat/openai-whisper-compression) is pure Python; its "FFI" for this path
+ * is the set of third-party entry points its module swaps reach.  Each function below names the
+ * interface it replaces (reference file:line of the call site, and the library routine behind
+ * it).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller (PyTorch)
+ *     owns all buffers, the library never frees or retains them beyond the call;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous and ordered on it;
+ *   - return value 0 = success, otherwise a wq_status code; wq_last_error() gives the text
+ *     (thread-local).  No exceptions or aborts cross the ABI.  There is no CPU fallback.
+ *   - matrices are row-major; "NT" GEMMs compute Y[M,N] = A[M,K] . W[N,K]^T.
+ */
+#ifndef WHISPERQ_H
+#define WHISPERQ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *wq_stream_t;
+
+enum wq_status {
+    WQ_OK = 0,
+    WQ_ERR_INVALID = 1,     /* bad argument (shape, alignment, dtype enum)   */
+    WQ_ERR_CUDA = 2,        /* a CUDA runtime / driver call failed           */
+    WQ_ERR_UNSUPPORTED = 3  /* device is not sm_100 or feature not built     */
+};
+
+enum wq_dtype { WQ_F32 = 0, WQ_F16 = 1, WQ_BF16 = 2 };
+enum wq_quant_type { WQ_NF4 = 0, WQ_FP4 = 1 };
+
+const char *wq_last_error(void);
+int wq_version(void);
+/* sm count and compute capability of the current device */
+int wq_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight packing / quantization (one-off at load; bit-exact against the oracle)
+ * ---------------------------------------------------------------------------------------- */
+
+/* bitsandbytes.functional.quantize_4bit -- reached from Params4bit.to(device)
+ * (pruning+quantization/bnb_implementation.py:1106-1116,1221; model_utils.py:24-49,112-118).
+ * w: n elements of w_dtype, flattened row-major.  packed: (n+1)/2 bytes, first element in the
+ * high nibble.  absmax: ceil(n/blocksize) fp32.  blocksize: power of two in [64, 4096]. */
+int wq_quant_4bit(const void *w, int w_dtype, int64_t n, int blocksize, int quant_type,
+                  uint8_t *packed, float *absmax, wq_stream_t stream);
+
+/* bitsandbytes.functional.dequantize_4bit (Linear4bit.forward; HF dequantize path
+ * transformers/integrations/bitsandbytes.py:249): out[i] = code[nibble] * absmax[block],
+ * rounded once to out_dtype. */
+int wq_dequant_4bit(const uint8_t *packed, const float *absmax, int64_t n, int blocksize,
+                    int quant_type, void *out, int out_dtype, wq_stream_t stream);
+
+/* bitsandbytes.functional.int8_vectorwise_quant -- Int8Params.to(device) for weights
+ * (threshold 0) and MatMul8bitLt.forward for activations (threshold 6.0); BASELINE.json
+ * config 2.  a: fp16 [rows, cols].  out int8 [rows, cols], row_stats fp32 [rows].
+ * threshold > 0: entries with |a| >= threshold are written as 0, excluded from the row absmax,
+ * and col_flags[c] (int32 [cols], must be zero on entry) is set to 1. col_flags may be NULL
+ * when threshold == 0. */
+int wq_quant_i8_rowwise_bnb(const void *a_f16, int64_t rows, int64_t cols, float threshold,
+                            int8_t *out, float *row_stats, int32_t *col_flags,
+                            wq_stream_t stream);
+
+/* Outlier bookkeeping of int8_vectorwise_quant / MatMul8bitLt without a host sync:
+ * compacts col_flags into outlier_cols[0..*n_outliers) (ascending), clears col_flags, then
+ * zeroes CA[:, outlier_cols].  n_outliers: device int32[1]. */
+int wq_outlier_columns(int32_t *col_flags, int64_t rows, int64_t cols, int8_t *ca,
+                       int32_t *outlier_cols, int32_t *n_outliers, wq_stream_t stream);
+
+/* optimum.quanto quantize(model, weights=qint8); freeze(model) -- model_utils.py:126-128,
+ * pruning+quantization/quanto_implementation.py:648-670.  Per output channel:
+ * scale[n] = max|W[n,:]| / 127 (fp32), q = clamp(rint(W / scale), -128, 127).  w: [N, K]. */
+int wq_quant_i8_rowwise_quanto(const void *w, int w_dtype, int64_t N, int64_t K, int8_t *q,
+                               float *scale, wq_stream_t stream);
+
+/* torch.quantization.quantize_dynamic weight observer + quantize_per_tensor --
+ * model_utils.py:131-134, pruning+quantization/pytorch_implementation.py:657-665.
+ * scale = max(-min, max) / 127.5 (>= FLT_EPSILON), q = clamp(nearbyint(w * (1/scale))).
+ * w fp32 [N, K]; scale: device fp32[1]; wsum: int32 [N] = sum_k q[n, k] (for the u8 zero
+ * point correction); workspace: device fp32[2] scratch. */
+int wq_quant_i8_tensor_torch(const float *w, int64_t N, int64_t K, int8_t *q, float *scale,
+                             int32_t *wsum, float *workspace, wq_stream_t stream);
+
+/* torch.ao.nn.quantized.dynamic.Linear activation quantization (per call): per-tensor affine
+ * uint8 over the whole tensor, reduce_range (0..127), FBGEMM ChooseQuantizationParams.
+ * x: n elements (fp32 or fp16); q: uint8[n]; qparams: device float[2] = {scale, (float)zp};
+ * workspace: device uint32[2] scratch. */
+int wq_quant_act_u8_tensor(const void *x, int x_dtype, int64_t n, uint8_t *q, float *qparams,
+                           uint32_t *workspace, wq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused GEMMs: TMA -> smem -> (in-register dequant) -> tcgen05.mma -> TMEM -> epilogue
+ * Alignment: all matrix base pointers 16 B; K % 16 == 0 (int8 operands) / K % 64 == 0 (4-bit).
+ * ---------------------------------------------------------------------------------------- */
+
+/* bnb.matmul(x, Int8Params, state) = int8_linear_matmul + int8_mm_dequant (+ fp16 outlier
+ * addmm) -- Linear8bitLt.forward, BASELINE.json config 2.
+ *   y[m,n] = fp16( fmaf(int32(CA[m,:].CB[n,:]) * SCA[m] * SCB[n], 1/127^2, bias[n]) )
+ *   if *n_outliers > 0:  y[m,n] = fp16( y[m,n] + sum_j A[m,c_j] * fp16(CB[n,c_j]*SCB[n]/127) )
+ * a_f16 / outlier_cols / n_outliers may be NULL (no outlier path).  bias: fp16 [N] or NULL. */
+int wq_gemm_llmint8(const int8_t *ca, const float *sca, const int8_t *cb, const float *scb,
+                    const void *bias_f16, void *y_f16, int64_t M, int64_t N, int64_t K,
+                    const void *a_f16, const int32_t *outlier_cols, const int32_t *n_outliers,
+                    wq_stream_t stream);
+
+/* quanto QLinear.forward, weights-only qint8 (W8A16) -- model_utils.py:126-128 call sites:
+ *   y = matmul(x, Wq.to(x.dtype).t()) * scale + bias, accumulated in fp32, rounded once.
+ * x: [M, K] of x_dtype (F16/BF16); wq int8 [N, K]; scale fp32 [N]; bias fp32 [N] or NULL;
+ * y: [M, N] of y_dtype. */
+int wq_gemm_w8a16(const void *x, int x_dtype, const int8_t *wq, const float *scale,
+                  const float *bias, void *y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                  wq_stream_t stream);
+
+/* bnb Linear4bit.forward (NF4/FP4, W4A16) -- bnb_implementation.py:1093-1118:
+ *   y = F.linear(x, dequantize_4bit(W).to(x.dtype), bias), fp32 accumulation.
+ * packed: [N*K/2] bytes, absmax fp32 [N*K/blocksize] (blocksize 64), x/y dtype F16 or BF16,
+ * bias fp32 [N] or NULL. */
+int wq_gemm_w4a16(const void *x, int x_dtype, const uint8_t *packed, const float *absmax,
+                  int quant_type, const float *bias, void *y, int y_dtype, int64_t M, int64_t N,
+                  int64_t K, wq_stream_t stream);
+
+/* torch.ao.nn.quantized.dynamic.Linear.forward GPU twin (quantized::linear_dynamic):
+ *   y[m,n] = float(acc[m,n] - zp * wsum[n]) * (s_x * s_w) + bias[n], fp32
+ * xq uint8 [M, K]; qparams device float[2] = {s_x, zp}; wq int8 [N, K]; w_scale device fp32[1];
+ * wsum int32 [N]; bias fp32 [N] or NULL; y fp32 [M, N]. */
+int wq_gemm_dyn_i8(const uint8_t *xq, const float *qparams, const int8_t *wq,
+                   const float *w_scale, const int32_t *wsum, const float *bias, float *y,
+                   int64_t M, int64_t N, int64_t K, wq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Log-mel frontend -- WhisperFeatureExtractor.__call__ as used by data_utils.py:55-59
+ * ---------------------------------------------------------------------------------------- */
+/* audio: fp32 [B, audio_stride]; lengths: int32 [B] valid samples per utterance (NULL = all
+ * n_samples); samples beyond the length are zero padding, utterances are truncated to
+ * n_samples.  filters: fp32 [201, n_mels].  out: fp32 or fp16 [B, n_mels, n_samples/160].
+ * Only WQ_F32 output is implemented.  workspace: device uint32[B + 2*n_mels] scratch. */
+int wq_logmel(const float *audio, int64_t B, int64_t audio_stride, const int32_t *lengths,
+              int64_t n_samples, const float *filters, int n_mels, void *out, int out_dtype,
+              uint32_t *workspace, wq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * WER / CER tallies -- evaluate.load("wer"/"cer").compute, evaluation.py:110-116
+ * ---------------------------------------------------------------------------------------- */
+/* Unit-cost Levenshtein distance for P pairs of int32 id sequences (word ids or code points).
+ * ref/hyp: concatenated ids; *_off: int64 [P+1] offsets; dist: int64 [P].  Sequences up to
+ * 4096 ids. */
+int wq_edit_distance(const int32_t *ref, const int64_t *ref_off, const int32_t *hyp,
+                     const int64_t *hyp_off, int64_t P, int64_t *dist, wq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WHISPERQ_H */

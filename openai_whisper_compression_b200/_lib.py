@@ -1,0 +1,65 @@
+"""ctypes loader for libwhisperq.so (the C ABI declared in include/whisperq.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, a
+RuntimeError is raised.  The library is never built implicitly at import time on a GPU box;
+run ``python -m openai_whisper_compression_b200.build`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwhisperq.so")
+
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_f32 = ctypes.c_float
+c_ptr = ctypes.c_void_p
+
+# name -> argtypes (restype is int unless listed in _RESTYPE); mirrors include/whisperq.h
+_PROTOS = {
+    "wq_version": [],
+    "wq_device_info": [c_ptr, c_ptr, c_ptr],
+    "wq_quant_4bit": [c_ptr, c_int, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr],
+    "wq_dequant_4bit": [c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_ptr],
+    "wq_quant_i8_rowwise_bnb": [c_ptr, c_i64, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_ptr],
+    "wq_outlier_columns": [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
+    "wq_quant_i8_rowwise_quanto": [c_ptr, c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
+    "wq_quant_i8_tensor_torch": [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    "wq_quant_act_u8_tensor": [c_ptr, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
+    "wq_gemm_llmint8": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
+    "wq_gemm_w8a16": [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],
+    "wq_gemm_w4a16": [c_ptr, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],
+    "wq_gemm_dyn_i8": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr],
+    "wq_logmel": [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_int, c_ptr, c_int, c_ptr, c_ptr],
+    "wq_edit_distance": [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr],
+}
+EXPORTS = tuple(["wq_last_error", *_PROTOS.keys()])
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the sm_100a CUDA library has not been built "
+            "(run `python -m openai_whisper_compression_b200.build`). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.wq_last_error.restype = ctypes.c_char_p
+    lib.wq_last_error.argtypes = []
+    for name, argtypes in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().wq_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libwhisperq {what} failed (status {rc}): {msg}")

@@ -1,0 +1,597 @@
+// gemm_tc.cu -- dequant-fused NT GEMMs on the 5th-generation tensor cores.
+//
+//   Y[M,N] = epilogue( A[M,K] . W[N,K]^T )
+//
+// One CTA computes a 128 x BN output tile.  Warp roles:
+//   warp 0      TMA producer: A tile (and the W tile, or the PACKED W tile) -> shared memory
+//   warp 1      TMEM allocation + single-thread tcgen05.mma issue, accumulator in TMEM
+//   warps 2..5  (W8A16 / W4A16 only) expand packed weights smem -> registers -> fp16/bf16 in the
+//               128-byte-swizzled UMMA operand layout; then the epilogue: tcgen05.ld the
+//               accumulator, apply the scheme's scale / bias formula, store.
+// Pipelines are mbarrier rings: full[s] (TMA bytes landed), bready[s] (dequantised operand
+// written + proxy fence), empty[s] (tcgen05.commit: the MMAs that read stage s are done),
+// tmem_full (accumulator complete).
+//
+// Schemes (reference call sites in include/whisperq.h):
+//   EPI_LLMINT8  s8 x s8 -> s32, y = fp16(fmaf(acc*SCA[m]*SCB[n], 1/127^2, bias[n]))   (bnb)
+//   EPI_DYN      u8 x s8 -> s32, y = (acc - zp*wsum[n]) * (s_x*s_w) + bias[n]          (torch)
+//   EPI_W8A16    f16 x f16(int8) -> f32, y = acc*scale[n] + bias[n]                    (quanto)
+//   EPI_W4A16    f16 x f16(code*absmax) -> f32, y = acc + bias[n]                       (bnb NF4)
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+using namespace wq;
+
+constexpr int BM = 128;            // rows of A per tile == TMEM lanes
+constexpr int ROW_BYTES = 128;     // bytes of K per smem row (one SW128 atom)
+constexpr int UMMA_K_BYTES = 32;   // one tcgen05.mma consumes 32 bytes of K per row
+constexpr int NUM_THREADS = 192;
+
+enum AKind { A_F16 = 0, A_BF16 = 1, A_S8 = 2, A_U8 = 3 };
+enum BMode { B_DIRECT = 0, B_I8 = 1, B_4BIT = 2 };
+enum Epi { EPI_LLMINT8 = 0, EPI_W8A16 = 1, EPI_W4A16 = 2, EPI_DYN = 3 };
+
+struct GemmArgs {
+    int M, N, K;
+    int num_kb;              // ceil(K / elements per 128-byte row)
+    const float *row_scale;  // SCA[m]                         (LLMINT8)
+    const float *col_scale;  // SCB[n] / quanto scale[n]       (LLMINT8, W8A16)
+    const void *bias;        // fp16 [N] (LLMINT8) / fp32 [N]  or nullptr
+    const float *absmax;     // [N, K/64]                      (W4A16)
+    int absmax_ld;           // K / 64
+    const float *qparams;    // {s_x, zp}                      (DYN)
+    const float *w_scale;    // s_w                            (DYN)
+    const int32_t *wsum;     // sum_k wq[n,k]                  (DYN)
+    void *out;
+    int quant_type;
+};
+
+template <int BN, int STAGES, int BMODE>
+struct SmemLayout {
+    static constexpr int A_BYTES = BM * ROW_BYTES;
+    static constexpr int B_BYTES = BN * ROW_BYTES;
+    static constexpr int P_ROW = BMODE == B_I8 ? 64 : (BMODE == B_4BIT ? 32 : 0);
+    static constexpr int P_BYTES = BN * P_ROW;
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
+    static constexpr int OFF_P = OFF_B + STAGES * B_BYTES;
+    static constexpr int OFF_CS = OFF_P + STAGES * P_BYTES;   // float col scale [BN]
+    static constexpr int OFF_BIAS = OFF_CS + BN * 4;          // float bias [BN]
+    static constexpr int OFF_AUX = OFF_BIAS + BN * 4;         // int32 wsum [BN]
+    static constexpr int OFF_LUT = OFF_AUX + BN * 4;          // float lut[16]
+    static constexpr int OFF_BAR = OFF_LUT + 64;              // uint64 barriers
+    static constexpr int NUM_BARS = 3 * STAGES + 1;
+    static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+    static constexpr int TOTAL = OFF_TMEM + 16 + 1024;        // + slack for manual 1024-B alignment
+    static constexpr int TX_BYTES = A_BYTES + (BMODE == B_DIRECT ? B_BYTES : P_BYTES);
+};
+
+template <typename OutT> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// 32 consecutive outputs of one row: vector stores when the row pitch allows, scalar otherwise.
+template <typename OutT>
+__device__ __forceinline__ void store_row32(OutT *row_ptr, int n_base, int N, const float (&v)[32], bool vec_ok) {
+    if (vec_ok && n_base + 32 <= N) {
+        if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                reinterpret_cast<float4 *>(row_ptr + n_base)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 u;
+                u.x = pack2<OutT>(v[8 * j + 0], v[8 * j + 1]);
+                u.y = pack2<OutT>(v[8 * j + 2], v[8 * j + 3]);
+                u.z = pack2<OutT>(v[8 * j + 4], v[8 * j + 5]);
+                u.w = pack2<OutT>(v[8 * j + 6], v[8 * j + 7]);
+                reinterpret_cast<uint4 *>(row_ptr + n_base)[j] = u;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (n_base + j < N) row_ptr[n_base + j] = from_f32<OutT>(v[j]);
+    }
+}
+
+template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT>
+__global__ void __launch_bounds__(NUM_THREADS)
+k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs args) {
+    using L = SmemLayout<BN, STAGES, BMODE>;
+    static_assert(BN == 64 || BN == 128, "BN must be 64 or 128 (power-of-two TMEM columns)");
+    constexpr bool kIntKind = (AKIND == A_S8 || AKIND == A_U8);
+    constexpr int A_ELEMS_PER_ROW = kIntKind ? 128 : 64;  // elements of K per 128-byte row
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::OFF_BAR);
+    uint64_t *bar_full = bars;
+    uint64_t *bar_empty = bars + STAGES;
+    uint64_t *bar_bready = bars + 2 * STAGES;
+    uint64_t *bar_tmem_full = bars + 3 * STAGES;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + L::OFF_TMEM);
+    float *s_cs = reinterpret_cast<float *>(smem + L::OFF_CS);
+    float *s_bias = reinterpret_cast<float *>(smem + L::OFF_BIAS);
+    int32_t *s_aux = reinterpret_cast<int32_t *>(smem + L::OFF_AUX);
+    float *s_lut = reinterpret_cast<float *>(smem + L::OFF_LUT);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    const int num_kb = args.num_kb;
+
+    // ---------------- setup ----------------
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+            mbar_init(&bar_bready[s], 4);
+        }
+        mbar_init(bar_tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_holder, BN);
+        tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < BN; i += NUM_THREADS) {
+        const int n = n0 + i;
+        const bool ok = n < args.N;
+        float cs = 0.0f, b = 0.0f;
+        int aux = 0;
+        if (ok) {
+            if constexpr (EPI == EPI_LLMINT8 || EPI == EPI_W8A16) cs = args.col_scale[n];
+            if (args.bias != nullptr) {
+                if constexpr (EPI == EPI_LLMINT8) b = __half2float(reinterpret_cast<const __half *>(args.bias)[n]);
+                else b = reinterpret_cast<const float *>(args.bias)[n];
+            }
+            if constexpr (EPI == EPI_DYN) aux = args.wsum[n];
+        }
+        s_cs[i] = cs;
+        s_bias[i] = b;
+        s_aux[i] = aux;
+    }
+    if constexpr (BMODE == B_4BIT) {
+        if (threadIdx.x < 16) s_lut[threadIdx.x] = args.quant_type ? kFP4Code[threadIdx.x] : kNF4Code[threadIdx.x];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&bar_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&bar_full[s], L::TX_BYTES);
+                tma_load_2d(smem + L::OFF_A + s * L::A_BYTES, &map_a, &bar_full[s], kb * A_ELEMS_PER_ROW, m0);
+                if constexpr (BMODE == B_DIRECT)
+                    tma_load_2d(smem + L::OFF_B + s * L::B_BYTES, &map_b, &bar_full[s], kb * 128, n0);
+                else
+                    tma_load_2d(smem + L::OFF_P + s * L::P_BYTES, &map_b, &bar_full[s], kb * L::P_ROW, n0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            constexpr uint32_t idesc =
+                kIntKind ? make_idesc(kAccS32, AKIND == A_S8 ? kFmtS8 : kFmtU8, kFmtS8, BM, BN)
+                         : make_idesc(kAccF32, AKIND == A_F16 ? kFmtF16 : kFmtBF16,
+                                      AKIND == A_F16 ? kFmtF16 : kFmtBF16, BM, BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&bar_full[s], ph);
+                if constexpr (BMODE != B_DIRECT) mbar_wait(&bar_bready[s], ph);
+                tc_fence_after();
+                const uint64_t adesc = make_smem_desc_sw128(smem + L::OFF_A + s * L::A_BYTES);
+                const uint64_t bdesc = make_smem_desc_sw128(smem + L::OFF_B + s * L::B_BYTES);
+#pragma unroll
+                for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
+                    const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                    if constexpr (kIntKind) umma_i8(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                    else umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                }
+                umma_commit(&bar_empty[s]);  // implicit tcgen05.fence::before_thread_sync
+            }
+            umma_commit(bar_tmem_full);
+        }
+        __syncwarp();
+    } else {
+        // ---------------- dequant (W8A16 / W4A16) then epilogue: warps 2..5 ----------------
+        const int t = threadIdx.x - 64;  // 0..127
+        if constexpr (BMODE == B_I8) {
+            const int qd = t & 3, row0 = t >> 2;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&bar_full[s], ph);
+                const uint8_t *P = smem + L::OFF_P + s * L::P_BYTES;
+                uint8_t *B = smem + L::OFF_B + s * L::B_BYTES;
+#pragma unroll
+                for (int p = 0; p < BN / 32; ++p) {
+                    const int r = row0 + 32 * p;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(P + r * 64 + qd * 16);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                    uint32_t o[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if constexpr (AKIND == A_F16) {
+                            // s8 -> fp16 exactly: (1024 + (s ^ 0x80)) - 1152
+                            const uint32_t x = w[j] ^ 0x80808080u;
+                            uint32_t lo = __byte_perm(x, 0x64646464u, 0x4140);
+                            uint32_t hi = __byte_perm(x, 0x64646464u, 0x4342);
+                            const __half2 bias2 = __half2half2(__ushort_as_half((unsigned short)0x6480));
+                            __half2 l2 = __hsub2(*reinterpret_cast<__half2 *>(&lo), bias2);
+                            __half2 h2 = __hsub2(*reinterpret_cast<__half2 *>(&hi), bias2);
+                            o[2 * j] = *reinterpret_cast<uint32_t *>(&l2);
+                            o[2 * j + 1] = *reinterpret_cast<uint32_t *>(&h2);
+                        } else {
+                            const float f0 = (float)(int8_t)(w[j] & 0xff), f1 = (float)(int8_t)((w[j] >> 8) & 0xff);
+                            const float f2 = (float)(int8_t)((w[j] >> 16) & 0xff), f3 = (float)(int8_t)(w[j] >> 24);
+                            o[2 * j] = pack2<__nv_bfloat16>(f0, f1);
+                            o[2 * j + 1] = pack2<__nv_bfloat16>(f2, f3);
+                        }
+                    }
+                    *reinterpret_cast<uint4 *>(B + sw128_offset(r, 2 * qd)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4 *>(B + sw128_offset(r, 2 * qd + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_bready[s]);
+            }
+        } else if constexpr (BMODE == B_4BIT) {
+            const int hf = t & 1, row0 = t >> 1;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                float am[BN / 64];
+#pragma unroll
+                for (int p = 0; p < BN / 64; ++p) {
+                    const int n = n0 + row0 + 64 * p;
+                    am[p] = (n < args.N) ? __ldg(args.absmax + (size_t)n * args.absmax_ld + kb) : 0.0f;
+                }
+                mbar_wait(&bar_full[s], ph);
+                const uint8_t *P = smem + L::OFF_P + s * L::P_BYTES;
+                uint8_t *B = smem + L::OFF_B + s * L::B_BYTES;
+#pragma unroll
+                for (int p = 0; p < BN / 64; ++p) {
+                    const int r = row0 + 64 * p;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(P + r * 32 + hf * 16);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t o[4];
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const uint32_t byte = (w[j] >> (8 * b)) & 0xffu;
+                            const float f0 = __fmul_rn(s_lut[byte >> 4], am[p]);
+                            const float f1 = __fmul_rn(s_lut[byte & 15u], am[p]);
+                            if constexpr (AKIND == A_F16) o[b] = pack2<__half>(f0, f1);
+                            else o[b] = pack2<__nv_bfloat16>(f0, f1);
+                        }
+                        *reinterpret_cast<uint4 *>(B + sw128_offset(r, 4 * hf + j)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_bready[s]);
+            }
+        }
+
+        // ---------------- epilogue ----------------
+        mbar_wait(bar_tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int m = m0 + q * 32 + lane;
+        const bool row_ok = m < args.M;
+        OutT *row_ptr = reinterpret_cast<OutT *>(args.out) + (size_t)(row_ok ? m : 0) * args.N;
+        const bool vec_ok = ((size_t)args.N * sizeof(OutT)) % 16 == 0;
+        float rs = 1.0f, dyn_s = 0.0f;
+        int dyn_zp = 0;
+        if constexpr (EPI == EPI_LLMINT8) rs = row_ok ? args.row_scale[m] : 0.0f;
+        if constexpr (EPI == EPI_DYN) {
+            dyn_s = __fmul_rn(args.qparams[0], args.w_scale[0]);
+            dyn_zp = (int)args.qparams[1];
+        }
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = c * 32 + j;
+                if constexpr (EPI == EPI_LLMINT8) {
+                    const float x = __fmul_rn(__fmul_rn((float)(int)r[j], rs), s_cs[col]);
+                    v[j] = __fmaf_rn(x, 6.200012e-05f, s_bias[col]);
+                } else if constexpr (EPI == EPI_DYN) {
+                    const int acc = (int)r[j] - dyn_zp * s_aux[col];
+                    v[j] = __fadd_rn(__fmul_rn((float)acc, dyn_s), s_bias[col]);
+                } else if constexpr (EPI == EPI_W8A16) {
+                    v[j] = __fadd_rn(__fmul_rn(__uint_as_float(r[j]), s_cs[col]), s_bias[col]);
+                } else {
+                    v[j] = __fadd_rn(__uint_as_float(r[j]), s_bias[col]);
+                }
+            }
+            if (row_ok) store_row32<OutT>(row_ptr, n0 + c * 32, args.N, v, vec_ok);
+        }
+    }
+
+    // ---------------- teardown ----------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LLM.int8 outlier term: y[m,n] = fp16(y[m,n] + sum_j A[m,c_j] * fp16(CB[n,c_j] * SCB[n] / 127))
+// (bitsandbytes MatMul8bitLt "mixed-precision decomposition"); exits at once when no outliers.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_llmint8_outliers(const __half *__restrict__ a, const int8_t *__restrict__ cb, const float *__restrict__ scb,
+                   const int32_t *__restrict__ cols, const int32_t *__restrict__ n_outliers, __half *__restrict__ y,
+                   int M, int N, int K) {
+    const int n_out = *n_outliers;
+    if (n_out == 0) return;
+    __shared__ float s_a[16][64 + 1];
+    __shared__ float s_w[16][64 + 1];
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 x 4 outputs each
+    float acc[4][4] = {};
+    for (int j0 = 0; j0 < n_out; j0 += 16) {
+        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+            const int jj = i >> 6, r = i & 63, j = j0 + jj;
+            float av = 0.0f, wv = 0.0f;
+            if (j < n_out) {
+                const int c = cols[j];
+                if (m0 + r < M) av = __half2float(a[(size_t)(m0 + r) * K + c]);
+                if (n0 + r < N) {
+                    const float d = __fmul_rn(__fmul_rn((float)cb[(size_t)(n0 + r) * K + c], scb[n0 + r]),
+                                              7.874015718698502e-3f);
+                    wv = __half2float(__float2half_rn(d));
+                }
+            }
+            s_a[jj][r] = av;
+            s_w[jj][r] = wv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[i][k] = fmaf(s_a[jj][ty * 4 + i], s_w[jj][tx * 4 + k], acc[i][k]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + k;
+            if (m < M && n < N) {
+                const size_t o = (size_t)m * N + n;
+                y[o] = __float2half_rn(__half2float(y[o]) + acc[i][k]);
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps + dispatch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D row-major matrix [rows, cols] of `elem_bytes`-byte elements, box = [box_rows, box_cols].
+int make_map_2d(CUtensorMap *map, const void *base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows,
+                uint64_t cols, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) {
+        wq_set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return WQ_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * (uint64_t)elem_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        wq_set_error("cuTensorMapEncodeTiled failed (%d): rows %llu cols %llu elem %d box %ux%u", (int)r,
+                     (unsigned long long)rows, (unsigned long long)cols, elem_bytes, box_rows, box_cols);
+        return WQ_ERR_CUDA;
+    }
+    return WQ_OK;
+}
+
+template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT>
+int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &args, cudaStream_t stream) {
+    using L = SmemLayout<BN, STAGES, BMODE>;
+    auto kfn = k_gemm_tc<BN, STAGES, AKIND, BMODE, EPI, OutT>;
+    static bool configured = false;
+    if (!configured) {
+        WQ_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        configured = true;
+    }
+    dim3 grid((args.N + BN - 1) / BN, (args.M + BM - 1) / BM);
+    kfn<<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma, mb, args);
+    WQ_LAUNCH_CHECK();
+    return WQ_OK;
+}
+
+// BN = 64 when a 128-wide tiling would leave most SMs idle (decode-shaped calls).
+bool use_narrow_tile(int64_t M, int64_t N) {
+    const int64_t tiles128 = ((M + BM - 1) / BM) * ((N + 127) / 128);
+    return tiles128 < wq_sm_count();
+}
+
+int check_common(const char *fn, int64_t M, int64_t N, int64_t K) {
+    WQ_REQUIRE(M >= 0 && N >= 0 && K > 0, "%s: bad shape M=%lld N=%lld K=%lld", fn, (long long)M, (long long)N,
+               (long long)K);
+    WQ_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "%s: shape exceeds int32", fn);
+    return wq_check_device();
+}
+
+}  // namespace
+
+extern "C" int wq_gemm_llmint8(const int8_t *ca, const float *sca, const int8_t *cb, const float *scb,
+                               const void *bias_f16, void *y_f16, int64_t M, int64_t N, int64_t K, const void *a_f16,
+                               const int32_t *outlier_cols, const int32_t *n_outliers, wq_stream_t stream) {
+    int rc = check_common("wq_gemm_llmint8", M, N, K);
+    if (rc != WQ_OK) return rc;
+    if (M == 0 || N == 0) return WQ_OK;
+    WQ_REQUIRE(ca && sca && cb && scb && y_f16, "wq_gemm_llmint8: null pointer");
+    WQ_REQUIRE(K % 16 == 0, "wq_gemm_llmint8: K=%lld must be a multiple of 16", (long long)K);
+    WQ_REQUIRE(wq_aligned(ca, 16) && wq_aligned(cb, 16) && wq_aligned(y_f16, 16), "wq_gemm_llmint8: misaligned buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    GemmArgs args = {};
+    args.M = (int)M; args.N = (int)N; args.K = (int)K;
+    args.num_kb = (int)((K + 127) / 128);
+    args.row_scale = sca; args.col_scale = scb; args.bias = bias_f16; args.out = y_f16;
+    CUtensorMap ma, mb;
+    rc = make_map_2d(&ma, ca, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, BM, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != WQ_OK) return rc;
+    if (use_narrow_tile(M, N)) {
+        rc = make_map_2d(&mb, cb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc != WQ_OK) return rc;
+        rc = launch_gemm<64, 4, A_S8, B_DIRECT, EPI_LLMINT8, __half>(ma, mb, args, s);
+    } else {
+        rc = make_map_2d(&mb, cb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc != WQ_OK) return rc;
+        rc = launch_gemm<128, 3, A_S8, B_DIRECT, EPI_LLMINT8, __half>(ma, mb, args, s);
+    }
+    if (rc != WQ_OK) return rc;
+    if (n_outliers != nullptr) {
+        WQ_REQUIRE(a_f16 && outlier_cols, "wq_gemm_llmint8: outlier path needs a_f16 and outlier_cols");
+        dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
+        k_llmint8_outliers<<<grid, 256, 0, s>>>((const __half *)a_f16, cb, scb, outlier_cols, n_outliers,
+                                                (__half *)y_f16, (int)M, (int)N, (int)K);
+        WQ_LAUNCH_CHECK();
+    }
+    return WQ_OK;
+}
+
+extern "C" int wq_gemm_dyn_i8(const uint8_t *xq, const float *qparams, const int8_t *wq, const float *w_scale,
+                              const int32_t *wsum, const float *bias, float *y, int64_t M, int64_t N, int64_t K,
+                              wq_stream_t stream) {
+    int rc = check_common("wq_gemm_dyn_i8", M, N, K);
+    if (rc != WQ_OK) return rc;
+    if (M == 0 || N == 0) return WQ_OK;
+    WQ_REQUIRE(xq && qparams && wq && w_scale && wsum && y, "wq_gemm_dyn_i8: null pointer");
+    WQ_REQUIRE(K % 16 == 0, "wq_gemm_dyn_i8: K=%lld must be a multiple of 16", (long long)K);
+    WQ_REQUIRE(wq_aligned(xq, 16) && wq_aligned(wq, 16) && wq_aligned(y, 16), "wq_gemm_dyn_i8: misaligned buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    GemmArgs args = {};
+    args.M = (int)M; args.N = (int)N; args.K = (int)K;
+    args.num_kb = (int)((K + 127) / 128);
+    args.qparams = qparams; args.w_scale = w_scale; args.wsum = wsum; args.bias = bias; args.out = y;
+    CUtensorMap ma, mb;
+    rc = make_map_2d(&ma, xq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, BM, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != WQ_OK) return rc;
+    if (use_narrow_tile(M, N)) {
+        rc = make_map_2d(&mb, wq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc != WQ_OK) return rc;
+        return launch_gemm<64, 4, A_U8, B_DIRECT, EPI_DYN, float>(ma, mb, args, s);
+    }
+    rc = make_map_2d(&mb, wq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != WQ_OK) return rc;
+    return launch_gemm<128, 3, A_U8, B_DIRECT, EPI_DYN, float>(ma, mb, args, s);
+}
+
+namespace {
+
+template <int BMODE, int EPI>
+int dispatch_a16(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &args, int x_dtype, int y_dtype,
+                 bool narrow, cudaStream_t s) {
+#define WQ_CASE(BN, AK, OT) return launch_gemm<BN, 4, AK, BMODE, EPI, OT>(ma, mb, args, s)
+    if (x_dtype == WQ_F16) {
+        if (y_dtype == WQ_F16) { if (narrow) WQ_CASE(64, A_F16, __half); else WQ_CASE(128, A_F16, __half); }
+        if (y_dtype == WQ_F32) { if (narrow) WQ_CASE(64, A_F16, float); else WQ_CASE(128, A_F16, float); }
+    } else if (x_dtype == WQ_BF16) {
+        if (y_dtype == WQ_BF16) { if (narrow) WQ_CASE(64, A_BF16, __nv_bfloat16); else WQ_CASE(128, A_BF16, __nv_bfloat16); }
+        if (y_dtype == WQ_F32) { if (narrow) WQ_CASE(64, A_BF16, float); else WQ_CASE(128, A_BF16, float); }
+    }
+#undef WQ_CASE
+    wq_set_error("unsupported dtype combination x=%d y=%d (x: F16/BF16, y: same as x or F32)", x_dtype, y_dtype);
+    return WQ_ERR_INVALID;
+}
+
+}  // namespace
+
+extern "C" int wq_gemm_w8a16(const void *x, int x_dtype, const int8_t *wq, const float *scale, const float *bias,
+                             void *y, int y_dtype, int64_t M, int64_t N, int64_t K, wq_stream_t stream) {
+    int rc = check_common("wq_gemm_w8a16", M, N, K);
+    if (rc != WQ_OK) return rc;
+    if (M == 0 || N == 0) return WQ_OK;
+    WQ_REQUIRE(x && wq && scale && y, "wq_gemm_w8a16: null pointer");
+    WQ_REQUIRE(K % 16 == 0, "wq_gemm_w8a16: K=%lld must be a multiple of 16", (long long)K);
+    WQ_REQUIRE(wq_aligned(x, 16) && wq_aligned(wq, 16) && wq_aligned(y, 16), "wq_gemm_w8a16: misaligned buffer");
+    GemmArgs args = {};
+    args.M = (int)M; args.N = (int)N; args.K = (int)K;
+    args.num_kb = (int)((K + 63) / 64);
+    args.col_scale = scale; args.bias = bias; args.out = y;
+    const bool narrow = use_narrow_tile(M, N);
+    CUtensorMap ma, mb;
+    rc = make_map_2d(&ma, x, x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     M, K, BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != WQ_OK) return rc;
+    rc = make_map_2d(&mb, wq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, narrow ? 64 : 128, 64,
+                     CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != WQ_OK) return rc;
+    return dispatch_a16<B_I8, EPI_W8A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream);
+}
+
+extern "C" int wq_gemm_w4a16(const void *x, int x_dtype, const uint8_t *packed, const float *absmax, int quant_type,
+                             const float *bias, void *y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                             wq_stream_t stream) {
+    int rc = check_common("wq_gemm_w4a16", M, N, K);
+    if (rc != WQ_OK) return rc;
+    if (M == 0 || N == 0) return WQ_OK;
+    WQ_REQUIRE(x && packed && absmax && y, "wq_gemm_w4a16: null pointer");
+    WQ_REQUIRE(K % 64 == 0, "wq_gemm_w4a16: K=%lld must be a multiple of the 64-element block", (long long)K);
+    WQ_REQUIRE(quant_type == WQ_NF4 || quant_type == WQ_FP4, "wq_gemm_w4a16: bad quant_type");
+    WQ_REQUIRE(wq_aligned(x, 16) && wq_aligned(packed, 16) && wq_aligned(y, 16), "wq_gemm_w4a16: misaligned buffer");
+    GemmArgs args = {};
+    args.M = (int)M; args.N = (int)N; args.K = (int)K;
+    args.num_kb = (int)(K / 64);
+    args.absmax = absmax; args.absmax_ld = (int)(K / 64);
+    args.bias = bias; args.out = y; args.quant_type = quant_type;
+    const bool narrow = use_narrow_tile(M, N);
+    CUtensorMap ma, mb;
+    rc = make_map_2d(&ma, x, x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     M, K, BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != WQ_OK) return rc;
+    rc = make_map_2d(&mb, packed, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K / 2, narrow ? 64 : 128, 32,
+                     CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != WQ_OK) return rc;
+    return dispatch_a16<B_4BIT, EPI_W4A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream);
+}

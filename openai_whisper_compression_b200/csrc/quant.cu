@@ -1,0 +1,528 @@
+// quant.cu -- weight packing and activation quantization kernels (HBM-bound, bit-exact).
+//
+// Every kernel here reads its input once from HBM (a second pass over the same warp-private
+// row / block hits L1), so the algorithmic bytes are sizeof(T)*n read + packed bytes written.
+// One warp owns one quantization group (a 64-element NF4 block or a matrix row), loads are
+// 16-byte vectors where alignment allows, reductions are warp shuffles.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+
+// ---------------------------------------------------------------------------------------------
+// 4-bit encode (bitsandbytes csrc/kernels.cu dQuantizeNF4 / dQuantizeFP4): strict '>' tree.
+// NaN (0 * inf for an all-zero block) fails every comparison and yields code 0.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t encode_nf4(float x) {
+    if (x > 0.03979014977812767f) {
+        if (x > 0.3893125355243683f) {
+            if (x > 0.6427869200706482f) return (x > 0.8614784181118011f) ? 15u : 14u;
+            return (x > 0.5016634166240692f) ? 13u : 12u;
+        }
+        if (x > 0.2035212516784668f) return (x > 0.2920137718319893f) ? 11u : 10u;
+        return (x > 0.1202552504837513f) ? 9u : 8u;
+    }
+    if (x > -0.33967943489551544f) {
+        if (x > -0.13791173323988914f) return (x > -0.045525018125772476f) ? 7u : 6u;
+        return (x > -0.23460740596055984f) ? 5u : 4u;
+    }
+    if (x > -0.6106329262256622f) return (x > -0.4599952697753906f) ? 3u : 2u;
+    return (x > -0.8480964004993439f) ? 1u : 0u;
+}
+
+__device__ __forceinline__ uint32_t encode_fp4(float x) {
+    uint32_t sign = x < 0.0f ? 8u : 0u;
+    x = fabsf(x);
+    if (x > 0.29166667f) {
+        if (x > 0.583333f) return (x > 0.8333333f ? 3u : 2u) + sign;
+        return (x > 0.4166667f ? 5u : 4u) + sign;
+    }
+    if (x > 0.0859375f) return (x > 0.20833333f ? 7u : 6u) + sign;
+    return (x > 0.00260417f ? 1u : 0u) + sign;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_quant_4bit(const T *__restrict__ w, int64_t n, int blocksize, int quant_type,
+             uint8_t *__restrict__ packed, float *__restrict__ absmax, int64_t nblocks) {
+    const int lane = threadIdx.x & 31;
+    const int64_t blk = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (blk >= nblocks) return;
+    const int64_t base = blk * blocksize;
+    const int64_t end = min(base + (int64_t)blocksize, n);
+
+    float am = 0.0f;
+    for (int64_t i = base + lane * 2; i < end; i += 64) {
+        float v0 = fabsf(to_f32(w[i]));
+        float v1 = (i + 1 < end) ? fabsf(to_f32(w[i + 1])) : 0.0f;
+        am = fmaxf(am, fmaxf(v0, v1));
+    }
+    am = warp_max(am);
+    if (lane == 0) absmax[blk] = am;
+    const float inv = __fdiv_rn(1.0f, am);
+
+    for (int64_t i = base + lane * 2; i < end; i += 64) {
+        float x0 = __fmul_rn(to_f32(w[i]), inv);
+        float x1 = (i + 1 < n) ? __fmul_rn(to_f32(w[i + 1]), inv) : 0.0f;
+        uint32_t c0 = quant_type ? encode_fp4(x0) : encode_nf4(x0);
+        uint32_t c1 = quant_type ? encode_fp4(x1) : encode_nf4(x1);
+        packed[i >> 1] = (uint8_t)((c0 << 4) | c1);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_dequant_4bit(const uint8_t *__restrict__ packed, const float *__restrict__ absmax, int64_t n,
+               int blocksize_log2, int quant_type, T *__restrict__ out) {
+    // one thread per packed byte pair group of 4 bytes (8 outputs)
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e0 = g * 8;
+    if (e0 >= n) return;
+    const float *code = quant_type ? kFP4Code : kNF4Code;
+    const float am = absmax[e0 >> blocksize_log2];
+    if (e0 + 8 <= n) {
+        const uint32_t p = *reinterpret_cast<const uint32_t *>(packed + (e0 >> 1));
+        T v[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t byte = (p >> (8 * j)) & 0xffu;
+            v[2 * j] = from_f32<T>(__fmul_rn(code[byte >> 4], am));
+            v[2 * j + 1] = from_f32<T>(__fmul_rn(code[byte & 15u], am));
+        }
+        if (sizeof(T) == 2) {
+            *reinterpret_cast<uint4 *>(out + e0) = *reinterpret_cast<uint4 *>(v);
+        } else {
+            reinterpret_cast<uint4 *>(out + e0)[0] = reinterpret_cast<uint4 *>(v)[0];
+            reinterpret_cast<uint4 *>(out + e0)[1] = reinterpret_cast<uint4 *>(v)[1];
+        }
+    } else {
+        for (int64_t i = e0; i < n; ++i) {
+            const uint32_t byte = packed[i >> 1];
+            const uint32_t c = (i & 1) ? (byte & 15u) : (byte >> 4);
+            out[i] = from_f32<T>(__fmul_rn(code[c], am));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bitsandbytes int8_vectorwise_quant: one warp per row of an fp16 matrix.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_quant_i8_rowwise_bnb(const __half *__restrict__ a, int64_t rows, int64_t cols, float threshold,
+                       int8_t *__restrict__ out, float *__restrict__ row_stats,
+                       int32_t *__restrict__ col_flags, int vec_ok) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const __half *pr = a + row * cols;
+    int8_t *po = out + row * cols;
+    const bool sparse = threshold > 0.0f;
+
+    float am = 0.0f;
+    if (vec_ok) {
+        for (int64_t c = lane * 8; c < cols; c += 256) {
+            const uint4 raw = *reinterpret_cast<const uint4 *>(pr + c);
+            const __half2 *h = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h[j]);
+                const float x = fabsf(f.x), y = fabsf(f.y);
+                if (!sparse || x < threshold) am = fmaxf(am, x);
+                if (!sparse || y < threshold) am = fmaxf(am, y);
+            }
+        }
+    } else {
+        for (int64_t c = lane; c < cols; c += 32) {
+            const float x = fabsf(__half2float(pr[c]));
+            if (!sparse || x < threshold) am = fmaxf(am, x);
+        }
+    }
+    am = warp_max(am);
+    if (lane == 0) row_stats[row] = am;
+    // bitsandbytes uses __fdividef(127, absmax); the IEEE quotient is used here so that the CPU
+    // oracle can be bit-exact (DESIGN.md "Known deviations").
+    const float scale = __fdiv_rn(127.0f, am);
+
+    if (vec_ok) {
+        for (int64_t c = lane * 8; c < cols; c += 256) {
+            const uint4 raw = *reinterpret_cast<const uint4 *>(pr + c);
+            const __half *h = reinterpret_cast<const __half *>(&raw);
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float v = __half2float(h[j]);
+                int q;
+                if (sparse && !(fabsf(v) < threshold)) {
+                    q = 0;
+                    col_flags[c + j] = 1;
+                } else {
+                    q = __float2int_rn(__fmul_rn(v, scale));  // NaN -> 0
+                }
+                const uint32_t b = (uint32_t)(q & 0xff);
+                if (j < 4) lo |= b << (8 * j); else hi |= b << (8 * (j - 4));
+            }
+            *reinterpret_cast<uint2 *>(po + c) = make_uint2(lo, hi);
+        }
+    } else {
+        for (int64_t c = lane; c < cols; c += 32) {
+            const float v = __half2float(pr[c]);
+            int q;
+            if (sparse && !(fabsf(v) < threshold)) {
+                q = 0;
+                col_flags[c] = 1;
+            } else {
+                q = __float2int_rn(__fmul_rn(v, scale));
+            }
+            po[c] = (int8_t)q;
+        }
+    }
+}
+
+// compaction of the outlier column flags (single CTA) -------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_outlier_compact(int32_t *__restrict__ col_flags, int cols, int32_t *__restrict__ outlier_cols,
+                  int32_t *__restrict__ n_outliers) {
+    __shared__ int s_warp[32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (cols + 1023) / 1024;
+    const int c0 = tid * per, c1 = min(c0 + per, cols);
+    int cnt = 0;
+    for (int c = c0; c < c1; ++c) cnt += col_flags[c] != 0;
+    // inclusive scan inside the warp, then across warps
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int v = s_warp[lane], w = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        s_warp[lane] = w - v;  // exclusive
+        if (lane == 31) s_total = w;
+    }
+    __syncthreads();
+    int pos = s_warp[wid] + inc - cnt;
+    for (int c = c0; c < c1; ++c) {
+        if (col_flags[c] != 0) {
+            outlier_cols[pos++] = c;
+            col_flags[c] = 0;
+        }
+    }
+    if (tid == 0) *n_outliers = s_total;
+}
+
+__global__ void __launch_bounds__(256)
+k_outlier_zero_cols(int8_t *__restrict__ ca, int64_t rows, int64_t cols,
+                    const int32_t *__restrict__ outlier_cols,
+                    const int32_t *__restrict__ n_outliers) {
+    const int n = *n_outliers;
+    if (n == 0) return;
+    const int64_t total = rows * (int64_t)n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n;
+        const int j = (int)(i - r * n);
+        ca[r * cols + outlier_cols[j]] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// quanto qint8 per-output-channel (warp per row)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_quant_i8_rowwise_quanto(const T *__restrict__ w, int64_t N, int64_t K, int8_t *__restrict__ q,
+                          float *__restrict__ scale) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (row >= N) return;
+    const T *pr = w + row * K;
+    float am = 0.0f;
+    for (int64_t c = lane; c < K; c += 32) am = fmaxf(am, fabsf(to_f32(pr[c])));
+    am = warp_max(am);
+    const float s = __fdiv_rn(am, 127.0f);
+    if (lane == 0) scale[row] = s;
+    for (int64_t c = lane; c < K; c += 32) {
+        float r = rintf(__fdiv_rn(to_f32(pr[c]), s));
+        if (r != r) r = 0.0f;
+        r = fminf(fmaxf(r, -128.0f), 127.0f);
+        q[row * K + c] = (int8_t)(int)r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// torch dynamic int8: per-tensor symmetric weights
+// ---------------------------------------------------------------------------------------------
+__global__ void k_minmax_init(uint32_t *ws) {
+    ws[0] = 0u;  // max of ordered(x)
+    ws[1] = 0u;  // max of ordered(-x)
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_minmax(const T *__restrict__ x, int64_t n, uint32_t *__restrict__ ws) {
+    float mx = -INFINITY, mn = INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = to_f32(x[i]);
+        mx = fmaxf(mx, v);
+        mn = fminf(mn, v);
+    }
+    mx = warp_max(mx);
+    mn = warp_min(mn);
+    __shared__ float s_mx[8], s_mn[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { s_mx[wid] = mx; s_mn[wid] = mn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) { mx = fmaxf(mx, s_mx[i]); mn = fminf(mn, s_mn[i]); }
+        if (mx >= mn) {  // at least one element seen by this CTA
+            atomicMax(&ws[0], float_to_ordered(mx));
+            atomicMax(&ws[1], float_to_ordered(-mn));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_quant_i8_tensor_torch(const float *__restrict__ w, int64_t N, int64_t K,
+                        const uint32_t *__restrict__ ws, int8_t *__restrict__ q,
+                        float *__restrict__ scale_out, int32_t *__restrict__ wsum) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    // MinMaxObserver(per_tensor_symmetric, qint8): torch/ao/quantization/observer.py
+    const float mx = ws[0] ? ordered_to_float(ws[0]) : 0.0f;
+    const float mn = ws[1] ? -ordered_to_float(ws[1]) : 0.0f;
+    const float min_neg = fminf(mn, 0.0f), max_pos = fmaxf(mx, 0.0f);
+    float scale = __fdiv_rn(fmaxf(-min_neg, max_pos), 127.5f);
+    scale = fmaxf(scale, 1.1920928955078125e-07f);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *scale_out = scale;
+    if (row >= N) return;
+    const float inv = __fdiv_rn(1.0f, scale);
+    int sum = 0;
+    for (int64_t c = lane; c < K; c += 32) {
+        float r = nearbyintf(__fmul_rn(w[row * K + c], inv));
+        r = fminf(fmaxf(r, -128.0f), 127.0f);
+        const int v = (int)r;
+        q[row * K + c] = (int8_t)v;
+        sum += v;
+    }
+    sum = warp_sum_i32(sum);
+    if (lane == 0) wsum[row] = sum;
+}
+
+// ---------------------------------------------------------------------------------------------
+// torch dynamic int8: per-tensor affine uint8 activations (FBGEMM ChooseQuantizationParams)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void choose_qparams_u8(float mn, float mx, float &scale, int &zp) {
+    const int qmin = 0, qmax = 127;  // reduce_range
+    mn = fminf(mn, 0.0f);
+    mx = fmaxf(mx, 0.0f);
+    scale = (float)(((double)mx - (double)mn) / (double)(qmax - qmin));
+    if (scale == 0.0f || isinf(__fdiv_rn(1.0f, scale))) scale = 0.1f;
+    const double zmin = qmin - (double)mn / (double)scale;
+    const double zmax = qmax - (double)mx / (double)scale;
+    const double emin = fabs((double)qmin) + fabs((double)mn / (double)scale);
+    const double emax = fabs((double)qmax) + fabs((double)mx / (double)scale);
+    const double init = emin < emax ? zmin : zmax;
+    if (init < qmin) zp = qmin;
+    else if (init > qmax) zp = qmax;
+    else zp = (int)nearbyint(init);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_quant_act_u8(const T *__restrict__ x, int64_t n, const uint32_t *__restrict__ ws,
+               uint8_t *__restrict__ q, float *__restrict__ qparams) {
+    float scale;
+    int zp;
+    choose_qparams_u8(ws[1] ? -ordered_to_float(ws[1]) : 0.0f, ws[0] ? ordered_to_float(ws[0]) : 0.0f,
+                      scale, zp);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        qparams[0] = scale;
+        qparams[1] = (float)zp;
+    }
+    const float inv = __fdiv_rn(1.0f, scale);
+    const float fzp = (float)zp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float r = __fadd_rn(nearbyintf(__fmul_rn(to_f32(x[i]), inv)), fzp);
+        r = fminf(fmaxf(r, 0.0f), 255.0f);
+        q[i] = (uint8_t)(int)r;
+    }
+}
+
+int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" int wq_quant_4bit(const void *w, int w_dtype, int64_t n, int blocksize, int quant_type,
+                             uint8_t *packed, float *absmax, wq_stream_t stream) {
+    WQ_REQUIRE(n >= 0, "wq_quant_4bit: n < 0");
+    WQ_REQUIRE(blocksize >= 64 && blocksize <= 4096 && (blocksize & (blocksize - 1)) == 0,
+               "wq_quant_4bit: blocksize %d must be a power of two in [64, 4096]", blocksize);
+    WQ_REQUIRE(quant_type == WQ_NF4 || quant_type == WQ_FP4, "wq_quant_4bit: bad quant_type");
+    if (n == 0) return WQ_OK;
+    WQ_REQUIRE(w && packed && absmax, "wq_quant_4bit: null pointer");
+    const int64_t nblocks = (n + blocksize - 1) / blocksize;
+    const unsigned grid = (unsigned)((nblocks + kWarpsPerCta - 1) / kWarpsPerCta);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (w_dtype) {
+        case WQ_F32:
+            k_quant_4bit<float><<<grid, kWarpsPerCta * 32, 0, s>>>((const float *)w, n, blocksize,
+                                                                    quant_type, packed, absmax, nblocks);
+            break;
+        case WQ_F16:
+            k_quant_4bit<__half><<<grid, kWarpsPerCta * 32, 0, s>>>((const __half *)w, n, blocksize,
+                                                                     quant_type, packed, absmax, nblocks);
+            break;
+        case WQ_BF16:
+            k_quant_4bit<__nv_bfloat16><<<grid, kWarpsPerCta * 32, 0, s>>>(
+                (const __nv_bfloat16 *)w, n, blocksize, quant_type, packed, absmax, nblocks);
+            break;
+        default:
+            WQ_REQUIRE(false, "wq_quant_4bit: bad dtype %d", w_dtype);
+    }
+    WQ_LAUNCH_CHECK();
+    return WQ_OK;
+}
+
+extern "C" int wq_dequant_4bit(const uint8_t *packed, const float *absmax, int64_t n, int blocksize,
+                               int quant_type, void *out, int out_dtype, wq_stream_t stream) {
+    WQ_REQUIRE(n >= 0, "wq_dequant_4bit: n < 0");
+    WQ_REQUIRE(blocksize >= 64 && blocksize <= 4096 && (blocksize & (blocksize - 1)) == 0,
+               "wq_dequant_4bit: blocksize %d must be a power of two in [64, 4096]", blocksize);
+    WQ_REQUIRE(quant_type == WQ_NF4 || quant_type == WQ_FP4, "wq_dequant_4bit: bad quant_type");
+    if (n == 0) return WQ_OK;
+    WQ_REQUIRE(packed && absmax && out, "wq_dequant_4bit: null pointer");
+    WQ_REQUIRE(wq_aligned(packed, 4) && wq_aligned(out, 16), "wq_dequant_4bit: misaligned buffer");
+    const int64_t groups = (n + 7) / 8;
+    const unsigned grid = (unsigned)((groups + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int lg = ilog2(blocksize);
+    switch (out_dtype) {
+        case WQ_F32:
+            k_dequant_4bit<float><<<grid, 256, 0, s>>>(packed, absmax, n, lg, quant_type, (float *)out);
+            break;
+        case WQ_F16:
+            k_dequant_4bit<__half><<<grid, 256, 0, s>>>(packed, absmax, n, lg, quant_type, (__half *)out);
+            break;
+        case WQ_BF16:
+            k_dequant_4bit<__nv_bfloat16><<<grid, 256, 0, s>>>(packed, absmax, n, lg, quant_type,
+                                                               (__nv_bfloat16 *)out);
+            break;
+        default:
+            WQ_REQUIRE(false, "wq_dequant_4bit: bad dtype %d", out_dtype);
+    }
+    WQ_LAUNCH_CHECK();
+    return WQ_OK;
+}
+
+extern "C" int wq_quant_i8_rowwise_bnb(const void *a_f16, int64_t rows, int64_t cols, float threshold,
+                                       int8_t *out, float *row_stats, int32_t *col_flags,
+                                       wq_stream_t stream) {
+    WQ_REQUIRE(rows >= 0 && cols >= 0, "wq_quant_i8_rowwise_bnb: negative shape");
+    WQ_REQUIRE(threshold >= 0.0f, "wq_quant_i8_rowwise_bnb: negative threshold");
+    if (rows == 0 || cols == 0) return WQ_OK;
+    WQ_REQUIRE(a_f16 && out && row_stats, "wq_quant_i8_rowwise_bnb: null pointer");
+    WQ_REQUIRE(threshold == 0.0f || col_flags, "wq_quant_i8_rowwise_bnb: threshold needs col_flags");
+    const int vec_ok = (cols % 8 == 0) && wq_aligned(a_f16, 16) && wq_aligned(out, 8);
+    const unsigned grid = (unsigned)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
+    k_quant_i8_rowwise_bnb<<<grid, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(
+        (const __half *)a_f16, rows, cols, threshold, out, row_stats, col_flags, vec_ok);
+    WQ_LAUNCH_CHECK();
+    return WQ_OK;
+}
+
+extern "C" int wq_outlier_columns(int32_t *col_flags, int64_t rows, int64_t cols, int8_t *ca,
+                                  int32_t *outlier_cols, int32_t *n_outliers, wq_stream_t stream) {
+    WQ_REQUIRE(rows >= 0 && cols >= 0 && cols < (1 << 30), "wq_outlier_columns: bad shape");
+    WQ_REQUIRE(col_flags && outlier_cols && n_outliers, "wq_outlier_columns: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    k_outlier_compact<<<1, 1024, 0, s>>>(col_flags, (int)cols, outlier_cols, n_outliers);
+    WQ_LAUNCH_CHECK();
+    if (rows > 0 && ca) {
+        const int grid = wq_sm_count() * 4;
+        k_outlier_zero_cols<<<grid, 256, 0, s>>>(ca, rows, cols, outlier_cols, n_outliers);
+        WQ_LAUNCH_CHECK();
+    }
+    return WQ_OK;
+}
+
+extern "C" int wq_quant_i8_rowwise_quanto(const void *w, int w_dtype, int64_t N, int64_t K, int8_t *q,
+                                          float *scale, wq_stream_t stream) {
+    WQ_REQUIRE(N >= 0 && K >= 0, "wq_quant_i8_rowwise_quanto: negative shape");
+    if (N == 0) return WQ_OK;
+    WQ_REQUIRE(w && q && scale, "wq_quant_i8_rowwise_quanto: null pointer");
+    const unsigned grid = (unsigned)((N + kWarpsPerCta - 1) / kWarpsPerCta);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (w_dtype) {
+        case WQ_F32:
+            k_quant_i8_rowwise_quanto<float><<<grid, kWarpsPerCta * 32, 0, s>>>((const float *)w, N, K, q, scale);
+            break;
+        case WQ_F16:
+            k_quant_i8_rowwise_quanto<__half><<<grid, kWarpsPerCta * 32, 0, s>>>((const __half *)w, N, K, q, scale);
+            break;
+        case WQ_BF16:
+            k_quant_i8_rowwise_quanto<__nv_bfloat16><<<grid, kWarpsPerCta * 32, 0, s>>>(
+                (const __nv_bfloat16 *)w, N, K, q, scale);
+            break;
+        default:
+            WQ_REQUIRE(false, "wq_quant_i8_rowwise_quanto: bad dtype %d", w_dtype);
+    }
+    WQ_LAUNCH_CHECK();
+    return WQ_OK;
+}
+
+extern "C" int wq_quant_i8_tensor_torch(const float *w, int64_t N, int64_t K, int8_t *q, float *scale,
+                                        int32_t *wsum, float *workspace, wq_stream_t stream) {
+    WQ_REQUIRE(N >= 0 && K >= 0, "wq_quant_i8_tensor_torch: negative shape");
+    WQ_REQUIRE(scale && workspace, "wq_quant_i8_tensor_torch: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t *ws = reinterpret_cast<uint32_t *>(workspace);
+    const int64_t n = N * K;
+    k_minmax_init<<<1, 1, 0, s>>>(ws);
+    if (n > 0) {
+        WQ_REQUIRE(w && q && wsum, "wq_quant_i8_tensor_torch: null pointer");
+        const int grid = (int)min((int64_t)wq_sm_count() * 8, (n + 255) / 256);
+        k_minmax<float><<<grid, 256, 0, s>>>(w, n, ws);
+    }
+    const unsigned grid2 = (unsigned)max((int64_t)1, (N + kWarpsPerCta - 1) / kWarpsPerCta);
+    k_quant_i8_tensor_torch<<<grid2, kWarpsPerCta * 32, 0, s>>>(w, N, K, ws, q, scale, wsum);
+    WQ_LAUNCH_CHECK();
+    return WQ_OK;
+}
+
+extern "C" int wq_quant_act_u8_tensor(const void *x, int x_dtype, int64_t n, uint8_t *q, float *qparams,
+                                      uint32_t *workspace, wq_stream_t stream) {
+    WQ_REQUIRE(n >= 0, "wq_quant_act_u8_tensor: n < 0");
+    WQ_REQUIRE(qparams && workspace, "wq_quant_act_u8_tensor: null pointer");
+    WQ_REQUIRE(x_dtype == WQ_F32 || x_dtype == WQ_F16, "wq_quant_act_u8_tensor: dtype must be F32/F16");
+    cudaStream_t s = (cudaStream_t)stream;
+    k_minmax_init<<<1, 1, 0, s>>>(workspace);
+    const int grid = (int)max((int64_t)1, min((int64_t)wq_sm_count() * 8, (n + 255) / 256));
+    if (x_dtype == WQ_F32) {
+        if (n > 0) k_minmax<float><<<grid, 256, 0, s>>>((const float *)x, n, workspace);
+        k_quant_act_u8<float><<<grid, 256, 0, s>>>((const float *)x, n, workspace, q, qparams);
+    } else {
+        if (n > 0) k_minmax<__half><<<grid, 256, 0, s>>>((const __half *)x, n, workspace);
+        k_quant_act_u8<__half><<<grid, 256, 0, s>>>((const __half *)x, n, workspace, q, qparams);
+    }
+    WQ_LAUNCH_CHECK();
+    return WQ_OK;
+}

@@ -1,0 +1,269 @@
+"""Tensor-level wrappers over the C ABI (include/whisperq.h).
+
+Names and argument meaning mirror the third-party routines the reference's module swaps reach
+(bitsandbytes.functional.*, optimum.quanto quantizers, torch dynamic quantization), so that the
+parity tests read like tests of those libraries.  PyTorch only provides device memory and the
+stream here; every computation is a hand-written sm_100a kernel in libwhisperq.so.  There is no
+CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+_QT = {"nf4": 0, "fp4": 1}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("openai_whisper_compression_b200 runs on CUDA (sm_100a) only; got a CPU tensor "
+                               "and there is no CPU fallback")
+        if not t.is_contiguous():
+            raise RuntimeError("expected a contiguous tensor")
+
+
+# ----------------------------------------------------------------------------------------------
+# bitsandbytes 4-bit
+# ----------------------------------------------------------------------------------------------
+def quantize_4bit(w: torch.Tensor, blocksize: int = 64, quant_type: str = "nf4"
+                  ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """bitsandbytes.functional.quantize_4bit -> (packed uint8 [(n+1)//2, 1], absmax f32 [n/bs])."""
+    w = w.contiguous()
+    _need_cuda(w)
+    n = w.numel()
+    packed = torch.empty(((n + 1) // 2, 1), dtype=torch.uint8, device=w.device)
+    absmax = torch.empty(((n + blocksize - 1) // blocksize,), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.load().wq_quant_4bit(_ptr(w), _DT[w.dtype], n, blocksize, _QT[quant_type], _ptr(packed),
+                                             _ptr(absmax), _stream()), "wq_quant_4bit")
+    return packed, absmax
+
+
+def dequantize_4bit(packed: torch.Tensor, absmax: torch.Tensor, shape, blocksize: int = 64,
+                    quant_type: str = "nf4", dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    """bitsandbytes.functional.dequantize_4bit."""
+    _need_cuda(packed, absmax)
+    out = torch.empty(tuple(shape), dtype=dtype, device=packed.device)
+    with torch.cuda.device(packed.device):
+        _lib.check(_lib.load().wq_dequant_4bit(_ptr(packed), _ptr(absmax), out.numel(), blocksize, _QT[quant_type],
+                                               _ptr(out), _DT[dtype], _stream()), "wq_dequant_4bit")
+    return out
+
+
+def gemm_w4a16(x: torch.Tensor, packed: torch.Tensor, absmax: torch.Tensor, N: int, K: int,
+               bias: Optional[torch.Tensor] = None, quant_type: str = "nf4",
+               out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Linear4bit.forward hot path: y = x @ dequantize_4bit(W).T + bias, fused (blocksize 64)."""
+    x2 = x.reshape(-1, K).contiguous()
+    _need_cuda(x2, packed, absmax, bias)
+    out_dtype = out_dtype or x2.dtype
+    y = torch.empty((x2.shape[0], N), dtype=out_dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().wq_gemm_w4a16(_ptr(x2), _DT[x2.dtype], _ptr(packed), _ptr(absmax), _QT[quant_type],
+                                             _ptr(bias), _ptr(y), _DT[out_dtype], x2.shape[0], N, K, _stream()),
+                   "wq_gemm_w4a16")
+    return y.reshape(*x.shape[:-1], N)
+
+
+# ----------------------------------------------------------------------------------------------
+# bitsandbytes LLM.int8
+# ----------------------------------------------------------------------------------------------
+class OutlierState:
+    """Per-device scratch for the outlier bookkeeping (flags are self-cleaning)."""
+
+    _cache = {}
+
+    def __init__(self, device: torch.device, cols: int):
+        self.col_flags = torch.zeros((cols,), dtype=torch.int32, device=device)
+        self.outlier_cols = torch.empty((cols,), dtype=torch.int32, device=device)
+        self.n_outliers = torch.zeros((1,), dtype=torch.int32, device=device)
+
+    @classmethod
+    def get(cls, device: torch.device, cols: int) -> "OutlierState":
+        key = (device.index, cols)
+        st = cls._cache.get(key)
+        if st is None:
+            st = cls._cache[key] = cls(device, cols)
+        return st
+
+
+def int8_vectorwise_quant(a: torch.Tensor, threshold: float = 0.0, state: Optional[OutlierState] = None):
+    """bitsandbytes.functional.int8_vectorwise_quant.
+
+    Returns (CA int8, row_stats f32, state).  With threshold > 0 the outlier columns stay on the
+    device (state.outlier_cols[: state.n_outliers]) -- no host synchronisation."""
+    a2 = a.reshape(-1, a.shape[-1])
+    if a2.dtype != torch.float16:
+        a2 = a2.to(torch.float16)
+    a2 = a2.contiguous()
+    _need_cuda(a2)
+    rows, cols = a2.shape
+    ca = torch.empty((rows, cols), dtype=torch.int8, device=a.device)
+    stats = torch.empty((rows,), dtype=torch.float32, device=a.device)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        if threshold > 0.0:
+            state = state or OutlierState.get(a.device, cols)
+            _lib.check(lib.wq_quant_i8_rowwise_bnb(_ptr(a2), rows, cols, float(threshold), _ptr(ca), _ptr(stats),
+                                                   _ptr(state.col_flags), _stream()), "wq_quant_i8_rowwise_bnb")
+            _lib.check(lib.wq_outlier_columns(_ptr(state.col_flags), rows, cols, _ptr(ca), _ptr(state.outlier_cols),
+                                              _ptr(state.n_outliers), _stream()), "wq_outlier_columns")
+        else:
+            state = None
+            _lib.check(lib.wq_quant_i8_rowwise_bnb(_ptr(a2), rows, cols, 0.0, _ptr(ca), _ptr(stats), None,
+                                                   _stream()), "wq_quant_i8_rowwise_bnb")
+    return ca.reshape(a.shape), stats, state
+
+
+def gemm_llmint8(ca: torch.Tensor, sca: torch.Tensor, cb: torch.Tensor, scb: torch.Tensor,
+                 bias: Optional[torch.Tensor] = None, a_f16: Optional[torch.Tensor] = None,
+                 state: Optional[OutlierState] = None) -> torch.Tensor:
+    """int8_linear_matmul + int8_mm_dequant (+ outlier addmm), fused; returns fp16 [M, N]."""
+    ca2 = ca.reshape(-1, ca.shape[-1])
+    _need_cuda(ca2, sca, cb, scb, bias, a_f16)
+    M, K = ca2.shape
+    N = cb.shape[0]
+    y = torch.empty((M, N), dtype=torch.float16, device=ca.device)
+    if bias is not None and bias.dtype != torch.float16:
+        raise RuntimeError("gemm_llmint8: bias must be fp16")
+    with torch.cuda.device(ca.device):
+        _lib.check(_lib.load().wq_gemm_llmint8(
+            _ptr(ca2), _ptr(sca), _ptr(cb), _ptr(scb), _ptr(bias), _ptr(y), M, N, K,
+            _ptr(a_f16) if state is not None else None,
+            _ptr(state.outlier_cols) if state is not None else None,
+            _ptr(state.n_outliers) if state is not None else None, _stream()), "wq_gemm_llmint8")
+    return y
+
+
+def linear8bitlt(x: torch.Tensor, cb: torch.Tensor, scb: torch.Tensor, bias: Optional[torch.Tensor],
+                 threshold: float) -> torch.Tensor:
+    """bnb.matmul(x, Int8Params, state) for has_fp16_weights=False."""
+    a = x.reshape(-1, x.shape[-1])
+    if a.dtype != torch.float16:
+        a = a.to(torch.float16)
+    a = a.contiguous()
+    ca, sca, st = int8_vectorwise_quant(a, threshold)
+    y = gemm_llmint8(ca, sca, cb, scb, bias, a if st is not None else None, st)
+    return y.reshape(*x.shape[:-1], cb.shape[0]).to(x.dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# optimum-quanto qint8
+# ----------------------------------------------------------------------------------------------
+def quanto_quantize_qint8(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """quanto AbsmaxOptimizer + SymmetricQuantizer (axis 0): (int8 [N, K], scale f32 [N, 1])."""
+    w = w.contiguous()
+    _need_cuda(w)
+    N, K = w.shape
+    q = torch.empty((N, K), dtype=torch.int8, device=w.device)
+    scale = torch.empty((N, 1), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.load().wq_quant_i8_rowwise_quanto(_ptr(w), _DT[w.dtype], N, K, _ptr(q), _ptr(scale),
+                                                          _stream()), "wq_quant_i8_rowwise_quanto")
+    return q, scale
+
+
+def gemm_w8a16(x: torch.Tensor, wq: torch.Tensor, scale: torch.Tensor, bias: Optional[torch.Tensor] = None,
+               out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """QLinear.forward hot path: y = (x @ Wq.T) * scale + bias with fp32 accumulation."""
+    N, K = wq.shape
+    x2 = x.reshape(-1, K).contiguous()
+    _need_cuda(x2, wq, scale, bias)
+    out_dtype = out_dtype or x2.dtype
+    y = torch.empty((x2.shape[0], N), dtype=out_dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().wq_gemm_w8a16(_ptr(x2), _DT[x2.dtype], _ptr(wq), _ptr(scale), _ptr(bias), _ptr(y),
+                                             _DT[out_dtype], x2.shape[0], N, K, _stream()), "wq_gemm_w8a16")
+    return y.reshape(*x.shape[:-1], N)
+
+
+# ----------------------------------------------------------------------------------------------
+# torch dynamic int8 (GPU twin)
+# ----------------------------------------------------------------------------------------------
+def torch_quantize_weight(w: torch.Tensor):
+    """MinMaxObserver(per_tensor_symmetric, qint8) + quantize_per_tensor.
+
+    Returns (int8 [N, K], scale f32 [1] on device, wsum int32 [N])."""
+    w = w.to(torch.float32).contiguous()
+    _need_cuda(w)
+    N, K = w.shape
+    q = torch.empty((N, K), dtype=torch.int8, device=w.device)
+    scale = torch.empty((1,), dtype=torch.float32, device=w.device)
+    wsum = torch.empty((N,), dtype=torch.int32, device=w.device)
+    ws = torch.empty((2,), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.load().wq_quant_i8_tensor_torch(_ptr(w), N, K, _ptr(q), _ptr(scale), _ptr(wsum), _ptr(ws),
+                                                        _stream()), "wq_quant_i8_tensor_torch")
+    return q, scale, wsum
+
+
+def torch_quantize_activation(x: torch.Tensor):
+    """Dynamic per-tensor quint8 (reduce_range): (uint8 like x, qparams f32 [2] = {scale, zp})."""
+    x = x.contiguous()
+    _need_cuda(x)
+    q = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    qparams = torch.empty((2,), dtype=torch.float32, device=x.device)
+    ws = torch.empty((2,), dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().wq_quant_act_u8_tensor(_ptr(x), _DT[x.dtype], x.numel(), _ptr(q), _ptr(qparams),
+                                                      _ptr(ws), _stream()), "wq_quant_act_u8_tensor")
+    return q, qparams
+
+
+def gemm_dyn_i8(xq: torch.Tensor, qparams: torch.Tensor, wq: torch.Tensor, w_scale: torch.Tensor,
+                wsum: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    N, K = wq.shape
+    x2 = xq.reshape(-1, K)
+    _need_cuda(x2, qparams, wq, w_scale, wsum, bias)
+    y = torch.empty((x2.shape[0], N), dtype=torch.float32, device=xq.device)
+    with torch.cuda.device(xq.device):
+        _lib.check(_lib.load().wq_gemm_dyn_i8(_ptr(x2), _ptr(qparams), _ptr(wq), _ptr(w_scale), _ptr(wsum),
+                                              _ptr(bias), _ptr(y), x2.shape[0], N, K, _stream()), "wq_gemm_dyn_i8")
+    return y.reshape(*xq.shape[:-1], N)
+
+
+# ----------------------------------------------------------------------------------------------
+# log-mel frontend and tallies
+# ----------------------------------------------------------------------------------------------
+def log_mel(audio: torch.Tensor, filters: torch.Tensor, n_samples: int = 480000,
+            lengths: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """WhisperFeatureExtractor numerics: audio f32 [B, L] -> [B, n_mels, n_samples // 160]."""
+    audio = audio.contiguous()
+    _need_cuda(audio, filters, lengths)
+    if audio.dtype != torch.float32 or filters.dtype != torch.float32:
+        raise RuntimeError("log_mel: audio and filters must be float32")
+    B, L = audio.shape
+    n_mels = filters.shape[1]
+    out = torch.empty((B, n_mels, n_samples // 160), dtype=out_dtype, device=audio.device)
+    ws = torch.empty((B + 2 * n_mels,), dtype=torch.int32, device=audio.device)
+    with torch.cuda.device(audio.device):
+        _lib.check(_lib.load().wq_logmel(_ptr(audio), B, L, _ptr(lengths), n_samples, _ptr(filters), n_mels,
+                                         _ptr(out), _DT[out_dtype], _ptr(ws), _stream()), "wq_logmel")
+    return out
+
+
+def edit_distance(ref: torch.Tensor, ref_off: torch.Tensor, hyp: torch.Tensor, hyp_off: torch.Tensor
+                  ) -> torch.Tensor:
+    """Levenshtein distance per pair (ids int32 concatenated, offsets int64 [P+1]) -> int64 [P]."""
+    _need_cuda(ref, ref_off, hyp, hyp_off)
+    P = ref_off.numel() - 1
+    dist = torch.empty((P,), dtype=torch.int64, device=ref.device)
+    with torch.cuda.device(ref.device):
+        _lib.check(_lib.load().wq_edit_distance(_ptr(ref), _ptr(ref_off), _ptr(hyp), _ptr(hyp_off), P, _ptr(dist),
+                                                _stream()), "wq_edit_distance")
+    return dist

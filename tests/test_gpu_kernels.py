@@ -1,0 +1,293 @@
+"""Parity of the sm_100a kernels (through the C ABI) against the CPU oracle on seeded inputs.
+
+Bars: bit-exact for codes, scales, integer accumulators and the fp32-formula epilogues that the
+oracle restates operation by operation (LLM.int8 without outliers, torch-dynamic requant);
+stated tolerances for floating-point accumulation (W8A16 / W4A16 GEMMs, outlier addmm, log-mel).
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.helpers import synth_audio
+
+pytestmark = pytest.mark.gpu
+
+F = None
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _load():
+    global F
+    from openai_whisper_compression_b200 import functional
+    F = functional
+    yield
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# 4-bit packing
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("quant_type", ["nf4", "fp4"])
+@pytest.mark.parametrize("shape,blocksize", [((96, 128), 64), ((33, 70), 64), ((7, 67), 64), ((64, 512), 256),
+                                             ((1, 64), 64), ((3, 4096), 4096)])
+def test_quantize_4bit_bit_exact(dtype, quant_type, shape, blocksize):
+    rng = np.random.RandomState(hash((shape, blocksize)) % 2**31)
+    w = (rng.randn(*shape) * 0.02).astype(np.float32)
+    w[rng.rand(*shape) < 0.3] = 0.0          # pruned weights
+    if shape[0] > 2:
+        w[2] = 0.0                            # all-zero blocks (absmax 0)
+    wt = dev(w, dtype)
+    w_ref = wt.float().cpu().numpy()          # exact values the kernel sees
+    packed, absmax = F.quantize_4bit(wt, blocksize, quant_type)
+    p_ref, a_ref = oracle.quantize_4bit(w_ref, blocksize, quant_type)
+    assert packed.shape == p_ref.shape and absmax.shape == a_ref.shape
+    np.testing.assert_array_equal(absmax.cpu().numpy(), a_ref)
+    np.testing.assert_array_equal(packed.cpu().numpy(), p_ref)
+    for out_dtype, np_dtype in ((torch.float16, np.float16), (torch.float32, np.float32)):
+        back = F.dequantize_4bit(packed, absmax, shape, blocksize, quant_type, out_dtype)
+        ref = oracle.dequantize_4bit(p_ref, a_ref, shape, blocksize, quant_type, np_dtype)
+        np.testing.assert_array_equal(back.cpu().numpy(), ref)
+    # pruned zeros survive the round trip exactly (SURVEY section 8 a8 contract) -- NF4 only:
+    # FP4 has no exact interior... it does (code 0), check both
+    back32 = F.dequantize_4bit(packed, absmax, shape, blocksize, quant_type, torch.float32).cpu().numpy()
+    assert np.all(back32[w_ref == 0] == 0)
+
+
+def test_quantize_4bit_empty():
+    w = torch.empty((0,), dtype=torch.float16, device="cuda")
+    packed, absmax = F.quantize_4bit(w)
+    assert packed.shape == (0, 1) and absmax.shape == (0,)
+
+
+def test_cpu_tensor_raises():
+    with pytest.raises(RuntimeError):
+        F.quantize_4bit(torch.zeros(64))
+
+
+# ------------------------------------------------------------------------------------------------
+# LLM.int8
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,cols", [(16, 96), (5, 384), (130, 512), (3, 50), (1, 2048)])
+@pytest.mark.parametrize("threshold", [0.0, 6.0])
+def test_int8_vectorwise_quant_bit_exact(rows, cols, threshold):
+    rng = np.random.RandomState(rows * 1000 + cols)
+    a = rng.randn(rows, cols).astype(np.float16)
+    if threshold > 0:
+        a[rows // 2, cols // 3] = 7.5
+        a[0, cols - 1] = -6.0
+        a[rows - 1, 0] = 100.0
+    if rows > 3:
+        a[3] = 0
+    ca, stats, st = F.int8_vectorwise_quant(dev(a), threshold)
+    ca_ref, stats_ref, cols_ref = oracle.int8_vectorwise_quant(a, threshold)
+    np.testing.assert_array_equal(stats.cpu().numpy(), stats_ref)
+    np.testing.assert_array_equal(ca.cpu().numpy(), ca_ref)
+    if threshold > 0:
+        n = int(st.n_outliers.item())
+        got = st.outlier_cols[:n].cpu().numpy()
+        np.testing.assert_array_equal(got, cols_ref)
+        assert int(st.col_flags.sum().item()) == 0      # self-cleaning
+    else:
+        assert st is None
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (7, 48, 64), (300, 200, 384), (1, 512, 512), (64, 1536, 384),
+                                   (257, 130, 2048)])
+@pytest.mark.parametrize("use_bias", [True, False])
+def test_linear8bitlt_no_outliers_bit_exact(M, N, K, use_bias):
+    rng = np.random.RandomState(M + N + K)
+    W = (rng.randn(N, K) * 0.05).astype(np.float16)
+    W[rng.rand(N, K) < 0.5] = 0
+    x = rng.randn(M, K).astype(np.float16)
+    bias = (rng.randn(N) * 0.1).astype(np.float16) if use_bias else None
+    CB, SCB, _ = oracle.int8_vectorwise_quant(W, 0.0)
+    cb, scb, _ = F.int8_vectorwise_quant(dev(W), 0.0)
+    np.testing.assert_array_equal(cb.cpu().numpy(), CB)
+    y = F.linear8bitlt(dev(x), cb, scb, None if bias is None else dev(bias), 6.0)
+    y_ref, extra = oracle.linear8bitlt_forward(x, CB, SCB, bias, 6.0)
+    assert extra is None
+    np.testing.assert_array_equal(y.cpu().numpy(), y_ref)
+
+
+@pytest.mark.parametrize("M,N,K", [(40, 96, 128), (130, 200, 384)])
+def test_linear8bitlt_with_outliers(M, N, K):
+    rng = np.random.RandomState(M * N)
+    W = (rng.randn(N, K) * 0.05).astype(np.float16)
+    x = rng.randn(M, K).astype(np.float16)
+    for (r, c, v) in [(1, 3, 9.0), (M - 1, K - 2, -12.5), (M // 2, 3, 6.0), (0, K // 2, 30.0)]:
+        x[r, c] = v
+    bias = (rng.randn(N) * 0.1).astype(np.float16)
+    CB, SCB, _ = oracle.int8_vectorwise_quant(W, 0.0)
+    y = F.linear8bitlt(dev(x), dev(CB), dev(SCB), dev(bias), 6.0).cpu().numpy()
+    y_ref, extra = oracle.linear8bitlt_forward(x, CB, SCB, bias, 6.0)
+    assert extra is not None
+    # fp16 addmm: one fp16 rounding of (y_int8 + outlier term); accumulation order differs
+    scale = np.maximum(np.abs(y_ref.astype(np.float32)), 1.0)
+    assert np.max(np.abs(y.astype(np.float32) - y_ref.astype(np.float32)) / scale) <= 2 ** -9
+    # rows/cols without outlier contribution are untouched and bit-exact
+    untouched = np.abs(extra) == 0
+    np.testing.assert_array_equal(y[untouched], y_ref[untouched])
+
+
+# ------------------------------------------------------------------------------------------------
+# quanto qint8
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("N,K", [(48, 64), (130, 384), (5, 50)])
+def test_quanto_qint8_bit_exact(dtype, N, K):
+    rng = np.random.RandomState(N * K)
+    w = (rng.randn(N, K) * 0.02).astype(np.float32)
+    w[rng.rand(N, K) < 0.5] = 0
+    w[1] = 0
+    wt = dev(w, dtype)
+    q, scale = F.quanto_quantize_qint8(wt)
+    q_ref, s_ref = oracle.quanto_qint8(wt.float().cpu().numpy())
+    np.testing.assert_array_equal(scale.cpu().numpy(), s_ref)
+    np.testing.assert_array_equal(q.cpu().numpy(), q_ref)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (7, 48, 64), (300, 200, 384), (1, 512, 512), (130, 51, 1280)])
+def test_qlinear_w8a16(dtype, tol, M, N, K):
+    """tolerance: the fp32-accumulated result is rounded once to the activation dtype, so the
+    error bound is one half-ulp of the output (2^-11 fp16 / 2^-8 bf16) relative to max(|y|, 1),
+    plus fp32 accumulation noise; tol leaves 4x headroom."""
+    rng = np.random.RandomState(M + N + K)
+    w = (rng.randn(N, K) * 0.05).astype(np.float32)
+    w[rng.rand(N, K) < 0.5] = 0
+    x = dev(rng.randn(M, K).astype(np.float32), dtype)
+    bias = (rng.randn(N) * 0.1).astype(np.float32)
+    q_ref, s_ref = oracle.quanto_qint8(w)
+    q, scale = F.quanto_quantize_qint8(dev(w))
+    y = F.gemm_w8a16(x, q, scale, dev(bias))
+    assert y.dtype == dtype
+    y_ref = oracle.qlinear_forward(x.float().cpu().numpy(), q_ref, s_ref, bias)
+    err = np.abs(y.float().cpu().numpy() - y_ref) / np.maximum(np.abs(y_ref), 1.0)
+    assert err.max() <= tol
+    y32 = F.gemm_w8a16(x, q, scale, dev(bias), out_dtype=torch.float32).cpu().numpy()
+    err32 = np.abs(y32 - y_ref) / np.maximum(np.abs(y_ref), 1.0)
+    assert err32.max() <= 2e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# NF4 W4A16
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("quant_type", ["nf4", "fp4"])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (7, 48, 128), (300, 200, 384), (1, 768, 768), (130, 51, 1280)])
+def test_linear4bit_w4a16(dtype, tol, quant_type, M, N, K):
+    rng = np.random.RandomState(M + N + K)
+    w = (rng.randn(N, K) * 0.05).astype(np.float32)
+    w[rng.rand(N, K) < 0.5] = 0
+    np_dt = np.float16 if dtype == torch.float16 else np.float32
+    wt = dev(w, dtype)
+    x = dev(rng.randn(M, K).astype(np.float32), dtype)
+    bias = (rng.randn(N) * 0.1).astype(np.float32)
+    packed, absmax = F.quantize_4bit(wt, 64, quant_type)
+    p_ref, a_ref = oracle.quantize_4bit(wt.float().cpu().numpy(), 64, quant_type)
+    np.testing.assert_array_equal(packed.cpu().numpy(), p_ref)
+    y32 = F.gemm_w4a16(x, packed, absmax, N, K, dev(bias), quant_type, out_dtype=torch.float32).cpu().numpy()
+    # oracle: dequantised weight rounded to the compute dtype (as bnb does), exact product
+    wd = F.dequantize_4bit(packed, absmax, (N, K), 64, quant_type, dtype).float().cpu().numpy().astype(np.float64)
+    if dtype == torch.float16:
+        wd_ref = oracle.dequantize_4bit(p_ref, a_ref, (N, K), 64, quant_type, np_dt).astype(np.float64)
+        np.testing.assert_array_equal(wd, wd_ref)
+    y_ref = x.float().cpu().numpy().astype(np.float64) @ wd.T + bias.astype(np.float64)[None, :]
+    err32 = np.abs(y32 - y_ref) / np.maximum(np.abs(y_ref), 1.0)
+    assert err32.max() <= 2e-5
+    y = F.gemm_w4a16(x, packed, absmax, N, K, dev(bias), quant_type)
+    err = np.abs(y.float().cpu().numpy() - y_ref) / np.maximum(np.abs(y_ref), 1.0)
+    assert err.max() <= tol
+
+
+# ------------------------------------------------------------------------------------------------
+# torch dynamic int8 GPU twin
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_torch_dynamic_twin_against_live_torch_golden(golden_dir, tag):
+    import os
+    g = np.load(os.path.join(golden_dir, f"torch_dynamic_{tag}.npz"))
+    q, scale, wsum = F.torch_quantize_weight(dev(g["w"]))
+    np.testing.assert_array_equal(q.cpu().numpy(), g["w_int"])
+    assert np.float32(scale.item()) == g["w_scale"]
+    np.testing.assert_array_equal(wsum.cpu().numpy(), g["w_int"].astype(np.int32).sum(1))
+    xq, qparams = F.torch_quantize_activation(dev(g["x"]))
+    np.testing.assert_array_equal(xq.cpu().numpy(), g["x_int"])
+    qp = qparams.cpu().numpy()
+    assert np.float32(qp[0]) == g["x_scale"] and int(qp[1]) == int(g["x_zp"])
+    y = F.gemm_dyn_i8(xq, qparams, q, scale, wsum, dev(g["bias"])).cpu().numpy()
+    y_orc = oracle.torch_dynamic_linear(g["x"], g["w_int"], float(g["w_scale"]), g["bias"])
+    np.testing.assert_array_equal(y, y_orc)                       # same fp32 formula: bit-exact
+    np.testing.assert_allclose(y, g["y"], rtol=2e-6, atol=2e-6)   # live torch (FBGEMM rounding order)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 200, 384), (1, 512, 512), (12, 51, 1536)])
+def test_torch_dynamic_twin_vs_oracle(M, N, K):
+    rng = np.random.RandomState(M + N + K)
+    w = (rng.randn(N, K) * 0.02).astype(np.float32)
+    x = (rng.randn(M, K) * 2).astype(np.float32)
+    bias = (rng.randn(N) * 0.1).astype(np.float32)
+    q, scale, wsum = F.torch_quantize_weight(dev(w))
+    q_ref, s_ref = oracle.torch_weight_qint8(w)
+    np.testing.assert_array_equal(q.cpu().numpy(), q_ref)
+    xq, qparams = F.torch_quantize_activation(dev(x))
+    y = F.gemm_dyn_i8(xq, qparams, q, scale, wsum, dev(bias)).cpu().numpy()
+    y_ref = oracle.torch_dynamic_linear(x, q_ref, s_ref, bias)
+    np.testing.assert_array_equal(y, y_ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# log-mel and tallies
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mels", [80, 128])
+def test_logmel_2s_golden(golden_dir, mels):
+    """tolerance 1e-4 abs on the (x+4)/4-scaled log10 features: fp32 FFT/mel rounding (HF itself
+    claims 1e-5 between its numpy and torch paths)."""
+    import os
+    g = np.load(os.path.join(golden_dir, f"logmel_2s_{mels}.npz"))
+    L = 40000
+    audio = np.zeros((3, L), dtype=np.float32)
+    for i, (n, seed) in enumerate(zip(g["lengths"], g["seeds"])):
+        audio[i, :n] = synth_audio(int(seed), int(n))
+    filters = dev(oracle.mel_filter_bank_slaney(mels).astype(np.float32))
+    lengths = torch.tensor([int(x) for x in g["lengths"]], dtype=torch.int32, device="cuda")
+    out = F.log_mel(dev(audio), filters, n_samples=32000, lengths=lengths).cpu().numpy()
+    assert out.shape == (3, mels, 200)
+    np.testing.assert_allclose(out, g["feats"], rtol=0, atol=1e-4)
+
+
+def test_logmel_30s_golden_and_oracle(golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "logmel_30s_80.npz"))
+    audio = np.stack([synth_audio(0), synth_audio(1)])
+    filters = dev(oracle.mel_filter_bank_slaney(80).astype(np.float32))
+    out = F.log_mel(dev(audio), filters).cpu().numpy()
+    assert out.shape == (2, 80, 3000)
+    np.testing.assert_allclose(out[0][:, g["frames"]], g["feats"], rtol=0, atol=1e-4)
+    ref = oracle.log_mel_spectrogram(audio[1], 80)[0]
+    np.testing.assert_allclose(out[1], ref, rtol=0, atol=1e-4)
+
+
+def test_edit_distance_matches_oracle():
+    rng = np.random.RandomState(5)
+    refs, hyps = [], []
+    for n in (0, 1, 5, 60, 400, 1000):
+        r = rng.randint(0, 30, size=n).astype(np.int32)
+        h = r.copy()
+        if n:
+            h = np.delete(h, rng.randint(0, n, size=n // 7))
+            h = np.insert(h, rng.randint(0, len(h) + 1, size=n // 5), 99)
+        refs.append(r)
+        hyps.append(h.astype(np.int32))
+    refs.append(np.array([1, 2, 3], np.int32)); hyps.append(np.zeros((0,), np.int32))
+    ro = np.cumsum([0] + [len(r) for r in refs]).astype(np.int64)
+    ho = np.cumsum([0] + [len(h) for h in hyps]).astype(np.int64)
+    d = F.edit_distance(dev(np.concatenate(refs)), dev(ro), dev(np.concatenate(hyps)), dev(ho)).cpu().numpy()
+    want = [oracle.edit_distance(r, h) for r, h in zip(refs, hyps)]
+    np.testing.assert_array_equal(d, want)
