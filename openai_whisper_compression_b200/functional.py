@@ -18,6 +18,42 @@ _DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 _QT = {"nf4": 0, "fp4": 1}
 
 
+class _Stats:
+    """Kernel-launch accounting (bench.py's `gpu_launches`) and optional CUDA-event timing of the
+    GEMM launches (bench.py's live roofline).  `launches` counts kernels of libwhisperq.so only."""
+
+    def __init__(self):
+        self.launches = 0
+        self.profile_min_rows = None      # set to an int to time GEMM calls with M >= this
+        self.records = []                 # (kind, M, N, K, start_event, end_event)
+
+    def reset(self):
+        self.launches = 0
+        self.records = []
+
+
+STATS = _Stats()
+
+
+class _Timed:
+    def __init__(self, kind, M, N, K):
+        self.on = STATS.profile_min_rows is not None and M >= STATS.profile_min_rows
+        self.key = (kind, M, N, K)
+
+    def __enter__(self):
+        if self.on:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.e1.record()
+            STATS.records.append((*self.key, self.e0, self.e1))
+        return False
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -51,6 +87,7 @@ def quantize_4bit(w: torch.Tensor, blocksize: int = 64, quant_type: str = "nf4"
     with torch.cuda.device(w.device):
         _lib.check(_lib.load().wq_quant_4bit(_ptr(w), _DT[w.dtype], n, blocksize, _QT[quant_type], _ptr(packed),
                                              _ptr(absmax), _stream()), "wq_quant_4bit")
+    STATS.launches += 1
     return packed, absmax
 
 
@@ -62,6 +99,7 @@ def dequantize_4bit(packed: torch.Tensor, absmax: torch.Tensor, shape, blocksize
     with torch.cuda.device(packed.device):
         _lib.check(_lib.load().wq_dequant_4bit(_ptr(packed), _ptr(absmax), out.numel(), blocksize, _QT[quant_type],
                                                _ptr(out), _DT[dtype], _stream()), "wq_dequant_4bit")
+    STATS.launches += 1
     return out
 
 
@@ -73,10 +111,11 @@ def gemm_w4a16(x: torch.Tensor, packed: torch.Tensor, absmax: torch.Tensor, N: i
     _need_cuda(x2, packed, absmax, bias)
     out_dtype = out_dtype or x2.dtype
     y = torch.empty((x2.shape[0], N), dtype=out_dtype, device=x.device)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _Timed("w4a16", x2.shape[0], N, K):
         _lib.check(_lib.load().wq_gemm_w4a16(_ptr(x2), _DT[x2.dtype], _ptr(packed), _ptr(absmax), _QT[quant_type],
                                              _ptr(bias), _ptr(y), _DT[out_dtype], x2.shape[0], N, K, _stream()),
                    "wq_gemm_w4a16")
+    STATS.launches += 1
     return y.reshape(*x.shape[:-1], N)
 
 
@@ -123,10 +162,12 @@ def int8_vectorwise_quant(a: torch.Tensor, threshold: float = 0.0, state: Option
                                                    _ptr(state.col_flags), _stream()), "wq_quant_i8_rowwise_bnb")
             _lib.check(lib.wq_outlier_columns(_ptr(state.col_flags), rows, cols, _ptr(ca), _ptr(state.outlier_cols),
                                               _ptr(state.n_outliers), _stream()), "wq_outlier_columns")
+            STATS.launches += 3
         else:
             state = None
             _lib.check(lib.wq_quant_i8_rowwise_bnb(_ptr(a2), rows, cols, 0.0, _ptr(ca), _ptr(stats), None,
                                                    _stream()), "wq_quant_i8_rowwise_bnb")
+            STATS.launches += 1
     return ca.reshape(a.shape), stats, state
 
 
@@ -141,12 +182,13 @@ def gemm_llmint8(ca: torch.Tensor, sca: torch.Tensor, cb: torch.Tensor, scb: tor
     y = torch.empty((M, N), dtype=torch.float16, device=ca.device)
     if bias is not None and bias.dtype != torch.float16:
         raise RuntimeError("gemm_llmint8: bias must be fp16")
-    with torch.cuda.device(ca.device):
+    with torch.cuda.device(ca.device), _Timed("llmint8", M, N, K):
         _lib.check(_lib.load().wq_gemm_llmint8(
             _ptr(ca2), _ptr(sca), _ptr(cb), _ptr(scb), _ptr(bias), _ptr(y), M, N, K,
             _ptr(a_f16) if state is not None else None,
             _ptr(state.outlier_cols) if state is not None else None,
             _ptr(state.n_outliers) if state is not None else None, _stream()), "wq_gemm_llmint8")
+    STATS.launches += 2 if state is not None else 1
     return y
 
 
@@ -175,6 +217,7 @@ def quanto_quantize_qint8(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     with torch.cuda.device(w.device):
         _lib.check(_lib.load().wq_quant_i8_rowwise_quanto(_ptr(w), _DT[w.dtype], N, K, _ptr(q), _ptr(scale),
                                                           _stream()), "wq_quant_i8_rowwise_quanto")
+    STATS.launches += 1
     return q, scale
 
 
@@ -186,9 +229,10 @@ def gemm_w8a16(x: torch.Tensor, wq: torch.Tensor, scale: torch.Tensor, bias: Opt
     _need_cuda(x2, wq, scale, bias)
     out_dtype = out_dtype or x2.dtype
     y = torch.empty((x2.shape[0], N), dtype=out_dtype, device=x.device)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _Timed("w8a16", x2.shape[0], N, K):
         _lib.check(_lib.load().wq_gemm_w8a16(_ptr(x2), _DT[x2.dtype], _ptr(wq), _ptr(scale), _ptr(bias), _ptr(y),
                                              _DT[out_dtype], x2.shape[0], N, K, _stream()), "wq_gemm_w8a16")
+    STATS.launches += 1
     return y.reshape(*x.shape[:-1], N)
 
 
@@ -209,6 +253,7 @@ def torch_quantize_weight(w: torch.Tensor):
     with torch.cuda.device(w.device):
         _lib.check(_lib.load().wq_quant_i8_tensor_torch(_ptr(w), N, K, _ptr(q), _ptr(scale), _ptr(wsum), _ptr(ws),
                                                         _stream()), "wq_quant_i8_tensor_torch")
+    STATS.launches += 3
     return q, scale, wsum
 
 
@@ -222,6 +267,7 @@ def torch_quantize_activation(x: torch.Tensor):
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().wq_quant_act_u8_tensor(_ptr(x), _DT[x.dtype], x.numel(), _ptr(q), _ptr(qparams),
                                                       _ptr(ws), _stream()), "wq_quant_act_u8_tensor")
+    STATS.launches += 3
     return q, qparams
 
 
@@ -231,9 +277,10 @@ def gemm_dyn_i8(xq: torch.Tensor, qparams: torch.Tensor, wq: torch.Tensor, w_sca
     x2 = xq.reshape(-1, K)
     _need_cuda(x2, qparams, wq, w_scale, wsum, bias)
     y = torch.empty((x2.shape[0], N), dtype=torch.float32, device=xq.device)
-    with torch.cuda.device(xq.device):
+    with torch.cuda.device(xq.device), _Timed("dyn_i8", x2.shape[0], N, K):
         _lib.check(_lib.load().wq_gemm_dyn_i8(_ptr(x2), _ptr(qparams), _ptr(wq), _ptr(w_scale), _ptr(wsum),
                                               _ptr(bias), _ptr(y), x2.shape[0], N, K, _stream()), "wq_gemm_dyn_i8")
+    STATS.launches += 1
     return y.reshape(*xq.shape[:-1], N)
 
 
@@ -254,6 +301,7 @@ def log_mel(audio: torch.Tensor, filters: torch.Tensor, n_samples: int = 480000,
     with torch.cuda.device(audio.device):
         _lib.check(_lib.load().wq_logmel(_ptr(audio), B, L, _ptr(lengths), n_samples, _ptr(filters), n_mels,
                                          _ptr(out), _DT[out_dtype], _ptr(ws), _stream()), "wq_logmel")
+    STATS.launches += 3
     return out
 
 
@@ -266,4 +314,5 @@ def edit_distance(ref: torch.Tensor, ref_off: torch.Tensor, hyp: torch.Tensor, h
     with torch.cuda.device(ref.device):
         _lib.check(_lib.load().wq_edit_distance(_ptr(ref), _ptr(ref_off), _ptr(hyp), _ptr(hyp_off), P, _ptr(dist),
                                                 _stream()), "wq_edit_distance")
+    STATS.launches += 1
     return dist

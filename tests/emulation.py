@@ -22,7 +22,8 @@ class EmuLinear8bitLt(nn.Module):
         super().__init__()
         W = lin.weight.detach().half().float()
         self.SCB = W.abs().amax(1)
-        self.CB = torch.nan_to_num(torch.round(W * (127.0 / self.SCB)[:, None])).to(torch.int8)
+        # NB: `127.0 / t` in torch is reciprocal(t) * 127 (two roundings); the kernel/oracle use the IEEE quotient
+        self.CB = torch.nan_to_num(torch.round(W * torch.div(torch.full_like(self.SCB, 127.0), self.SCB)[:, None])).to(torch.int8)
         self.bias = None if lin.bias is None else lin.bias.detach().half()
         self.threshold = threshold
 
@@ -31,7 +32,7 @@ class EmuLinear8bitLt(nn.Module):
         Af = A.float()
         out = Af.abs() >= self.threshold
         am = torch.where(out, torch.zeros_like(Af), Af.abs()).amax(1)
-        CA = torch.nan_to_num(torch.round(Af * (127.0 / am)[:, None]))
+        CA = torch.nan_to_num(torch.round(Af * torch.div(torch.full_like(am, 127.0), am)[:, None]))
         CA = torch.where(out, torch.zeros_like(CA), CA)
         cols = out.any(0)
         CA[:, cols] = 0
