@@ -2,15 +2,18 @@
 //
 //   Y[M,N] = epilogue( A[M,K] . W[N,K]^T )
 //
-// One CTA computes a 128 x BN output tile.  Warp roles:
-//   warp 0      TMA producer: A tile (and the W tile, or the PACKED W tile) -> shared memory
-//   warp 1      TMEM allocation + single-thread tcgen05.mma issue, accumulator in TMEM
-//   warps 2..5  (W8A16 / W4A16 only) expand packed weights smem -> registers -> fp16/bf16 in the
-//               128-byte-swizzled UMMA operand layout; then the epilogue: tcgen05.ld the
-//               accumulator, apply the scheme's scale / bias formula, store.
+// Persistent kernel: one CTA per SM walks 256 x BN output tiles (two 128-row UMMA halves; n fastest, so the CTAs that
+// share an A row-block run together and hit L2).  Warp roles:
+//   warp 0      TMA producer: A tile (and the W tile, or the PACKED W tile) -> shared memory ring
+//   warp 1      TMEM allocation + single-thread tcgen05.mma issue into a 2-deep TMEM accumulator ring
+//   warps 2..9  epilogue (2 halves x 4 TMEM lane quarters): tcgen05.ld the accumulator (one TMEM lane
+//               = one output row per thread), apply the scheme's scale / bias formula, stage 32 x 128 B
+//               boxes in swizzled shared memory and hand them to TMA stores -- overlaps the next tile
+//   warps 10..  (W8A16: 4, W4A16: 8) expand packed weights smem -> registers -> fp16/bf16 in the
+//               128-byte-swizzled UMMA operand layout; one expanded W tile feeds both 128-row halves
 // Pipelines are mbarrier rings: full[s] (TMA bytes landed), bready[s] (dequantised operand
 // written + proxy fence), empty[s] (tcgen05.commit: the MMAs that read stage s are done),
-// tmem_full (accumulator complete).
+// tmem_full[a] / tmem_empty[a] (accumulator complete / drained).
 //
 // Schemes (reference call sites in include/whisperq.h):
 //   EPI_LLMINT8  s8 x s8 -> s32, y = fp16(fmaf(acc*SCA[m]*SCB[n], 1/127^2, bias[n]))   (bnb)
@@ -23,10 +26,13 @@
 namespace {
 using namespace wq;
 
-constexpr int BM = 128;            // rows of A per tile == TMEM lanes
+constexpr int BM = 256;            // rows of A per tile: two 128-row UMMA halves sharing one W tile
+constexpr int BMH = 128;           // rows per UMMA (== TMEM lanes)
 constexpr int ROW_BYTES = 128;     // bytes of K per smem row (one SW128 atom)
 constexpr int UMMA_K_BYTES = 32;   // one tcgen05.mma consumes 32 bytes of K per row
-constexpr int NUM_THREADS = 192;
+constexpr int ACC_STAGES = 2;      // TMEM accumulator ring (epilogue of tile i overlaps mainloop of i+1)
+constexpr int EPI_WARPS = 8;       // 2 halves x 4 TMEM lane quarters
+constexpr int BOX_BYTES = 32 * 128;  // one TMA-store box: 32 rows x 128 bytes (SWIZZLE_128B)
 
 enum AKind { A_F16 = 0, A_BF16 = 1, A_S8 = 2, A_U8 = 3 };
 enum BMode { B_DIRECT = 0, B_I8 = 1, B_4BIT = 2 };
@@ -35,6 +41,8 @@ enum Epi { EPI_LLMINT8 = 0, EPI_W8A16 = 1, EPI_W4A16 = 2, EPI_DYN = 3 };
 struct GemmArgs {
     int M, N, K;
     int num_kb;              // ceil(K / elements per 128-byte row)
+    int tiles_m, tiles_n;
+    int tma_store;           // 1: epilogue stores through smem + TMA; 0: direct global stores
     const float *row_scale;  // SCA[m]                         (LLMINT8)
     const float *col_scale;  // SCB[n] / quanto scale[n]       (LLMINT8, W8A16)
     const void *bias;        // fp16 [N] (LLMINT8) / fp32 [N]  or nullptr
@@ -47,7 +55,10 @@ struct GemmArgs {
     int quant_type;
 };
 
-template <int BN, int STAGES, int BMODE>
+template <int BMODE> constexpr int dq_warps() { return BMODE == B_DIRECT ? 0 : (BMODE == B_4BIT ? 8 : 4); }
+template <int BMODE> constexpr int num_threads() { return 32 * (2 + EPI_WARPS + dq_warps<BMODE>()); }
+
+template <int BN, int STAGES, int BMODE, int OUT_BUFS>
 struct SmemLayout {
     static constexpr int A_BYTES = BM * ROW_BYTES;
     static constexpr int B_BYTES = BN * ROW_BYTES;
@@ -56,15 +67,14 @@ struct SmemLayout {
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
     static constexpr int OFF_P = OFF_B + STAGES * B_BYTES;
-    static constexpr int OFF_CS = OFF_P + STAGES * P_BYTES;   // float col scale [BN]
-    static constexpr int OFF_BIAS = OFF_CS + BN * 4;          // float bias [BN]
-    static constexpr int OFF_AUX = OFF_BIAS + BN * 4;         // int32 wsum [BN]
-    static constexpr int OFF_LUT = OFF_AUX + BN * 4;          // float lut[16]
-    static constexpr int OFF_BAR = OFF_LUT + 64;              // uint64 barriers
-    static constexpr int NUM_BARS = 3 * STAGES + 1;
+    static constexpr int OFF_OUT = OFF_P + STAGES * P_BYTES;   // EPI_WARPS x OUT_BUFS boxes, 1024-byte aligned
+    static constexpr int OFF_LUT = OFF_OUT + EPI_WARPS * OUT_BUFS * BOX_BYTES;  // float lut[16]
+    static constexpr int OFF_BAR = OFF_LUT + 64;               // uint64 barriers
+    static constexpr int NUM_BARS = 3 * STAGES + 2 * ACC_STAGES;
     static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
-    static constexpr int TOTAL = OFF_TMEM + 16 + 1024;        // + slack for manual 1024-B alignment
+    static constexpr int TOTAL = OFF_TMEM + 16 + 1024;         // + slack for manual 1024-B alignment
     static constexpr int TX_BYTES = A_BYTES + (BMODE == B_DIRECT ? B_BYTES : P_BYTES);
+    static_assert(TOTAL <= 232448, "shared memory budget exceeded");
 };
 
 template <typename OutT> __device__ __forceinline__ uint32_t pack2(float a, float b);
@@ -77,39 +87,102 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, fl
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-// 32 consecutive outputs of one row: vector stores when the row pitch allows, scalar otherwise.
-template <typename OutT>
-__device__ __forceinline__ void store_row32(OutT *row_ptr, int n_base, int N, const float (&v)[32], bool vec_ok) {
-    if (vec_ok && n_base + 32 <= N) {
-        if constexpr (sizeof(OutT) == 4) {
+// Epilogue arithmetic (operation order fixed: the CPU oracle restates it step by step).
+template <int EPI>
+__device__ __forceinline__ float epi_one(uint32_t r, float cs, float b, int aux, float rs, float dyn_s, int dyn_zp) {
+    if constexpr (EPI == EPI_LLMINT8) {
+        const float x = __fmul_rn(__fmul_rn((float)(int)r, rs), cs);
+        return __fmaf_rn(x, 6.200012e-05f, b);
+    } else if constexpr (EPI == EPI_DYN) {
+        const int acc = (int)r - dyn_zp * aux;
+        return __fadd_rn(__fmul_rn((float)acc, dyn_s), b);
+    } else if constexpr (EPI == EPI_W8A16) {
+        return __fadd_rn(__fmul_rn(__uint_as_float(r), cs), b);
+    } else {
+        return __fadd_rn(__uint_as_float(r), b);
+    }
+}
+
+// 32 adjacent columns starting at absolute column n, all inside [0, N): straight-line vector loads
+// of the per-column constants (L1-resident after the first tile) followed by the arithmetic.
+template <int EPI, bool HAS_BIAS>
+__device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[32], float (&v)[32], const GemmArgs &args, int n,
+                                               float rs, float dyn_s, int dyn_zp) {
+    float cs[32], b[32];
+    int aux[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                reinterpret_cast<float4 *>(row_ptr + n_base)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    for (int g = 0; g < 8; ++g) {
+        if constexpr (EPI == EPI_LLMINT8 || EPI == EPI_W8A16) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(args.col_scale + n) + g);
+            cs[4 * g] = t.x; cs[4 * g + 1] = t.y; cs[4 * g + 2] = t.z; cs[4 * g + 3] = t.w;
+        } else {
+            cs[4 * g] = cs[4 * g + 1] = cs[4 * g + 2] = cs[4 * g + 3] = 0.0f;
+        }
+        if constexpr (EPI == EPI_DYN) {
+            const int4 t = __ldg(reinterpret_cast<const int4 *>(args.wsum + n) + g);
+            aux[4 * g] = t.x; aux[4 * g + 1] = t.y; aux[4 * g + 2] = t.z; aux[4 * g + 3] = t.w;
+        } else {
+            aux[4 * g] = aux[4 * g + 1] = aux[4 * g + 2] = aux[4 * g + 3] = 0;
+        }
+    }
+    if constexpr (HAS_BIAS) {
+        if constexpr (EPI == EPI_LLMINT8) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint4 t = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(args.bias) + n) + g);
+                const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[j]));
+                    b[8 * g + 2 * j] = f.x;
+                    b[8 * g + 2 * j + 1] = f.y;
+                }
+            }
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint4 u;
-                u.x = pack2<OutT>(v[8 * j + 0], v[8 * j + 1]);
-                u.y = pack2<OutT>(v[8 * j + 2], v[8 * j + 3]);
-                u.z = pack2<OutT>(v[8 * j + 4], v[8 * j + 5]);
-                u.w = pack2<OutT>(v[8 * j + 6], v[8 * j + 7]);
-                reinterpret_cast<uint4 *>(row_ptr + n_base)[j] = u;
+            for (int g = 0; g < 8; ++g) {
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(args.bias) + n) + g);
+                b[4 * g] = t.x; b[4 * g + 1] = t.y; b[4 * g + 2] = t.z; b[4 * g + 3] = t.w;
             }
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (n_base + j < N) row_ptr[n_base + j] = from_f32<OutT>(v[j]);
+        for (int j = 0; j < 32; ++j) b[j] = 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = epi_one<EPI>(r[j], cs[j], b[j], aux[j], rs, dyn_s, dyn_zp);
+}
+
+// N-tail chunk: per-column bounds checks (columns >= N produce unused values)
+template <int EPI>
+__device__ __forceinline__ void epi_chunk_tail(const uint32_t (&r)[32], float (&v)[32], const GemmArgs &args, int n,
+                                            float rs, float dyn_s, int dyn_zp) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float cs = 0.0f, b = 0.0f;
+        int aux = 0;
+        if (n + j < args.N) {
+            if constexpr (EPI == EPI_LLMINT8 || EPI == EPI_W8A16) cs = __ldg(args.col_scale + n + j);
+            if (args.bias != nullptr) {
+                if constexpr (EPI == EPI_LLMINT8) b = __half2float(reinterpret_cast<const __half *>(args.bias)[n + j]);
+                else b = __ldg(reinterpret_cast<const float *>(args.bias) + n + j);
+            }
+            if constexpr (EPI == EPI_DYN) aux = __ldg(args.wsum + n + j);
+        }
+        v[j] = epi_one<EPI>(r[j], cs, b, aux, rs, dyn_s, dyn_zp);
     }
 }
 
-template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT>
-__global__ void __launch_bounds__(NUM_THREADS)
-k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs args) {
-    using L = SmemLayout<BN, STAGES, BMODE>;
-    static_assert(BN == 64 || BN == 128, "BN must be 64 or 128 (power-of-two TMEM columns)");
+template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT, int OUT_BUFS>
+__global__ void __launch_bounds__(num_threads<BMODE>(), 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+          const __grid_constant__ CUtensorMap map_y, const GemmArgs args) {
+    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS>;
+    static_assert(BN == 64 || BN == 128, "BN must be 64 or 128 (2 halves x 2 stages x BN <= 512 TMEM columns)");
     constexpr bool kIntKind = (AKIND == A_S8 || AKIND == A_U8);
     constexpr int A_ELEMS_PER_ROW = kIntKind ? 128 : 64;  // elements of K per 128-byte row
+    constexpr int DQ_WARPS = dq_warps<BMODE>();
+    constexpr int ACC_COLS = 2 * BN;                      // one accumulator stage: half 0 | half 1
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -118,48 +191,33 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     uint64_t *bar_empty = bars + STAGES;
     uint64_t *bar_bready = bars + 2 * STAGES;
     uint64_t *bar_tmem_full = bars + 3 * STAGES;
+    uint64_t *bar_tmem_empty = bars + 3 * STAGES + ACC_STAGES;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + L::OFF_TMEM);
-    float *s_cs = reinterpret_cast<float *>(smem + L::OFF_CS);
-    float *s_bias = reinterpret_cast<float *>(smem + L::OFF_BIAS);
-    int32_t *s_aux = reinterpret_cast<int32_t *>(smem + L::OFF_AUX);
     float *s_lut = reinterpret_cast<float *>(smem + L::OFF_LUT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
     const int num_kb = args.num_kb;
+    const int total_tiles = args.tiles_m * args.tiles_n;
 
     // ---------------- setup ----------------
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
+        if (args.tma_store) tma_prefetch_desc(&map_y);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_empty[s], 1);
-            mbar_init(&bar_bready[s], 4);
+            mbar_init(&bar_bready[s], DQ_WARPS > 0 ? DQ_WARPS : 1);
         }
-        mbar_init(bar_tmem_full, 1);
+        for (int a = 0; a < ACC_STAGES; ++a) {
+            mbar_init(&bar_tmem_full[a], 1);
+            mbar_init(&bar_tmem_empty[a], EPI_WARPS);
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_holder, BN);
+        tmem_alloc(tmem_holder, ACC_STAGES * ACC_COLS);
         tmem_relinquish();
-    }
-    for (int i = threadIdx.x; i < BN; i += NUM_THREADS) {
-        const int n = n0 + i;
-        const bool ok = n < args.N;
-        float cs = 0.0f, b = 0.0f;
-        int aux = 0;
-        if (ok) {
-            if constexpr (EPI == EPI_LLMINT8 || EPI == EPI_W8A16) cs = args.col_scale[n];
-            if (args.bias != nullptr) {
-                if constexpr (EPI == EPI_LLMINT8) b = __half2float(reinterpret_cast<const __half *>(args.bias)[n]);
-                else b = reinterpret_cast<const float *>(args.bias)[n];
-            }
-            if constexpr (EPI == EPI_DYN) aux = args.wsum[n];
-        }
-        s_cs[i] = cs;
-        s_bias[i] = b;
-        s_aux[i] = aux;
     }
     if constexpr (BMODE == B_4BIT) {
         if (threadIdx.x < 16) s_lut[threadIdx.x] = args.quant_type ? kFP4Code[threadIdx.x] : kNF4Code[threadIdx.x];
@@ -172,16 +230,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     if (warp == 0) {
         // ---------------- TMA producer ----------------
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&bar_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&bar_full[s], L::TX_BYTES);
-                tma_load_2d(smem + L::OFF_A + s * L::A_BYTES, &map_a, &bar_full[s], kb * A_ELEMS_PER_ROW, m0);
-                if constexpr (BMODE == B_DIRECT)
-                    tma_load_2d(smem + L::OFF_B + s * L::B_BYTES, &map_b, &bar_full[s], kb * 128, n0);
-                else
-                    tma_load_2d(smem + L::OFF_P + s * L::P_BYTES, &map_b, &bar_full[s], kb * L::P_ROW, n0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n0 = (tile % args.tiles_n) * BN, m0 = (tile / args.tiles_n) * BM;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&bar_empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&bar_full[s], L::TX_BYTES);
+                    tma_load_2d(smem + L::OFF_A + s * L::A_BYTES, &map_a, &bar_full[s], kb * A_ELEMS_PER_ROW, m0);
+                    if constexpr (BMODE == B_DIRECT)
+                        tma_load_2d(smem + L::OFF_B + s * L::B_BYTES, &map_b, &bar_full[s], kb * 128, n0);
+                    else
+                        tma_load_2d(smem + L::OFF_P + s * L::P_BYTES, &map_b, &bar_full[s], kb * L::P_ROW, n0);
+                }
             }
         }
         __syncwarp();
@@ -189,154 +251,248 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             constexpr uint32_t idesc =
-                kIntKind ? make_idesc(kAccS32, AKIND == A_S8 ? kFmtS8 : kFmtU8, kFmtS8, BM, BN)
+                kIntKind ? make_idesc(kAccS32, AKIND == A_S8 ? kFmtS8 : kFmtU8, kFmtS8, BMH, BN)
                          : make_idesc(kAccF32, AKIND == A_F16 ? kFmtF16 : kFmtBF16,
-                                      AKIND == A_F16 ? kFmtF16 : kFmtBF16, BM, BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&bar_full[s], ph);
-                if constexpr (BMODE != B_DIRECT) mbar_wait(&bar_bready[s], ph);
+                                      AKIND == A_F16 ? kFmtF16 : kFmtBF16, BMH, BN);
+            uint32_t it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+                const int m0 = (tile / args.tiles_n) * BM;
+                const bool two_halves = m0 + BMH < args.M;   // second 128 rows hold real data
+                const uint32_t as = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1;
+                mbar_wait(&bar_tmem_empty[as], aph ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint64_t adesc = make_smem_desc_sw128(smem + L::OFF_A + s * L::A_BYTES);
-                const uint64_t bdesc = make_smem_desc_sw128(smem + L::OFF_B + s * L::B_BYTES);
+                const uint32_t tmem_acc = tmem_base + as * ACC_COLS;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&bar_full[s], ph);
+                    if constexpr (BMODE != B_DIRECT) mbar_wait(&bar_bready[s], ph);
+                    tc_fence_after();
+                    const uint64_t adesc0 = make_smem_desc_sw128(smem + L::OFF_A + s * L::A_BYTES);
+                    const uint64_t adesc1 = make_smem_desc_sw128(smem + L::OFF_A + s * L::A_BYTES + BMH * ROW_BYTES);
+                    const uint64_t bdesc = make_smem_desc_sw128(smem + L::OFF_B + s * L::B_BYTES);
 #pragma unroll
-                for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
-                    const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-                    if constexpr (kIntKind) umma_i8(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
-                    else umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                    for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
+                        const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                        if constexpr (kIntKind) {
+                            umma_i8(tmem_acc, adesc0 + 2 * k, bdesc + 2 * k, idesc, acc);
+                            if (two_halves) umma_i8(tmem_acc + BN, adesc1 + 2 * k, bdesc + 2 * k, idesc, acc);
+                        } else {
+                            umma_f16(tmem_acc, adesc0 + 2 * k, bdesc + 2 * k, idesc, acc);
+                            if (two_halves) umma_f16(tmem_acc + BN, adesc1 + 2 * k, bdesc + 2 * k, idesc, acc);
+                        }
+                    }
+                    umma_commit(&bar_empty[s]);  // implicit tcgen05.fence::before_thread_sync
                 }
-                umma_commit(&bar_empty[s]);  // implicit tcgen05.fence::before_thread_sync
+                umma_commit(&bar_tmem_full[as]);
             }
-            umma_commit(bar_tmem_full);
         }
         __syncwarp();
-    } else {
-        // ---------------- dequant (W8A16 / W4A16) then epilogue: warps 2..5 ----------------
-        const int t = threadIdx.x - 64;  // 0..127
-        if constexpr (BMODE == B_I8) {
-            const int qd = t & 3, row0 = t >> 2;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&bar_full[s], ph);
-                const uint8_t *P = smem + L::OFF_P + s * L::P_BYTES;
-                uint8_t *B = smem + L::OFF_B + s * L::B_BYTES;
-#pragma unroll
-                for (int p = 0; p < BN / 32; ++p) {
-                    const int r = row0 + 32 * p;
-                    const uint4 v = *reinterpret_cast<const uint4 *>(P + r * 64 + qd * 16);
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                    uint32_t o[8];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if constexpr (AKIND == A_F16) {
-                            // s8 -> fp16 exactly: (1024 + (s ^ 0x80)) - 1152
-                            const uint32_t x = w[j] ^ 0x80808080u;
-                            uint32_t lo = __byte_perm(x, 0x64646464u, 0x4140);
-                            uint32_t hi = __byte_perm(x, 0x64646464u, 0x4342);
-                            const __half2 bias2 = __half2half2(__ushort_as_half((unsigned short)0x6480));
-                            __half2 l2 = __hsub2(*reinterpret_cast<__half2 *>(&lo), bias2);
-                            __half2 h2 = __hsub2(*reinterpret_cast<__half2 *>(&hi), bias2);
-                            o[2 * j] = *reinterpret_cast<uint32_t *>(&l2);
-                            o[2 * j + 1] = *reinterpret_cast<uint32_t *>(&h2);
-                        } else {
-                            const float f0 = (float)(int8_t)(w[j] & 0xff), f1 = (float)(int8_t)((w[j] >> 8) & 0xff);
-                            const float f2 = (float)(int8_t)((w[j] >> 16) & 0xff), f3 = (float)(int8_t)(w[j] >> 24);
-                            o[2 * j] = pack2<__nv_bfloat16>(f0, f1);
-                            o[2 * j + 1] = pack2<__nv_bfloat16>(f2, f3);
-                        }
-                    }
-                    *reinterpret_cast<uint4 *>(B + sw128_offset(r, 2 * qd)) = make_uint4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<uint4 *>(B + sw128_offset(r, 2 * qd + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_bready[s]);
-            }
-        } else if constexpr (BMODE == B_4BIT) {
-            const int hf = t & 1, row0 = t >> 1;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                float am[BN / 64];
-#pragma unroll
-                for (int p = 0; p < BN / 64; ++p) {
-                    const int n = n0 + row0 + 64 * p;
-                    am[p] = (n < args.N) ? __ldg(args.absmax + (size_t)n * args.absmax_ld + kb) : 0.0f;
-                }
-                mbar_wait(&bar_full[s], ph);
-                const uint8_t *P = smem + L::OFF_P + s * L::P_BYTES;
-                uint8_t *B = smem + L::OFF_B + s * L::B_BYTES;
-#pragma unroll
-                for (int p = 0; p < BN / 64; ++p) {
-                    const int r = row0 + 64 * p;
-                    const uint4 v = *reinterpret_cast<const uint4 *>(P + r * 32 + hf * 16);
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t o[4];
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const uint32_t byte = (w[j] >> (8 * b)) & 0xffu;
-                            const float f0 = __fmul_rn(s_lut[byte >> 4], am[p]);
-                            const float f1 = __fmul_rn(s_lut[byte & 15u], am[p]);
-                            if constexpr (AKIND == A_F16) o[b] = pack2<__half>(f0, f1);
-                            else o[b] = pack2<__nv_bfloat16>(f0, f1);
-                        }
-                        *reinterpret_cast<uint4 *>(B + sw128_offset(r, 4 * hf + j)) = make_uint4(o[0], o[1], o[2], o[3]);
-                    }
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_bready[s]);
-            }
-        }
-
-        // ---------------- epilogue ----------------
-        mbar_wait(bar_tmem_full, 0);
-        tc_fence_after();
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
-        const int m = m0 + q * 32 + lane;
-        const bool row_ok = m < args.M;
-        OutT *row_ptr = reinterpret_cast<OutT *>(args.out) + (size_t)(row_ok ? m : 0) * args.N;
+    } else if (warp < 2 + EPI_WARPS) {
+        // ---------------- epilogue: warps 2..9 ----------------
+        const int e = warp - 2;
+        const int h = e >> 2;                         // 128-row half of the tile
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        uint8_t *boxes = smem + L::OFF_OUT + e * OUT_BUFS * BOX_BYTES;
+        constexpr int BOX_COLS = 128 / (int)sizeof(OutT);   // columns per TMA-store box (64 or 32)
+        constexpr int N_BOX = BN / BOX_COLS;
         const bool vec_ok = ((size_t)args.N * sizeof(OutT)) % 16 == 0;
-        float rs = 1.0f, dyn_s = 0.0f;
+        const bool has_bias = args.bias != nullptr;
+        float dyn_s = 0.0f;
         int dyn_zp = 0;
-        if constexpr (EPI == EPI_LLMINT8) rs = row_ok ? args.row_scale[m] : 0.0f;
         if constexpr (EPI == EPI_DYN) {
             dyn_s = __fmul_rn(args.qparams[0], args.w_scale[0]);
             dyn_zp = (int)args.qparams[1];
         }
+        uint32_t t = 0, nstore = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+            const int n0 = (tile % args.tiles_n) * BN, m0 = (tile / args.tiles_n) * BM;
+            const uint32_t as = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1;
+            const int mrow0 = m0 + h * BMH + q * 32;  // first row of this warp's 32-row slab
+            const int m = mrow0 + lane;
+            const bool row_ok = m < args.M;
+            const bool slab_ok = mrow0 < args.M;      // warp-uniform
+            float rs = 1.0f;
+            if constexpr (EPI == EPI_LLMINT8) rs = row_ok ? __ldg(args.row_scale + m) : 0.0f;
+
+            mbar_wait(&bar_tmem_full[as], aph);
+            tc_fence_after();
+            if (slab_ok) {
+                OutT *row_ptr = reinterpret_cast<OutT *>(args.out) + (size_t)(row_ok ? m : 0) * args.N;
+                const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + h * BN;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
-            tmem_ld_wait();
-            float v[32];
+                for (int bx = 0; bx < N_BOX; ++bx) {
+                    uint8_t *box = boxes + (nstore % OUT_BUFS) * BOX_BYTES;
+                    if (args.tma_store) {
+                        // the store that last used this box must have finished reading it
+                        if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();
+                        __syncwarp();
+                    }
+                    constexpr int NCH = BOX_COLS / 32;              // tcgen05.ld chunks per box (2 or 1)
+                    uint32_t r[NCH][32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int col = c * 32 + j;
-                if constexpr (EPI == EPI_LLMINT8) {
-                    const float x = __fmul_rn(__fmul_rn((float)(int)r[j], rs), s_cs[col]);
-                    v[j] = __fmaf_rn(x, 6.200012e-05f, s_bias[col]);
-                } else if constexpr (EPI == EPI_DYN) {
-                    const int acc = (int)r[j] - dyn_zp * s_aux[col];
-                    v[j] = __fadd_rn(__fmul_rn((float)acc, dyn_s), s_bias[col]);
-                } else if constexpr (EPI == EPI_W8A16) {
-                    v[j] = __fadd_rn(__fmul_rn(__uint_as_float(r[j]), s_cs[col]), s_bias[col]);
-                } else {
-                    v[j] = __fadd_rn(__uint_as_float(r[j]), s_bias[col]);
+                    for (int cc = 0; cc < NCH; ++cc) tmem_ld_32x32(tmem_row + bx * BOX_COLS + cc * 32, r[cc]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int cc = 0; cc < NCH; ++cc) {
+                        const int col0 = bx * BOX_COLS + cc * 32;   // column inside the tile
+                        float v[32];
+                        if (n0 + col0 + 32 <= args.N) {
+                            if (has_bias) epi_chunk_fast<EPI, true>(r[cc], v, args, n0 + col0, rs, dyn_s, dyn_zp);
+                            else epi_chunk_fast<EPI, false>(r[cc], v, args, n0 + col0, rs, dyn_s, dyn_zp);
+                        } else {
+                            epi_chunk_tail<EPI>(r[cc], v, args, n0 + col0, rs, dyn_s, dyn_zp);
+                        }
+                        if (args.tma_store) {
+                            constexpr int CH = 32 * (int)sizeof(OutT) / 16;   // 16-byte chunks per 32 columns
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) {
+                                const int c16 = cc * CH + j;                   // chunk index inside the 128-byte row
+                                uint8_t *dst = box + lane * 128 + ((c16 ^ (lane & 7)) << 4);
+                                if constexpr (sizeof(OutT) == 4) {
+                                    *reinterpret_cast<float4 *>(dst) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                                } else {
+                                    uint4 u;
+                                    u.x = pack2<OutT>(v[8 * j + 0], v[8 * j + 1]);
+                                    u.y = pack2<OutT>(v[8 * j + 2], v[8 * j + 3]);
+                                    u.z = pack2<OutT>(v[8 * j + 4], v[8 * j + 5]);
+                                    u.w = pack2<OutT>(v[8 * j + 6], v[8 * j + 7]);
+                                    *reinterpret_cast<uint4 *>(dst) = u;
+                                }
+                            }
+                        } else if (row_ok) {
+                            const int nb = n0 + col0;
+                            if (vec_ok && nb + 32 <= args.N) {
+                                if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j)
+                                        reinterpret_cast<float4 *>(row_ptr + nb)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        uint4 u;
+                                        u.x = pack2<OutT>(v[8 * j + 0], v[8 * j + 1]);
+                                        u.y = pack2<OutT>(v[8 * j + 2], v[8 * j + 3]);
+                                        u.z = pack2<OutT>(v[8 * j + 4], v[8 * j + 5]);
+                                        u.w = pack2<OutT>(v[8 * j + 6], v[8 * j + 7]);
+                                        reinterpret_cast<uint4 *>(row_ptr + nb)[j] = u;
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (nb + j < args.N) row_ptr[nb + j] = from_f32<OutT>(v[j]);
+                            }
+                        }
+                    }
+                    if (args.tma_store) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&map_y, box, n0 + bx * BOX_COLS, mrow0);
+                            tma_store_commit();
+                        }
+                        ++nstore;
+                    }
                 }
             }
-            if (row_ok) store_row32<OutT>(row_ptr, n0 + c * 32, args.N, v, vec_ok);
+            // accumulator fully read: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tmem_empty[as]);
+        }
+        if (args.tma_store && lane == 0) tma_store_wait<0>();
+        __syncwarp();
+    } else {
+        // ---------------- weight expansion (W8A16 / W4A16): warps 10.. ----------------
+        const int t = threadIdx.x - 32 * (2 + EPI_WARPS);
+        if constexpr (BMODE == B_I8) {
+            const int qd = t & 3, row0 = t >> 2;      // 128 threads: 4 per row, 32 rows per pass
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&bar_full[s], ph);
+                    const uint8_t *P = smem + L::OFF_P + s * L::P_BYTES;
+                    uint8_t *B = smem + L::OFF_B + s * L::B_BYTES;
+#pragma unroll
+                    for (int p = 0; p < BN / 32; ++p) {
+                        const int r = row0 + 32 * p;
+                        const uint4 v = *reinterpret_cast<const uint4 *>(P + r * 64 + qd * 16);
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                        uint32_t o[8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if constexpr (AKIND == A_F16) {
+                                // s8 -> fp16 exactly: (1024 + (s ^ 0x80)) - 1152
+                                const uint32_t x = w[j] ^ 0x80808080u;
+                                uint32_t lo = __byte_perm(x, 0x64646464u, 0x4140);
+                                uint32_t hi = __byte_perm(x, 0x64646464u, 0x4342);
+                                const __half2 bias2 = __half2half2(__ushort_as_half((unsigned short)0x6480));
+                                __half2 l2 = __hsub2(*reinterpret_cast<__half2 *>(&lo), bias2);
+                                __half2 h2 = __hsub2(*reinterpret_cast<__half2 *>(&hi), bias2);
+                                o[2 * j] = *reinterpret_cast<uint32_t *>(&l2);
+                                o[2 * j + 1] = *reinterpret_cast<uint32_t *>(&h2);
+                            } else {
+                                const float f0 = (float)(int8_t)(w[j] & 0xff), f1 = (float)(int8_t)((w[j] >> 8) & 0xff);
+                                const float f2 = (float)(int8_t)((w[j] >> 16) & 0xff), f3 = (float)(int8_t)(w[j] >> 24);
+                                o[2 * j] = pack2<__nv_bfloat16>(f0, f1);
+                                o[2 * j + 1] = pack2<__nv_bfloat16>(f2, f3);
+                            }
+                        }
+                        *reinterpret_cast<uint4 *>(B + sw128_offset(r, 2 * qd)) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<uint4 *>(B + sw128_offset(r, 2 * qd + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_bready[s]);
+                }
+            }
+        } else if constexpr (BMODE == B_4BIT) {
+            const int hf = t & 1, r = t >> 1;         // 256 threads: 2 per row; rows >= BN idle
+            const bool active = r < BN;
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n = (tile % args.tiles_n) * BN + r;
+                const float *am_row = args.absmax + (size_t)(n < args.N ? n : 0) * args.absmax_ld;
+                const bool n_ok = active && n < args.N;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    const float am = n_ok ? __ldg(am_row + kb) : 0.0f;
+                    mbar_wait(&bar_full[s], ph);
+                    if (active) {
+                        const uint8_t *P = smem + L::OFF_P + s * L::P_BYTES;
+                        uint8_t *B = smem + L::OFF_B + s * L::B_BYTES;
+                        const uint4 v = *reinterpret_cast<const uint4 *>(P + r * 32 + hf * 16);
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t o[4];
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                const uint32_t byte = (w[j] >> (8 * b)) & 0xffu;
+                                const float f0 = __fmul_rn(s_lut[byte >> 4], am);
+                                const float f1 = __fmul_rn(s_lut[byte & 15u], am);
+                                if constexpr (AKIND == A_F16) o[b] = pack2<__half>(f0, f1);
+                                else o[b] = pack2<__nv_bfloat16>(f0, f1);
+                            }
+                            *reinterpret_cast<uint4 *>(B + sw128_offset(r, 4 * hf + j)) = make_uint4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_bready[s]);
+                }
+            }
         }
     }
 
     // ---------------- teardown ----------------
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, BN);
+    if (warp == 1) tmem_dealloc(tmem_base, ACC_STAGES * ACC_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -433,24 +589,59 @@ int make_map_2d(CUtensorMap *map, const void *base, CUtensorMapDataType dt, int 
     return WQ_OK;
 }
 
-template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT>
-int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &args, cudaStream_t stream) {
-    using L = SmemLayout<BN, STAGES, BMODE>;
-    auto kfn = k_gemm_tc<BN, STAGES, AKIND, BMODE, EPI, OutT>;
+// TMA-store boxes per epilogue warp (double-buffered when shared memory allows)
+template <int BN, int BMODE> constexpr int pick_out_bufs() { return (BMODE == B_I8 && BN == 128) ? 1 : 2; }
+
+// deepest smem ring that fits next to the epilogue staging boxes
+template <int BN, int BMODE, int OUT_BUFS>
+constexpr int pick_stages() {
+    int best = 2;
+    for (int st = 2; st <= 6; ++st) {
+        const int stage = BM * ROW_BYTES + BN * ROW_BYTES + BN * (BMODE == B_I8 ? 64 : (BMODE == B_4BIT ? 32 : 0));
+        const int total = st * stage + EPI_WARPS * OUT_BUFS * BOX_BYTES + 64 + (3 * st + 2 * ACC_STAGES) * 8 + 16 + 1024;
+        if (total <= 232448) best = st;
+    }
+    return best;
+}
+
+template <typename OutT> CUtensorMapDataType out_dtype_enum();
+template <> CUtensorMapDataType out_dtype_enum<float>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT32; }
+template <> CUtensorMapDataType out_dtype_enum<__half>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT16; }
+template <> CUtensorMapDataType out_dtype_enum<__nv_bfloat16>() { return CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
+
+template <int BN, int AKIND, int BMODE, int EPI, typename OutT>
+int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cudaStream_t stream) {
+    constexpr int OUT_BUFS = pick_out_bufs<BN, BMODE>();
+    constexpr int STAGES = pick_stages<BN, BMODE, OUT_BUFS>();
+    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS>;
+    auto kfn = k_gemm_tc<BN, STAGES, AKIND, BMODE, EPI, OutT, OUT_BUFS>;
     static bool configured = false;
     if (!configured) {
         WQ_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
     }
-    dim3 grid((args.N + BN - 1) / BN, (args.M + BM - 1) / BM);
-    kfn<<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma, mb, args);
+    args.tiles_m = (args.M + BM - 1) / BM;
+    args.tiles_n = (args.N + BN - 1) / BN;
+    // TMA store needs a 16-byte-aligned row pitch; otherwise the epilogue stores directly
+    args.tma_store = (((size_t)args.N * sizeof(OutT)) % 16 == 0 && wq_aligned(args.out, 16)) ? 1 : 0;
+    CUtensorMap my;
+    if (args.tma_store) {
+        int rc = make_map_2d(&my, args.out, out_dtype_enum<OutT>(), (int)sizeof(OutT), args.M, args.N, 32,
+                             128 / (int)sizeof(OutT), CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc != WQ_OK) return rc;
+    } else {
+        my = ma;  // unused
+    }
+    const int total = args.tiles_m * args.tiles_n;
+    const int grid = total < wq_sm_count() ? total : wq_sm_count();
+    kfn<<<grid, num_threads<BMODE>(), L::TOTAL, stream>>>(ma, mb, my, args);
     WQ_LAUNCH_CHECK();
     return WQ_OK;
 }
 
 // BN = 64 when a 128-wide tiling would leave most SMs idle (decode-shaped calls).
 bool use_narrow_tile(int64_t M, int64_t N) {
-    const int64_t tiles128 = ((M + BM - 1) / BM) * ((N + 127) / 128);
+    const int64_t tiles128 = ((M + BM - 1) / BM) * ((N + 127) / 128);  // BM = 256
     return tiles128 < wq_sm_count();
 }
 
@@ -483,11 +674,11 @@ extern "C" int wq_gemm_llmint8(const int8_t *ca, const float *sca, const int8_t 
     if (use_narrow_tile(M, N)) {
         rc = make_map_2d(&mb, cb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc != WQ_OK) return rc;
-        rc = launch_gemm<64, 4, A_S8, B_DIRECT, EPI_LLMINT8, __half>(ma, mb, args, s);
+        rc = launch_gemm<64, A_S8, B_DIRECT, EPI_LLMINT8, __half>(ma, mb, args, s);
     } else {
         rc = make_map_2d(&mb, cb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc != WQ_OK) return rc;
-        rc = launch_gemm<128, 3, A_S8, B_DIRECT, EPI_LLMINT8, __half>(ma, mb, args, s);
+        rc = launch_gemm<128, A_S8, B_DIRECT, EPI_LLMINT8, __half>(ma, mb, args, s);
     }
     if (rc != WQ_OK) return rc;
     if (n_outliers != nullptr) {
@@ -520,11 +711,11 @@ extern "C" int wq_gemm_dyn_i8(const uint8_t *xq, const float *qparams, const int
     if (use_narrow_tile(M, N)) {
         rc = make_map_2d(&mb, wq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc != WQ_OK) return rc;
-        return launch_gemm<64, 4, A_U8, B_DIRECT, EPI_DYN, float>(ma, mb, args, s);
+        return launch_gemm<64, A_U8, B_DIRECT, EPI_DYN, float>(ma, mb, args, s);
     }
     rc = make_map_2d(&mb, wq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
-    return launch_gemm<128, 3, A_U8, B_DIRECT, EPI_DYN, float>(ma, mb, args, s);
+    return launch_gemm<128, A_U8, B_DIRECT, EPI_DYN, float>(ma, mb, args, s);
 }
 
 namespace {
@@ -532,7 +723,7 @@ namespace {
 template <int BMODE, int EPI>
 int dispatch_a16(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &args, int x_dtype, int y_dtype,
                  bool narrow, cudaStream_t s) {
-#define WQ_CASE(BN, AK, OT) return launch_gemm<BN, 4, AK, BMODE, EPI, OT>(ma, mb, args, s)
+#define WQ_CASE(BN, AK, OT) return launch_gemm<BN, AK, BMODE, EPI, OT>(ma, mb, args, s)
     if (x_dtype == WQ_F16) {
         if (y_dtype == WQ_F16) { if (narrow) WQ_CASE(64, A_F16, __half); else WQ_CASE(128, A_F16, __half); }
         if (y_dtype == WQ_F32) { if (narrow) WQ_CASE(64, A_F16, float); else WQ_CASE(128, A_F16, float); }
