@@ -1,0 +1,196 @@
+"""CUDA-graph greedy decoding behind ``model.generate`` (the decode
+step's host/launch overhead).
+
+``transcribe_batch`` (data_utils.py:152) calls ``model.generate(features)``.  HF's generate prepares
+everything -- encoder pass, initial decoder tokens, the Whisper logits processors, stopping criteria
+-- and then runs ``model._sample``, a Python loop that re-dispatches several hundred tiny kernels
+per token.  ``enable(model)`` replaces only that inner loop: the decoder step (the model's own
+sub-modules, i.e. the drop-in quantized linears, LayerNorms and embeddings, with a static KV cache)
+is captured once per (batch, max length) as a CUDA graph and replayed per token; HF's own
+``logits_processor`` and ``stopping_criteria`` objects are applied between replays, so the call
+``model.generate(features)`` and its result format are unchanged.  Anything the fast loop does not
+cover (sampling, beams, return_dict_in_generate, streamer, CPU) falls through to HF's ``_sample``.
+
+Numerics: same modules and weights as HF's loop; attention over the static cache is
+``scaled_dot_product_attention`` with a position mask instead of HF's exact-length SDPA call, so
+logits can differ in the last fp16 bits (tests compare tokens with HF's loop).
+"""
+from __future__ import annotations
+
+import types
+from typing import Dict, Tuple
+
+import torch
+import torch.nn.functional as TF
+
+from . import functional as F
+
+
+class _State:
+    pass
+
+
+class GraphedGreedy:
+    def __init__(self, model, len_bucket: int = 64):
+        self.model = model
+        self.len_bucket = len_bucket
+        self._states: Dict[Tuple[int, int, torch.dtype], _State] = {}
+        self._orig_sample = None
+        self.replays = 0
+        self.fallbacks = 0
+
+    # ------------------------------------------------------------------------------------------
+    def install(self):
+        # HF dispatches with getattr(type(model), "_sample") (generation/utils.py), so the hook has to
+        # live on the class: give this one model instance a subclass that overrides _sample.
+        if self._orig_sample is None:
+            base = type(self.model)
+            self._orig_sample = types.MethodType(base._sample, self.model)
+
+            def _sample(model_self, input_ids, **kwargs):
+                return model_self._whisperq_fastgen._sample(input_ids, **kwargs)
+
+            self._base_cls = base
+            self.model.__class__ = type(base.__name__, (base,), {"_sample": _sample, "__module__": base.__module__})
+            self.model._whisperq_fastgen = self
+        return self
+
+    def uninstall(self):
+        if self._orig_sample is not None:
+            self.model.__class__ = self._base_cls
+            self._orig_sample = None
+            del self.model._whisperq_fastgen
+
+    # ------------------------------------------------------------------------------------------
+    def _decoder_step(self, st: _State):
+        """One token for every utterance: reads st.tok / st.pos, writes st.logits."""
+        model = self.model
+        dec = model.model.decoder
+        B, H, hd, d = st.B, st.H, st.hd, st.d
+        pos = st.pos
+        x = dec.embed_tokens(st.tok) + dec.embed_positions.weight.index_select(0, pos)
+        st.mask.copy_(st.arange <= pos)
+        mask = st.mask.view(1, 1, 1, -1)
+        for li, layer in enumerate(dec.layers):
+            sa, ca = layer.self_attn, layer.encoder_attn
+            res = x
+            h = layer.self_attn_layer_norm(x)
+            q = (sa.q_proj(h) * sa.scaling).view(B, 1, H, hd).transpose(1, 2)
+            k = sa.k_proj(h).view(B, 1, H, hd).transpose(1, 2)
+            v = sa.v_proj(h).view(B, 1, H, hd).transpose(1, 2)
+            st.k[li].index_copy_(2, pos, k)
+            st.v[li].index_copy_(2, pos, v)
+            a = TF.scaled_dot_product_attention(q, st.k[li], st.v[li], attn_mask=mask, scale=1.0)
+            x = res + sa.out_proj(a.transpose(1, 2).reshape(B, 1, d))
+            res = x
+            h = layer.encoder_attn_layer_norm(x)
+            q = (ca.q_proj(h) * ca.scaling).view(B, 1, H, hd).transpose(1, 2)
+            a = TF.scaled_dot_product_attention(q, st.ck[li], st.cv[li], scale=1.0)
+            x = res + ca.out_proj(a.transpose(1, 2).reshape(B, 1, d))
+            res = x
+            h = layer.final_layer_norm(x)
+            x = res + layer.fc2(layer.activation_fn(layer.fc1(h)))
+        x = dec.layer_norm(x)
+        st.logits.copy_(model.proj_out(x)[:, -1, :])
+
+    def _get_state(self, B: int, t_max: int, dtype: torch.dtype, device) -> _State:
+        key = (B, t_max, dtype)
+        st = self._states.get(key)
+        if st is not None:
+            return st
+        cfg = self.model.config
+        st = _State()
+        st.B, st.d = B, cfg.d_model
+        st.H = cfg.decoder_attention_heads
+        st.hd = st.d // st.H
+        S = cfg.max_source_positions
+        L = cfg.decoder_layers
+        st.tok = torch.zeros((B, 1), dtype=torch.long, device=device)
+        st.pos = torch.zeros((1,), dtype=torch.long, device=device)
+        st.arange = torch.arange(t_max, device=device)
+        st.mask = torch.zeros((t_max,), dtype=torch.bool, device=device)
+        st.k = [torch.zeros((B, st.H, t_max, st.hd), dtype=dtype, device=device) for _ in range(L)]
+        st.v = [torch.zeros((B, st.H, t_max, st.hd), dtype=dtype, device=device) for _ in range(L)]
+        st.ck = [torch.zeros((B, st.H, S, st.hd), dtype=dtype, device=device) for _ in range(L)]
+        st.cv = [torch.zeros((B, st.H, S, st.hd), dtype=dtype, device=device) for _ in range(L)]
+        st.logits = torch.zeros((B, self.model.proj_out.out_features), dtype=dtype, device=device)
+        # warm up on a side stream (lazy inits, autotuning), then capture
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(3):
+                self._decoder_step(st)
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        before = F.STATS.launches
+        st.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(st.graph):
+            self._decoder_step(st)
+        st.launches_per_replay = F.STATS.launches - before
+        self._states[key] = st
+        return st
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _sample(self, input_ids, logits_processor=None, stopping_criteria=None, generation_config=None,
+                synced_gpus=False, streamer=None, **model_kwargs):
+        model = self.model
+        enc_out = model_kwargs.get("encoder_outputs")
+        eligible = (input_ids.is_cuda and not generation_config.do_sample
+                    and not generation_config.return_dict_in_generate and streamer is None and not synced_gpus
+                    and enc_out is not None and model_kwargs.get("use_cache", True)
+                    and generation_config.max_length is not None
+                    and generation_config.max_length <= model.config.max_target_positions)
+        if not eligible:
+            self.fallbacks += 1
+            return self._orig_sample(input_ids, logits_processor=logits_processor,
+                                     stopping_criteria=stopping_criteria, generation_config=generation_config,
+                                     synced_gpus=synced_gpus, streamer=streamer, **model_kwargs)
+        enc = enc_out[0] if not hasattr(enc_out, "last_hidden_state") else enc_out.last_hidden_state
+        B, P = input_ids.shape
+        t_max = -(-int(generation_config.max_length) // self.len_bucket) * self.len_bucket
+        t_max = min(t_max, model.config.max_target_positions)
+        st = self._get_state(B, t_max, enc.dtype, input_ids.device)
+
+        # cross-attention keys / values once per call (encoder-shaped GEMMs)
+        S = enc.shape[1]
+        for li, layer in enumerate(model.model.decoder.layers):
+            ca = layer.encoder_attn
+            st.ck[li].copy_(ca.k_proj(enc).view(B, S, st.H, st.hd).transpose(1, 2))
+            st.cv[li].copy_(ca.v_proj(enc).view(B, S, st.H, st.hd).transpose(1, 2))
+
+        pad_token_id = generation_config._pad_token_tensor
+        has_eos = any(hasattr(c, "eos_token_id") for c in stopping_criteria)
+        unfinished = torch.ones(B, dtype=torch.long, device=input_ids.device)
+
+        def run(tokens, position):
+            st.tok.copy_(tokens.view(B, 1))
+            st.pos.fill_(position)
+            st.graph.replay()
+            self.replays += 1
+            F.STATS.launches += st.launches_per_replay
+
+        for i in range(P):                       # prompt tokens (normally just <|startoftranscript|>)
+            run(input_ids[:, i], i)
+        cur = P
+        while True:
+            next_token_logits = st.logits.to(copy=True, dtype=torch.float32)
+            next_token_scores = logits_processor(input_ids, next_token_logits)
+            next_tokens = torch.argmax(next_token_scores, dim=-1)
+            if has_eos:
+                next_tokens = next_tokens * unfinished + pad_token_id * (1 - unfinished)
+            input_ids = torch.cat([input_ids, next_tokens[:, None]], dim=-1)
+            unfinished = unfinished & ~stopping_criteria(input_ids, None)
+            if bool(unfinished.max() == 0):
+                break
+            run(next_tokens, cur)
+            cur += 1
+        return input_ids
+
+
+def enable(model, len_bucket: int = 64) -> GraphedGreedy:
+    """Install the graph-replay greedy loop on `model` (idempotent)."""
+    existing = getattr(model, "_whisperq_fastgen", None)
+    if existing is not None:
+        return existing
+    return GraphedGreedy(model, len_bucket).install()

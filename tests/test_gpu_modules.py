@@ -268,3 +268,37 @@ def test_tally_matches_oracle(pkg):
     np.testing.assert_array_equal(t, oracle.wer_cer_tally(refs, hyps))
     m = tally.load_metric("wer")
     assert abs(m.compute(references=refs, predictions=hyps) - t[0] / t[1]) < 1e-12
+
+
+@pytest.mark.parametrize("scheme", ["llm_int8", "fp16"])
+def test_graphed_greedy_matches_hf_generate(pkg, scheme):
+    """fastgen: model.generate through the CUDA-graph decode loop returns the same ids as HF's own
+    loop (same modules and weights; attention over the static cache may differ in the last fp16
+    bits, so positions where HF's own top-1/top-2 margin is below 2e-2 are excluded)."""
+    from openai_whisper_compression_b200 import fastgen, harness
+    model = harness.apply_scheme(harness.build_model("tiny", **MICRO), scheme, "cuda")
+    feats = _feats(n=6).half().cuda()
+    T = 24
+    ref = model.generate(feats, do_sample=False, num_beams=1, min_new_tokens=T, max_new_tokens=T,
+                         return_dict_in_generate=True, output_logits=True)   # HF loop (fallback criteria)
+    ref_ids = ref.sequences
+    eng = fastgen.enable(model)
+    ids = harness.greedy_generate(model, feats, T)
+    assert eng.replays > 0 and eng.fallbacks == 0
+    assert ids.shape == ref_ids.shape
+    logits = torch.stack(ref.logits, 1).float()
+    top2 = logits.topk(2, -1).values
+    decisive = (top2[..., 0] - top2[..., 1]) > 2e-2
+    # compare up to the first non-decisive position of each utterance (later tokens depend on it)
+    first_bad = torch.where(decisive.all(1), decisive.shape[1], (~decisive).float().argmax(1))
+    P = ids.shape[1] - T
+    for b in range(ids.shape[0]):
+        n = P + int(first_bad[b])
+        assert torch.equal(ids[b, :n], ref_ids[b, :n])
+    assert (ids == ref_ids).float().mean().item() > 0.9
+    # second call re-uses the captured graph
+    ids2 = harness.greedy_generate(model, feats, T)
+    assert torch.equal(ids, ids2)
+    eng.uninstall()
+    ids3 = harness.greedy_generate(model, feats, T)
+    assert torch.equal(ids3, ref_ids)
