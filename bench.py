@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--new-tokens", type=int, default=64)
     ap.add_argument("--cpu-sample", type=int, default=4, help="utterances in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hf-loop", action="store_true",
+                    help="keep HF's Python decode loop instead of the CUDA-graph replay loop (fastgen)")
     return ap.parse_args()
 
 
@@ -170,6 +172,8 @@ def workload_config(args):
                         f"{args.new_tokens} new tokens (BASELINE.json configs[1])",
             "size": args.size, "scheme": args.scheme, "utterances_per_gpu": args.batch,
             "new_tokens": args.new_tokens, "parallelism": f"utterance-sharded dp{args.gpus}",
+            "decode_loop": "HF _sample (Python)" if getattr(args, "hf_loop", False) else
+                           "model.generate -> CUDA-graph replay per token (fastgen), HF logits processors",
             "l2": "256 MiB write before every step (inside the timed bracket; < 0.1 % of a step); per-step "
                   "activations (>= 98 MB per encoder linear) exceed the 126 MB L2 as well"}
 
@@ -198,6 +202,9 @@ def run_ours(args):
     B, T, K, W = args.batch, args.new_tokens, args.steps, max(args.warmup, 0)
     n_mels = harness.WHISPER_SIZES[args.size]["mels"]
     model = harness.apply_scheme(harness.build_model(args.size), args.scheme, dev)
+    if not args.hf_loop:
+        from openai_whisper_compression_b200 import fastgen
+        fastgen.enable(model)
     proc = harness.StubProcessor(n_mels, device=dev)
     fe = proc.feature_extractor
     half = harness.model_dtype(model) == torch.float16

@@ -281,7 +281,7 @@ def test_graphed_greedy_matches_hf_generate(pkg, scheme):
     T = 24
     ref = model.generate(feats, do_sample=False, num_beams=1, min_new_tokens=T, max_new_tokens=T,
                          return_dict_in_generate=True, output_logits=True)   # HF loop (fallback criteria)
-    ref_ids = ref.sequences
+    ref_ids = harness.greedy_generate(model, feats, T)      # HF's own loop, plain call
     eng = fastgen.enable(model)
     ids = harness.greedy_generate(model, feats, T)
     assert eng.replays > 0 and eng.fallbacks == 0
@@ -291,7 +291,7 @@ def test_graphed_greedy_matches_hf_generate(pkg, scheme):
     decisive = (top2[..., 0] - top2[..., 1]) > 2e-2
     # compare up to the first non-decisive position of each utterance (later tokens depend on it)
     first_bad = torch.where(decisive.all(1), decisive.shape[1], (~decisive).float().argmax(1))
-    P = ids.shape[1] - T
+    P = ids.shape[1] - T      # 0 or 1 depending on whether generate keeps the start token
     for b in range(ids.shape[0]):
         n = P + int(first_bad[b])
         assert torch.equal(ids[b, :n], ref_ids[b, :n])
