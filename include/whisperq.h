@@ -62,15 +62,18 @@ int wq_dequant_4bit(const uint8_t *packed, const float *absmax, int64_t n, int b
  * (threshold 0) and MatMul8bitLt.forward for activations (threshold 6.0); BASELINE.json
  * config 2.  a: fp16 [rows, cols].  out int8 [rows, cols], row_stats fp32 [rows].
  * threshold > 0: entries with |a| >= threshold are written as 0, excluded from the row absmax,
- * and col_flags[c] (int32 [cols], must be zero on entry) is set to 1. col_flags may be NULL
- * when threshold == 0. */
+ * col_flags[c] is set to 1 and col_flags[cols] ("any outlier") is set to 1.  col_flags: int32
+ * [cols + 2], all zero on entry (word cols + 1 is a completion counter owned by wq_gemm_llmint8);
+ * may be NULL when threshold == 0. */
 int wq_quant_i8_rowwise_bnb(const void *a_f16, int64_t rows, int64_t cols, float threshold,
                             int8_t *out, float *row_stats, int32_t *col_flags,
                             wq_stream_t stream);
 
-/* Outlier bookkeeping of int8_vectorwise_quant / MatMul8bitLt without a host sync:
- * compacts col_flags into outlier_cols[0..*n_outliers) (ascending), clears col_flags, then
- * zeroes CA[:, outlier_cols].  n_outliers: device int32[1]. */
+/* Stand-alone outlier bookkeeping of int8_vectorwise_quant (returns the library's exact CA and
+ * column list) without a host sync: compacts col_flags into outlier_cols[0..*n_outliers)
+ * (ascending), clears col_flags (all cols + 2 words), then zeroes CA[:, outlier_cols].
+ * n_outliers: device int32[1].  The module forward path does NOT need this call: wq_gemm_llmint8
+ * consumes the flags directly. */
 int wq_outlier_columns(int32_t *col_flags, int64_t rows, int64_t cols, int8_t *ca,
                        int32_t *outlier_cols, int32_t *n_outliers, wq_stream_t stream);
 
@@ -103,12 +106,15 @@ int wq_quant_act_u8_tensor(const void *x, int x_dtype, int64_t n, uint8_t *q, fl
 /* bnb.matmul(x, Int8Params, state) = int8_linear_matmul + int8_mm_dequant (+ fp16 outlier
  * addmm) -- Linear8bitLt.forward, BASELINE.json config 2.
  *   y[m,n] = fp16( fmaf(int32(CA[m,:].CB[n,:]) * SCA[m] * SCB[n], 1/127^2, bias[n]) )
- *   if *n_outliers > 0:  y[m,n] = fp16( y[m,n] + sum_j A[m,c_j] * fp16(CB[n,c_j]*SCB[n]/127) )
- * a_f16 / outlier_cols / n_outliers may be NULL (no outlier path).  bias: fp16 [N] or NULL. */
+ *   outlier columns c (col_flags[c] != 0): their int8 products are removed from the accumulator
+ *   (== bitsandbytes zeroing CA[:, c]) and y[m,n] = fp16( y[m,n] + sum_c A[m,c] *
+ *   fp16(CB[n,c]*SCB[n]/127) ), all inside the GEMM epilogue (taken only when col_flags[K] != 0).
+ * col_flags: the int32 [K + 2] array written by wq_quant_i8_rowwise_bnb for THIS activation; the
+ * kernel clears it again when outliers were present.  a_f16 / col_flags may be NULL (CA already
+ * has its outlier columns zeroed or threshold == 0).  bias: fp16 [N] or NULL. */
 int wq_gemm_llmint8(const int8_t *ca, const float *sca, const int8_t *cb, const float *scb,
                     const void *bias_f16, void *y_f16, int64_t M, int64_t N, int64_t K,
-                    const void *a_f16, const int32_t *outlier_cols, const int32_t *n_outliers,
-                    wq_stream_t stream);
+                    const void *a_f16, int32_t *col_flags, wq_stream_t stream);
 
 /* quanto QLinear.forward, weights-only qint8 (W8A16) -- model_utils.py:126-128 call sites:
  *   y = matmul(x, Wq.to(x.dtype).t()) * scale + bias, accumulated in fp32, rounded once.

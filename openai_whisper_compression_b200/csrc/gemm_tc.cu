@@ -53,6 +53,10 @@ struct GemmArgs {
     const int32_t *wsum;     // sum_k wq[n,k]                  (DYN)
     void *out;
     int quant_type;
+    // LLM.int8 mixed-precision decomposition (consumed only when flags != nullptr && flags[K] != 0)
+    const int8_t *ca, *cb;
+    const __half *a16;
+    int32_t *flags;          // [K + 2]: per-column flags, "any", completion counter
 };
 
 template <int BMODE> constexpr int dq_warps() { return BMODE == B_DIRECT ? 0 : (BMODE == B_4BIT ? 8 : 4); }
@@ -298,6 +302,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         constexpr int N_BOX = BN / BOX_COLS;
         const bool vec_ok = ((size_t)args.N * sizeof(OutT)) % 16 == 0;
         const bool has_bias = args.bias != nullptr;
+        const bool any_outlier = (EPI == EPI_LLMINT8) && args.flags != nullptr && args.flags[args.K] != 0;
         float dyn_s = 0.0f;
         int dyn_zp = 0;
         if constexpr (EPI == EPI_DYN) {
@@ -337,11 +342,44 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     for (int cc = 0; cc < NCH; ++cc) {
                         const int col0 = bx * BOX_COLS + cc * 32;   // column inside the tile
                         float v[32];
+                        float o[32];
+                        if constexpr (EPI == EPI_LLMINT8) {
+                            if (any_outlier) {
+                                // rare path: remove the outlier columns' int8 products from the exact
+                                // int32 accumulator and build the fp16 side product (ascending column)
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) o[j] = 0.0f;
+#pragma unroll 1
+                                for (int c = 0; c < args.K; ++c) {
+                                    if (args.flags[c] == 0) continue;
+                                    const int a8 = row_ok ? (int)args.ca[(size_t)m * args.K + c] : 0;
+                                    const float af = row_ok ? __half2float(args.a16[(size_t)m * args.K + c]) : 0.0f;
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) {
+                                        const int n = n0 + col0 + j;
+                                        if (n < args.N) {
+                                            const int b8 = (int)args.cb[(size_t)n * args.K + c];
+                                            r[cc][j] = (uint32_t)((int)r[cc][j] - a8 * b8);
+                                            const float d = __fmul_rn(__fmul_rn((float)b8, __ldg(args.col_scale + n)),
+                                                                      7.874015718698502e-3f);
+                                            o[j] = fmaf(af, __half2float(__float2half_rn(d)), o[j]);
+                                        }
+                                    }
+                                }
+                            }
+                        }
                         if (n0 + col0 + 32 <= args.N) {
                             if (has_bias) epi_chunk_fast<EPI, true>(r[cc], v, args, n0 + col0, rs, dyn_s, dyn_zp);
                             else epi_chunk_fast<EPI, false>(r[cc], v, args, n0 + col0, rs, dyn_s, dyn_zp);
                         } else {
                             epi_chunk_tail<EPI>(r[cc], v, args, n0 + col0, rs, dyn_s, dyn_zp);
+                        }
+                        if constexpr (EPI == EPI_LLMINT8) {
+                            if (any_outlier) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    v[j] = __half2float(__float2half_rn(v[j])) + o[j];   // fp16 addmm
+                            }
                         }
                         if (args.tma_store) {
                             constexpr int CH = 32 * (int)sizeof(OutT) / 16;   // 16-byte chunks per 32 columns
@@ -493,59 +531,26 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, ACC_STAGES * ACC_COLS);
-}
-
-// ---------------------------------------------------------------------------------------------
-// LLM.int8 outlier term: y[m,n] = fp16(y[m,n] + sum_j A[m,c_j] * fp16(CB[n,c_j] * SCB[n] / 127))
-// (bitsandbytes MatMul8bitLt "mixed-precision decomposition"); exits at once when no outliers.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_llmint8_outliers(const __half *__restrict__ a, const int8_t *__restrict__ cb, const float *__restrict__ scb,
-                   const int32_t *__restrict__ cols, const int32_t *__restrict__ n_outliers, __half *__restrict__ y,
-                   int M, int N, int K) {
-    const int n_out = *n_outliers;
-    if (n_out == 0) return;
-    __shared__ float s_a[16][64 + 1];
-    __shared__ float s_w[16][64 + 1];
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 x 4 outputs each
-    float acc[4][4] = {};
-    for (int j0 = 0; j0 < n_out; j0 += 16) {
-        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-            const int jj = i >> 6, r = i & 63, j = j0 + jj;
-            float av = 0.0f, wv = 0.0f;
-            if (j < n_out) {
-                const int c = cols[j];
-                if (m0 + r < M) av = __half2float(a[(size_t)(m0 + r) * K + c]);
-                if (n0 + r < N) {
-                    const float d = __fmul_rn(__fmul_rn((float)cb[(size_t)(n0 + r) * K + c], scb[n0 + r]),
-                                              7.874015718698502e-3f);
-                    wv = __half2float(__float2half_rn(d));
+    if constexpr (EPI == EPI_LLMINT8) {
+        // outlier flags are self-cleaning: the last CTA to finish clears them for the next call
+        if (args.flags != nullptr && args.flags[args.K] != 0) {
+            __shared__ int s_last;
+            if (threadIdx.x == 0) {
+                __threadfence();
+                s_last = (atomicAdd(&args.flags[args.K + 1], 1) == (int)gridDim.x - 1);
+            }
+            __syncthreads();
+            if (s_last) {
+                for (int c = threadIdx.x; c < args.K; c += blockDim.x) args.flags[c] = 0;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    args.flags[args.K + 1] = 0;
+                    __threadfence();
+                    args.flags[args.K] = 0;
                 }
             }
-            s_a[jj][r] = av;
-            s_w[jj][r] = wv;
         }
-        __syncthreads();
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc[i][k] = fmaf(s_a[jj][ty * 4 + i], s_w[jj][tx * 4 + k], acc[i][k]);
-        }
-        __syncthreads();
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + k;
-            if (m < M && n < N) {
-                const size_t o = (size_t)m * N + n;
-                y[o] = __float2half_rn(__half2float(y[o]) + acc[i][k]);
-            }
-        }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -656,39 +661,31 @@ int check_common(const char *fn, int64_t M, int64_t N, int64_t K) {
 
 extern "C" int wq_gemm_llmint8(const int8_t *ca, const float *sca, const int8_t *cb, const float *scb,
                                const void *bias_f16, void *y_f16, int64_t M, int64_t N, int64_t K, const void *a_f16,
-                               const int32_t *outlier_cols, const int32_t *n_outliers, wq_stream_t stream) {
+                               int32_t *col_flags, wq_stream_t stream) {
     int rc = check_common("wq_gemm_llmint8", M, N, K);
     if (rc != WQ_OK) return rc;
     if (M == 0 || N == 0) return WQ_OK;
     WQ_REQUIRE(ca && sca && cb && scb && y_f16, "wq_gemm_llmint8: null pointer");
     WQ_REQUIRE(K % 16 == 0, "wq_gemm_llmint8: K=%lld must be a multiple of 16", (long long)K);
     WQ_REQUIRE(wq_aligned(ca, 16) && wq_aligned(cb, 16) && wq_aligned(y_f16, 16), "wq_gemm_llmint8: misaligned buffer");
+    WQ_REQUIRE(col_flags == nullptr || a_f16 != nullptr, "wq_gemm_llmint8: the outlier path needs a_f16");
     cudaStream_t s = (cudaStream_t)stream;
     GemmArgs args = {};
     args.M = (int)M; args.N = (int)N; args.K = (int)K;
     args.num_kb = (int)((K + 127) / 128);
     args.row_scale = sca; args.col_scale = scb; args.bias = bias_f16; args.out = y_f16;
+    args.ca = ca; args.cb = cb; args.a16 = (const __half *)a_f16; args.flags = col_flags;
     CUtensorMap ma, mb;
     rc = make_map_2d(&ma, ca, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, BM, 128, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
     if (use_narrow_tile(M, N)) {
         rc = make_map_2d(&mb, cb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc != WQ_OK) return rc;
-        rc = launch_gemm<64, A_S8, B_DIRECT, EPI_LLMINT8, __half>(ma, mb, args, s);
-    } else {
-        rc = make_map_2d(&mb, cb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc != WQ_OK) return rc;
-        rc = launch_gemm<128, A_S8, B_DIRECT, EPI_LLMINT8, __half>(ma, mb, args, s);
+        return launch_gemm<64, A_S8, B_DIRECT, EPI_LLMINT8, __half>(ma, mb, args, s);
     }
+    rc = make_map_2d(&mb, cb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
-    if (n_outliers != nullptr) {
-        WQ_REQUIRE(a_f16 && outlier_cols, "wq_gemm_llmint8: outlier path needs a_f16 and outlier_cols");
-        dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
-        k_llmint8_outliers<<<grid, 256, 0, s>>>((const __half *)a_f16, cb, scb, outlier_cols, n_outliers,
-                                                (__half *)y_f16, (int)M, (int)N, (int)K);
-        WQ_LAUNCH_CHECK();
-    }
-    return WQ_OK;
+    return launch_gemm<128, A_S8, B_DIRECT, EPI_LLMINT8, __half>(ma, mb, args, s);
 }
 
 extern "C" int wq_gemm_dyn_i8(const uint8_t *xq, const float *qparams, const int8_t *wq, const float *w_scale,

@@ -156,6 +156,7 @@ k_quant_i8_rowwise_bnb(const __half *__restrict__ a, int64_t rows, int64_t cols,
                 if (sparse && !(fabsf(v) < threshold)) {
                     q = 0;
                     col_flags[c + j] = 1;
+                    col_flags[cols] = 1;   // "any outlier in this call"
                 } else {
                     q = __float2int_rn(__fmul_rn(v, scale));  // NaN -> 0
                 }
@@ -171,6 +172,7 @@ k_quant_i8_rowwise_bnb(const __half *__restrict__ a, int64_t rows, int64_t cols,
             if (sparse && !(fabsf(v) < threshold)) {
                 q = 0;
                 col_flags[c] = 1;
+                col_flags[cols] = 1;
             } else {
                 q = __float2int_rn(__fmul_rn(v, scale));
             }
@@ -217,7 +219,11 @@ k_outlier_compact(int32_t *__restrict__ col_flags, int cols, int32_t *__restrict
             col_flags[c] = 0;
         }
     }
-    if (tid == 0) *n_outliers = s_total;
+    if (tid == 0) {
+        *n_outliers = s_total;
+        col_flags[cols] = 0;       // the "any outlier" word
+        col_flags[cols + 1] = 0;   // completion counter used by the fused GEMM
+    }
 }
 
 __global__ void __launch_bounds__(256)

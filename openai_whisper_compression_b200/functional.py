@@ -128,7 +128,7 @@ class OutlierState:
     _cache = {}
 
     def __init__(self, device: torch.device, cols: int):
-        self.col_flags = torch.zeros((cols,), dtype=torch.int32, device=device)
+        self.col_flags = torch.zeros((cols + 2,), dtype=torch.int32, device=device)   # flags, any, counter
         self.outlier_cols = torch.empty((cols,), dtype=torch.int32, device=device)
         self.n_outliers = torch.zeros((1,), dtype=torch.int32, device=device)
 
@@ -141,11 +141,15 @@ class OutlierState:
         return st
 
 
-def int8_vectorwise_quant(a: torch.Tensor, threshold: float = 0.0, state: Optional[OutlierState] = None):
+def int8_vectorwise_quant(a: torch.Tensor, threshold: float = 0.0, state: Optional[OutlierState] = None,
+                          finalize: bool = True):
     """bitsandbytes.functional.int8_vectorwise_quant.
 
     Returns (CA int8, row_stats f32, state).  With threshold > 0 the outlier columns stay on the
-    device (state.outlier_cols[: state.n_outliers]) -- no host synchronisation."""
+    device -- no host synchronisation.  finalize=True reproduces the library's outputs exactly
+    (CA[:, outlier_cols] zeroed, state.outlier_cols[: state.n_outliers] filled, flags cleared);
+    finalize=False leaves the raw flags in state.col_flags for gemm_llmint8 to consume (the module
+    forward path: two kernel launches per linear)."""
     a2 = a.reshape(-1, a.shape[-1])
     if a2.dtype != torch.float16:
         a2 = a2.to(torch.float16)
@@ -160,9 +164,12 @@ def int8_vectorwise_quant(a: torch.Tensor, threshold: float = 0.0, state: Option
             state = state or OutlierState.get(a.device, cols)
             _lib.check(lib.wq_quant_i8_rowwise_bnb(_ptr(a2), rows, cols, float(threshold), _ptr(ca), _ptr(stats),
                                                    _ptr(state.col_flags), _stream()), "wq_quant_i8_rowwise_bnb")
-            _lib.check(lib.wq_outlier_columns(_ptr(state.col_flags), rows, cols, _ptr(ca), _ptr(state.outlier_cols),
-                                              _ptr(state.n_outliers), _stream()), "wq_outlier_columns")
-            STATS.launches += 3
+            STATS.launches += 1
+            if finalize:
+                _lib.check(lib.wq_outlier_columns(_ptr(state.col_flags), rows, cols, _ptr(ca),
+                                                  _ptr(state.outlier_cols), _ptr(state.n_outliers), _stream()),
+                           "wq_outlier_columns")
+                STATS.launches += 2
         else:
             state = None
             _lib.check(lib.wq_quant_i8_rowwise_bnb(_ptr(a2), rows, cols, 0.0, _ptr(ca), _ptr(stats), None,
@@ -174,7 +181,8 @@ def int8_vectorwise_quant(a: torch.Tensor, threshold: float = 0.0, state: Option
 def gemm_llmint8(ca: torch.Tensor, sca: torch.Tensor, cb: torch.Tensor, scb: torch.Tensor,
                  bias: Optional[torch.Tensor] = None, a_f16: Optional[torch.Tensor] = None,
                  state: Optional[OutlierState] = None) -> torch.Tensor:
-    """int8_linear_matmul + int8_mm_dequant (+ outlier addmm), fused; returns fp16 [M, N]."""
+    """int8_linear_matmul + int8_mm_dequant (+ mixed-precision outlier decomposition when `state`
+    carries raw flags from int8_vectorwise_quant(..., finalize=False)), one kernel; fp16 [M, N]."""
     ca2 = ca.reshape(-1, ca.shape[-1])
     _need_cuda(ca2, sca, cb, scb, bias, a_f16)
     M, K = ca2.shape
@@ -186,20 +194,19 @@ def gemm_llmint8(ca: torch.Tensor, sca: torch.Tensor, cb: torch.Tensor, scb: tor
         _lib.check(_lib.load().wq_gemm_llmint8(
             _ptr(ca2), _ptr(sca), _ptr(cb), _ptr(scb), _ptr(bias), _ptr(y), M, N, K,
             _ptr(a_f16) if state is not None else None,
-            _ptr(state.outlier_cols) if state is not None else None,
-            _ptr(state.n_outliers) if state is not None else None, _stream()), "wq_gemm_llmint8")
-    STATS.launches += 2 if state is not None else 1
+            _ptr(state.col_flags) if state is not None else None, _stream()), "wq_gemm_llmint8")
+    STATS.launches += 1
     return y
 
 
 def linear8bitlt(x: torch.Tensor, cb: torch.Tensor, scb: torch.Tensor, bias: Optional[torch.Tensor],
                  threshold: float) -> torch.Tensor:
-    """bnb.matmul(x, Int8Params, state) for has_fp16_weights=False."""
+    """bnb.matmul(x, Int8Params, state) for has_fp16_weights=False: quantize + fused GEMM."""
     a = x.reshape(-1, x.shape[-1])
     if a.dtype != torch.float16:
         a = a.to(torch.float16)
     a = a.contiguous()
-    ca, sca, st = int8_vectorwise_quant(a, threshold)
+    ca, sca, st = int8_vectorwise_quant(a, threshold, finalize=False)
     y = gemm_llmint8(ca, sca, cb, scb, bias, a if st is not None else None, st)
     return y.reshape(*x.shape[:-1], cb.shape[0]).to(x.dtype)
 
