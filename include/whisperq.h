@@ -105,15 +105,16 @@ int wq_quant_act_u8_tensor(const void *x, int x_dtype, int64_t n, uint8_t *q, fl
 
 /* bnb.matmul(x, Int8Params, state) = int8_linear_matmul + int8_mm_dequant (+ fp16 outlier
  * addmm) -- Linear8bitLt.forward, BASELINE.json config 2.
- *   y[m,n] = fp16( fmaf(int32(CA[m,:].CB[n,:]) * SCA[m] * SCB[n], 1/127^2, bias[n]) )
+ *   y[m,n] = fp16( fmaf(int32(CA[m,:].CB[n,:]) * SCA[m] * SCB[n], 1/127^2, float(bias[n])) )
  *   outlier columns c (col_flags[c] != 0): their int8 products are removed from the accumulator
  *   (== bitsandbytes zeroing CA[:, c]) and y[m,n] = fp16( y[m,n] + sum_c A[m,c] *
  *   fp16(CB[n,c]*SCB[n]/127) ), all inside the GEMM epilogue (taken only when col_flags[K] != 0).
  * col_flags: the int32 [K + 2] array written by wq_quant_i8_rowwise_bnb for THIS activation; the
  * kernel clears it again when outliers were present.  a_f16 / col_flags may be NULL (CA already
- * has its outlier columns zeroed or threshold == 0).  bias: fp16 [N] or NULL. */
+ * has its outlier columns zeroed or threshold == 0).  bias: fp32 [N] holding the module's fp16
+ * bias widened exactly (bitsandbytes converts it per element inside int8_mm_dequant), or NULL. */
 int wq_gemm_llmint8(const int8_t *ca, const float *sca, const int8_t *cb, const float *scb,
-                    const void *bias_f16, void *y_f16, int64_t M, int64_t N, int64_t K,
+                    const float *bias, void *y_f16, int64_t M, int64_t N, int64_t K,
                     const void *a_f16, int32_t *col_flags, wq_stream_t stream);
 
 /* quanto QLinear.forward, weights-only qint8 (W8A16) -- model_utils.py:126-128 call sites:

@@ -392,7 +392,14 @@ class Linear8bitLt(nn.Linear):
             self.bias.data = self.bias.data.to(x.dtype)
         bias = self.bias
         if bias is None or bias.dtype == torch.float16:
-            # fused bias (bitsandbytes int8_mm_dequant applies an fp16 bias inside the kernel)
+            # fused bias (bitsandbytes int8_mm_dequant applies an fp16 bias inside the kernel); the
+            # kernel reads its exact fp32 widening, cached per parameter version
+            if bias is not None:
+                key = (bias.data_ptr(), bias._version)
+                if getattr(self, "_bias_f32_key", None) != key:
+                    self._bias_f32 = bias.detach().float()
+                    self._bias_f32_key = key
+                bias = self._bias_f32
             return F.linear8bitlt(x, self.state.CB, self.state.SCB, bias, float(self.state.threshold))
         out = F.linear8bitlt(x, self.state.CB, self.state.SCB, None, float(self.state.threshold))
         return out.add_(bias)

@@ -45,7 +45,7 @@ struct GemmArgs {
     int tma_store;           // 1: epilogue stores through smem + TMA; 0: direct global stores
     const float *row_scale;  // SCA[m]                         (LLMINT8)
     const float *col_scale;  // SCB[n] / quanto scale[n]       (LLMINT8, W8A16)
-    const void *bias;        // fp16 [N] (LLMINT8) / fp32 [N]  or nullptr
+    const void *bias;        // fp32 [N] or nullptr (LLM.int8: the fp16 bias widened exactly)
     const float *absmax;     // [N, K/64]                      (W4A16)
     int absmax_ld;           // K / 64
     const float *qparams;    // {s_x, zp}                      (DYN)
@@ -72,7 +72,8 @@ struct SmemLayout {
     static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
     static constexpr int OFF_P = OFF_B + STAGES * B_BYTES;
     static constexpr int OFF_OUT = OFF_P + STAGES * P_BYTES;   // EPI_WARPS x OUT_BUFS boxes, 1024-byte aligned
-    static constexpr int OFF_LUT = OFF_OUT + EPI_WARPS * OUT_BUFS * BOX_BYTES;  // float lut[16]
+    static constexpr int OFF_CONST = OFF_OUT + EPI_WARPS * OUT_BUFS * BOX_BYTES;  // float [2][3][BN] per-tile constants
+    static constexpr int OFF_LUT = OFF_CONST + 2 * 3 * BN * 4;                    // float lut[16]
     static constexpr int OFF_BAR = OFF_LUT + 64;               // uint64 barriers
     static constexpr int NUM_BARS = 3 * STAGES + 2 * ACC_STAGES;
     static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
@@ -91,90 +92,216 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, fl
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-// Epilogue arithmetic (operation order fixed: the CPU oracle restates it step by step).
+// Epilogue arithmetic on a pair of adjacent columns (operation order fixed: the CPU oracle restates
+// it step by step; the packed f32x2 instructions round exactly like their scalar forms).
 template <int EPI>
-__device__ __forceinline__ float epi_one(uint32_t r, float cs, float b, int aux, float rs, float dyn_s, int dyn_zp) {
+__device__ __forceinline__ void epi_pair(uint32_t r0, uint32_t r1, float cs0, float cs1, float b0, float b1, int aux0,
+                                         int aux1, float rs, float dyn_s, int dyn_zp, float &v0, float &v1) {
     if constexpr (EPI == EPI_LLMINT8) {
-        const float x = __fmul_rn(__fmul_rn((float)(int)r, rs), cs);
-        return __fmaf_rn(x, 6.200012e-05f, b);
+        v0 = (float)(int)r0;
+        v1 = (float)(int)r1;
+        mul2(v0, v1, rs, rs);
+        mul2(v0, v1, cs0, cs1);
+        fma2(v0, v1, 6.200012e-05f, 6.200012e-05f, b0, b1);
     } else if constexpr (EPI == EPI_DYN) {
-        const int acc = (int)r - dyn_zp * aux;
-        return __fadd_rn(__fmul_rn((float)acc, dyn_s), b);
+        // scalar mul + add: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2, which
+        // would round differently from the reference's two operations
+        v0 = __fadd_rn(__fmul_rn((float)((int)r0 - dyn_zp * aux0), dyn_s), b0);
+        v1 = __fadd_rn(__fmul_rn((float)((int)r1 - dyn_zp * aux1), dyn_s), b1);
     } else if constexpr (EPI == EPI_W8A16) {
-        return __fadd_rn(__fmul_rn(__uint_as_float(r), cs), b);
+        v0 = __fadd_rn(__fmul_rn(__uint_as_float(r0), cs0), b0);
+        v1 = __fadd_rn(__fmul_rn(__uint_as_float(r1), cs1), b1);
     } else {
-        return __fadd_rn(__uint_as_float(r), b);
+        v0 = __fadd_rn(__uint_as_float(r0), b0);
+        v1 = __fadd_rn(__uint_as_float(r1), b1);
     }
 }
 
-// 32 adjacent columns starting at absolute column n, all inside [0, N): straight-line vector loads
-// of the per-column constants (L1-resident after the first tile) followed by the arithmetic.
-template <int EPI, bool HAS_BIAS>
-__device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[32], float (&v)[32], const GemmArgs &args, int n,
-                                               float rs, float dyn_s, int dyn_zp) {
-    float cs[32], b[32];
-    int aux[32];
+// 32 adjacent columns starting at tile column `col0`; the per-column constants of the tile were
+// staged in shared memory (sc: [3][BN] = col scale | bias | wsum) by the epilogue warps.
+template <int BN, int EPI>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], float (&v)[32], const float *sc, int col0, float rs,
+                                          float dyn_s, int dyn_zp) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-        if constexpr (EPI == EPI_LLMINT8 || EPI == EPI_W8A16) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(args.col_scale + n) + g);
-            cs[4 * g] = t.x; cs[4 * g + 1] = t.y; cs[4 * g + 2] = t.z; cs[4 * g + 3] = t.w;
-        } else {
-            cs[4 * g] = cs[4 * g + 1] = cs[4 * g + 2] = cs[4 * g + 3] = 0.0f;
-        }
-        if constexpr (EPI == EPI_DYN) {
-            const int4 t = __ldg(reinterpret_cast<const int4 *>(args.wsum + n) + g);
-            aux[4 * g] = t.x; aux[4 * g + 1] = t.y; aux[4 * g + 2] = t.z; aux[4 * g + 3] = t.w;
-        } else {
-            aux[4 * g] = aux[4 * g + 1] = aux[4 * g + 2] = aux[4 * g + 3] = 0;
-        }
+        const float4 cs = *reinterpret_cast<const float4 *>(sc + col0 + 4 * g);
+        const float4 b = *reinterpret_cast<const float4 *>(sc + BN + col0 + 4 * g);
+        int4 aux = make_int4(0, 0, 0, 0);
+        if constexpr (EPI == EPI_DYN) aux = *reinterpret_cast<const int4 *>(sc + 2 * BN + col0 + 4 * g);
+        epi_pair<EPI>(r[4 * g], r[4 * g + 1], cs.x, cs.y, b.x, b.y, aux.x, aux.y, rs, dyn_s, dyn_zp, v[4 * g],
+                      v[4 * g + 1]);
+        epi_pair<EPI>(r[4 * g + 2], r[4 * g + 3], cs.z, cs.w, b.z, b.w, aux.z, aux.w, rs, dyn_s, dyn_zp, v[4 * g + 2],
+                      v[4 * g + 3]);
     }
-    if constexpr (HAS_BIAS) {
-        if constexpr (EPI == EPI_LLMINT8) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const uint4 t = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(args.bias) + n) + g);
-                const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[j]));
-                    b[8 * g + 2 * j] = f.x;
-                    b[8 * g + 2 * j + 1] = f.y;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const float4 t = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(args.bias) + n) + g);
-                b[4 * g] = t.x; b[4 * g + 1] = t.y; b[4 * g + 2] = t.z; b[4 * g + 3] = t.w;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) b[j] = 0.0f;
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = epi_one<EPI>(r[j], cs[j], b[j], aux[j], rs, dyn_s, dyn_zp);
 }
 
-// N-tail chunk: per-column bounds checks (columns >= N produce unused values)
-template <int EPI>
-__device__ __forceinline__ void epi_chunk_tail(const uint32_t (&r)[32], float (&v)[32], const GemmArgs &args, int n,
-                                            float rs, float dyn_s, int dyn_zp) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        float cs = 0.0f, b = 0.0f;
-        int aux = 0;
-        if (n + j < args.N) {
-            if constexpr (EPI == EPI_LLMINT8 || EPI == EPI_W8A16) cs = __ldg(args.col_scale + n + j);
-            if (args.bias != nullptr) {
-                if constexpr (EPI == EPI_LLMINT8) b = __half2float(reinterpret_cast<const __half *>(args.bias)[n + j]);
-                else b = __ldg(reinterpret_cast<const float *>(args.bias) + n + j);
-            }
-            if constexpr (EPI == EPI_DYN) aux = __ldg(args.wsum + n + j);
-        }
-        v[j] = epi_one<EPI>(r[j], cs, b, aux, rs, dyn_s, dyn_zp);
+// Body of one epilogue warp: drains its 32-row slab of every tile this CTA owns.
+template <int BN, int EPI, typename OutT, int OUT_BUFS, bool TMA_STORE>
+__device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtensorMap *map_y, uint8_t *boxes,
+                                              float *s_const, uint64_t *bar_tmem_full, uint64_t *bar_tmem_empty,
+                                              uint32_t tmem_base, int warp, int lane, int total_tiles) {
+    constexpr int ACC_COLS = 2 * BN;
+    constexpr int BOX_COLS = 128 / (int)sizeof(OutT);   // columns per TMA-store box (64 or 32)
+    constexpr int N_BOX = BN / BOX_COLS;
+    constexpr int NCH = BOX_COLS / 32;                  // tcgen05.ld chunks per box (2 or 1)
+    const int h = (warp - 2) >> 2;                      // 128-row half of the tile
+    const int q = warp & 3;                             // TMEM lane quarter this warp may access
+    const bool vec_ok = ((size_t)args.N * sizeof(OutT)) % 16 == 0;
+    const bool any_outlier = (EPI == EPI_LLMINT8) && args.flags != nullptr && args.flags[args.K] != 0;
+    float dyn_s = 0.0f;
+    int dyn_zp = 0;
+    if constexpr (EPI == EPI_DYN) {
+        dyn_s = __fmul_rn(args.qparams[0], args.w_scale[0]);
+        dyn_zp = (int)args.qparams[1];
     }
+    uint32_t t = 0, nstore = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+        const int n0 = (tile % args.tiles_n) * BN, m0 = (tile / args.tiles_n) * BM;
+        const uint32_t as = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1;
+        const int mrow0 = m0 + h * BMH + q * 32;  // first row of this warp's 32-row slab
+        const int m = mrow0 + lane;
+        const bool row_ok = m < args.M;
+        const bool slab_ok = mrow0 < args.M;      // warp-uniform
+        float rs = 1.0f;
+        if constexpr (EPI == EPI_LLMINT8) rs = row_ok ? __ldg(args.row_scale + m) : 0.0f;
+        // stage this tile's per-column constants once (the 8 epilogue warps share them); two
+        // buffers, so a warp that runs ahead never overwrites constants still in use
+        float *sc = s_const + (t & 1) * 3 * BN;
+        {
+            const float *bias = reinterpret_cast<const float *>(args.bias);
+            for (int i = (warp - 2) * 32 + lane; i < 3 * BN; i += EPI_WARPS * 32) {
+                const int which = i / BN;
+                const int n = min(n0 + (i - which * BN), args.N - 1);
+                float val = 0.0f;
+                if (which == 0) {
+                    if constexpr (EPI == EPI_LLMINT8 || EPI == EPI_W8A16) val = __ldg(args.col_scale + n);
+                } else if (which == 1) {
+                    if (bias != nullptr) val = __ldg(bias + n);
+                } else {
+                    if constexpr (EPI == EPI_DYN) val = __int_as_float(__ldg(args.wsum + n));
+                }
+                sc[i] = val;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        }
+
+        mbar_wait(&bar_tmem_full[as], aph);
+        tc_fence_after();
+        if (slab_ok) {
+            OutT *row_ptr = reinterpret_cast<OutT *>(args.out) + (size_t)(row_ok ? m : 0) * args.N;
+            const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + h * BN;
+#pragma unroll 1
+            for (int bx = 0; bx < N_BOX; ++bx) {
+                uint8_t *box = boxes + (nstore % OUT_BUFS) * BOX_BYTES;
+                if constexpr (TMA_STORE) {
+                    // the store that last used this box must have finished reading it
+                    if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();
+                    __syncwarp();
+                }
+                uint32_t r[NCH][32];
+#pragma unroll
+                for (int cc = 0; cc < NCH; ++cc) tmem_ld_32x32(tmem_row + bx * BOX_COLS + cc * 32, r[cc]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int cc = 0; cc < NCH; ++cc) {
+                    const int col0 = bx * BOX_COLS + cc * 32;   // column inside the tile
+                    float v[32];
+                    float o[32];
+                    if constexpr (EPI == EPI_LLMINT8) {
+                        if (any_outlier) {
+                            // rare path: remove the outlier columns' int8 products from the exact
+                            // int32 accumulator and build the fp16 side product (ascending column)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) o[j] = 0.0f;
+#pragma unroll 1
+                            for (int c = 0; c < args.K; ++c) {
+                                if (args.flags[c] == 0) continue;
+                                const int a8 = row_ok ? (int)args.ca[(size_t)m * args.K + c] : 0;
+                                const float af = row_ok ? __half2float(args.a16[(size_t)m * args.K + c]) : 0.0f;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const int n = n0 + col0 + j;
+                                    if (n < args.N) {
+                                        const int b8 = (int)args.cb[(size_t)n * args.K + c];
+                                        r[cc][j] = (uint32_t)((int)r[cc][j] - a8 * b8);
+                                        const float d = __fmul_rn(__fmul_rn((float)b8, __ldg(args.col_scale + n)),
+                                                                  7.874015718698502e-3f);
+                                        o[j] = fmaf(af, __half2float(__float2half_rn(d)), o[j]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    epi_chunk<BN, EPI>(r[cc], v, sc, col0, rs, dyn_s, dyn_zp);
+                    if constexpr (EPI == EPI_LLMINT8) {
+                        if (any_outlier) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                v[j] = __half2float(__float2half_rn(v[j])) + o[j];   // fp16 addmm
+                        }
+                    }
+                    if constexpr (TMA_STORE) {
+                        constexpr int CH = 32 * (int)sizeof(OutT) / 16;   // 16-byte chunks per 32 columns
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            const int c16 = cc * CH + j;                   // chunk index inside the 128-byte row
+                            uint8_t *dst = box + lane * 128 + ((c16 ^ (lane & 7)) << 4);
+                            if constexpr (sizeof(OutT) == 4) {
+                                *reinterpret_cast<float4 *>(dst) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            } else {
+                                uint4 u;
+                                u.x = pack2<OutT>(v[8 * j + 0], v[8 * j + 1]);
+                                u.y = pack2<OutT>(v[8 * j + 2], v[8 * j + 3]);
+                                u.z = pack2<OutT>(v[8 * j + 4], v[8 * j + 5]);
+                                u.w = pack2<OutT>(v[8 * j + 6], v[8 * j + 7]);
+                                *reinterpret_cast<uint4 *>(dst) = u;
+                            }
+                        }
+                    } else if (row_ok) {
+                        const int nb = n0 + col0;
+                        if (vec_ok && nb + 32 <= args.N) {
+                            if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    reinterpret_cast<float4 *>(row_ptr + nb)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    uint4 u;
+                                    u.x = pack2<OutT>(v[8 * j + 0], v[8 * j + 1]);
+                                    u.y = pack2<OutT>(v[8 * j + 2], v[8 * j + 3]);
+                                    u.z = pack2<OutT>(v[8 * j + 4], v[8 * j + 5]);
+                                    u.w = pack2<OutT>(v[8 * j + 6], v[8 * j + 7]);
+                                    reinterpret_cast<uint4 *>(row_ptr + nb)[j] = u;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (nb + j < args.N) row_ptr[nb + j] = from_f32<OutT>(v[j]);
+                        }
+                    }
+                }
+                if constexpr (TMA_STORE) {
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(map_y, box, n0 + bx * BOX_COLS, mrow0);
+                        tma_store_commit();
+                    }
+                    ++nstore;
+                }
+            }
+        }
+        // accumulator fully read: hand the TMEM stage back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tmem_empty[as]);
+    }
+    if constexpr (TMA_STORE) {
+        if (lane == 0) tma_store_wait<0>();
+    }
+    __syncwarp();
 }
 
 template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT, int OUT_BUFS>
@@ -294,153 +421,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         __syncwarp();
     } else if (warp < 2 + EPI_WARPS) {
         // ---------------- epilogue: warps 2..9 ----------------
-        const int e = warp - 2;
-        const int h = e >> 2;                         // 128-row half of the tile
-        const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        uint8_t *boxes = smem + L::OFF_OUT + e * OUT_BUFS * BOX_BYTES;
-        constexpr int BOX_COLS = 128 / (int)sizeof(OutT);   // columns per TMA-store box (64 or 32)
-        constexpr int N_BOX = BN / BOX_COLS;
-        const bool vec_ok = ((size_t)args.N * sizeof(OutT)) % 16 == 0;
-        const bool has_bias = args.bias != nullptr;
-        const bool any_outlier = (EPI == EPI_LLMINT8) && args.flags != nullptr && args.flags[args.K] != 0;
-        float dyn_s = 0.0f;
-        int dyn_zp = 0;
-        if constexpr (EPI == EPI_DYN) {
-            dyn_s = __fmul_rn(args.qparams[0], args.w_scale[0]);
-            dyn_zp = (int)args.qparams[1];
-        }
-        uint32_t t = 0, nstore = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-            const int n0 = (tile % args.tiles_n) * BN, m0 = (tile / args.tiles_n) * BM;
-            const uint32_t as = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1;
-            const int mrow0 = m0 + h * BMH + q * 32;  // first row of this warp's 32-row slab
-            const int m = mrow0 + lane;
-            const bool row_ok = m < args.M;
-            const bool slab_ok = mrow0 < args.M;      // warp-uniform
-            float rs = 1.0f;
-            if constexpr (EPI == EPI_LLMINT8) rs = row_ok ? __ldg(args.row_scale + m) : 0.0f;
-
-            mbar_wait(&bar_tmem_full[as], aph);
-            tc_fence_after();
-            if (slab_ok) {
-                OutT *row_ptr = reinterpret_cast<OutT *>(args.out) + (size_t)(row_ok ? m : 0) * args.N;
-                const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + h * BN;
-#pragma unroll 1
-                for (int bx = 0; bx < N_BOX; ++bx) {
-                    uint8_t *box = boxes + (nstore % OUT_BUFS) * BOX_BYTES;
-                    if (args.tma_store) {
-                        // the store that last used this box must have finished reading it
-                        if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();
-                        __syncwarp();
-                    }
-                    constexpr int NCH = BOX_COLS / 32;              // tcgen05.ld chunks per box (2 or 1)
-                    uint32_t r[NCH][32];
-#pragma unroll
-                    for (int cc = 0; cc < NCH; ++cc) tmem_ld_32x32(tmem_row + bx * BOX_COLS + cc * 32, r[cc]);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int cc = 0; cc < NCH; ++cc) {
-                        const int col0 = bx * BOX_COLS + cc * 32;   // column inside the tile
-                        float v[32];
-                        float o[32];
-                        if constexpr (EPI == EPI_LLMINT8) {
-                            if (any_outlier) {
-                                // rare path: remove the outlier columns' int8 products from the exact
-                                // int32 accumulator and build the fp16 side product (ascending column)
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) o[j] = 0.0f;
-#pragma unroll 1
-                                for (int c = 0; c < args.K; ++c) {
-                                    if (args.flags[c] == 0) continue;
-                                    const int a8 = row_ok ? (int)args.ca[(size_t)m * args.K + c] : 0;
-                                    const float af = row_ok ? __half2float(args.a16[(size_t)m * args.K + c]) : 0.0f;
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) {
-                                        const int n = n0 + col0 + j;
-                                        if (n < args.N) {
-                                            const int b8 = (int)args.cb[(size_t)n * args.K + c];
-                                            r[cc][j] = (uint32_t)((int)r[cc][j] - a8 * b8);
-                                            const float d = __fmul_rn(__fmul_rn((float)b8, __ldg(args.col_scale + n)),
-                                                                      7.874015718698502e-3f);
-                                            o[j] = fmaf(af, __half2float(__float2half_rn(d)), o[j]);
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                        if (n0 + col0 + 32 <= args.N) {
-                            if (has_bias) epi_chunk_fast<EPI, true>(r[cc], v, args, n0 + col0, rs, dyn_s, dyn_zp);
-                            else epi_chunk_fast<EPI, false>(r[cc], v, args, n0 + col0, rs, dyn_s, dyn_zp);
-                        } else {
-                            epi_chunk_tail<EPI>(r[cc], v, args, n0 + col0, rs, dyn_s, dyn_zp);
-                        }
-                        if constexpr (EPI == EPI_LLMINT8) {
-                            if (any_outlier) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    v[j] = __half2float(__float2half_rn(v[j])) + o[j];   // fp16 addmm
-                            }
-                        }
-                        if (args.tma_store) {
-                            constexpr int CH = 32 * (int)sizeof(OutT) / 16;   // 16-byte chunks per 32 columns
-#pragma unroll
-                            for (int j = 0; j < CH; ++j) {
-                                const int c16 = cc * CH + j;                   // chunk index inside the 128-byte row
-                                uint8_t *dst = box + lane * 128 + ((c16 ^ (lane & 7)) << 4);
-                                if constexpr (sizeof(OutT) == 4) {
-                                    *reinterpret_cast<float4 *>(dst) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                                } else {
-                                    uint4 u;
-                                    u.x = pack2<OutT>(v[8 * j + 0], v[8 * j + 1]);
-                                    u.y = pack2<OutT>(v[8 * j + 2], v[8 * j + 3]);
-                                    u.z = pack2<OutT>(v[8 * j + 4], v[8 * j + 5]);
-                                    u.w = pack2<OutT>(v[8 * j + 6], v[8 * j + 7]);
-                                    *reinterpret_cast<uint4 *>(dst) = u;
-                                }
-                            }
-                        } else if (row_ok) {
-                            const int nb = n0 + col0;
-                            if (vec_ok && nb + 32 <= args.N) {
-                                if constexpr (sizeof(OutT) == 4) {
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j)
-                                        reinterpret_cast<float4 *>(row_ptr + nb)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                                } else {
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        uint4 u;
-                                        u.x = pack2<OutT>(v[8 * j + 0], v[8 * j + 1]);
-                                        u.y = pack2<OutT>(v[8 * j + 2], v[8 * j + 3]);
-                                        u.z = pack2<OutT>(v[8 * j + 4], v[8 * j + 5]);
-                                        u.w = pack2<OutT>(v[8 * j + 6], v[8 * j + 7]);
-                                        reinterpret_cast<uint4 *>(row_ptr + nb)[j] = u;
-                                    }
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (nb + j < args.N) row_ptr[nb + j] = from_f32<OutT>(v[j]);
-                            }
-                        }
-                    }
-                    if (args.tma_store) {
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            tma_store_2d(&map_y, box, n0 + bx * BOX_COLS, mrow0);
-                            tma_store_commit();
-                        }
-                        ++nstore;
-                    }
-                }
-            }
-            // accumulator fully read: hand the TMEM stage back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tmem_empty[as]);
-        }
-        if (args.tma_store && lane == 0) tma_store_wait<0>();
-        __syncwarp();
+        uint8_t *boxes = smem + L::OFF_OUT + (warp - 2) * OUT_BUFS * BOX_BYTES;
+        float *s_const = reinterpret_cast<float *>(smem + L::OFF_CONST);
+        if (args.tma_store)
+            epilogue_warp<BN, EPI, OutT, OUT_BUFS, true>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane, total_tiles);
+        else
+            epilogue_warp<BN, EPI, OutT, OUT_BUFS, false>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane, total_tiles);
     } else {
         // ---------------- weight expansion (W8A16 / W4A16): warps 10.. ----------------
         const int t = threadIdx.x - 32 * (2 + EPI_WARPS);
@@ -534,13 +520,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     if constexpr (EPI == EPI_LLMINT8) {
         // outlier flags are self-cleaning: the last CTA to finish clears them for the next call
         if (args.flags != nullptr && args.flags[args.K] != 0) {
-            __shared__ int s_last;
+            int *s_last = reinterpret_cast<int *>(tmem_holder) + 1;   // spare word next to the TMEM handle
             if (threadIdx.x == 0) {
                 __threadfence();
-                s_last = (atomicAdd(&args.flags[args.K + 1], 1) == (int)gridDim.x - 1);
+                *s_last = (atomicAdd(&args.flags[args.K + 1], 1) == (int)gridDim.x - 1);
             }
             __syncthreads();
-            if (s_last) {
+            if (*s_last) {
                 for (int c = threadIdx.x; c < args.K; c += blockDim.x) args.flags[c] = 0;
                 __syncthreads();
                 if (threadIdx.x == 0) {
@@ -603,7 +589,7 @@ constexpr int pick_stages() {
     int best = 2;
     for (int st = 2; st <= 6; ++st) {
         const int stage = BM * ROW_BYTES + BN * ROW_BYTES + BN * (BMODE == B_I8 ? 64 : (BMODE == B_4BIT ? 32 : 0));
-        const int total = st * stage + EPI_WARPS * OUT_BUFS * BOX_BYTES + 64 + (3 * st + 2 * ACC_STAGES) * 8 + 16 + 1024;
+        const int total = st * stage + EPI_WARPS * OUT_BUFS * BOX_BYTES + 2 * 3 * BN * 4 + 64 + (3 * st + 2 * ACC_STAGES) * 8 + 16 + 1024;
         if (total <= 232448) best = st;
     }
     return best;
@@ -639,6 +625,7 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cud
     }
     const int total = args.tiles_m * args.tiles_n;
     const int grid = total < wq_sm_count() ? total : wq_sm_count();
+
     kfn<<<grid, num_threads<BMODE>(), L::TOTAL, stream>>>(ma, mb, my, args);
     WQ_LAUNCH_CHECK();
     return WQ_OK;
@@ -660,7 +647,7 @@ int check_common(const char *fn, int64_t M, int64_t N, int64_t K) {
 }  // namespace
 
 extern "C" int wq_gemm_llmint8(const int8_t *ca, const float *sca, const int8_t *cb, const float *scb,
-                               const void *bias_f16, void *y_f16, int64_t M, int64_t N, int64_t K, const void *a_f16,
+                               const float *bias, void *y_f16, int64_t M, int64_t N, int64_t K, const void *a_f16,
                                int32_t *col_flags, wq_stream_t stream) {
     int rc = check_common("wq_gemm_llmint8", M, N, K);
     if (rc != WQ_OK) return rc;
@@ -673,7 +660,7 @@ extern "C" int wq_gemm_llmint8(const int8_t *ca, const float *sca, const int8_t 
     GemmArgs args = {};
     args.M = (int)M; args.N = (int)N; args.K = (int)K;
     args.num_kb = (int)((K + 127) / 128);
-    args.row_scale = sca; args.col_scale = scb; args.bias = bias_f16; args.out = y_f16;
+    args.row_scale = sca; args.col_scale = scb; args.bias = bias; args.out = y_f16;
     args.ca = ca; args.cb = cb; args.a16 = (const __half *)a_f16; args.flags = col_flags;
     CUtensorMap ma, mb;
     rc = make_map_2d(&ma, ca, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, BM, 128, CU_TENSOR_MAP_SWIZZLE_128B);

@@ -174,6 +174,28 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t c_fmt, uint32_t a_fmt
     return (c_fmt << 4) | (a_fmt << 7) | (b_fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// packed fp32x2 arithmetic (sm_100): two IEEE-rn operations per instruction, same results as the
+// scalar forms -- halves the epilogue's FP32 instruction count
+__device__ __forceinline__ void mul2(float &x0, float &x1, float y0, float y1) {
+    asm("{\n.reg .b64 a, b;\nmov.b64 a, {%0, %1};\nmov.b64 b, {%2, %3};\nmul.rn.f32x2 a, a, b;\n"
+        "mov.b64 {%0, %1}, a;\n}"
+        : "+f"(x0), "+f"(x1)
+        : "f"(y0), "f"(y1));
+}
+__device__ __forceinline__ void add2(float &x0, float &x1, float y0, float y1) {
+    asm("{\n.reg .b64 a, b;\nmov.b64 a, {%0, %1};\nmov.b64 b, {%2, %3};\nadd.rn.f32x2 a, a, b;\n"
+        "mov.b64 {%0, %1}, a;\n}"
+        : "+f"(x0), "+f"(x1)
+        : "f"(y0), "f"(y1));
+}
+// x = x * y + z
+__device__ __forceinline__ void fma2(float &x0, float &x1, float y0, float y1, float z0, float z1) {
+    asm("{\n.reg .b64 a, b, c;\nmov.b64 a, {%0, %1};\nmov.b64 b, {%2, %3};\nmov.b64 c, {%4, %5};\n"
+        "fma.rn.f32x2 a, a, b, c;\nmov.b64 {%0, %1}, a;\n}"
+        : "+f"(x0), "+f"(x1)
+        : "f"(y0), "f"(y1), "f"(z0), "f"(z1));
+}
+
 // byte offset of 16-byte chunk `c` (0..7) of row `r` inside a SW128 K-major tile
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c) {
     return r * 128u + ((c ^ (r & 7u)) << 4);

@@ -188,8 +188,10 @@ def gemm_llmint8(ca: torch.Tensor, sca: torch.Tensor, cb: torch.Tensor, scb: tor
     M, K = ca2.shape
     N = cb.shape[0]
     y = torch.empty((M, N), dtype=torch.float16, device=ca.device)
-    if bias is not None and bias.dtype != torch.float16:
-        raise RuntimeError("gemm_llmint8: bias must be fp16")
+    if bias is not None and bias.dtype != torch.float32:
+        if bias.dtype != torch.float16:
+            raise RuntimeError("gemm_llmint8: bias must be fp16 (or its exact fp32 widening)")
+        bias = bias.float()          # exact; modules pass a cached fp32 copy instead
     with torch.cuda.device(ca.device), _Timed("llmint8", M, N, K):
         _lib.check(_lib.load().wq_gemm_llmint8(
             _ptr(ca2), _ptr(sca), _ptr(cb), _ptr(scb), _ptr(bias), _ptr(y), M, N, K,
