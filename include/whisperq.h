@@ -117,6 +117,14 @@ int wq_gemm_llmint8(const int8_t *ca, const float *sca, const int8_t *cb, const 
                     const float *bias, void *y_f16, int64_t M, int64_t N, int64_t K,
                     const void *a_f16, int32_t *col_flags, wq_stream_t stream);
 
+/* The same Linear8bitLt forward for decode-shaped calls (M <= 64 rows, 64*K + K + 272 <= 200 KiB):
+ * activation quantization (threshold rule), int8 products (dp4a), int8_mm_dequant and the outlier
+ * side product in ONE launch; bit-identical to wq_quant_i8_rowwise_bnb + wq_gemm_llmint8.
+ * a_f16: fp16 [M, K]; bias: fp32 [N] (exact widening of the fp16 bias) or NULL; y: fp16 [M, N]. */
+int wq_linear_llmint8_small(const void *a_f16, int64_t M, int64_t K, float threshold, const int8_t *cb,
+                            const float *scb, const float *bias, void *y_f16, int64_t N,
+                            wq_stream_t stream);
+
 /* quanto QLinear.forward, weights-only qint8 (W8A16) -- model_utils.py:126-128 call sites:
  *   y = matmul(x, Wq.to(x.dtype).t()) * scale + bias, accumulated in fp32, rounded once.
  * x: [M, K] of x_dtype (F16/BF16); wq int8 [N, K]; scale fp32 [N]; bias fp32 [N] or NULL;

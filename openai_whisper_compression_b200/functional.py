@@ -33,6 +33,7 @@ class _Stats:
 
 
 STATS = _Stats()
+SMALL_M_ROWS = 64    # Linear8bitLt calls with at most this many rows take the fused single-launch kernel
 
 
 class _Timed:
@@ -208,6 +209,20 @@ def linear8bitlt(x: torch.Tensor, cb: torch.Tensor, scb: torch.Tensor, bias: Opt
     if a.dtype != torch.float16:
         a = a.to(torch.float16)
     a = a.contiguous()
+    M, K = a.shape
+    if 0 < M <= SMALL_M_ROWS and K % 16 == 0 and 64 * K + K + 272 <= 200 * 1024:
+        # decode-shaped call: quantize + int8 GEMV + dequant (+ outliers) in one launch
+        _need_cuda(a, cb, scb, bias)
+        if bias is not None and bias.dtype != torch.float32:
+            bias = bias.float()
+        N = cb.shape[0]
+        y = torch.empty((M, N), dtype=torch.float16, device=a.device)
+        with torch.cuda.device(a.device):
+            _lib.check(_lib.load().wq_linear_llmint8_small(_ptr(a), M, K, float(threshold), _ptr(cb), _ptr(scb),
+                                                           _ptr(bias), _ptr(y), N, _stream()),
+                       "wq_linear_llmint8_small")
+        STATS.launches += 1
+        return y.reshape(*x.shape[:-1], N).to(x.dtype)
     ca, sca, st = int8_vectorwise_quant(a, threshold, finalize=False)
     y = gemm_llmint8(ca, sca, cb, scb, bias, a if st is not None else None, st)
     return y.reshape(*x.shape[:-1], cb.shape[0]).to(x.dtype)

@@ -291,3 +291,34 @@ def test_edit_distance_matches_oracle():
     d = F.edit_distance(dev(np.concatenate(refs)), dev(ro), dev(np.concatenate(hyps)), dev(ho)).cpu().numpy()
     want = [oracle.edit_distance(r, h) for r, h in zip(refs, hyps)]
     np.testing.assert_array_equal(d, want)
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 512, 512), (17, 200, 384), (33, 2048, 512), (64, 512, 2048), (64, 51, 64)])
+@pytest.mark.parametrize("outliers", [False, True])
+def test_llmint8_small_m_kernel_bit_identical_to_tensor_core_path(M, N, K, outliers):
+    """decode-shaped calls take the fused single-launch kernel (csrc/gemv_small.cu); it must give
+    exactly the bits of quantize + tcgen05 GEMM, and of the oracle when there are no outliers."""
+    rng = np.random.RandomState(M * 7 + N + K)
+    W = (rng.randn(N, K) * 0.05).astype(np.float16)
+    x = rng.randn(M, K).astype(np.float16)
+    if outliers:
+        x[0, 3] = 8.0
+        x[M - 1, K - 1] = -6.0
+        x[M // 2, K // 2] = 40.0
+    bias = (rng.randn(N) * 0.1).astype(np.float16)
+    CB, SCB, _ = oracle.int8_vectorwise_quant(W, 0.0)
+    cb, scb, b = dev(CB), dev(SCB), dev(bias)
+    y_small = F.linear8bitlt(dev(x), cb, scb, b, 6.0).cpu().numpy()
+    saved = F.SMALL_M_ROWS
+    try:
+        F.SMALL_M_ROWS = 0
+        y_tc = F.linear8bitlt(dev(x), cb, scb, b, 6.0).cpu().numpy()
+    finally:
+        F.SMALL_M_ROWS = saved
+    np.testing.assert_array_equal(y_small, y_tc)
+    y_ref, extra = oracle.linear8bitlt_forward(x, CB, SCB, bias, 6.0)
+    if not outliers:
+        assert extra is None
+        np.testing.assert_array_equal(y_small, y_ref)
+    else:
+        assert np.abs(y_small.astype(np.float32) - y_ref.astype(np.float32)).max() <= 2 ** -7
