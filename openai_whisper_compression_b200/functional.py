@@ -33,7 +33,9 @@ class _Stats:
 
 
 STATS = _Stats()
-SMALL_M_ROWS = 64    # Linear8bitLt calls with at most this many rows take the fused single-launch kernel
+# Linear8bitLt calls with at most this many rows take the fused single-launch kernel (the kernel
+# supports up to 64; every CTA re-quantizes all rows, which stops paying off beyond ~16 rows)
+SMALL_M_ROWS = 16
 
 
 class _Timed:

@@ -308,9 +308,10 @@ def test_llmint8_small_m_kernel_bit_identical_to_tensor_core_path(M, N, K, outli
     bias = (rng.randn(N) * 0.1).astype(np.float16)
     CB, SCB, _ = oracle.int8_vectorwise_quant(W, 0.0)
     cb, scb, b = dev(CB), dev(SCB), dev(bias)
-    y_small = F.linear8bitlt(dev(x), cb, scb, b, 6.0).cpu().numpy()
     saved = F.SMALL_M_ROWS
     try:
+        F.SMALL_M_ROWS = 64
+        y_small = F.linear8bitlt(dev(x), cb, scb, b, 6.0).cpu().numpy()
         F.SMALL_M_ROWS = 0
         y_tc = F.linear8bitlt(dev(x), cb, scb, b, 6.0).cpu().numpy()
     finally:
