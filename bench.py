@@ -157,7 +157,7 @@ def run_reference(args):
         "impl": "reference", "metric": "audio-seconds/sec", "value": r["audio_s_per_s"], "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-        "config": workload_config(args),
+        "config": dict(workload_config(args), decode_loop="HF _sample (the reference's model.generate), CPU"),
         "cpu_baseline": {"value": r["audio_s_per_s"], "unit": "audio-s/s", "cores": r["cores"],
                          "kind": "reference", "sample": sample},
         "e2e": {"value": r["audio_s_per_s"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
