@@ -83,6 +83,15 @@ int wq_outlier_columns(int32_t *col_flags, int64_t rows, int64_t cols, int8_t *c
 int wq_quant_i8_rowwise_quanto(const void *w, int w_dtype, int64_t N, int64_t K, int8_t *q,
                                float *scale, wq_stream_t stream);
 
+/* optimum.quanto quantize(model, weights=qint4); freeze(model) -- model_utils.py:126-128
+ * ("quanto_int4", quantization.py:45-47).  MaxOptimizer + AffineQuantizer per group of `group`
+ * consecutive in-features of one output channel (quanto: 128, reduced in steps of 32 until it
+ * divides K; the whole row when K <= 128): scale = (max - min) / 15, shift = -min,
+ * q = clamp(rint((w + shift) / scale), 0, 15).  packed: N*K/2 bytes, first code in the high nibble;
+ * scale / shift: fp32 [N, K/group].  NB exact zeros are not preserved by this scheme. */
+int wq_quant_u4_group_quanto(const void *w, int w_dtype, int64_t N, int64_t K, int group,
+                             uint8_t *packed, float *scale, float *shift, wq_stream_t stream);
+
 /* torch.quantization.quantize_dynamic weight observer + quantize_per_tensor --
  * model_utils.py:131-134, pruning+quantization/pytorch_implementation.py:657-665.
  * scale = max(-min, max) / 127.5 (>= FLT_EPSILON), q = clamp(nearbyint(w * (1/scale))).
@@ -140,6 +149,13 @@ int wq_gemm_w8a16(const void *x, int x_dtype, const int8_t *wq, const float *sca
 int wq_gemm_w4a16(const void *x, int x_dtype, const uint8_t *packed, const float *absmax,
                   int quant_type, const float *bias, void *y, int y_dtype, int64_t M, int64_t N,
                   int64_t K, wq_stream_t stream);
+
+/* quanto QLinear.forward with weights=qint4: y = x @ (scale * q - shift)^T + bias; the dequantised
+ * weight is rounded once to the operand dtype (x_dtype F16/BF16), fp32 accumulation.
+ * group: multiple of 32 dividing K; K % 64 == 0; bias fp32 [N] or NULL. */
+int wq_gemm_u4a16(const void *x, int x_dtype, const uint8_t *packed, const float *scale,
+                  const float *shift, int group, const float *bias, void *y, int y_dtype, int64_t M,
+                  int64_t N, int64_t K, wq_stream_t stream);
 
 /* torch.ao.nn.quantized.dynamic.Linear.forward GPU twin (quantized::linear_dynamic):
  *   y[m,n] = float(acc[m,n] - zp * wsum[n]) * (s_x * s_w) + bias[n], fp32

@@ -26,12 +26,14 @@ _PROTOS = {
     "wq_quant_i8_rowwise_bnb": [c_ptr, c_i64, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_outlier_columns": [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_quant_i8_rowwise_quanto": [c_ptr, c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
+    "wq_quant_u4_group_quanto": [c_ptr, c_int, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_quant_i8_tensor_torch": [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_quant_act_u8_tensor": [c_ptr, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_gemm_llmint8": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
     "wq_linear_llmint8_small": [c_ptr, c_i64, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     "wq_gemm_w8a16": [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],
     "wq_gemm_w4a16": [c_ptr, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],
+    "wq_gemm_u4a16": [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],
     "wq_gemm_dyn_i8": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr],
     "wq_logmel": [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_int, c_ptr, c_int, c_ptr, c_ptr],
     "wq_edit_distance": [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr],

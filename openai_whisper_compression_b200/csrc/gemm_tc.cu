@@ -35,7 +35,7 @@ constexpr int EPI_WARPS = 8;       // 2 halves x 4 TMEM lane quarters
 constexpr int BOX_BYTES = 32 * 128;  // one TMA-store box: 32 rows x 128 bytes (SWIZZLE_128B)
 
 enum AKind { A_F16 = 0, A_BF16 = 1, A_S8 = 2, A_U8 = 3 };
-enum BMode { B_DIRECT = 0, B_I8 = 1, B_4BIT = 2 };
+enum BMode { B_DIRECT = 0, B_I8 = 1, B_4BIT = 2, B_U4 = 3 };   // B_U4: quanto group-wise affine uint4
 enum Epi { EPI_LLMINT8 = 0, EPI_W8A16 = 1, EPI_W4A16 = 2, EPI_DYN = 3 };
 
 struct GemmArgs {
@@ -46,8 +46,10 @@ struct GemmArgs {
     const float *row_scale;  // SCA[m]                         (LLMINT8)
     const float *col_scale;  // SCB[n] / quanto scale[n]       (LLMINT8, W8A16)
     const void *bias;        // fp32 [N] or nullptr (LLM.int8: the fp16 bias widened exactly)
-    const float *absmax;     // [N, K/64]                      (W4A16)
-    int absmax_ld;           // K / 64
+    const float *absmax;     // [N, K/64] (W4A16 NF4/FP4) / group scale [N, K/group] (quanto qint4)
+    int absmax_ld;           // K / 64 or K / group
+    const float *shift;      // group shift [N, K/group]       (quanto qint4)
+    int group;               // quanto group size (multiple of 32)
     const float *qparams;    // {s_x, zp}                      (DYN)
     const float *w_scale;    // s_w                            (DYN)
     const int32_t *wsum;     // sum_k wq[n,k]                  (DYN)
@@ -59,14 +61,15 @@ struct GemmArgs {
     int32_t *flags;          // [K + 2]: per-column flags, "any", completion counter
 };
 
-template <int BMODE> constexpr int dq_warps() { return BMODE == B_DIRECT ? 0 : (BMODE == B_4BIT ? 8 : 4); }
+template <int BMODE> constexpr bool is_nibble() { return BMODE == B_4BIT || BMODE == B_U4; }
+template <int BMODE> constexpr int dq_warps() { return BMODE == B_DIRECT ? 0 : (is_nibble<BMODE>() ? 8 : 4); }
 template <int BMODE> constexpr int num_threads() { return 32 * (2 + EPI_WARPS + dq_warps<BMODE>()); }
 
 template <int BN, int STAGES, int BMODE, int OUT_BUFS>
 struct SmemLayout {
     static constexpr int A_BYTES = BM * ROW_BYTES;
     static constexpr int B_BYTES = BN * ROW_BYTES;
-    static constexpr int P_ROW = BMODE == B_I8 ? 64 : (BMODE == B_4BIT ? 32 : 0);
+    static constexpr int P_ROW = BMODE == B_I8 ? 64 : (is_nibble<BMODE>() ? 32 : 0);
     static constexpr int P_BYTES = BN * P_ROW;
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
@@ -473,18 +476,24 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     if (lane == 0) mbar_arrive(&bar_bready[s]);
                 }
             }
-        } else if constexpr (BMODE == B_4BIT) {
+        } else if constexpr (is_nibble<BMODE>()) {
             const int hf = t & 1, r = t >> 1;         // 256 threads: 2 per row; rows >= BN idle
             const bool active = r < BN;
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n = (tile % args.tiles_n) * BN + r;
                 const float *am_row = args.absmax + (size_t)(n < args.N ? n : 0) * args.absmax_ld;
+                const float *sh_row = (BMODE == B_U4) ? args.shift + (size_t)(n < args.N ? n : 0) * args.absmax_ld : nullptr;
                 const bool n_ok = active && n < args.N;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
-                    const float am = n_ok ? __ldg(am_row + kb) : 0.0f;
+                    // NF4/FP4: one absmax per 64-element block; quanto qint4: scale / shift of the
+                    // group holding this thread's 32 weights
+                    const int gi = (BMODE == B_U4) ? (kb * 64 + hf * 32) / args.group : kb;
+                    const float am = n_ok ? __ldg(am_row + gi) : 0.0f;
+                    float sh = 0.0f;
+                    if constexpr (BMODE == B_U4) sh = n_ok ? __ldg(sh_row + gi) : 0.0f;
                     mbar_wait(&bar_full[s], ph);
                     if (active) {
                         const uint8_t *P = smem + L::OFF_P + s * L::P_BYTES;
@@ -497,8 +506,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
                             for (int b = 0; b < 4; ++b) {
                                 const uint32_t byte = (w[j] >> (8 * b)) & 0xffu;
-                                const float f0 = __fmul_rn(s_lut[byte >> 4], am);
-                                const float f1 = __fmul_rn(s_lut[byte & 15u], am);
+                                float f0, f1;
+                                if constexpr (BMODE == B_U4) {   // quanto AffineQuantizer: scale * q - shift
+                                    f0 = __fsub_rn(__fmul_rn(am, (float)(byte >> 4)), sh);
+                                    f1 = __fsub_rn(__fmul_rn(am, (float)(byte & 15u)), sh);
+                                } else {
+                                    f0 = __fmul_rn(s_lut[byte >> 4], am);
+                                    f1 = __fmul_rn(s_lut[byte & 15u], am);
+                                }
                                 if constexpr (AKIND == A_F16) o[b] = pack2<__half>(f0, f1);
                                 else o[b] = pack2<__nv_bfloat16>(f0, f1);
                             }
@@ -588,7 +603,7 @@ template <int BN, int BMODE, int OUT_BUFS>
 constexpr int pick_stages() {
     int best = 2;
     for (int st = 2; st <= 6; ++st) {
-        const int stage = BM * ROW_BYTES + BN * ROW_BYTES + BN * (BMODE == B_I8 ? 64 : (BMODE == B_4BIT ? 32 : 0));
+        const int stage = BM * ROW_BYTES + BN * ROW_BYTES + BN * (BMODE == B_I8 ? 64 : (is_nibble<BMODE>() ? 32 : 0));
         const int total = st * stage + EPI_WARPS * OUT_BUFS * BOX_BYTES + 2 * 3 * BN * 4 + 64 + (3 * st + 2 * ACC_STAGES) * 8 + 16 + 1024;
         if (total <= 232448) best = st;
     }
@@ -769,4 +784,32 @@ extern "C" int wq_gemm_w4a16(const void *x, int x_dtype, const uint8_t *packed, 
                      CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc != WQ_OK) return rc;
     return dispatch_a16<B_4BIT, EPI_W4A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream);
+}
+
+/* quanto QLinear.forward with weights=qint4 (group-wise affine uint4, MaxOptimizer):
+ * y = x @ (scale * q - shift)^T + bias, dequantised weight rounded once to the operand dtype. */
+extern "C" int wq_gemm_u4a16(const void *x, int x_dtype, const uint8_t *packed, const float *scale, const float *shift,
+                             int group, const float *bias, void *y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                             wq_stream_t stream) {
+    int rc = check_common("wq_gemm_u4a16", M, N, K);
+    if (rc != WQ_OK) return rc;
+    if (M == 0 || N == 0) return WQ_OK;
+    WQ_REQUIRE(x && packed && scale && shift && y, "wq_gemm_u4a16: null pointer");
+    WQ_REQUIRE(K % 64 == 0, "wq_gemm_u4a16: K=%lld must be a multiple of 64", (long long)K);
+    WQ_REQUIRE(group >= 32 && group % 32 == 0 && K % group == 0, "wq_gemm_u4a16: group %d must be a multiple of 32 dividing K", group);
+    WQ_REQUIRE(wq_aligned(x, 16) && wq_aligned(packed, 16) && wq_aligned(y, 16), "wq_gemm_u4a16: misaligned buffer");
+    GemmArgs args = {};
+    args.M = (int)M; args.N = (int)N; args.K = (int)K;
+    args.num_kb = (int)(K / 64);
+    args.absmax = scale; args.shift = shift; args.group = group; args.absmax_ld = (int)(K / group);
+    args.bias = bias; args.out = y;
+    const bool narrow = use_narrow_tile(M, N);
+    CUtensorMap ma, mb;
+    rc = make_map_2d(&ma, x, x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     M, K, BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != WQ_OK) return rc;
+    rc = make_map_2d(&mb, packed, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K / 2, narrow ? 64 : 128, 32,
+                     CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != WQ_OK) return rc;
+    return dispatch_a16<B_U4, EPI_W4A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream);
 }

@@ -262,6 +262,50 @@ def gemm_w8a16(x: torch.Tensor, wq: torch.Tensor, scale: torch.Tensor, bias: Opt
     return y.reshape(*x.shape[:-1], N)
 
 
+def quanto_group_size(in_features: int) -> int:
+    """optimum.quanto QModuleMixin group size for qint4/qint2 weights."""
+    g = 128
+    if in_features > g:
+        while in_features % g != 0 and g > 32:
+            g -= 32
+        if in_features % g == 0:
+            return g
+    return in_features
+
+
+def quanto_quantize_qint4(w: torch.Tensor, group: Optional[int] = None):
+    """quanto MaxOptimizer + AffineQuantizer: (packed uint8 [N, K/2], scale f32 [N, K/g],
+    shift f32 [N, K/g], group)."""
+    w = w.contiguous()
+    _need_cuda(w)
+    N, K = w.shape
+    g = group or quanto_group_size(K)
+    packed = torch.empty((N, K // 2), dtype=torch.uint8, device=w.device)
+    scale = torch.empty((N, K // g), dtype=torch.float32, device=w.device)
+    shift = torch.empty((N, K // g), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.load().wq_quant_u4_group_quanto(_ptr(w), _DT[w.dtype], N, K, g, _ptr(packed), _ptr(scale),
+                                                        _ptr(shift), _stream()), "wq_quant_u4_group_quanto")
+    STATS.launches += 1
+    return packed, scale, shift, g
+
+
+def gemm_u4a16(x: torch.Tensor, packed: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, group: int,
+               bias: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """QLinear.forward with qint4 weights: y = x @ (scale*q - shift).T + bias, fused."""
+    N, K = packed.shape[0], packed.shape[1] * 2
+    x2 = x.reshape(-1, K).contiguous()
+    _need_cuda(x2, packed, scale, shift, bias)
+    out_dtype = out_dtype or x2.dtype
+    y = torch.empty((x2.shape[0], N), dtype=out_dtype, device=x.device)
+    with torch.cuda.device(x.device), _Timed("u4a16", x2.shape[0], N, K):
+        _lib.check(_lib.load().wq_gemm_u4a16(_ptr(x2), _DT[x2.dtype], _ptr(packed), _ptr(scale), _ptr(shift), group,
+                                             _ptr(bias), _ptr(y), _DT[out_dtype], x2.shape[0], N, K, _stream()),
+                   "wq_gemm_u4a16")
+    STATS.launches += 1
+    return y.reshape(*x.shape[:-1], N)
+
+
 # ----------------------------------------------------------------------------------------------
 # torch dynamic int8 (GPU twin)
 # ----------------------------------------------------------------------------------------------

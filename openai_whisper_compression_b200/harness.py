@@ -22,7 +22,7 @@ WHISPER_SIZES = {
     "medium":   dict(d_model=1024, heads=16, ffn=4096, enc=24, dec=24, mels=80,  vocab=51865),
     "large-v3": dict(d_model=1280, heads=20, ffn=5120, enc=32, dec=32, mels=128, vocab=51866),
 }
-SCHEMES = ("fp16", "llm_int8", "bnb_nf4", "bnb_nf4_direct", "quanto_int8", "dynamic_int8")
+SCHEMES = ("fp16", "llm_int8", "bnb_nf4", "bnb_nf4_direct", "quanto_int8", "quanto_int4", "dynamic_int8")
 
 
 def whisper_config(size: str, **overrides):
@@ -84,6 +84,10 @@ def apply_scheme(model: nn.Module, scheme: str, device, threshold: float = 6.0) 
         return model.to(device)
     if scheme == "quanto_int8":   # model_utils.py:126-137 order: quantize, freeze, then .to(device)
         quanto.quantize(model, weights=quanto.qint8)
+        quanto.freeze(model)
+        return model.to(device)
+    if scheme == "quanto_int4":   # model_utils.py "quanto_int4": group-wise affine uint4 weights
+        quanto.quantize(model, weights=quanto.qint4)
         quanto.freeze(model)
         return model.to(device)
     if scheme == "quanto_int8_fp16":

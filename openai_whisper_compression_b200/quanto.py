@@ -4,13 +4,14 @@
 pruning+quantization/quanto_implementation.py:648-670).
 
 Implemented on the sm_100a library: weights-only ``qint8`` (per-output-channel absmax / 127,
-``torch.round`` half-to-even, W8A16 fused GEMM).  ``quantize`` swaps every ``nn.Linear`` (incl.
+``torch.round`` half-to-even, W8A16 fused GEMM) and weights-only ``qint4`` (group-wise affine uint4,
+MaxOptimizer: scale = (max - min) / 15, float shift = -min; fused W4A16 GEMM).  ``quantize`` swaps every ``nn.Linear`` (incl.
 ``proj_out``) for ``QLinear``; ``freeze`` fixes the integer weights.  The reference quantizes a
 CPU model and moves it to the device afterwards (model_utils.py:126-137): ``freeze`` on a CPU
 module records the request and the integer codes are produced by the CUDA kernel the moment the
 module reaches a CUDA device -- there is no CPU arithmetic path.  Not implemented yet (SURVEY.md
-section 8f rank 2, raise NotImplementedError): qint4 / qint2 / qfloat8 weights, activation
-quantization + Calibration.
+section 8f rank 2, raise NotImplementedError): qint2 / qfloat8 weights, activation quantization +
+Calibration.
 """
 from __future__ import annotations
 
@@ -56,9 +57,11 @@ class QLinear(nn.Linear):
         if activations is not None:
             raise NotImplementedError("quanto activation quantization (static, Calibration) is outside the "
                                       "built hot path (SURVEY.md section 8f rank 2)")
-        if weights is not None and weights is not qint8 and getattr(weights, "name", None) != "qint8":
-            raise NotImplementedError(f"quanto weights={weights} is not implemented yet; qint8 is "
+        if weights is not None and getattr(weights, "name", None) not in ("qint8", "qint4"):
+            raise NotImplementedError(f"quanto weights={weights} is not implemented yet; qint8 and qint4 are "
                                       "(SURVEY.md section 8f rank 2)")
+        if weights is not None and weights.name == "qint4" and in_features % 64 != 0:
+            raise NotImplementedError("qint4 weights need in_features % 64 == 0 in the fused GEMM")
         self.weight_qtype = weights
         self.activation_qtype = activations
         self.optimizer = optimizer
@@ -66,8 +69,10 @@ class QLinear(nn.Linear):
         self.register_buffer("output_scale", torch.ones((), dtype=self.weight.dtype))
         self._frozen = False
         self._freeze_pending = False
-        self._wq: Optional[torch.Tensor] = None       # int8 [N, K]
-        self._wscale: Optional[torch.Tensor] = None   # fp32 [N, 1] (kernel epilogue precision)
+        self._wq: Optional[torch.Tensor] = None       # int8 [N, K] (qint8) / packed uint8 [N, K/2] (qint4)
+        self._wscale: Optional[torch.Tensor] = None   # fp32 [N, 1] (qint8) / [N, K/group] (qint4)
+        self._wshift: Optional[torch.Tensor] = None   # fp32 [N, K/group] (qint4)
+        self._group = 0
         self._bias_f32: Optional[torch.Tensor] = None
 
     @classmethod
@@ -93,7 +98,10 @@ class QLinear(nn.Linear):
 
     def _quantize_now(self):
         w = self.weight.data
-        q, scale = F.quanto_quantize_qint8(w)
+        if self.weight_qtype.name == "qint4":
+            q, scale, self._wshift, self._group = F.quanto_quantize_qint4(w)
+        else:
+            q, scale = F.quanto_quantize_qint8(w)
         self._wq, self._wscale = q, scale
         self._scale_dtype = w.dtype
         # the float weight is gone after freeze (as in quanto): `weight` now holds the int8 codes
@@ -105,6 +113,8 @@ class QLinear(nn.Linear):
             dev = fn(torch.empty(0, device=self._wq.device, dtype=torch.float32)).device
             self._wq = self._wq.to(dev)
             self._wscale = self._wscale.to(dev)
+            if self._wshift is not None:
+                self._wshift = self._wshift.to(dev)
             self._parameters["weight"] = nn.Parameter(self._wq, requires_grad=False)
             self._bias_f32 = None
             for k, v in self._parameters.items():
@@ -131,6 +141,8 @@ class QLinear(nn.Linear):
             return super()._save_to_state_dict(destination, prefix, keep_vars)
         destination[prefix + "weight._data"] = self._wq
         destination[prefix + "weight._scale"] = self._wscale.to(self._scale_dtype)
+        if self._wshift is not None:
+            destination[prefix + "weight._shift"] = self._wshift.to(self._scale_dtype)
         if self.bias is not None:
             destination[prefix + "bias"] = self.bias if keep_vars else self.bias.detach()
         destination[prefix + "input_scale"] = self.input_scale
@@ -150,6 +162,11 @@ class QLinear(nn.Linear):
         if self.bias is not None and (self._bias_f32 is None or self._bias_f32.device != x.device):
             self._bias_f32 = self.bias.detach().float().contiguous()
         bias = self._bias_f32 if self.bias is not None else None
+        if self._wshift is not None:      # qint4
+            if x.dtype == torch.float32:
+                return F.gemm_u4a16(x.to(torch.float16), self._wq, self._wscale, self._wshift, self._group, bias,
+                                    torch.float32)
+            return F.gemm_u4a16(x, self._wq, self._wscale, self._wshift, self._group, bias)
         if x.dtype == torch.float32:
             # fp32 flow of the reference (model never .half()-ed, model_utils.py:139-142): operands go
             # to the tensor cores as fp16, accumulate fp32, result written fp32 (DESIGN.md "Numerics")

@@ -201,6 +201,45 @@ def qlinear_forward(x: np.ndarray, q: np.ndarray, scale: np.ndarray, bias=None) 
     return y.reshape(tuple(np.asarray(x).shape[:-1]) + (q.shape[0],))
 
 
+def quanto_group_size(in_features: int) -> int:
+    """quanto QModuleMixin: 128, reduced in steps of 32 until it divides in_features; the whole
+    row (per-axis quantization) when in_features <= 128 or nothing divides."""
+    g = 128
+    if in_features > g:
+        while in_features % g != 0 and g > 32:
+            g -= 32
+        if in_features % g == 0:
+            return g
+    return in_features
+
+
+def quanto_qint4(w: np.ndarray, group: Optional[int] = None):
+    """(codes uint8 [N, K] one per element, scale f32 [N, K/g], shift f32 [N, K/g], group)."""
+    wf = _f32(w)
+    N, K = wf.shape
+    g = group or quanto_group_size(K)
+    q = np.zeros((N, K), dtype=np.uint8)
+    scale = np.zeros((N, K // g), dtype=np.float32)
+    shift = np.zeros((N, K // g), dtype=np.float32)
+    lib().orc_quanto_qint4(_p(wf), ctypes.c_int64(N), ctypes.c_int64(K), ctypes.c_int(g), _p(q), _p(scale),
+                           _p(shift))
+    return q, scale, shift, g
+
+
+def quanto_qint4_pack(q: np.ndarray) -> np.ndarray:
+    """libwhisperq packing: two codes per byte along K, first code in the high nibble."""
+    return ((q[:, 0::2] << 4) | q[:, 1::2]).astype(np.uint8)
+
+
+def quanto_qint4_dequant(q, scale, shift, group) -> np.ndarray:
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    N, K = q.shape
+    out = np.empty((N, K), dtype=np.float32)
+    lib().orc_quanto_qint4_dequant(_p(q), _p(_f32(scale)), _p(_f32(shift)), ctypes.c_int64(N), ctypes.c_int64(K),
+                                   ctypes.c_int(group), _p(out))
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # torch dynamic int8 (SURVEY.md A.4)
 # --------------------------------------------------------------------------------------

@@ -239,6 +239,45 @@ void orc_quanto_qint8(const float *w, int64_t N, int64_t K, int8_t *q, float *sc
     }
 }
 
+/* quanto qint4 (MaxOptimizer + AffineQuantizer, float shift), groups of `group`
+ * consecutive in-features of one output channel: scale = (max - min) / 15,
+ * shift = -min, q = clamp(round_half_even((w + shift) / scale), 0, 15).
+ * q holds one code per element (unpacked). */
+void orc_quanto_qint4(const float *w, int64_t N, int64_t K, int group, uint8_t *q,
+                      float *scale, float *shift) {
+    int64_t ng = K / group;
+    for (int64_t n = 0; n < N; ++n)
+        for (int64_t g = 0; g < ng; ++g) {
+            const float *p = w + n * K + g * group;
+            float mn = p[0], mx = p[0];
+            for (int i = 1; i < group; ++i) {
+                if (p[i] < mn) mn = p[i];
+                if (p[i] > mx) mx = p[i];
+            }
+            float s = (mx - mn) / 15.0f, sh = -mn;
+            scale[n * ng + g] = s;
+            shift[n * ng + g] = sh;
+            for (int i = 0; i < group; ++i) {
+                float r = rintf((p[i] + sh) / s);
+                if (r != r) r = 0.0f;
+                if (r < 0.0f) r = 0.0f;
+                if (r > 15.0f) r = 15.0f;
+                q[n * K + g * group + i] = (uint8_t)r;
+            }
+        }
+}
+
+/* dequantize: scale * q - shift (fp32, two operations) */
+void orc_quanto_qint4_dequant(const uint8_t *q, const float *scale, const float *shift,
+                              int64_t N, int64_t K, int group, float *out) {
+    int64_t ng = K / group;
+    for (int64_t n = 0; n < N; ++n)
+        for (int64_t k = 0; k < K; ++k) {
+            float v = scale[n * ng + k / group] * (float)q[n * K + k];
+            out[n * K + k] = v - shift[n * ng + k / group];
+        }
+}
+
 /* ------------------------------------------------------------------------- */
 /* torch dynamic int8 (torch/ao/quantization/observer.py       */
 /* MinMaxObserver per_tensor_symmetric; quantize_per_tensor; FBGEMM           */

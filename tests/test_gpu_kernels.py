@@ -323,3 +323,40 @@ def test_llmint8_small_m_kernel_bit_identical_to_tensor_core_path(M, N, K, outli
         np.testing.assert_array_equal(y_small, y_ref)
     else:
         assert np.abs(y_small.astype(np.float32) - y_ref.astype(np.float32)).max() <= 2 ** -7
+
+
+# ------------------------------------------------------------------------------------------------
+# quanto qint4 (group-wise affine uint4)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("N,K", [(48, 64), (130, 384), (33, 1280), (5, 160)])
+def test_quanto_qint4_codes_bit_exact(dtype, N, K):
+    rng = np.random.RandomState(N * K)
+    w = (rng.randn(N, K) * 0.02).astype(np.float32)
+    w[1, :] = 0.25                       # constant group: scale 0 -> codes 0
+    wt = dev(w, dtype)
+    packed, scale, shift, g = F.quanto_quantize_qint4(wt)
+    q_ref, s_ref, sh_ref, g_ref = oracle.quanto_qint4(wt.float().cpu().numpy())
+    assert g == g_ref == oracle.quanto_group_size(K)
+    np.testing.assert_array_equal(scale.cpu().numpy(), s_ref)
+    np.testing.assert_array_equal(shift.cpu().numpy(), sh_ref)
+    np.testing.assert_array_equal(packed.cpu().numpy(), oracle.quanto_qint4_pack(q_ref))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (7, 48, 128), (300, 200, 384), (1, 768, 768), (130, 51, 1280)])
+def test_qlinear_qint4_w4a16(dtype, tol, M, N, K):
+    rng = np.random.RandomState(M + N + K)
+    w = (rng.randn(N, K) * 0.05).astype(np.float32)
+    x = dev(rng.randn(M, K).astype(np.float32), dtype)
+    bias = (rng.randn(N) * 0.1).astype(np.float32)
+    packed, scale, shift, g = F.quanto_quantize_qint4(dev(w))
+    q_ref, s_ref, sh_ref, _ = oracle.quanto_qint4(w)
+    # the kernel rounds the dequantised weight once to the operand dtype
+    wd = torch.from_numpy(oracle.quanto_qint4_dequant(q_ref, s_ref, sh_ref, g)).to(dtype).double().numpy()
+    y_ref = x.double().cpu().numpy() @ wd.T + bias.astype(np.float64)[None, :]
+    y32 = F.gemm_u4a16(x, packed, scale, shift, g, dev(bias), out_dtype=torch.float32).cpu().numpy()
+    assert (np.abs(y32 - y_ref) / np.maximum(np.abs(y_ref), 1.0)).max() <= 2e-5
+    y = F.gemm_u4a16(x, packed, scale, shift, g, dev(bias))
+    assert y.dtype == dtype
+    assert (np.abs(y.float().cpu().numpy() - y_ref) / np.maximum(np.abs(y_ref), 1.0)).max() <= tol

@@ -302,3 +302,26 @@ def test_graphed_greedy_matches_hf_generate(pkg, scheme):
     eng.uninstall()
     ids3 = harness.greedy_generate(model, feats, T)
     assert torch.equal(ids3, ref_ids)
+
+
+def test_quanto_int4_model_flow(pkg):
+    """model_utils.py 'quanto_int4' flow: quantize(weights=qint4) + freeze on the CPU model, then
+    .to(device); every linear (incl. proj_out) becomes a qint4 QLinear and the model decodes."""
+    from openai_whisper_compression_b200 import harness, quanto
+    model = harness.apply_scheme(harness.build_model("tiny", **MICRO), "quanto_int4", "cuda")
+    qs = [m for m in model.modules() if isinstance(m, quanto.QLinear)]
+    assert len(qs) == 33 and all(m.frozen and m._wshift is not None for m in qs)
+    fc1 = model.model.decoder.layers[0].fc1
+    sd = fc1.state_dict()
+    assert sd["weight._data"].dtype == torch.uint8 and sd["weight._data"].shape == (256, 32)
+    assert sd["weight._scale"].shape == sd["weight._shift"].shape == (256, 1)
+    ref = harness.build_model("tiny", **MICRO).model.decoder.layers[0].fc1
+    q_ref, s_ref, sh_ref, g = oracle.quanto_qint4(ref.weight.detach().numpy())
+    np.testing.assert_array_equal(sd["weight._data"].cpu().numpy(), oracle.quanto_qint4_pack(q_ref))
+    x = torch.randn(3, 5, 64)
+    y = fc1(x.cuda()).cpu().numpy()
+    wd = oracle.quanto_qint4_dequant(q_ref, s_ref, sh_ref, g).astype(np.float16).astype(np.float64)
+    y_ref = x.half().double().numpy() @ wd.T + ref.bias.detach().double().numpy()
+    assert np.abs(y - y_ref).max() < 1e-3
+    ids = harness.greedy_generate(model, _feats().cuda(), 6)
+    assert ids.shape[0] == 4

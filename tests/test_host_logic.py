@@ -75,7 +75,7 @@ def test_cpu_forward_raises_no_fallback():
     with pytest.raises(RuntimeError):
         d(torch.zeros(1, 64))
     with pytest.raises(NotImplementedError):
-        quanto.quantize(nn.Sequential(nn.Linear(8, 8)), weights=quanto.qint4)
+        quanto.quantize(nn.Sequential(nn.Linear(8, 8)), weights=quanto.qint2)
 
 
 def test_product_never_imports_oracle():
@@ -128,6 +128,8 @@ def test_reference_modules_import_and_run_unchanged_with_shims(tmp_path, monkeyp
     model = model_utils.load_whisper_model(str(tmp_path / "m"), torch.device("cpu"), quantization="quanto_int8")
     assert isinstance(model.proj_out, quanto.QLinear) and model.model.decoder.layers[0].fc2._freeze_pending
     assert model_utils.get_model_disk_size_in_mb(model) > 0
+    m4 = model_utils.load_whisper_model(str(tmp_path / "m"), torch.device("cpu"), quantization="quanto_int4")
+    assert m4.model.encoder.layers[0].fc1.weight_qtype is quanto.qint4
     cfg = model_utils._create_bnb_config("bnb_nf4_16")
     assert cfg.bnb_4bit_quant_type == "nf4" and cfg.llm_int8_threshold == 6.0
 
