@@ -5,8 +5,9 @@
 //   max(., utterance max - 8) -> (. + 4) / 4
 //
 // One CTA owns 16 consecutive frames of one utterance: the 2800 samples they span are loaded
-// once into shared memory (coalesced), each real 400-point DFT is computed as a 200-point
-// complex FFT (10 x 20 Cooley-Tukey, constant-memory twiddles) plus the even/odd split, the
+// once into shared memory (coalesced 16-byte loads), each real 400-point DFT is computed as a
+// 200-point complex FFT (10 x 20 Cooley-Tukey; warp-uniform twiddles in constant memory, per-thread
+// tables in shared memory, padded strides against bank conflicts) plus the even/odd split, the
 // mel projection only walks each triangle's non-zero support, and the per-utterance maximum is
 // reduced with warp shuffles + one atomicMax per CTA.  A second elementwise pass applies the
 // max-8 floor (the output of pass one is still L2-resident for typical batches).
@@ -23,11 +24,19 @@ constexpr int FR = 16;                          // frames per CTA
 constexpr int SPAN = (FR - 1) * HOP + NFFT;     // 2800 samples
 constexpr int LM_THREADS = 256;
 
-__constant__ float c_win[NFFT];
+// twiddles with compile-time (warp-uniform) indices stay in constant memory; tables indexed per
+// thread (window, W200^(n2*k1), W400^k) would serialise on the constant cache, so they live in
+// global memory and are staged into shared memory by every CTA
 __constant__ float2 c_w10[10];
 __constant__ float2 c_w20[20];
-__constant__ float2 c_w200[HALF];
-__constant__ float2 c_w400[NBIN];
+struct LmTables {
+    float win[NFFT];
+    float2 w200[HALF];
+    float2 w400[NBIN + 1];
+};
+__device__ LmTables g_tables;
+constexpr int S1 = 21;                 // padded k1 stride of the stage-1 output (bank-conflict free)
+constexpr int SF = 10 * S1;            // per-frame stride of the stage-1 output
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -58,26 +67,48 @@ k_logmel_main(const float *__restrict__ audio, int64_t audio_stride, const int32
               int n_samples, int n_frames, const float *__restrict__ filters, int n_mels,
               const int *__restrict__ mel_lo, const int *__restrict__ mel_hi, float *__restrict__ out,
               uint32_t *__restrict__ umax) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     float *s_x = sm;                                        // [SPAN]
-    float2 *s_a = reinterpret_cast<float2 *>(s_x + SPAN);   // [FR][200] stage-1 output, later power
-    float2 *s_b = s_a + FR * HALF;                          // [FR][200] FFT output
+    float2 *s_a = reinterpret_cast<float2 *>(s_x + SPAN);   // [FR][SF] stage-1 output, later power
+    float2 *s_b = s_a + FR * SF;                            // [FR][200] FFT output
     float *s_p = reinterpret_cast<float *>(s_a);            // [FR][201] power spectrum (aliases s_a)
+    float *s_win = reinterpret_cast<float *>(s_b + FR * HALF);          // [400]
+    float2 *s_w200 = reinterpret_cast<float2 *>(s_win + NFFT);          // [200]
+    float2 *s_w400 = s_w200 + HALF;                                     // [201]
     __shared__ float s_red[LM_THREADS / 32];
 
-    const int b = blockIdx.y, f0 = blockIdx.x * FR, tid = threadIdx.x;
+    const int b = blockIdx.y, f0 = blockIdx.x * FR, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int len = n_samples;
     if (lengths != nullptr) len = min(len, lengths[b]);
     len = (int)min((int64_t)len, audio_stride);
     const float *pa = audio + (int64_t)b * audio_stride;
 
-    // 1. samples f0*160-200 .. +2800 of the zero-padded, reflect-padded signal
-    const int base = f0 * HOP - NFFT / 2;
-    for (int i = tid; i < SPAN; i += LM_THREADS) {
-        int j = base + i;
-        if (j < 0) j = -j;
-        if (j >= n_samples) j = 2 * (n_samples - 1) - j;
-        s_x[i] = (j >= 0 && j < len) ? __ldg(pa + j) : 0.0f;
+    // 0. twiddle / window tables -> shared memory
+    for (int i = tid; i < NFFT; i += LM_THREADS) s_win[i] = g_tables.win[i];
+    for (int i = tid; i < HALF; i += LM_THREADS) s_w200[i] = g_tables.w200[i];
+    for (int i = tid; i < NBIN; i += LM_THREADS) s_w400[i] = g_tables.w400[i];
+
+    // 1. samples f0*160-200 .. +2800 of the zero-padded, reflect-padded signal: 16-byte loads in
+    //    the interior, scalar loads where reflection / padding / the utterance end interferes
+    const int base = f0 * HOP - NFFT / 2;                   // multiple of 8
+    const bool vec_base = ((reinterpret_cast<uintptr_t>(pa) & 15) == 0);
+    for (int i4 = tid; i4 < SPAN / 4; i4 += LM_THREADS) {
+        const int j = base + 4 * i4;
+        float4 v;
+        if (vec_base && j >= 0 && j + 4 <= len) {
+            v = __ldg(reinterpret_cast<const float4 *>(pa + j));
+        } else {
+            float t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int jj = j + u;
+                if (jj < 0) jj = -jj;
+                if (jj >= n_samples) jj = 2 * (n_samples - 1) - jj;
+                t[u] = (jj >= 0 && jj < len) ? __ldg(pa + jj) : 0.0f;
+            }
+            v = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        reinterpret_cast<float4 *>(s_x)[i4] = v;
     }
     __syncthreads();
 
@@ -85,19 +116,20 @@ k_logmel_main(const float *__restrict__ audio, int64_t audio_stride, const int32
     //    stage 1 = 10-point DFTs over n1 (for each n2), times W200^(n2*k1)
     for (int task = tid; task < FR * 20; task += LM_THREADS) {
         const int f = task / 20, n2 = task - f * 20;
-        const float *xf = s_x + f * HOP;
+        const float2 *xf = reinterpret_cast<const float2 *>(s_x + f * HOP);
+        const float2 *wf = reinterpret_cast<const float2 *>(s_win);
         float2 in[10];
 #pragma unroll
         for (int n1 = 0; n1 < 10; ++n1) {
-            const int n = 2 * (20 * n1 + n2);
-            in[n1] = make_float2(xf[n] * c_win[n], xf[n + 1] * c_win[n + 1]);
+            const float2 xv = xf[20 * n1 + n2], wv = wf[20 * n1 + n2];
+            in[n1] = make_float2(xv.x * wv.x, xv.y * wv.y);
         }
 #pragma unroll
         for (int k1 = 0; k1 < 10; ++k1) {
             float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll
             for (int n1 = 0; n1 < 10; ++n1) cfma(acc, in[n1], c_w10[(n1 * k1) % 10]);
-            s_a[f * HALF + k1 * 20 + n2] = cmul(acc, c_w200[n2 * k1]);
+            s_a[f * SF + k1 * S1 + n2] = cmul(acc, s_w200[n2 * k1]);
         }
     }
     __syncthreads();
@@ -106,7 +138,7 @@ k_logmel_main(const float *__restrict__ audio, int64_t audio_stride, const int32
         const int f = task / 10, k1 = task - f * 10;
         float2 in[20];
 #pragma unroll
-        for (int n2 = 0; n2 < 20; ++n2) in[n2] = s_a[f * HALF + k1 * 20 + n2];
+        for (int n2 = 0; n2 < 20; ++n2) in[n2] = s_a[f * SF + k1 * S1 + n2];
 #pragma unroll
         for (int k2 = 0; k2 < 20; ++k2) {
             float2 acc = make_float2(0.0f, 0.0f);
@@ -117,18 +149,20 @@ k_logmel_main(const float *__restrict__ audio, int64_t audio_stride, const int32
     }
     __syncthreads();
 
-    // 3. even/odd split -> X[k], k = 0..200, power spectrum
-    for (int task = tid; task < FR * NBIN; task += LM_THREADS) {
-        const int f = task / NBIN, k = task - f * NBIN;
-        const float2 zk = s_b[f * HALF + (k == HALF ? 0 : k)];
-        const float2 zr = s_b[f * HALF + ((HALF - k) % HALF)];
-        const float2 zc = make_float2(zr.x, -zr.y);
-        const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
-        const float2 d = make_float2(zk.x - zc.x, zk.y - zc.y);
-        const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);  // d / (2i)
-        const float2 t = cmul(o, c_w400[k]);
-        const float re = e.x + t.x, im = e.y + t.y;
-        s_p[f * NBIN + k] = re * re + im * im;
+    // 3. even/odd split -> X[k], k = 0..200, power spectrum (one warp per frame)
+    for (int f = warp; f < FR; f += LM_THREADS / 32) {
+        const float2 *zb = s_b + f * HALF;
+        for (int k = lane; k < NBIN; k += 32) {
+            const float2 zk = zb[k == HALF ? 0 : k];
+            const float2 zr = zb[k == 0 ? 0 : HALF - k];
+            const float2 zc = make_float2(zr.x, -zr.y);
+            const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+            const float2 d = make_float2(zk.x - zc.x, zk.y - zc.y);
+            const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);  // d / (2i)
+            const float2 t = cmul(o, s_w400[k]);
+            const float re = e.x + t.x, im = e.y + t.y;
+            s_p[f * NBIN + k] = re * re + im * im;
+        }
     }
     __syncthreads();
 
@@ -145,7 +179,7 @@ k_logmel_main(const float *__restrict__ audio, int64_t audio_stride, const int32
         mx = fmaxf(mx, v);
     }
     mx = warp_max(mx);
-    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+    if (lane == 0) s_red[warp] = mx;
     __syncthreads();
     if (tid == 0) {
         for (int i = 1; i < LM_THREADS / 32; ++i) mx = fmaxf(mx, s_red[i]);
@@ -179,21 +213,19 @@ int upload_tables() {
     int dev = 0;
     WQ_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && done[dev]) return WQ_OK;
-    float win[NFFT];
-    float2 w10[10], w20[20], w200[HALF], w400[NBIN];
+    static LmTables host;
+    float2 w10[10], w20[20];
     const double two_pi = 6.283185307179586476925286766559;
-    for (int n = 0; n < NFFT; ++n) win[n] = (float)(0.5 - 0.5 * std::cos(two_pi * n / NFFT));
+    for (int n = 0; n < NFFT; ++n) host.win[n] = (float)(0.5 - 0.5 * std::cos(two_pi * n / NFFT));
     for (int j = 0; j < 10; ++j) w10[j] = make_float2((float)std::cos(two_pi * j / 10), (float)-std::sin(two_pi * j / 10));
     for (int j = 0; j < 20; ++j) w20[j] = make_float2((float)std::cos(two_pi * j / 20), (float)-std::sin(two_pi * j / 20));
     for (int j = 0; j < HALF; ++j)
-        w200[j] = make_float2((float)std::cos(two_pi * j / HALF), (float)-std::sin(two_pi * j / HALF));
-    for (int j = 0; j < NBIN; ++j)
-        w400[j] = make_float2((float)std::cos(two_pi * j / NFFT), (float)-std::sin(two_pi * j / NFFT));
-    err = cudaMemcpyToSymbol(c_win, win, sizeof(win));
-    if (err == cudaSuccess) err = cudaMemcpyToSymbol(c_w10, w10, sizeof(w10));
+        host.w200[j] = make_float2((float)std::cos(two_pi * j / HALF), (float)-std::sin(two_pi * j / HALF));
+    for (int j = 0; j <= NBIN; ++j)
+        host.w400[j] = make_float2((float)std::cos(two_pi * j / NFFT), (float)-std::sin(two_pi * j / NFFT));
+    err = cudaMemcpyToSymbol(c_w10, w10, sizeof(w10));
     if (err == cudaSuccess) err = cudaMemcpyToSymbol(c_w20, w20, sizeof(w20));
-    if (err == cudaSuccess) err = cudaMemcpyToSymbol(c_w200, w200, sizeof(w200));
-    if (err == cudaSuccess) err = cudaMemcpyToSymbol(c_w400, w400, sizeof(w400));
+    if (err == cudaSuccess) err = cudaMemcpyToSymbol(g_tables, &host, sizeof(host));
     WQ_CUDA(err);
     if (dev >= 0 && dev < 64) done[dev] = true;
     return WQ_OK;
@@ -223,7 +255,8 @@ extern "C" int wq_logmel(const float *audio, int64_t B, int64_t audio_stride, co
     WQ_CUDA(cudaMemsetAsync(umax, 0, sizeof(uint32_t) * B, s));
     k_mel_ranges<<<(n_mels + 127) / 128, 128, 0, s>>>(filters, n_mels, mel_lo, mel_hi);
     WQ_LAUNCH_CHECK();
-    const size_t smem = sizeof(float) * SPAN + 2 * sizeof(float2) * FR * HALF;
+    const size_t smem = sizeof(float) * SPAN + sizeof(float2) * FR * (SF + HALF) + sizeof(float) * NFFT +
+                        sizeof(float2) * (HALF + NBIN + 1);
     static bool configured = false;
     if (!configured) {
         WQ_CUDA(cudaFuncSetAttribute(k_logmel_main, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
