@@ -6,7 +6,7 @@
 //
 // One CTA owns 16 consecutive frames of one utterance: the 2800 samples they span are loaded
 // once into shared memory (coalesced 16-byte loads), each real 400-point DFT is computed as a
-// 200-point complex FFT (10 x 20 Cooley-Tukey; warp-uniform twiddles in constant memory, per-thread
+// 200-point complex FFT (10 x 20 Cooley-Tukey, the 10- and 20-point DFTs as 2x5 and 4x5; warp-uniform twiddles in constant memory, per-thread
 // tables in shared memory, padded strides against bank conflicts) plus the even/odd split, the
 // mel projection only walks each triangle's non-zero support, and the per-utterance maximum is
 // reduced with warp shuffles + one atomicMax per CTA.  A second elementwise pass applies the
@@ -48,18 +48,84 @@ __device__ __forceinline__ void cfma(float2 &acc, float2 a, float2 w) {
     acc.y = fmaf(a.y, w.x, acc.y);
 }
 
+// 5-point DFT, twiddles W5^j = W10^(2j) from constant memory (compile-time indices)
+__device__ __forceinline__ void dft5(const float2 (&y)[5], float2 (&z)[5]) {
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+        float2 acc = y[0];
+#pragma unroll
+        for (int b = 1; b < 5; ++b) cfma(acc, y[b], c_w10[(2 * b * d) % 10]);
+        z[d] = acc;
+    }
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+// 10-point DFT = 2 x 5 (index m = 5a + b, k = c + 2d)
+__device__ __forceinline__ void dft10(const float2 (&in)[10], float2 (&out)[10]) {
+    float2 y0[5], y1[5], z[5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        y0[b] = cadd(in[b], in[5 + b]);
+        y1[b] = csub(in[b], in[5 + b]);
+        if (b) y1[b] = cmul(y1[b], c_w10[b]);
+    }
+    dft5(y0, z);
+#pragma unroll
+    for (int d = 0; d < 5; ++d) out[2 * d] = z[d];
+    dft5(y1, z);
+#pragma unroll
+    for (int d = 0; d < 5; ++d) out[2 * d + 1] = z[d];
+}
+
+// 20-point DFT = 4 x 5 (index n = 5a + b, k = c + 4d); W4 = -i is free
+__device__ __forceinline__ void dft20(const float2 (&in)[20], float2 (&out)[20]) {
+    float2 y[4][5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        const float2 t0 = cadd(in[b], in[10 + b]), t1 = csub(in[b], in[10 + b]);
+        const float2 t2 = cadd(in[5 + b], in[15 + b]), t3 = mul_neg_i(csub(in[5 + b], in[15 + b]));
+        y[0][b] = cadd(t0, t2);
+        y[1][b] = cadd(t1, t3);
+        y[2][b] = csub(t0, t2);
+        y[3][b] = csub(t1, t3);
+        if (b) {
+            y[1][b] = cmul(y[1][b], c_w20[b]);
+            y[2][b] = cmul(y[2][b], c_w20[2 * b]);
+            y[3][b] = cmul(y[3][b], c_w20[(3 * b) % 20]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float2 z[5];
+        dft5(y[c], z);
+#pragma unroll
+        for (int d = 0; d < 5; ++d) out[c + 4 * d] = z[d];
+    }
+}
+
+// one warp per mel filter: first / last non-zero bin of its triangle
 __global__ void k_mel_ranges(const float *__restrict__ filters, int n_mels, int *__restrict__ lo,
                              int *__restrict__ hi) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (m >= n_mels) return;
     int l = NBIN, h = -1;
-    for (int k = 0; k < NBIN; ++k)
+    for (int k = lane; k < NBIN; k += 32)
         if (filters[k * n_mels + m] != 0.0f) {
             l = min(l, k);
             h = max(h, k);
         }
-    lo[m] = l;
-    hi[m] = h;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        l = min(l, __shfl_xor_sync(0xffffffffu, l, o));
+        h = max(h, __shfl_xor_sync(0xffffffffu, h, o));
+    }
+    if (lane == 0) {
+        lo[m] = l;
+        hi[m] = h;
+    }
 }
 
 __global__ void __launch_bounds__(LM_THREADS)
@@ -124,13 +190,10 @@ k_logmel_main(const float *__restrict__ audio, int64_t audio_stride, const int32
             const float2 xv = xf[20 * n1 + n2], wv = wf[20 * n1 + n2];
             in[n1] = make_float2(xv.x * wv.x, xv.y * wv.y);
         }
+        float2 y[10];
+        dft10(in, y);
 #pragma unroll
-        for (int k1 = 0; k1 < 10; ++k1) {
-            float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll
-            for (int n1 = 0; n1 < 10; ++n1) cfma(acc, in[n1], c_w10[(n1 * k1) % 10]);
-            s_a[f * SF + k1 * S1 + n2] = cmul(acc, s_w200[n2 * k1]);
-        }
+        for (int k1 = 0; k1 < 10; ++k1) s_a[f * SF + k1 * S1 + n2] = cmul(y[k1], s_w200[n2 * k1]);
     }
     __syncthreads();
     //    stage 2 = 20-point DFTs over n2 (for each k1): Z[k1 + 10*k2]
@@ -139,13 +202,10 @@ k_logmel_main(const float *__restrict__ audio, int64_t audio_stride, const int32
         float2 in[20];
 #pragma unroll
         for (int n2 = 0; n2 < 20; ++n2) in[n2] = s_a[f * SF + k1 * S1 + n2];
+        float2 z[20];
+        dft20(in, z);
 #pragma unroll
-        for (int k2 = 0; k2 < 20; ++k2) {
-            float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll
-            for (int n2 = 0; n2 < 20; ++n2) cfma(acc, in[n2], c_w20[(n2 * k2) % 20]);
-            s_b[f * HALF + k1 + 10 * k2] = acc;
-        }
+        for (int k2 = 0; k2 < 20; ++k2) s_b[f * HALF + k1 + 10 * k2] = z[k2];
     }
     __syncthreads();
 
@@ -253,7 +313,7 @@ extern "C" int wq_logmel(const float *audio, int64_t B, int64_t audio_stride, co
     int *mel_lo = reinterpret_cast<int *>(workspace + B);
     int *mel_hi = mel_lo + n_mels;
     WQ_CUDA(cudaMemsetAsync(umax, 0, sizeof(uint32_t) * B, s));
-    k_mel_ranges<<<(n_mels + 127) / 128, 128, 0, s>>>(filters, n_mels, mel_lo, mel_hi);
+    k_mel_ranges<<<(n_mels * 32 + 127) / 128, 128, 0, s>>>(filters, n_mels, mel_lo, mel_hi);
     WQ_LAUNCH_CHECK();
     const size_t smem = sizeof(float) * SPAN + sizeof(float2) * FR * (SF + HALF) + sizeof(float) * NFFT +
                         sizeof(float2) * (HALF + NBIN + 1);
