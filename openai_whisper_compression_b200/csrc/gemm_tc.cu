@@ -31,7 +31,9 @@ constexpr int BMH = 128;           // rows per UMMA (== TMEM lanes)
 constexpr int ROW_BYTES = 128;     // bytes of K per smem row (one SW128 atom)
 constexpr int UMMA_K_BYTES = 32;   // one tcgen05.mma consumes 32 bytes of K per row
 constexpr int ACC_STAGES = 2;      // TMEM accumulator ring (epilogue of tile i overlaps mainloop of i+1)
-constexpr int EPI_WARPS = 8;       // 2 halves x 4 TMEM lane quarters
+// epilogue warps: 2 halves x 4 TMEM lane quarters.  The kernel also supports 16 (two warps split the
+// columns of each 32-row slab); measured slower on B200 (56 vs 46 us at 96000x512x512), so 8 is used.
+template <int BN, int BMODE> constexpr int epi_warps() { return 8; }
 constexpr int BOX_BYTES = 32 * 128;  // one TMA-store box: 32 rows x 128 bytes (SWIZZLE_128B)
 
 enum AKind { A_F16 = 0, A_BF16 = 1, A_S8 = 2, A_U8 = 3 };
@@ -63,7 +65,7 @@ struct GemmArgs {
 
 template <int BMODE> constexpr bool is_nibble() { return BMODE == B_4BIT || BMODE == B_U4; }
 template <int BMODE> constexpr int dq_warps() { return BMODE == B_DIRECT ? 0 : (is_nibble<BMODE>() ? 8 : 4); }
-template <int BMODE> constexpr int num_threads() { return 32 * (2 + EPI_WARPS + dq_warps<BMODE>()); }
+template <int BN, int BMODE> constexpr int num_threads() { return 32 * (2 + epi_warps<BN, BMODE>() + dq_warps<BMODE>()); }
 
 template <int BN, int STAGES, int BMODE, int OUT_BUFS>
 struct SmemLayout {
@@ -74,8 +76,9 @@ struct SmemLayout {
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
     static constexpr int OFF_P = OFF_B + STAGES * B_BYTES;
-    static constexpr int OFF_OUT = OFF_P + STAGES * P_BYTES;   // EPI_WARPS x OUT_BUFS boxes, 1024-byte aligned
-    static constexpr int OFF_CONST = OFF_OUT + EPI_WARPS * OUT_BUFS * BOX_BYTES;  // float [2][3][BN] per-tile constants
+    static constexpr int EW = epi_warps<BN, BMODE>();
+    static constexpr int OFF_OUT = OFF_P + STAGES * P_BYTES;   // EW x OUT_BUFS boxes, 1024-byte aligned
+    static constexpr int OFF_CONST = OFF_OUT + EW * OUT_BUFS * BOX_BYTES;  // float [2][3][BN] per-tile constants
     static constexpr int OFF_LUT = OFF_CONST + 2 * 3 * BN * 4;                    // float lut[16]
     static constexpr int OFF_BAR = OFF_LUT + 64;               // uint64 barriers
     static constexpr int NUM_BARS = 3 * STAGES + 2 * ACC_STAGES;
@@ -138,16 +141,103 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], float (&v)[32
     }
 }
 
+// Write 32 finished columns of one row: into the swizzled staging box (TMA store path) or
+// straight to global memory (row pitches that are not 16-byte multiples).
+template <typename OutT, bool TMA_STORE>
+__device__ __forceinline__ void emit_chunk(const float (&v)[32], uint8_t *box, int cc, int lane, OutT *row_ptr,
+                                           int nb, int N, bool row_ok, bool vec_ok) {
+    if constexpr (TMA_STORE) {
+        constexpr int CH = 32 * (int)sizeof(OutT) / 16;   // 16-byte chunks per 32 columns
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int c16 = cc * CH + j;                   // chunk index inside the 128-byte row
+            uint8_t *dst = box + lane * 128 + ((c16 ^ (lane & 7)) << 4);
+            if constexpr (sizeof(OutT) == 4) {
+                *reinterpret_cast<float4 *>(dst) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+                uint4 u;
+                u.x = pack2<OutT>(v[8 * j + 0], v[8 * j + 1]);
+                u.y = pack2<OutT>(v[8 * j + 2], v[8 * j + 3]);
+                u.z = pack2<OutT>(v[8 * j + 4], v[8 * j + 5]);
+                u.w = pack2<OutT>(v[8 * j + 6], v[8 * j + 7]);
+                *reinterpret_cast<uint4 *>(dst) = u;
+            }
+        }
+    } else if (row_ok) {
+        if (vec_ok && nb + 32 <= N) {
+            if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    reinterpret_cast<float4 *>(row_ptr + nb)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 u;
+                    u.x = pack2<OutT>(v[8 * j + 0], v[8 * j + 1]);
+                    u.y = pack2<OutT>(v[8 * j + 2], v[8 * j + 3]);
+                    u.z = pack2<OutT>(v[8 * j + 4], v[8 * j + 5]);
+                    u.w = pack2<OutT>(v[8 * j + 6], v[8 * j + 7]);
+                    reinterpret_cast<uint4 *>(row_ptr + nb)[j] = u;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (nb + j < N) row_ptr[nb + j] = from_f32<OutT>(v[j]);
+        }
+    }
+}
+
+// LLM.int8 mixed-precision decomposition for one 32-column chunk -- the RARE path (an activation
+// entry with |a| >= threshold exists).  Kept out of line so that the hot epilogue loop stays small
+// enough for the instruction cache.  Re-reads the accumulator itself, removes the outlier columns'
+// int8 products from the exact int32 sums (== bitsandbytes zeroing CA[:, cols]) and adds the fp16
+// side product sum_c A[m,c] * fp16(CB[n,c] * SCB[n] / 127) in ascending column order.
+template <int BN, typename OutT, bool TMA_STORE>
+__device__ __noinline__ void llmint8_outlier_chunk(const GemmArgs &args, const float *sc, uint32_t taddr, int n_abs,
+                                                   int col0, int m, bool row_ok, float rs, uint8_t *box, int cc,
+                                                   int lane, OutT *row_ptr, bool vec_ok) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr, r);
+    tmem_ld_wait();
+    float o[32], v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = 0.0f;
+#pragma unroll 1
+    for (int c = 0; c < args.K; ++c) {
+        if (args.flags[c] == 0) continue;
+        const int a8 = row_ok ? (int)args.ca[(size_t)m * args.K + c] : 0;
+        const float af = row_ok ? __half2float(args.a16[(size_t)m * args.K + c]) : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int n = n_abs + j;
+            if (n < args.N) {
+                const int b8 = (int)args.cb[(size_t)n * args.K + c];
+                r[j] = (uint32_t)((int)r[j] - a8 * b8);
+                const float d = __fmul_rn(__fmul_rn((float)b8, __ldg(args.col_scale + n)), 7.874015718698502e-3f);
+                o[j] = fmaf(af, __half2float(__float2half_rn(d)), o[j]);
+            }
+        }
+    }
+    epi_chunk<BN, EPI_LLMINT8>(r, v, sc, col0, rs, 0.0f, 0);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __half2float(__float2half_rn(v[j])) + o[j];   // fp16 addmm
+    emit_chunk<OutT, TMA_STORE>(v, box, cc, lane, row_ptr, n_abs, args.N, row_ok, vec_ok);
+}
+
 // Body of one epilogue warp: drains its 32-row slab of every tile this CTA owns.
-template <int BN, int EPI, typename OutT, int OUT_BUFS, bool TMA_STORE>
+template <int BN, int EW, int EPI, typename OutT, int OUT_BUFS, bool TMA_STORE>
 __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtensorMap *map_y, uint8_t *boxes,
                                               float *s_const, uint64_t *bar_tmem_full, uint64_t *bar_tmem_empty,
                                               uint32_t tmem_base, int warp, int lane, int total_tiles) {
     constexpr int ACC_COLS = 2 * BN;
     constexpr int BOX_COLS = 128 / (int)sizeof(OutT);   // columns per TMA-store box (64 or 32)
-    constexpr int N_BOX = BN / BOX_COLS;
+    constexpr int CSPLIT = EW / 8;                      // warps sharing a 32-row slab split its columns
+    constexpr int N_BOX = BN / BOX_COLS / CSPLIT;       // boxes per warp per tile
     constexpr int NCH = BOX_COLS / 32;                  // tcgen05.ld chunks per box (2 or 1)
-    const int h = (warp - 2) >> 2;                      // 128-row half of the tile
+    const int grp = (warp - 2) >> 2;
+    const int h = grp & 1;                              // 128-row half of the tile
+    const int bx0 = (grp >> 1) * N_BOX;                 // first box (column range) of this warp
     const int q = warp & 3;                             // TMEM lane quarter this warp may access
     const bool vec_ok = ((size_t)args.N * sizeof(OutT)) % 16 == 0;
     const bool any_outlier = (EPI == EPI_LLMINT8) && args.flags != nullptr && args.flags[args.K] != 0;
@@ -172,7 +262,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
         float *sc = s_const + (t & 1) * 3 * BN;
         {
             const float *bias = reinterpret_cast<const float *>(args.bias);
-            for (int i = (warp - 2) * 32 + lane; i < 3 * BN; i += EPI_WARPS * 32) {
+            for (int i = (warp - 2) * 32 + lane; i < 3 * BN; i += EW * 32) {
                 const int which = i / BN;
                 const int n = min(n0 + (i - which * BN), args.N - 1);
                 float val = 0.0f;
@@ -185,7 +275,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
                 }
                 sc[i] = val;
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
         }
 
         mbar_wait(&bar_tmem_full[as], aph);
@@ -194,94 +284,48 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
             OutT *row_ptr = reinterpret_cast<OutT *>(args.out) + (size_t)(row_ok ? m : 0) * args.N;
             const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + h * BN;
 #pragma unroll 1
-            for (int bx = 0; bx < N_BOX; ++bx) {
+            for (int bx = bx0; bx < bx0 + N_BOX; ++bx) {
                 uint8_t *box = boxes + (nstore % OUT_BUFS) * BOX_BYTES;
                 if constexpr (TMA_STORE) {
                     // the store that last used this box must have finished reading it
                     if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();
                     __syncwarp();
                 }
-                uint32_t r[NCH][32];
-#pragma unroll
-                for (int cc = 0; cc < NCH; ++cc) tmem_ld_32x32(tmem_row + bx * BOX_COLS + cc * 32, r[cc]);
-                tmem_ld_wait();
-#pragma unroll
-                for (int cc = 0; cc < NCH; ++cc) {
-                    const int col0 = bx * BOX_COLS + cc * 32;   // column inside the tile
-                    float v[32];
-                    float o[32];
-                    if constexpr (EPI == EPI_LLMINT8) {
-                        if (any_outlier) {
-                            // rare path: remove the outlier columns' int8 products from the exact
-                            // int32 accumulator and build the fp16 side product (ascending column)
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) o[j] = 0.0f;
+                bool fast = true;
+                if constexpr (EPI == EPI_LLMINT8) {
+                    if (any_outlier) {
+                        fast = false;
 #pragma unroll 1
-                            for (int c = 0; c < args.K; ++c) {
-                                if (args.flags[c] == 0) continue;
-                                const int a8 = row_ok ? (int)args.ca[(size_t)m * args.K + c] : 0;
-                                const float af = row_ok ? __half2float(args.a16[(size_t)m * args.K + c]) : 0.0f;
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    const int n = n0 + col0 + j;
-                                    if (n < args.N) {
-                                        const int b8 = (int)args.cb[(size_t)n * args.K + c];
-                                        r[cc][j] = (uint32_t)((int)r[cc][j] - a8 * b8);
-                                        const float d = __fmul_rn(__fmul_rn((float)b8, __ldg(args.col_scale + n)),
-                                                                  7.874015718698502e-3f);
-                                        o[j] = fmaf(af, __half2float(__float2half_rn(d)), o[j]);
-                                    }
-                                }
-                            }
+                        for (int cc = 0; cc < NCH; ++cc) {
+                            const int col0 = bx * BOX_COLS + cc * 32;
+                            llmint8_outlier_chunk<BN, OutT, TMA_STORE>(args, sc, tmem_row + col0, n0 + col0, col0, m, row_ok,
+                                                                       rs, box, cc, lane, row_ptr, vec_ok);
                         }
                     }
-                    epi_chunk<BN, EPI>(r[cc], v, sc, col0, rs, dyn_s, dyn_zp);
-                    if constexpr (EPI == EPI_LLMINT8) {
-                        if (any_outlier) {
+                }
+                if (fast) {
+                    if constexpr (EW == 16) {   // 576 threads: 113 registers each -> one chunk in flight
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                v[j] = __half2float(__float2half_rn(v[j])) + o[j];   // fp16 addmm
+                        for (int cc = 0; cc < NCH; ++cc) {
+                            const int col0 = bx * BOX_COLS + cc * 32;   // column inside the tile
+                            uint32_t r[32];
+                            tmem_ld_32x32(tmem_row + col0, r);
+                            tmem_ld_wait();
+                            float v[32];
+                            epi_chunk<BN, EPI>(r, v, sc, col0, rs, dyn_s, dyn_zp);
+                            emit_chunk<OutT, TMA_STORE>(v, box, cc, lane, row_ptr, n0 + col0, args.N, row_ok, vec_ok);
                         }
-                    }
-                    if constexpr (TMA_STORE) {
-                        constexpr int CH = 32 * (int)sizeof(OutT) / 16;   // 16-byte chunks per 32 columns
+                    } else {
+                        uint32_t r[NCH][32];
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) {
-                            const int c16 = cc * CH + j;                   // chunk index inside the 128-byte row
-                            uint8_t *dst = box + lane * 128 + ((c16 ^ (lane & 7)) << 4);
-                            if constexpr (sizeof(OutT) == 4) {
-                                *reinterpret_cast<float4 *>(dst) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            } else {
-                                uint4 u;
-                                u.x = pack2<OutT>(v[8 * j + 0], v[8 * j + 1]);
-                                u.y = pack2<OutT>(v[8 * j + 2], v[8 * j + 3]);
-                                u.z = pack2<OutT>(v[8 * j + 4], v[8 * j + 5]);
-                                u.w = pack2<OutT>(v[8 * j + 6], v[8 * j + 7]);
-                                *reinterpret_cast<uint4 *>(dst) = u;
-                            }
-                        }
-                    } else if (row_ok) {
-                        const int nb = n0 + col0;
-                        if (vec_ok && nb + 32 <= args.N) {
-                            if constexpr (sizeof(OutT) == 4) {
+                        for (int cc = 0; cc < NCH; ++cc) tmem_ld_32x32(tmem_row + bx * BOX_COLS + cc * 32, r[cc]);
+                        tmem_ld_wait();
 #pragma unroll
-                                for (int j = 0; j < 8; ++j)
-                                    reinterpret_cast<float4 *>(row_ptr + nb)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    uint4 u;
-                                    u.x = pack2<OutT>(v[8 * j + 0], v[8 * j + 1]);
-                                    u.y = pack2<OutT>(v[8 * j + 2], v[8 * j + 3]);
-                                    u.z = pack2<OutT>(v[8 * j + 4], v[8 * j + 5]);
-                                    u.w = pack2<OutT>(v[8 * j + 6], v[8 * j + 7]);
-                                    reinterpret_cast<uint4 *>(row_ptr + nb)[j] = u;
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (nb + j < args.N) row_ptr[nb + j] = from_f32<OutT>(v[j]);
+                        for (int cc = 0; cc < NCH; ++cc) {
+                            const int col0 = bx * BOX_COLS + cc * 32;   // column inside the tile
+                            float v[32];
+                            epi_chunk<BN, EPI>(r[cc], v, sc, col0, rs, dyn_s, dyn_zp);
+                            emit_chunk<OutT, TMA_STORE>(v, box, cc, lane, row_ptr, n0 + col0, args.N, row_ok, vec_ok);
                         }
                     }
                 }
@@ -308,7 +352,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
 }
 
 template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT, int OUT_BUFS>
-__global__ void __launch_bounds__(num_threads<BMODE>(), 1)
+__global__ void __launch_bounds__(num_threads<BN, BMODE>(), 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ CUtensorMap map_y, const GemmArgs args) {
     using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS>;
@@ -316,6 +360,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     constexpr bool kIntKind = (AKIND == A_S8 || AKIND == A_U8);
     constexpr int A_ELEMS_PER_ROW = kIntKind ? 128 : 64;  // elements of K per 128-byte row
     constexpr int DQ_WARPS = dq_warps<BMODE>();
+    constexpr int EW = epi_warps<BN, BMODE>();
     constexpr int ACC_COLS = 2 * BN;                      // one accumulator stage: half 0 | half 1
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -345,7 +390,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         }
         for (int a = 0; a < ACC_STAGES; ++a) {
             mbar_init(&bar_tmem_full[a], 1);
-            mbar_init(&bar_tmem_empty[a], EPI_WARPS);
+            mbar_init(&bar_tmem_empty[a], EW);
         }
         fence_mbar_init();
     }
@@ -422,17 +467,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             }
         }
         __syncwarp();
-    } else if (warp < 2 + EPI_WARPS) {
+    } else if (warp < 2 + EW) {
         // ---------------- epilogue: warps 2..9 ----------------
-        uint8_t *boxes = smem + L::OFF_OUT + (warp - 2) * OUT_BUFS * BOX_BYTES;
+        uint8_t *boxes = smem + L::OFF_OUT + (warp - 2) * OUT_BUFS * BOX_BYTES;   // private staging of this warp
         float *s_const = reinterpret_cast<float *>(smem + L::OFF_CONST);
         if (args.tma_store)
-            epilogue_warp<BN, EPI, OutT, OUT_BUFS, true>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane, total_tiles);
+            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, true>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane, total_tiles);
         else
-            epilogue_warp<BN, EPI, OutT, OUT_BUFS, false>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane, total_tiles);
+            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, false>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane, total_tiles);
     } else {
         // ---------------- weight expansion (W8A16 / W4A16): warps 10.. ----------------
-        const int t = threadIdx.x - 32 * (2 + EPI_WARPS);
+        const int t = threadIdx.x - 32 * (2 + EW);
         if constexpr (BMODE == B_I8) {
             const int qd = t & 3, row0 = t >> 2;      // 128 threads: 4 per row, 32 rows per pass
             uint32_t it = 0;
@@ -596,7 +641,9 @@ int make_map_2d(CUtensorMap *map, const void *base, CUtensorMapDataType dt, int 
 }
 
 // TMA-store boxes per epilogue warp (double-buffered when shared memory allows)
-template <int BN, int BMODE> constexpr int pick_out_bufs() { return (BMODE == B_I8 && BN == 128) ? 1 : 2; }
+template <int BN, int BMODE> constexpr int pick_out_bufs() {
+    return ((BMODE == B_I8 && BN == 128) || epi_warps<BN, BMODE>() == 16) ? 1 : 2;
+}
 
 // deepest smem ring that fits next to the epilogue staging boxes
 template <int BN, int BMODE, int OUT_BUFS>
@@ -604,7 +651,7 @@ constexpr int pick_stages() {
     int best = 2;
     for (int st = 2; st <= 6; ++st) {
         const int stage = BM * ROW_BYTES + BN * ROW_BYTES + BN * (BMODE == B_I8 ? 64 : (is_nibble<BMODE>() ? 32 : 0));
-        const int total = st * stage + EPI_WARPS * OUT_BUFS * BOX_BYTES + 2 * 3 * BN * 4 + 64 + (3 * st + 2 * ACC_STAGES) * 8 + 16 + 1024;
+        const int total = st * stage + epi_warps<BN, BMODE>() * OUT_BUFS * BOX_BYTES + 2 * 3 * BN * 4 + 64 + (3 * st + 2 * ACC_STAGES) * 8 + 16 + 1024;
         if (total <= 232448) best = st;
     }
     return best;
@@ -641,7 +688,7 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cud
     const int total = args.tiles_m * args.tiles_n;
     const int grid = total < wq_sm_count() ? total : wq_sm_count();
 
-    kfn<<<grid, num_threads<BMODE>(), L::TOTAL, stream>>>(ma, mb, my, args);
+    kfn<<<grid, num_threads<BN, BMODE>(), L::TOTAL, stream>>>(ma, mb, my, args);
     WQ_LAUNCH_CHECK();
     return WQ_OK;
 }
