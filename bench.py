@@ -43,9 +43,10 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", default="base")
     ap.add_argument("--scheme", default="llm_int8")
-    ap.add_argument("--batch", type=int, default=64, help="utterances per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step")
     ap.add_argument("--new-tokens", type=int, default=64)
-    ap.add_argument("--cpu-sample", type=int, default=4, help="utterances in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=8,
+                    help="utterances in the CPU baseline sample (the reference's own CPU batch size, BASELINE config 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hf-loop", action="store_true",
                     help="keep HF's Python decode loop instead of the CUDA-graph replay loop (fastgen)")
