@@ -317,10 +317,24 @@ def run_ours(args):
         tot_time += sum(ts)
         n_launch += len(ts)
     roofline = None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if n_launch and os.path.exists(tpath):
+        # DRAM bytes per launch from the committed ncu --set full capture of this command's kernel
+        # (same shapes): launch-weighted average, None when a shape was not captured
+        per = json.load(open(tpath)).get("traffic_bytes_per_launch", {})
+        tot_t = 0.0
+        for sh in shapes:
+            key = f"{sh['M']}x{sh['N']}x{sh['K']}"
+            if key not in per:
+                tot_t = None
+                break
+            tot_t += per[key] * sh["launches"]
+        traffic = None if tot_t is None else tot_t / n_launch
     if n_launch:
         achieved = tot_bytes / tot_time / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
                     "kernel": "k_gemm_tc<A_S8,B_DIRECT,EPI_LLMINT8> (tcgen05 s8xs8->s32, fused dequant epilogue), "
                               "encoder-shaped launches (M >= 1024)",
                     "peak_source": peaks["source"] + " (burst copy bandwidth, kernel timed alone by events)",
