@@ -162,6 +162,31 @@ class GraphedGreedy:
         pad_token_id = generation_config._pad_token_tensor
         has_eos = any(hasattr(c, "eos_token_id") for c in stopping_criteria)
         unfinished = torch.ones(B, dtype=torch.long, device=input_ids.device)
+        max_length = int(generation_config.max_length)
+
+        # Whisper's processors only write -inf at positions that depend on the current LENGTH
+        # (suppress lists, begin-suppress, min-new-tokens): evaluate them on a single zero row
+        # (cost independent of the batch) and apply the resulting mask to the fp16 logits.  argmax
+        # of the masked fp16 logits == argmax of HF's masked fp32 copy (exact widening, same ties).
+        from transformers.generation.logits_process import (MinLengthLogitsProcessor,
+                                                            MinNewTokensLengthLogitsProcessor,
+                                                            SuppressTokensAtBeginLogitsProcessor,
+                                                            SuppressTokensLogitsProcessor)
+        mask_only = (SuppressTokensLogitsProcessor, SuppressTokensAtBeginLogitsProcessor,
+                     MinNewTokensLengthLogitsProcessor, MinLengthLogitsProcessor)
+        maskable = all(type(p) in mask_only for p in logits_processor)
+        zero_row = torch.zeros((1, st.logits.shape[1]), dtype=torch.float32, device=input_ids.device)
+
+        def eos_suppressed(length: int) -> bool:
+            """True when a min-length processor forces EOS to -inf for a prefix of this length."""
+            for p in logits_processor:
+                if type(p) is MinNewTokensLengthLogitsProcessor:
+                    if length - p.prompt_length_to_skip < p.min_new_tokens:
+                        return True
+                elif type(p) is MinLengthLogitsProcessor:
+                    if length < p.min_length:
+                        return True
+            return False
 
         def run(tokens, position):
             st.tok.copy_(tokens.view(B, 1))
@@ -174,15 +199,25 @@ class GraphedGreedy:
             run(input_ids[:, i], i)
         cur = P
         while True:
-            next_token_logits = st.logits.to(copy=True, dtype=torch.float32)
-            next_token_scores = logits_processor(input_ids, next_token_logits)
-            next_tokens = torch.argmax(next_token_scores, dim=-1)
+            length = input_ids.shape[1]
+            if maskable:
+                row = logits_processor(input_ids[:1], zero_row.clone())
+                next_tokens = torch.argmax(st.logits.masked_fill(torch.isinf(row), float("-inf")), dim=-1)
+            else:
+                next_token_logits = st.logits.to(copy=True, dtype=torch.float32)
+                next_tokens = torch.argmax(logits_processor(input_ids, next_token_logits), dim=-1)
             if has_eos:
                 next_tokens = next_tokens * unfinished + pad_token_id * (1 - unfinished)
             input_ids = torch.cat([input_ids, next_tokens[:, None]], dim=-1)
-            unfinished = unfinished & ~stopping_criteria(input_ids, None)
-            if bool(unfinished.max() == 0):
-                break
+            if maskable and has_eos and eos_suppressed(length):
+                # no sequence can finish at this step except by reaching max_length, which the host
+                # knows: no device->host synchronisation, the next replay is queued immediately
+                if length + 1 >= max_length:
+                    break
+            else:
+                unfinished = unfinished & ~stopping_criteria(input_ids, None)
+                if bool(unfinished.max() == 0):
+                    break
             run(next_tokens, cur)
             cur += 1
         return input_ids

@@ -325,3 +325,21 @@ def test_quanto_int4_model_flow(pkg):
     assert np.abs(y - y_ref).max() < 1e-3
     ids = harness.greedy_generate(model, _feats().cuda(), 6)
     assert ids.shape[0] == 4
+
+
+def test_graphed_greedy_early_stop_paths_match_hf(pkg):
+    """min_new_tokens < max_new_tokens: after the minimum the loop must evaluate HF's stopping
+    criteria every step (EOS possible); before it, it may skip the host sync.  Same ids as HF."""
+    from openai_whisper_compression_b200 import fastgen, harness
+    model = harness.apply_scheme(harness.build_model("tiny", **MICRO), "fp16", "cuda")
+    feats = _feats(n=3).half().cuda()
+    kw = dict(do_sample=False, num_beams=1, min_new_tokens=4, max_new_tokens=12)
+    ref = model.generate(feats, **kw)
+    eng = fastgen.enable(model)
+    got = model.generate(feats, **kw)
+    assert eng.replays > 0 and eng.fallbacks == 0
+    assert torch.equal(got, ref)
+    # beams are not covered by the fast loop: falls through to HF's own implementation
+    out = model.generate(feats, do_sample=False, num_beams=2, max_new_tokens=4)
+    assert out.shape[0] == 3
+    eng.uninstall()
