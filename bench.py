@@ -230,12 +230,35 @@ def run_ours(args):
         flush_buf.zero_()
         return hot_path(audio_dev)
 
+    # e2e: every step's audio is copied from pinned host memory inside the timed region; the copy of
+    # step i+1 runs on a side stream while step i computes (two device buffers)
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty_like(audio_dev), torch.empty_like(audio_dev)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"i": 0}
+
+    def issue_copy(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[i % 2])                  # buffer no longer read by step i-2
+            bufs[i % 2].copy_(audio_host, non_blocking=True)     # H2D of step i's inputs
+            ready[i % 2].record(copy_stream)
+
+    def e2e_begin():
+        e2e_state["i"] = 0
+        done[0].record(); done[1].record()
+        issue_copy(0)
+
     def step_e2e():
+        i = e2e_state["i"]
+        e2e_state["i"] = i + 1
         flush_buf.zero_()
-        a = audio_host.to(dev, non_blocking=True)            # H2D of this step's inputs
-        ids = hot_path(a)
+        issue_copy(i + 1)                                        # next step's inputs, overlapped
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        ids = hot_path(bufs[i % 2])
+        done[i % 2].record()
         out = ids_host[:, :ids.shape[1]]
-        out.copy_(ids, non_blocking=True)                    # D2H of the result
+        out.copy_(ids, non_blocking=True)                        # D2H of the result
         torch.cuda.current_stream().synchronize()
         hyps = proc.batch_decode(out)
         t = tally.all_reduce_tally(tally.tally_on_device(refs, hyps, dev))
@@ -255,6 +278,7 @@ def run_ours(args):
 
     for _ in range(W):
         step_device()
+    e2e_begin()
     for _ in range(max(1, min(W, 2))):
         step_e2e()
 
@@ -282,6 +306,7 @@ def run_ours(args):
     # ---- host buffers through the drop-in API: `e2e` ----
     barrier()
     e0.record()
+    e2e_begin()                                                  # first copy is inside the timed region
     for _ in range(K):
         ids, t = step_e2e()
     e1.record()
@@ -350,7 +375,9 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
         "config": workload_config(args),
         "e2e": {"value": total_audio / (ms_e2e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e / K,
-                "h2d_bytes_per_step": B * N_SAMPLES * 4, "d2h_bytes_per_step": int(ids.shape[1]) * B * 8 + 32},
+                "h2d_bytes_per_step": B * N_SAMPLES * 4, "d2h_bytes_per_step": int(ids.shape[1]) * B * 8 + 32,
+                "note": "per step: pinned-host audio H2D (prefetched one step ahead on a copy stream), log-mel, "
+                        "model.generate, ids D2H, decode to text, WER/CER tally on the GPU (+ all-reduce)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "tally": {"WER": tally.rates(t)["WER"], "CER": tally.rates(t)["CER"], "ref_words": int(t[1])},
     }

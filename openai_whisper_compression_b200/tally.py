@@ -17,11 +17,16 @@ import torch
 from . import functional as F
 
 
-def _pack(seqs: Sequence[Sequence[int]]):
+def _pack(seqs):
+    """list of int32 arrays -> (concatenated ids, int64 offsets [P+1])"""
     off = np.zeros(len(seqs) + 1, dtype=np.int64)
     np.cumsum([len(s) for s in seqs], out=off[1:])
-    flat = np.fromiter((v for s in seqs for v in s), dtype=np.int32, count=int(off[-1]))
+    flat = np.concatenate(seqs).astype(np.int32, copy=False) if len(seqs) else np.zeros((0,), np.int32)
     return flat, off
+
+
+def _codepoints(text: str) -> np.ndarray:
+    return np.frombuffer(text.encode("utf-32-le"), dtype=np.uint32).astype(np.int32)
 
 
 def tally_on_device(references: Sequence[str], predictions: Sequence[str], device) -> torch.Tensor:
@@ -32,12 +37,12 @@ def tally_on_device(references: Sequence[str], predictions: Sequence[str], devic
     if len(references) == 0:
         return torch.zeros(4, dtype=torch.int64, device=dev)
     rw, hw, rc, hc = [], [], [], []
+    vocab = {}                      # one id space for the whole batch (ids only need to be consistent)
     for ref, hyp in zip(references, predictions):
-        vocab = {}
-        rw.append([vocab.setdefault(w, len(vocab)) for w in ref.split()])
-        hw.append([vocab.setdefault(w, len(vocab)) for w in hyp.split()])
-        rc.append([ord(c) for c in ref])
-        hc.append([ord(c) for c in hyp])
+        rw.append(np.fromiter((vocab.setdefault(w, len(vocab)) for w in ref.split()), dtype=np.int32))
+        hw.append(np.fromiter((vocab.setdefault(w, len(vocab)) for w in hyp.split()), dtype=np.int32))
+        rc.append(_codepoints(ref))
+        hc.append(_codepoints(hyp))
     out = torch.zeros(4, dtype=torch.int64, device=dev)
     for slot, (rs, hs) in enumerate(((rw, hw), (rc, hc))):
         r, ro = _pack(rs)

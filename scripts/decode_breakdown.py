@@ -33,3 +33,19 @@ print(f"B={B}: logmel {1e3*(t1-t0):.2f} ms, encoder {1e3*(t2-t1):.2f} ms, genera
       f"launches per replay {st.launches_per_replay}")
 per_tok = (1e3*(t3-t2) - 1e3*(t2-t1)) / T
 print(f"  per-token wall {per_tok:.3f} ms -> eager/host part ~{per_tok - e0.elapsed_time(e1)/20:.3f} ms")
+
+# finer split of generate(): HF preamble (+ encoder) | cross-KV | token loop
+import types
+orig = eng._sample
+marks = {}
+def timed_sample(input_ids, **kw):
+    sync(); marks["enter"] = time.perf_counter()
+    out = orig(input_ids, **kw)
+    sync(); marks["exit"] = time.perf_counter()
+    return out
+eng._sample = timed_sample
+sync(); g0 = time.perf_counter()
+ids = harness.greedy_generate(model, feats, T)
+sync(); g1 = time.perf_counter()
+print(f"  generate {1e3*(g1-g0):.1f} ms = HF preamble + encoder {1e3*(marks['enter']-g0):.1f} ms + fast loop (cross-KV + tokens) "
+      f"{1e3*(marks['exit']-marks['enter']):.1f} ms + post {1e3*(g1-marks['exit']):.1f} ms")
