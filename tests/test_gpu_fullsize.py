@@ -1,0 +1,98 @@
+"""Parity at BASELINE.json's full sizes, through size-independent properties (the oracle is too
+slow there): exact integer identities against torch integer matmuls on the same device,
+quantize/dequantize idempotence, linearity of the weight-only GEMMs, pruned-zero survival, and the
+log-mel kernel against the float64 oracle on whole 30 s utterances."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.helpers import synth_audio
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def F():
+    from openai_whisper_compression_b200 import functional
+    return functional
+
+
+@pytest.mark.parametrize("M,N,K", [(96000, 512, 512), (24000, 2048, 512), (24000, 512, 2048), (12000, 1280, 5120)])
+def test_llmint8_full_size_bit_exact_vs_integer_matmul(F, M, N, K):
+    """configs[1] encoder shapes (64 x 1500 rows): the fused tcgen05 path equals the reference
+    formula evaluated with exact integer sums (torch._int_mm) on every element."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    bias = (torch.randn(N, device="cuda", generator=g) * 0.1).half()
+    cb, scb, _ = F.int8_vectorwise_quant(W, 0.0)
+    y = F.linear8bitlt(x, cb, scb, bias, 6.0)
+    ca, sca, _ = F.int8_vectorwise_quant(x, 0.0)
+    # row max of every quantized row is +-127 (or the row is all zero)
+    assert int(ca.abs().amax(1).min().item()) == 127
+    c32 = torch._int_mm(ca, cb.t().contiguous())
+    v = (c32.float() * sca[:, None]) * scb[None, :]
+    ref = (v.double() * float(np.float32(6.200012e-05)) + bias.double()[None, :]).float().half()
+    mism = (y != ref)
+    # fmaf vs (exact double product + add, rounded twice) can differ only in double-rounding ties
+    assert mism.float().mean().item() < 1e-6
+    assert (y.float() - ref.float()).abs().max().item() <= 2 ** -10 * max(1.0, ref.float().abs().max().item())
+
+
+@pytest.mark.parametrize("N,K", [(768, 3072), (5120, 1280)])
+def test_nf4_quantize_is_idempotent_and_preserves_zeros(F, N, K):
+    """whisper-small / large-v3 fc shapes: quantize(dequantize(quantize(w))) reproduces the same
+    codes and absmax (every code value is a fixed point), 50 % pruned zeros stay exactly zero."""
+    g = torch.Generator(device="cuda").manual_seed(N)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.02)
+    w[torch.rand(N, K, device="cuda", generator=g) < 0.5] = 0
+    p1, a1 = F.quantize_4bit(w, 64, "nf4")
+    d1 = F.dequantize_4bit(p1, a1, (N, K), 64, "nf4", torch.float32)
+    p2, a2 = F.quantize_4bit(d1, 64, "nf4")
+    assert torch.equal(a1, a2)
+    assert torch.equal(p1, p2)
+    assert torch.all(d1[w == 0] == 0)
+    # the block maximum is reproduced exactly (code +-1.0)
+    assert torch.equal(d1.abs().view(-1, 64).amax(1), a1)
+
+
+@pytest.mark.parametrize("scheme", ["w8a16", "w4a16", "u4a16"])
+def test_weight_only_gemm_linearity_full_size(F, scheme):
+    """y(x1 + x2) == y(x1) + y(x2) - y(0) up to fp32 accumulation noise (fp32 output, inputs
+    chosen so that x1 + x2 is exact in fp16): M = 48000 rows (32 utterances), large-v3 width."""
+    M, N, K = 48000, 1280, 1280
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x1 = (torch.randint(-64, 64, (M, K), device="cuda", generator=g).float() / 64).half()
+    x2 = (torch.randint(-64, 64, (M, K), device="cuda", generator=g).float() / 64).half()
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.02
+    bias = torch.randn(N, device="cuda", generator=g)
+    if scheme == "w8a16":
+        q, s = F.quanto_quantize_qint8(w)
+        f = lambda x: F.gemm_w8a16(x, q, s, bias, torch.float32)
+    elif scheme == "w4a16":
+        p, a = F.quantize_4bit(w.half(), 64, "nf4")
+        f = lambda x: F.gemm_w4a16(x, p, a, N, K, bias, "nf4", torch.float32)
+    else:
+        p, s, sh, grp = F.quanto_quantize_qint4(w)
+        f = lambda x: F.gemm_u4a16(x, p, s, sh, grp, bias, torch.float32)
+    y12, y1, y2 = f(x1 + x2), f(x1), f(x2)
+    y0 = f(torch.zeros_like(x1))
+    assert torch.equal(y0, bias[None, :].expand(M, N))           # zero input -> exactly the bias
+    err = (y12 - (y1 + y2 - y0)).abs().max().item()
+    assert err < 2e-4 * max(1.0, y12.abs().max().item())
+
+
+def test_logmel_full_batch_matches_oracle_on_sampled_utterances(F):
+    from openai_whisper_compression_b200.frontend import LogMelFrontend
+    fe = LogMelFrontend(128)                                      # large-v3 frontend
+    B = 32
+    audio = np.stack([synth_audio(100 + i) for i in range(B)])
+    audio[5, 300000:] = 0                                         # padded utterance inside the batch
+    out = fe.features_from_device_audio(torch.from_numpy(audio).cuda()).cpu().numpy()
+    assert out.shape == (B, 128, 3000)
+    for i in (0, 5, 31):
+        ref = oracle.log_mel_spectrogram(audio[i], 128)[0]
+        np.testing.assert_allclose(out[i], ref, rtol=0, atol=1e-4)
+    # per-utterance normalisation: max(x) - min(x) <= 8/4 everywhere
+    assert float((out.max(axis=(1, 2)) - out.min(axis=(1, 2))).max()) <= 2.0 + 1e-6
