@@ -58,6 +58,21 @@ int wq_quant_4bit(const void *w, int w_dtype, int64_t n, int blocksize, int quan
 int wq_dequant_4bit(const uint8_t *packed, const float *absmax, int64_t n, int blocksize,
                     int quant_type, void *out, int out_dtype, wq_stream_t stream);
 
+/* Nested ("double") quantization of the 4-bit statistics -- quantize_4bit(compress_statistics=
+ * True), i.e. bnb_4bit_use_double_quant (model_utils.py:42,48 "bnb_*_double"):
+ *   offset = mean(absmax); blockwise (256) 8-bit quantization of absmax - offset against the
+ *   256-entry dynamic code book (binary search + nearest neighbour as csrc/kernels.cu dQuantize).
+ * absmax: fp32 [n] (unchanged); code256: fp32 [256]; q: uint8 [n]; absmax2: fp32 [ceil(n/256)];
+ * offset: fp32 [1]; absmax_deq: fp32 [n] = code[q] * absmax2 + offset, the statistics that
+ * dequantize_4bit / the fused GEMM use from then on.  Deviation: the mean is accumulated in double
+ * (bitsandbytes: torch.mean in fp32) so that the CPU oracle can reproduce it bit for bit. */
+int wq_quant_absmax_double(const float *absmax, int64_t n, const float *code256, uint8_t *q,
+                           float *absmax2, float *offset, float *absmax_deq, wq_stream_t stream);
+
+/* dequantize_blockwise(absmax, state2) + offset: rebuilds the fp32 statistics from a state dict. */
+int wq_dequant_absmax_double(const uint8_t *q, const float *absmax2, const float *code256,
+                             const float *offset, int64_t n, float *absmax_out, wq_stream_t stream);
+
 /* bitsandbytes.functional.int8_vectorwise_quant -- Int8Params.to(device) for weights
  * (threshold 0) and MatMul8bitLt.forward for activations (threshold 6.0); BASELINE.json
  * config 2.  a: fp16 [rows, cols].  out int8 [rows, cols], row_stats fp32 [rows].

@@ -23,6 +23,8 @@ _PROTOS = {
     "wq_device_info": [c_ptr, c_ptr, c_ptr],
     "wq_quant_4bit": [c_ptr, c_int, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr],
     "wq_dequant_4bit": [c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_int, c_ptr],
+    "wq_quant_absmax_double": [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    "wq_dequant_absmax_double": [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr],
     "wq_quant_i8_rowwise_bnb": [c_ptr, c_i64, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_outlier_columns": [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_quant_i8_rowwise_quanto": [c_ptr, c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr],

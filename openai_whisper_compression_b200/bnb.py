@@ -49,10 +49,24 @@ class QuantState:
         self.state2 = state2
         self.nested = state2 is not None
 
+    def effective_absmax(self) -> torch.Tensor:
+        """fp32 per-block statistics as dequantize_4bit uses them (nested: code[q]*absmax2 + offset)."""
+        if not self.nested:
+            return self.absmax
+        cached = getattr(self, "_absmax_f32", None)
+        if cached is None or cached.device != self.absmax.device:
+            cached = self._absmax_f32 = F.dequantize_absmax_double(self.absmax, self.state2.absmax, self.offset)
+        return cached
+
     def as_dict(self, packed: bool = False) -> Dict[str, Any]:
         meta = {"quant_type": self.quant_type, "blocksize": self.blocksize,
                 "dtype": str(self.dtype).replace("torch.", ""), "shape": tuple(self.shape)}
         out: Dict[str, Any] = {"absmax": self.absmax, "quant_map": self.code}
+        if self.nested:
+            out["nested_absmax"] = self.state2.absmax
+            out["nested_quant_map"] = self.state2.code
+            meta.update(nested_blocksize=self.state2.blocksize, nested_dtype="float32",
+                        nested_offset=float(self.offset.item()))
         if not packed:
             out.update(meta)
             return out
@@ -63,6 +77,10 @@ class QuantState:
     def to(self, device):
         self.absmax = self.absmax.to(device)
         self.code = self.code.to(device)
+        if self.nested:
+            self.offset = self.offset.to(device)
+            self.state2.to(device)
+            self._absmax_f32 = None
         return self
 
 
@@ -71,13 +89,18 @@ def quantize_4bit(A: torch.Tensor, absmax=None, out=None, blocksize: int = 64, c
     """bitsandbytes.functional.quantize_4bit -> (packed uint8 [(n+1)//2, 1], QuantState)."""
     if quant_type not in ("fp4", "nf4"):
         raise NotImplementedError(f"4-bit quantization data type {quant_type} is not implemented.")
-    if compress_statistics:
-        raise NotImplementedError("nested (double) quantization of absmax is not implemented yet "
-                                  "(SURVEY.md section 8f rank 2)")
     if quant_storage != torch.uint8:
         raise NotImplementedError("only quant_storage=torch.uint8 is implemented")
     packed, am = F.quantize_4bit(A, blocksize, quant_type)
     code = torch.tensor(_NF4 if quant_type == "nf4" else _FP4, dtype=torch.float32, device=A.device)
+    if compress_statistics:
+        # nested ("double") quantization: offset = mean(absmax), 8-bit blockwise (256) dynamic map
+        q, absmax2, offset, absmax_deq = F.quantize_absmax_double(am)
+        state2 = QuantState(absmax=absmax2, code=F.dynamic_map(A.device), blocksize=256, dtype=torch.float32)
+        qs = QuantState(absmax=q, shape=A.shape, dtype=A.dtype, blocksize=blocksize, code=code,
+                        quant_type=quant_type, offset=offset, state2=state2)
+        qs._absmax_f32 = absmax_deq
+        return packed, qs
     return packed, QuantState(absmax=am, shape=A.shape, dtype=A.dtype, blocksize=blocksize, code=code,
                               quant_type=quant_type)
 
@@ -87,7 +110,7 @@ def dequantize_4bit(A: torch.Tensor, quant_state: Optional[QuantState] = None, a
     """bitsandbytes.functional.dequantize_4bit."""
     if quant_state is None:
         raise ValueError("dequantize_4bit needs a quant_state")
-    return F.dequantize_4bit(A, quant_state.absmax, quant_state.shape, quant_state.blocksize,
+    return F.dequantize_4bit(A, quant_state.effective_absmax(), quant_state.shape, quant_state.blocksize,
                              quant_state.quant_type, quant_state.dtype)
 
 
@@ -126,9 +149,9 @@ def matmul_4bit(A: torch.Tensor, B: torch.Tensor, quant_state: QuantState, out=N
     if x.dtype == torch.float32:
         # fp32 compute flow (bnb_implementation.py:1216-1218): tensor cores take fp16 operands,
         # accumulate fp32 and write fp32 (DESIGN.md "Numerics")
-        return F.gemm_w4a16(x.to(torch.float16), B, quant_state.absmax, N, K,
+        return F.gemm_w4a16(x.to(torch.float16), B, quant_state.effective_absmax(), N, K,
                             None if bias is None else bias.float(), quant_state.quant_type, torch.float32)
-    return F.gemm_w4a16(x, B, quant_state.absmax, N, K, None if bias is None else bias.float(),
+    return F.gemm_w4a16(x, B, quant_state.effective_absmax(), N, K, None if bias is None else bias.float(),
                         quant_state.quant_type)
 
 

@@ -266,6 +266,100 @@ k_quant_i8_rowwise_quanto(const T *__restrict__ w, int64_t N, int64_t K, int8_t 
 }
 
 // ---------------------------------------------------------------------------------------------
+// bitsandbytes nested ("double") quantization of the 4-bit absmax statistics
+// (quantize_4bit(compress_statistics=True)): offset = mean(absmax); absmax - offset is quantized
+// block-wise (256) to 8 bits against the 256-entry "dynamic" code book with the library's binary
+// search + nearest-neighbour rule (csrc/kernels.cu dQuantize<0>).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t dquantize8(const float *code, float x) {
+    int pivot = 127, upper_pivot = 255, lower_pivot = 0;
+    float lower = -1.0f, upper = 1.0f;
+    float val = code[pivot];
+    for (int i = 64; i > 0; i >>= 1) {
+        if (x > val) {
+            lower_pivot = pivot;
+            lower = val;
+            pivot += i;
+        } else {
+            upper_pivot = pivot;
+            upper = val;
+            pivot -= i;
+        }
+        val = code[pivot];
+    }
+    if (upper_pivot == 255) upper = code[upper_pivot];
+    if (lower_pivot == 0) lower = code[lower_pivot];
+    if (x > val) {
+        const float midpoint = (upper + val) * 0.5f;
+        return x > midpoint ? upper_pivot : pivot;
+    }
+    const float midpoint = (lower + val) * 0.5f;
+    return x < midpoint ? lower_pivot : pivot;
+}
+
+// single CTA: offset = mean (double accumulation, one rounding to fp32)
+__global__ void __launch_bounds__(1024)
+k_absmax_mean(const float *__restrict__ absmax, int64_t n, float *__restrict__ offset) {
+    __shared__ double s_sum[32];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) acc += (double)absmax[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = s_sum[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (threadIdx.x == 0) *offset = (float)(acc / (double)n);
+    }
+}
+
+// one warp per 256-element block of (absmax - offset)
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_quant_absmax_blockwise8(const float *__restrict__ absmax, int64_t n, const float *__restrict__ offset,
+                          const float *__restrict__ code, uint8_t *__restrict__ q, float *__restrict__ absmax2,
+                          float *__restrict__ absmax_deq) {
+    __shared__ float s_code[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_code[i] = code[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t blk = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const int64_t base = blk * 256;
+    if (base >= n) return;
+    const float off = *offset;
+    float v[8];
+    float am = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int64_t i = base + lane + 32 * j;
+        v[j] = i < n ? __fsub_rn(absmax[i], off) : 0.0f;
+        am = fmaxf(am, fabsf(v[j]));
+    }
+    am = warp_max(am);
+    if (lane == 0) absmax2[blk] = am;
+    const float inv = __fdiv_rn(1.0f, am);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int64_t i = base + lane + 32 * j;
+        if (i < n) {
+            const uint32_t c = dquantize8(s_code, __fmul_rn(v[j], inv));
+            q[i] = (uint8_t)c;
+            absmax_deq[i] = __fadd_rn(__fmul_rn(s_code[c], am), off);   // what dequantize_4bit will see
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_dequant_absmax_blockwise8(const uint8_t *__restrict__ q, const float *__restrict__ absmax2,
+                            const float *__restrict__ code, const float *__restrict__ offset, int64_t n,
+                            float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = __fadd_rn(__fmul_rn(__ldg(code + q[i]), absmax2[i >> 8]), *offset);
+}
+
+// ---------------------------------------------------------------------------------------------
 // quanto qint4: group-wise affine uint4 (MaxOptimizer + AffineQuantizer), one warp per group
 // ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -595,6 +689,31 @@ extern "C" int wq_quant_u4_group_quanto(const void *w, int w_dtype, int64_t N, i
         default:
             WQ_REQUIRE(false, "wq_quant_u4_group_quanto: bad dtype %d", w_dtype);
     }
+    WQ_LAUNCH_CHECK();
+    return WQ_OK;
+}
+
+extern "C" int wq_quant_absmax_double(const float *absmax, int64_t n, const float *code256, uint8_t *q,
+                                      float *absmax2, float *offset, float *absmax_deq, wq_stream_t stream) {
+    WQ_REQUIRE(n >= 0, "wq_quant_absmax_double: n < 0");
+    if (n == 0) return WQ_OK;
+    WQ_REQUIRE(absmax && code256 && q && absmax2 && offset && absmax_deq, "wq_quant_absmax_double: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    k_absmax_mean<<<1, 1024, 0, s>>>(absmax, n, offset);
+    const int64_t nblocks = (n + 255) / 256;
+    k_quant_absmax_blockwise8<<<(unsigned)((nblocks + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, 0, s>>>(
+        absmax, n, offset, code256, q, absmax2, absmax_deq);
+    WQ_LAUNCH_CHECK();
+    return WQ_OK;
+}
+
+extern "C" int wq_dequant_absmax_double(const uint8_t *q, const float *absmax2, const float *code256,
+                                        const float *offset, int64_t n, float *absmax_out, wq_stream_t stream) {
+    WQ_REQUIRE(n >= 0, "wq_dequant_absmax_double: n < 0");
+    if (n == 0) return WQ_OK;
+    WQ_REQUIRE(q && absmax2 && code256 && offset && absmax_out, "wq_dequant_absmax_double: null pointer");
+    k_dequant_absmax_blockwise8<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q, absmax2, code256,
+                                                                                              offset, n, absmax_out);
     WQ_LAUNCH_CHECK();
     return WQ_OK;
 }

@@ -106,6 +106,60 @@ def dequantize_4bit(packed: torch.Tensor, absmax: torch.Tensor, shape, blocksize
     return out
 
 
+_DYNAMIC_MAP = {}
+
+
+def dynamic_map(device) -> torch.Tensor:
+    """bitsandbytes create_dynamic_map(signed=True, max_exponent_bits=7, total_bits=8): the 256-entry
+    code book of blockwise 8-bit quantization (a constant table, built once per device with the
+    library's own formula)."""
+    dev = torch.device(device)
+    t = _DYNAMIC_MAP.get(dev)
+    if t is None:
+        data = []
+        for i in range(7):
+            boundaries = torch.linspace(0.1, 1, 2 ** i + 1)
+            means = (boundaries[:-1] + boundaries[1:]) / 2.0
+            data += ((10 ** (-6 + i)) * means).tolist()
+            data += (-(10 ** (-6 + i)) * means).tolist()
+        data += [0, 1.0]
+        data.sort()
+        t = _DYNAMIC_MAP[dev] = torch.tensor(data, dtype=torch.float32, device=dev)
+    return t
+
+
+def quantize_absmax_double(absmax: torch.Tensor):
+    """Nested quantization of the 4-bit statistics (quantize_4bit(compress_statistics=True)).
+
+    Returns (q uint8 [n], absmax2 f32 [ceil(n/256)], offset f32 [1], absmax_deq f32 [n])."""
+    absmax = absmax.contiguous()
+    _need_cuda(absmax)
+    n = absmax.numel()
+    code = dynamic_map(absmax.device)
+    q = torch.empty((n,), dtype=torch.uint8, device=absmax.device)
+    a2 = torch.empty(((n + 255) // 256,), dtype=torch.float32, device=absmax.device)
+    off = torch.empty((1,), dtype=torch.float32, device=absmax.device)
+    deq = torch.empty((n,), dtype=torch.float32, device=absmax.device)
+    with torch.cuda.device(absmax.device):
+        _lib.check(_lib.load().wq_quant_absmax_double(_ptr(absmax), n, _ptr(code), _ptr(q), _ptr(a2), _ptr(off),
+                                                      _ptr(deq), _stream()), "wq_quant_absmax_double")
+    STATS.launches += 2
+    return q, a2, off, deq
+
+
+def dequantize_absmax_double(q: torch.Tensor, absmax2: torch.Tensor, offset: torch.Tensor) -> torch.Tensor:
+    """dequantize_blockwise(absmax, state2) + offset -> fp32 statistics."""
+    _need_cuda(q, absmax2, offset)
+    n = q.numel()
+    out = torch.empty((n,), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.load().wq_dequant_absmax_double(_ptr(q), _ptr(absmax2), _ptr(dynamic_map(q.device)),
+                                                        _ptr(offset), n, _ptr(out), _stream()),
+                   "wq_dequant_absmax_double")
+    STATS.launches += 1
+    return out
+
+
 def gemm_w4a16(x: torch.Tensor, packed: torch.Tensor, absmax: torch.Tensor, N: int, K: int,
                bias: Optional[torch.Tensor] = None, quant_type: str = "nf4",
                out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:

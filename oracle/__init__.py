@@ -104,6 +104,36 @@ def linear4bit_forward(x: np.ndarray, packed, absmax, shape, bias=None, blocksiz
     return y.reshape(tuple(np.asarray(x).shape[:-1]) + (shape[0],))
 
 
+def dynamic_map() -> np.ndarray:
+    """bitsandbytes.functional.create_dynamic_map(signed=True, max_exponent_bits=7, total_bits=8):
+    the 256-entry code book of blockwise 8-bit quantization.  Built with torch.linspace exactly as
+    the library does (the table is data defined by that formula)."""
+    import torch
+    data = []
+    for i in range(7):
+        boundaries = torch.linspace(0.1, 1, 2 ** i + 1)
+        means = (boundaries[:-1] + boundaries[1:]) / 2.0
+        data += ((10 ** (-6 + i)) * means).tolist()
+        data += (-(10 ** (-6 + i)) * means).tolist()
+    data += [0, 1.0]
+    assert len(data) == 256
+    data.sort()
+    return torch.tensor(data, dtype=torch.float32).numpy()
+
+
+def quantize_absmax_double(absmax: np.ndarray):
+    """nested quantization of absmax: (q uint8 [n], absmax2 f32 [n/256], offset f32, absmax_deq f32 [n])."""
+    a = _f32(absmax).reshape(-1)
+    n = a.size
+    code = dynamic_map()
+    q = np.zeros((n,), dtype=np.uint8)
+    a2 = np.zeros(((n + 255) // 256,), dtype=np.float32)
+    deq = np.zeros((n,), dtype=np.float32)
+    off = ctypes.c_float(0)
+    lib().orc_quant_absmax_double(_p(a), ctypes.c_int64(n), _p(code), _p(q), _p(a2), ctypes.byref(off), _p(deq))
+    return q, a2, np.float32(off.value), deq
+
+
 # --------------------------------------------------------------------------------------
 # bitsandbytes LLM.int8 (SURVEY.md A.2)
 # --------------------------------------------------------------------------------------

@@ -121,6 +121,52 @@ void orc_dequant_4bit(const uint8_t *packed, const float *absmax, int64_t n,
     }
 }
 
+/* bitsandbytes nested quantization of absmax (quantize_4bit(compress_statistics=True)):
+ * offset = mean(absmax) [double accumulation -- documented deviation], blockwise-256 8-bit
+ * quantization of absmax - offset against the 256-entry dynamic map (kernels.cu dQuantize<0>). */
+static uint8_t dquantize8(const float *code, float x) {
+    int pivot = 127, upper_pivot = 255, lower_pivot = 0;
+    float lower = -1.0f, upper = 1.0f, val = code[pivot];
+    for (int i = 64; i > 0; i >>= 1) {
+        if (x > val) { lower_pivot = pivot; lower = val; pivot += i; }
+        else { upper_pivot = pivot; upper = val; pivot -= i; }
+        val = code[pivot];
+    }
+    if (upper_pivot == 255) upper = code[upper_pivot];
+    if (lower_pivot == 0) lower = code[lower_pivot];
+    if (x > val) {
+        float midpoint = (upper + val) * 0.5f;
+        return (uint8_t)(x > midpoint ? upper_pivot : pivot);
+    }
+    float midpoint = (lower + val) * 0.5f;
+    return (uint8_t)(x < midpoint ? lower_pivot : pivot);
+}
+
+void orc_quant_absmax_double(const float *absmax, int64_t n, const float *code, uint8_t *q,
+                             float *absmax2, float *offset_out, float *absmax_deq) {
+    double acc = 0.0;
+    for (int64_t i = 0; i < n; ++i) acc += (double)absmax[i];
+    float off = (float)(acc / (double)n);
+    *offset_out = off;
+    for (int64_t b = 0; b * 256 < n; ++b) {
+        int64_t lo = b * 256, hi = lo + 256 < n ? lo + 256 : n;
+        float am = 0.0f;
+        for (int64_t i = lo; i < hi; ++i) {
+            float v = fabsf(absmax[i] - off);
+            if (v > am) am = v;
+        }
+        absmax2[b] = am;
+        float inv = 1.0f / am;
+        for (int64_t i = lo; i < hi; ++i) {
+            float v = absmax[i] - off;
+            uint8_t c = dquantize8(code, v * inv);
+            q[i] = c;
+            float d = code[c] * am;
+            absmax_deq[i] = d + off;
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------- */
 /* bitsandbytes LLM.int8                                      */
 /* ------------------------------------------------------------------------- */

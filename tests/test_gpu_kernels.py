@@ -360,3 +360,51 @@ def test_qlinear_qint4_w4a16(dtype, tol, M, N, K):
     y = F.gemm_u4a16(x, packed, scale, shift, g, dev(bias))
     assert y.dtype == dtype
     assert (np.abs(y.float().cpu().numpy() - y_ref) / np.maximum(np.abs(y_ref), 1.0)).max() <= tol
+
+
+# ------------------------------------------------------------------------------------------------
+# bitsandbytes nested ("double") quantization of the 4-bit statistics
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [256, 1000, 12288, 7])
+def test_absmax_double_quant_bit_exact(n):
+    rng = np.random.RandomState(n)
+    absmax = (np.abs(rng.randn(n)) * 0.03 + 0.01).astype(np.float32)
+    if n > 300:
+        absmax[256:300] = 0.0                 # all-zero weight blocks (pruned)
+    q, a2, off, deq = F.quantize_absmax_double(dev(absmax))
+    q_ref, a2_ref, off_ref, deq_ref = oracle.quantize_absmax_double(absmax)
+    np.testing.assert_array_equal(F.dynamic_map("cuda").cpu().numpy(), oracle.dynamic_map())
+    assert np.float32(off.item()) == off_ref
+    np.testing.assert_array_equal(a2.cpu().numpy(), a2_ref)
+    np.testing.assert_array_equal(q.cpu().numpy(), q_ref)
+    np.testing.assert_array_equal(deq.cpu().numpy(), deq_ref)
+    back = F.dequantize_absmax_double(q, a2, off)
+    np.testing.assert_array_equal(back.cpu().numpy(), deq_ref)
+    # 8-bit dynamic map: relative error of the reconstructed statistics stays below 1 % of the block max
+    assert np.abs(deq_ref - absmax).max() <= 0.01 * np.abs(absmax - off_ref).max() + 1e-7
+
+
+def test_linear4bit_double_quant_module():
+    """bnb_nf4_16_double flow (model_utils.py:36-48): Linear4bit(compress_statistics=True)."""
+    from openai_whisper_compression_b200 import bnb
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(256, 192).half()
+    m = bnb.Linear4bit(256, 192, bias=True, compute_dtype=torch.float16, compress_statistics=True, quant_type="nf4")
+    m.load_state_dict(lin.state_dict(), strict=False)
+    m = m.to("cuda")
+    qs = m.weight.quant_state
+    assert qs.nested and qs.absmax.dtype == torch.uint8 and qs.state2.blocksize == 256
+    p_ref, a_ref = oracle.quantize_4bit(lin.weight.detach().float().numpy(), 64, "nf4")
+    q_ref, a2_ref, off_ref, deq_ref = oracle.quantize_absmax_double(a_ref)
+    np.testing.assert_array_equal(m.weight.data.cpu().numpy(), p_ref)
+    np.testing.assert_array_equal(qs.absmax.cpu().numpy(), q_ref)
+    wd = bnb.dequantize_4bit(m.weight.data, qs).cpu().numpy()
+    wd_ref = oracle.dequantize_4bit(p_ref, deq_ref, (192, 256), 64, "nf4", np.float16)
+    np.testing.assert_array_equal(wd, wd_ref)
+    sd = m.state_dict()
+    assert {"weight.absmax", "weight.nested_absmax", "weight.nested_quant_map", "weight.quant_map"} <= set(sd)
+    assert sd["weight.absmax"].dtype == torch.uint8
+    x = torch.randn(9, 256).half()
+    y = m(x.cuda()).float().cpu().numpy()
+    y_ref = x.double().numpy() @ wd_ref.astype(np.float64).T + lin.bias.detach().double().numpy()
+    assert np.abs(y - y_ref).max() < 4e-3
