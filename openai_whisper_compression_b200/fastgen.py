@@ -36,6 +36,7 @@ class GraphedGreedy:
         self.len_bucket = len_bucket
         self._states: Dict[Tuple[int, int, torch.dtype], _State] = {}
         self._orig_sample = None
+        self.max_states = 4
         self.replays = 0
         self.fallbacks = 0
 
@@ -98,6 +99,8 @@ class GraphedGreedy:
         st = self._states.get(key)
         if st is not None:
             return st
+        if len(self._states) >= self.max_states:       # static caches are large: keep a few shapes
+            self._states.pop(next(iter(self._states)))
         cfg = self.model.config
         st = _State()
         st.B, st.d = B, cfg.d_model

@@ -190,3 +190,39 @@ def test_edit_distance_and_tally():
     t = oracle.wer_cer_tally(["the cat sat", "a b"], ["the cat sat down", "a c"])
     assert list(t[:2]) == [2, 5]
     assert t[3] == len("the cat sat") + len("a b")
+
+
+def test_quanto_qint4_invariants():
+    rng = np.random.RandomState(4)
+    W = (rng.randn(16, 384) * 0.02).astype(np.float32)
+    q, scale, shift, g = oracle.quanto_qint4(W)
+    assert g == 128 and scale.shape == shift.shape == (16, 3)
+    grp = W.reshape(16, 3, 128)
+    np.testing.assert_array_equal(shift, -grp.min(-1))
+    np.testing.assert_array_equal(scale, ((grp.max(-1) - grp.min(-1)) / np.float32(15)).astype(np.float32))
+    # group minimum -> code 0, group maximum -> code 15; reconstruction within half a step
+    qg = q.reshape(16, 3, 128)
+    assert np.all(np.take_along_axis(qg, grp.argmin(-1)[..., None], -1) == 0)
+    assert np.all(np.take_along_axis(qg, grp.argmax(-1)[..., None], -1) == 15)
+    deq = oracle.quanto_qint4_dequant(q, scale, shift, g)
+    assert np.abs(deq - W).max() <= scale.max() * 0.5 * (1 + 1e-5)
+    assert oracle.quanto_group_size(64) == 64 and oracle.quanto_group_size(160) == 32
+    assert oracle.quanto_qint4_pack(q).shape == (16, 192)
+
+
+def test_dynamic_map_and_nested_absmax_quantization():
+    code = oracle.dynamic_map()
+    assert code.shape == (256,) and np.all(np.diff(code) > 0) and code[-1] == 1.0 and 0.0 in code
+    assert code[0] == -code[-2]                       # signed, symmetric except for the extra +1.0
+    rng = np.random.RandomState(5)
+    absmax = (np.abs(rng.randn(700)) * 0.03 + 0.01).astype(np.float32)
+    q, a2, off, deq = oracle.quantize_absmax_double(absmax)
+    assert q.dtype == np.uint8 and a2.shape == (3,)
+    assert off == np.float32(absmax.astype(np.float64).mean())
+    # every block's extreme element maps to code +-1 (255 or 0) and is reproduced exactly
+    for b in range(3):
+        blk = slice(256 * b, min(256 * (b + 1), 700))
+        i = np.abs(absmax[blk] - off).argmax()
+        assert q[blk][i] in (0, 255)
+        assert deq[blk][i] == np.float32(np.float32(code[q[blk][i]] * a2[b]) + off)
+    assert np.abs(deq - absmax).max() <= 0.01 * np.abs(absmax - off).max() + 1e-7
