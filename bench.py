@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--new-tokens", type=int, default=64)
     ap.add_argument("--cpu-sample", type=int, default=8,
                     help="utterances in the CPU baseline sample (the reference's own CPU batch size, BASELINE config 0)")
+    ap.add_argument("--prune", type=float, default=0.0,
+                    help="global L1 magnitude pruning amount applied before quantization (BASELINE config 4: 0.5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hf-loop", action="store_true",
                     help="keep HF's Python decode loop instead of the CUDA-graph replay loop (fastgen)")
@@ -168,9 +170,13 @@ def run_reference(args):
 
 
 def workload_config(args):
-    return {"workload": f"whisper-{args.size} bitsandbytes LLM.int8 (threshold 6.0) log-mel + encoder + greedy "
+    default = args.size == "base" and args.scheme == "llm_int8" and args.prune == 0
+    what = "bitsandbytes LLM.int8 (threshold 6.0)" if args.scheme == "llm_int8" else args.scheme
+    if args.prune > 0:
+        what = f"{int(args.prune * 100)} % global-L1 pruned + {what}"
+    return {"workload": f"whisper-{args.size} {what} log-mel + encoder + greedy "
                         f"decode, {args.batch} x 30 s synthetic utterances per GPU per step, "
-                        f"{args.new_tokens} new tokens (BASELINE.json configs[1])",
+                        f"{args.new_tokens} new tokens" + (" (BASELINE.json configs[1])" if default else ""),
             "size": args.size, "scheme": args.scheme, "utterances_per_gpu": args.batch,
             "new_tokens": args.new_tokens, "parallelism": f"utterance-sharded dp{args.gpus}",
             "decode_loop": "HF _sample (Python)" if getattr(args, "hf_loop", False) else
@@ -202,7 +208,11 @@ def run_ours(args):
 
     B, T, K, W = args.batch, args.new_tokens, args.steps, max(args.warmup, 0)
     n_mels = harness.WHISPER_SIZES[args.size]["mels"]
-    model = harness.apply_scheme(harness.build_model(args.size), args.scheme, dev)
+    master = harness.build_model(args.size)
+    if args.prune > 0:
+        harness.global_l1_prune(master, args.prune)
+    model = harness.apply_scheme(master, args.scheme, dev)
+    del master
     if not args.hf_loop:
         from openai_whisper_compression_b200 import fastgen
         fastgen.enable(model)
@@ -330,7 +340,7 @@ def run_ours(args):
     shapes = []
     for (kind, M, N, Kd), ts in sorted(by_shape.items()):
         a_bytes = 1 if kind in ("llmint8", "dyn_i8") else 2
-        w_bytes = {"llmint8": 1.0, "dyn_i8": 1.0, "w8a16": 1.0, "w4a16": 0.5 + 4.0 / 64}[kind]
+        w_bytes = {"llmint8": 1.0, "dyn_i8": 1.0, "w8a16": 1.0, "w4a16": 0.5 + 4.0 / 64, "u4a16": 0.5 + 8.0 / 128}[kind]
         o_bytes = 4 if kind == "dyn_i8" else 2
         nbytes = M * Kd * a_bytes + N * Kd * w_bytes + M * N * o_bytes + 4 * (M + N)
         flops = 2.0 * M * N * Kd
@@ -360,8 +370,8 @@ def run_ours(args):
         achieved = tot_bytes / tot_time / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
-                    "kernel": "k_gemm_tc<A_S8,B_DIRECT,EPI_LLMINT8> (tcgen05 s8xs8->s32, fused dequant epilogue), "
-                              "encoder-shaped launches (M >= 1024)",
+                    "kernel": "k_gemm_tc (TMA + tcgen05 + TMEM, fused dequant epilogue; LLM.int8: s8xs8->s32), "
+                              "encoder-shaped launches (M >= 1024), kinds: " + ",".join(sorted({k[0] for k in by_shape})),
                     "peak_source": peaks["source"] + " (burst copy bandwidth, kernel timed alone by events)",
                     "launches_timed": n_launch, "avg_launch_us": tot_time / n_launch * 1e6,
                     "algorithmic_bytes_per_launch": tot_bytes / n_launch,
