@@ -8,7 +8,9 @@ per token.  ``enable(model)`` replaces only that inner loop: the decoder step (t
 sub-modules, i.e. the drop-in quantized linears, LayerNorms and embeddings, with a static KV cache)
 is captured once per (batch, max length) as a CUDA graph and replayed per token; HF's own
 ``logits_processor`` and ``stopping_criteria`` objects are applied between replays, so the call
-``model.generate(features)`` and its result format are unchanged.  Anything the fast loop does not
+``model.generate(features)`` and its result format are unchanged.  The generated ids are handed to HF's
+per-utterance post-processing as a host tensor (one read-back instead of several blocking syncs per
+utterance) and returned to the model's device at the end of ``generate``.  Anything the fast loop does not
 cover (sampling, beams, return_dict_in_generate, streamer, CPU) falls through to HF's ``_sample``.
 
 Numerics: same modules and weights as HF's loop; attention over the static cache is
@@ -23,6 +25,7 @@ from typing import Dict, Tuple
 import torch
 import torch.nn.functional as TF
 
+from . import fastenc
 from . import functional as F
 
 
@@ -37,6 +40,7 @@ class GraphedGreedy:
         self._states: Dict[Tuple[int, int, torch.dtype], _State] = {}
         self._orig_sample = None
         self.max_states = 4
+        self.host_postprocess = True
         self.replays = 0
         self.fallbacks = 0
 
@@ -51,9 +55,19 @@ class GraphedGreedy:
             def _sample(model_self, input_ids, **kwargs):
                 return model_self._whisperq_fastgen._sample(input_ids, **kwargs)
 
+            def generate(model_self, *args, **kwargs):
+                out = base.generate(model_self, *args, **kwargs)
+                # the fast loop hands HF's per-utterance post-processing host-resident token ids (see
+                # _sample); the caller gets them back where HF would have put them
+                if isinstance(out, torch.Tensor) and out.device != model_self.device:
+                    out = out.to(model_self.device)
+                return out
+
             self._base_cls = base
-            self.model.__class__ = type(base.__name__, (base,), {"_sample": _sample, "__module__": base.__module__})
+            self.model.__class__ = type(base.__name__, (base,), {"_sample": _sample, "generate": generate,
+                                                                 "__module__": base.__module__})
             self.model._whisperq_fastgen = self
+            fastenc.enable(self.model)       # copy-free encoder self-attention (same arithmetic)
         return self
 
     def uninstall(self):
@@ -61,6 +75,7 @@ class GraphedGreedy:
             self.model.__class__ = self._base_cls
             self._orig_sample = None
             del self.model._whisperq_fastgen
+            fastenc.disable(self.model)
 
     # ------------------------------------------------------------------------------------------
     def _decoder_step(self, st: _State):
@@ -86,7 +101,7 @@ class GraphedGreedy:
             res = x
             h = layer.encoder_attn_layer_norm(x)
             q = (ca.q_proj(h) * ca.scaling).view(B, 1, H, hd).transpose(1, 2)
-            a = TF.scaled_dot_product_attention(q, st.ck[li], st.cv[li], scale=1.0)
+            a = TF.scaled_dot_product_attention(q, st.ck[li].transpose(1, 2), st.cv[li].transpose(1, 2), scale=1.0)
             x = res + ca.out_proj(a.transpose(1, 2).reshape(B, 1, d))
             res = x
             h = layer.final_layer_norm(x)
@@ -114,8 +129,10 @@ class GraphedGreedy:
         st.mask = torch.zeros((t_max,), dtype=torch.bool, device=device)
         st.k = [torch.zeros((B, st.H, t_max, st.hd), dtype=dtype, device=device) for _ in range(L)]
         st.v = [torch.zeros((B, st.H, t_max, st.hd), dtype=dtype, device=device) for _ in range(L)]
-        st.ck = [torch.zeros((B, st.H, S, st.hd), dtype=dtype, device=device) for _ in range(L)]
-        st.cv = [torch.zeros((B, st.H, S, st.hd), dtype=dtype, device=device) for _ in range(L)]
+        # cross-attention K/V stay in the projection's own [B, S, H, hd] layout: the q_len = 1 SDPA kernel
+        # streams them through their strides at the same HBM rate (scripts/attn_layout_bench.py)
+        st.ck = [torch.zeros((B, S, st.H, st.hd), dtype=dtype, device=device) for _ in range(L)]
+        st.cv = [torch.zeros((B, S, st.H, st.hd), dtype=dtype, device=device) for _ in range(L)]
         st.logits = torch.zeros((B, self.model.proj_out.out_features), dtype=dtype, device=device)
         # warm up on a side stream (lazy inits, autotuning), then capture
         side = torch.cuda.Stream(device=device)
@@ -159,8 +176,8 @@ class GraphedGreedy:
         S = enc.shape[1]
         for li, layer in enumerate(model.model.decoder.layers):
             ca = layer.encoder_attn
-            st.ck[li].copy_(ca.k_proj(enc).view(B, S, st.H, st.hd).transpose(1, 2))
-            st.cv[li].copy_(ca.v_proj(enc).view(B, S, st.H, st.hd).transpose(1, 2))
+            st.ck[li].copy_(ca.k_proj(enc).view(B, S, st.H, st.hd))
+            st.cv[li].copy_(ca.v_proj(enc).view(B, S, st.H, st.hd))
 
         pad_token_id = generation_config._pad_token_tensor
         has_eos = any(hasattr(c, "eos_token_id") for c in stopping_criteria)
@@ -223,7 +240,12 @@ class GraphedGreedy:
                     break
             run(next_tokens, cur)
             cur += 1
-        return input_ids
+        # WhisperGenerationMixin post-processes every utterance separately (generation_whisper.py,
+        # generate_with_fallback / _retrieve_segment: `seq[-1] == pad`, nonzero(), slicing): on device tensors
+        # that is ~4 blocking syncs per utterance, ~45 ms at B = 256 -- as long as 25 decode steps.  The ids
+        # are read back once here (HF's own dict path does the same with .cpu()) and HF's loops run on
+        # the host copy; `generate` above returns the final tensor to the model's device.
+        return input_ids.cpu() if self.host_postprocess else input_ids
 
 
 def enable(model, len_bucket: int = 64) -> GraphedGreedy:

@@ -338,8 +338,39 @@ def test_graphed_greedy_early_stop_paths_match_hf(pkg):
     eng = fastgen.enable(model)
     got = model.generate(feats, **kw)
     assert eng.replays > 0 and eng.fallbacks == 0
+    assert got.device == ref.device and got.dtype == ref.dtype      # host post-processing is internal
     assert torch.equal(got, ref)
+    # the same call with the post-processing left on the device (HF's default placement)
+    eng.host_postprocess = False
+    assert torch.equal(model.generate(feats, **kw), ref)
+    eng.host_postprocess = True
+    # timestamp mode walks HF's segment-splitting code with the host-resident ids
+    eng.uninstall()
+    model.generation_config.no_timestamps_token_id = 50363     # random-init config: HF needs it for timestamps
+    ref_ts = model.generate(feats, return_timestamps=True, **kw)
+    eng = fastgen.enable(model)
+    got_ts = model.generate(feats, return_timestamps=True, **kw)
+    assert got_ts.device == ref_ts.device and torch.equal(got_ts, ref_ts)
     # beams are not covered by the fast loop: falls through to HF's own implementation
     out = model.generate(feats, do_sample=False, num_beams=2, max_new_tokens=4)
     assert out.shape[0] == 3
     eng.uninstall()
+
+
+@pytest.mark.parametrize("scheme", ["llm_int8", "quanto_int8_fp16"])
+def test_copy_free_encoder_attention_is_bit_identical(pkg, scheme):
+    """fastenc: the encoder with the copy-free self-attention forward returns exactly what HF's forward
+    (q/k/v .contiguous() copies) returns -- same projections, same SDPA arithmetic, only strides differ."""
+    from openai_whisper_compression_b200 import fastenc, harness
+    model = harness.apply_scheme(harness.build_model("tiny", encoder_layers=2, decoder_layers=1), scheme, "cuda")
+    feats = _feats(n=5, frames=3000).half().cuda()       # real geometry: S = 1500, 6 heads x 64
+    with torch.no_grad():
+        ref = model.model.encoder(feats).last_hidden_state
+        assert fastenc.enable(model) == len(model.model.encoder.layers)
+        out = model.model.encoder(feats).last_hidden_state
+        fastenc.disable(model)
+        back = model.model.encoder(feats).last_hidden_state
+    assert torch.equal(back, ref)
+    assert torch.isfinite(out).all()
+    diff = (out.float() - ref.float()).abs().max().item()
+    assert diff <= 2e-3, diff      # expected 0.0: cuDNN picks the same kernel for both layouts
