@@ -192,6 +192,38 @@ int wq_logmel(const float *audio, int64_t B, int64_t audio_stride, const int32_t
               uint32_t *workspace, wq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Producers fused with the LLM.int8 activation quantizer.
+ * HF Whisper feeds every quantized linear from a LayerNorm, a GELU or an attention output
+ * (transformers modeling_whisper.py: WhisperEncoderLayer / WhisperDecoderLayer.forward,
+ * WhisperAttention.forward) and bitsandbytes' Linear8bitLt.forward then quantizes that tensor in a
+ * launch of its own (int8_vectorwise_quant).  These entry points write the fp16 tensor HF would have
+ * produced and, when `ca` is not NULL, its int8 rows + row absmax + outlier column flags exactly as
+ * wq_quant_i8_rowwise_bnb would from that tensor (same flag protocol: col_flags int32[cols + 2]).
+ * ---------------------------------------------------------------------------------------- */
+/* x_out = x + delta (skipped when delta is NULL; x_out may alias x); h_out = LayerNorm(x_out) * gamma +
+ * beta, fp32 statistics, eps as nn.LayerNorm.  dtype WQ_F16 / WQ_BF16 for x, delta, gamma, beta, x_out,
+ * h_out.  cols % 8 == 0, cols <= 2048.  int8 outputs only with WQ_F16. */
+int wq_add_layernorm_quant(const void *x, const void *delta, int dtype, const void *gamma,
+                           const void *beta, float eps, int64_t rows, int64_t cols, void *x_out,
+                           void *h_out, float threshold, int8_t *ca, float *row_stats,
+                           int32_t *col_flags, wq_stream_t stream);
+
+/* h_out = gelu(x) (erf form, torch approximate="none"), fp32 math.  cols % 8 == 0. */
+int wq_gelu_quant(const void *x, int dtype, int64_t rows, int64_t cols, void *h_out, float threshold,
+                  int8_t *ca, float *row_stats, int32_t *col_flags, wq_stream_t stream);
+
+/* Decoder self-attention for one new token per utterance (WhisperAttention.forward with a KV cache,
+ * q_len = 1).  q, k, v: this step's projections, rows of H*64 elements, row stride `ld` elements (so
+ * the three can be column blocks of one fused [B, 3*H*64] projection).  q is multiplied by `scaling`
+ * and rounded to `dtype` first, as HF does.  k_cache / v_cache: [B, t_max, H*64]; the new k/v rows are
+ * written at position *pos (device scalar), then softmax(q K^T) V over positions 0..*pos in fp32.
+ * out: [B, H*64].  Optional int8 row quantization of out as above.  head_dim is 64 (all Whisper sizes). */
+int wq_self_attn_decode(const void *q, const void *k, const void *v, int64_t ld, int dtype, float scaling,
+                        void *k_cache, void *v_cache, int64_t B, int H, int t_max, const int64_t *pos,
+                        void *out, float threshold, int8_t *ca, float *row_stats, int32_t *col_flags,
+                        wq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * WER / CER tallies -- evaluate.load("wer"/"cer").compute, evaluation.py:110-116
  * ---------------------------------------------------------------------------------------- */
 /* Unit-cost Levenshtein distance for P pairs of int32 id sequences (word ids or code points).

@@ -37,6 +37,11 @@ _PROTOS = {
     "wq_gemm_w4a16": [c_ptr, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],
     "wq_gemm_u4a16": [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],
     "wq_gemm_dyn_i8": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr],
+    "wq_add_layernorm_quant": [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_f32, c_i64, c_i64, c_ptr, c_ptr, c_f32, c_ptr,
+                               c_ptr, c_ptr, c_ptr],
+    "wq_gelu_quant": [c_ptr, c_int, c_i64, c_i64, c_ptr, c_f32, c_ptr, c_ptr, c_ptr, c_ptr],
+    "wq_self_attn_decode": [c_ptr, c_ptr, c_ptr, c_i64, c_int, c_f32, c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr,
+                            c_ptr, c_f32, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_logmel": [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_int, c_ptr, c_int, c_ptr, c_ptr],
     "wq_edit_distance": [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr],
 }

@@ -1,0 +1,188 @@
+// attn_decode.cu -- decoder self-attention for ONE new token per utterance over a static KV cache
+// (decoder attention at decode time).
+//
+// HF's WhisperAttention at decode time (modeling_whisper.py:310-355): q = q_proj(h) * scaling (rounded to the
+// activation dtype), the new k/v rows are appended to the cache, softmax(q K^T) V over the positions seen so far,
+// and the result feeds out_proj -- which, for bitsandbytes Linear8bitLt, quantizes it row-wise first.  Through
+// torch that is: mul, 2 x index_copy, mask build, SDPA (34 us for a 17 MB cache), quantize.  Here it is one
+// launch: CTA per utterance, warp per head (head_dim 64), cache kept in the projections' own [B, t_max, H*64]
+// layout so the append is one 128-byte row per head; scores and softmax in fp32; optional LLM.int8 row
+// quantization of the [H*64] output row (same arithmetic as k_quant_i8_rowwise_bnb, on the rounded fp16 values).
+// L2-resident, latency-bound: what matters is launch count, not bandwidth.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kHeadDim = 64;
+
+template <typename T>
+__device__ __forceinline__ void load8(const T *p, float (&f)[8]) {
+    const uint4 raw = *reinterpret_cast<const uint4 *>(p);
+    const T *h = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = to_f32(h[j]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+k_self_attn_decode(const T *__restrict__ q, const T *__restrict__ k, const T *__restrict__ v, int64_t ld,
+                   float scaling, T *__restrict__ kc, T *__restrict__ vc, int t_max,
+                   const int64_t *__restrict__ pos_ptr, int H, T *__restrict__ out, float threshold,
+                   int8_t *__restrict__ ca, float *__restrict__ row_stats, int32_t *__restrict__ col_flags) {
+    extern __shared__ float smem[];          // [H][t_max] scores, then [H*64] output row (fp32 of rounded values)
+    const int b = blockIdx.x;
+    const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 3, sub = lane & 7;  // 4 cache rows per warp step, 8 lanes x 8 dims per row
+    const int d = H * kHeadDim;
+    int pos = (int)*pos_ptr;
+    pos = pos < t_max ? pos : t_max - 1;
+    float *sc = smem + (size_t)h * t_max;
+    float *orow = smem + (size_t)H * t_max;
+
+    // q (scaled, rounded as HF's `q_proj(h) * scaling`), this lane's 8 dims
+    float q8[8];
+    load8(q + (int64_t)b * ld + h * kHeadDim + sub * 8, q8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q8[j] = to_f32(from_f32<T>(q8[j] * scaling));
+
+    // append this step's k / v rows (lanes 0-7: k, lanes 8-15: v)
+    T *kc_b = kc + ((int64_t)b * t_max) * d + h * kHeadDim;
+    T *vc_b = vc + ((int64_t)b * t_max) * d + h * kHeadDim;
+    if (lane < 8) {
+        *reinterpret_cast<uint4 *>(kc_b + (int64_t)pos * d + sub * 8) =
+            *reinterpret_cast<const uint4 *>(k + (int64_t)b * ld + h * kHeadDim + sub * 8);
+    } else if (lane < 16) {
+        *reinterpret_cast<uint4 *>(vc_b + (int64_t)pos * d + sub * 8) =
+            *reinterpret_cast<const uint4 *>(v + (int64_t)b * ld + h * kHeadDim + sub * 8);
+    }
+    __syncwarp();
+
+    // scores
+    float mx = -INFINITY;
+    for (int t0 = 0; t0 <= pos; t0 += 4) {
+        const int t = t0 + g;
+        float s = 0.0f;
+        if (t <= pos) {
+            float k8[8];
+            load8(kc_b + (int64_t)t * d + sub * 8, k8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s = fmaf(q8[j], k8[j], s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (t <= pos) {
+            if (sub == 0) sc[t] = s;
+            mx = fmaxf(mx, s);
+        }
+    }
+    mx = warp_max(mx);
+    __syncwarp();
+    float sum = 0.0f;
+    for (int t = lane; t <= pos; t += 32) {
+        const float p = expf(sc[t] - mx);
+        sc[t] = p;
+        sum += p;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    __syncwarp();
+
+    // P V
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int t0 = 0; t0 <= pos; t0 += 4) {
+        const int t = t0 + g;
+        if (t <= pos) {
+            float v8[8];
+            load8(vc_b + (int64_t)t * d + sub * 8, v8);
+            const float p = sc[t];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(p, v8[j], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+    }
+    if (g == 0) {
+        uint4 raw;
+        T *o8 = reinterpret_cast<T *>(&raw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            o8[j] = from_f32<T>(acc[j] * inv);
+            if (ca != nullptr) orow[h * kHeadDim + sub * 8 + j] = to_f32(o8[j]);
+        }
+        *reinterpret_cast<uint4 *>(out + (int64_t)b * d + h * kHeadDim + sub * 8) = raw;
+    }
+    if (ca == nullptr) return;
+
+    // LLM.int8 row quantization of the [d] output row (int8_vectorwise_quant)
+    __shared__ float s_red[32];
+    __syncthreads();
+    const bool sparse = threshold > 0.0f;
+    float am = 0.0f;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        const float x = fabsf(orow[c]);
+        if (!sparse || x < threshold) am = fmaxf(am, x);
+    }
+    am = warp_max(am);
+    if (lane == 0) s_red[h] = am;
+    __syncthreads();
+    am = 0.0f;
+    for (int w = 0; w < H; ++w) am = fmaxf(am, s_red[w]);
+    if (threadIdx.x == 0) row_stats[b] = am;
+    const float scale = __fdiv_rn(127.0f, am);
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        const float x = orow[c];
+        int qv;
+        if (sparse && !(fabsf(x) < threshold)) {
+            qv = 0;
+            col_flags[c] = 1;
+            col_flags[d] = 1;
+        } else {
+            qv = __float2int_rn(__fmul_rn(x, scale));
+        }
+        ca[(int64_t)b * d + c] = (int8_t)qv;
+    }
+}
+
+}  // namespace
+
+extern "C" int wq_self_attn_decode(const void *q, const void *k, const void *v, int64_t ld, int dtype, float scaling,
+                                   void *k_cache, void *v_cache, int64_t B, int H, int t_max, const int64_t *pos,
+                                   void *out, float threshold, int8_t *ca, float *row_stats, int32_t *col_flags,
+                                   wq_stream_t stream) {
+    WQ_REQUIRE(B >= 0 && H >= 1 && H <= 32 && t_max >= 1, "wq_self_attn_decode: bad shape (H must be 1..32)");
+    WQ_REQUIRE(dtype == WQ_F16 || dtype == WQ_BF16, "wq_self_attn_decode: dtype must be f16 or bf16");
+    WQ_REQUIRE(threshold >= 0.0f, "wq_self_attn_decode: negative threshold");
+    if (B == 0) return WQ_OK;
+    WQ_REQUIRE(q && k && v && k_cache && v_cache && pos && out, "wq_self_attn_decode: null pointer");
+    WQ_REQUIRE(ld % 8 == 0 && ld >= (int64_t)H * kHeadDim, "wq_self_attn_decode: bad row stride %lld", (long long)ld);
+    WQ_REQUIRE(wq_aligned(q, 16) && wq_aligned(k, 16) && wq_aligned(v, 16) && wq_aligned(k_cache, 16) &&
+                   wq_aligned(v_cache, 16) && wq_aligned(out, 16),
+               "wq_self_attn_decode: pointers must be 16-byte aligned");
+    WQ_REQUIRE(ca == nullptr || (dtype == WQ_F16 && row_stats != nullptr),
+               "wq_self_attn_decode: the int8 outputs need fp16 rows and row_stats");
+    WQ_REQUIRE(ca == nullptr || threshold == 0.0f || col_flags, "wq_self_attn_decode: threshold needs col_flags");
+    const size_t smem = ((size_t)H * t_max + (size_t)H * kHeadDim) * sizeof(float);
+    WQ_REQUIRE(smem <= 200 * 1024, "wq_self_attn_decode: H * t_max too large for shared memory");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == WQ_F16) {
+        auto kern = k_self_attn_decode<__half>;
+        if (smem > 48 * 1024) WQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)B, H * 32, smem, s>>>((const __half *)q, (const __half *)k, (const __half *)v, ld, scaling,
+                                               (__half *)k_cache, (__half *)v_cache, t_max, pos, H, (__half *)out,
+                                               threshold, ca, row_stats, col_flags);
+    } else {
+        auto kern = k_self_attn_decode<__nv_bfloat16>;
+        if (smem > 48 * 1024) WQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)B, H * 32, smem, s>>>((const __nv_bfloat16 *)q, (const __nv_bfloat16 *)k,
+                                               (const __nv_bfloat16 *)v, ld, scaling, (__nv_bfloat16 *)k_cache,
+                                               (__nv_bfloat16 *)v_cache, t_max, pos, H, (__nv_bfloat16 *)out,
+                                               threshold, nullptr, nullptr, nullptr);
+    }
+    WQ_LAUNCH_CHECK();
+    return WQ_OK;
+}

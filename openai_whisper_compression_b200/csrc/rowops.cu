@@ -1,0 +1,249 @@
+// rowops.cu -- row-wise producers fused with the LLM.int8 activation quantizer.
+//
+// The quantized linears of a Whisper layer are fed by three kinds of producer: a LayerNorm (q/k/v, cross q,
+// fc1), a GELU (fc2) and an attention output (out_proj).  bitsandbytes' Linear8bitLt quantizes its input row by
+// row (int8_vectorwise_quant) in a launch of its own, and HF adds the residual in another
+// (modeling_whisper.py: `hidden_states = residual + hidden_states`, `self_attn_layer_norm`, `activation_fn`).
+// These kernels produce the fp16 tensor HF would have produced AND its int8 row quantization in one pass:
+//
+//   k_add_ln_quant : x' = x + delta (fp16 add, as torch), h = LayerNorm(x') -> x', h, [CA, SCA, outlier flags]
+//   k_gelu_quant   : h = gelu(x) (erf form, fp32 math, as torch)          -> h,     [CA, SCA, outlier flags]
+//
+// The int8 codes are computed from the ROUNDED fp16 h, with exactly the arithmetic of k_quant_i8_rowwise_bnb
+// (quant.cu), so `CA, SCA, flags` are bit-identical to running the stand-alone quantizer on the h written here.
+// One warp per row; HBM-bound (decode: launch-bound, which is the point of fusing).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;        // rows per CTA
+constexpr int kMaxChunks = 8;    // 8 x 256 columns held in registers by the LayerNorm kernel
+
+__device__ __forceinline__ float warp_sum_f32(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// |v| contribution to the row absmax under the LLM.int8 rule: outliers (|v| >= threshold) do not count.
+__device__ __forceinline__ float absmax_step(float am, float v, bool sparse, float threshold) {
+    const float x = fabsf(v);
+    return (!sparse || x < threshold) ? fmaxf(am, x) : am;
+}
+
+// int8 code of one element (same arithmetic as k_quant_i8_rowwise_bnb); raises the column flag for outliers.
+__device__ __forceinline__ uint32_t quant_elem(float v, float scale, bool sparse, float threshold,
+                                               int32_t *col_flags, int64_t col, int64_t cols) {
+    int q;
+    if (sparse && !(fabsf(v) < threshold)) {
+        q = 0;
+        col_flags[col] = 1;
+        col_flags[cols] = 1;
+    } else {
+        q = __float2int_rn(__fmul_rn(v, scale));
+    }
+    return (uint32_t)(q & 0xff);
+}
+
+template <typename T> struct Vec8 {
+    uint4 raw;
+    __device__ __forceinline__ T get(int j) const { return reinterpret_cast<const T *>(&raw)[j]; }
+    __device__ __forceinline__ void set(int j, T v) { reinterpret_cast<T *>(&raw)[j] = v; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// x' = x + delta ; h = LayerNorm(x') ; optional int8 row quantization of h.  cols % 8 == 0, cols <= 2048.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kWarps * 32)
+k_add_ln_quant(const T *x, const T *__restrict__ delta, const T *__restrict__ gamma,
+               const T *__restrict__ beta, float eps, int64_t rows, int cols, T *x_out /* may alias x */,
+               T *__restrict__ h_out, float threshold, int8_t *__restrict__ ca, float *__restrict__ row_stats,
+               int32_t *__restrict__ col_flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int64_t base = row * cols;
+    const bool sparse = threshold > 0.0f;
+
+    float v[kMaxChunks][8];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kMaxChunks; ++i) {
+        const int c = i * 256 + lane * 8;
+        if (c < cols) {
+            Vec8<T> a;
+            a.raw = *reinterpret_cast<const uint4 *>(x + base + c);
+            if (delta != nullptr) {
+                Vec8<T> d;
+                d.raw = *reinterpret_cast<const uint4 *>(delta + base + c);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a.set(j, from_f32<T>(__fadd_rn(to_f32(a.get(j)), to_f32(d.get(j)))));
+                *reinterpret_cast<uint4 *>(x_out + base + c) = a.raw;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[i][j] = to_f32(a.get(j));
+                sum += v[i][j];
+            }
+        }
+    }
+    const float mean = warp_sum_f32(sum) / (float)cols;
+    float m2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kMaxChunks; ++i) {
+        if (i * 256 + lane * 8 < cols) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = v[i][j] - mean;
+                m2 += d * d;
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum_f32(m2) / (float)cols + eps);
+
+    float am = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kMaxChunks; ++i) {
+        const int c = i * 256 + lane * 8;
+        if (c < cols) {
+            Vec8<T> g, b, h;
+            g.raw = *reinterpret_cast<const uint4 *>(gamma + c);
+            b.raw = *reinterpret_cast<const uint4 *>(beta + c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                // torch's layer_norm kernel: gamma * (rstd * (x - mean)) + beta in fp32, rounded once
+                const T r = from_f32<T>(to_f32(g.get(j)) * (rstd * (v[i][j] - mean)) + to_f32(b.get(j)));
+                h.set(j, r);
+                v[i][j] = to_f32(r);
+                am = absmax_step(am, v[i][j], sparse, threshold);
+            }
+            *reinterpret_cast<uint4 *>(h_out + base + c) = h.raw;
+        }
+    }
+    if (ca == nullptr) return;
+    am = warp_max(am);
+    if (lane == 0) row_stats[row] = am;
+    const float scale = __fdiv_rn(127.0f, am);
+#pragma unroll
+    for (int i = 0; i < kMaxChunks; ++i) {
+        const int c = i * 256 + lane * 8;
+        if (c < cols) {
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t q = quant_elem(v[i][j], scale, sparse, threshold, col_flags, c + j, cols);
+                if (j < 4) lo |= q << (8 * j); else hi |= q << (8 * (j - 4));
+            }
+            *reinterpret_cast<uint2 *>(ca + base + c) = make_uint2(lo, hi);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// h = gelu(x) (torch approximate='none': x * 0.5 * (1 + erf(x / sqrt(2))) in fp32); optional int8 row
+// quantization of h.  Two passes over the row (the second re-reads the lane's own stores); cols % 8 == 0.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kWarps * 32)
+k_gelu_quant(const T *__restrict__ x, int64_t rows, int64_t cols, T *__restrict__ h_out, float threshold,
+             int8_t *__restrict__ ca, float *__restrict__ row_stats, int32_t *__restrict__ col_flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int64_t base = row * cols;
+    const bool sparse = threshold > 0.0f;
+    float am = 0.0f;
+    for (int64_t c = lane * 8; c < cols; c += 256) {
+        Vec8<T> a, h;
+        a.raw = *reinterpret_cast<const uint4 *>(x + base + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float f = to_f32(a.get(j));
+            const T r = from_f32<T>(f * 0.5f * (1.0f + erff(f * 0.70710678118654752440f)));
+            h.set(j, r);
+            am = absmax_step(am, to_f32(r), sparse, threshold);
+        }
+        *reinterpret_cast<uint4 *>(h_out + base + c) = h.raw;
+    }
+    if (ca == nullptr) return;
+    am = warp_max(am);
+    if (lane == 0) row_stats[row] = am;
+    const float scale = __fdiv_rn(127.0f, am);
+    for (int64_t c = lane * 8; c < cols; c += 256) {
+        Vec8<T> h;
+        h.raw = *reinterpret_cast<const uint4 *>(h_out + base + c);     // this lane's own store
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t q = quant_elem(to_f32(h.get(j)), scale, sparse, threshold, col_flags, c + j, cols);
+            if (j < 4) lo |= q << (8 * j); else hi |= q << (8 * (j - 4));
+        }
+        *reinterpret_cast<uint2 *>(ca + base + c) = make_uint2(lo, hi);
+    }
+}
+
+}  // namespace
+
+extern "C" int wq_add_layernorm_quant(const void *x, const void *delta, int dtype, const void *gamma,
+                                      const void *beta, float eps, int64_t rows, int64_t cols, void *x_out,
+                                      void *h_out, float threshold, int8_t *ca, float *row_stats,
+                                      int32_t *col_flags, wq_stream_t stream) {
+    WQ_REQUIRE(rows >= 0 && cols > 0, "wq_add_layernorm_quant: bad shape");
+    WQ_REQUIRE(cols % 8 == 0 && cols <= 256 * kMaxChunks,
+               "wq_add_layernorm_quant: cols must be a multiple of 8 and <= %d (got %lld)", 256 * kMaxChunks,
+               (long long)cols);
+    WQ_REQUIRE(dtype == WQ_F16 || dtype == WQ_BF16, "wq_add_layernorm_quant: dtype must be f16 or bf16");
+    WQ_REQUIRE(threshold >= 0.0f, "wq_add_layernorm_quant: negative threshold");
+    if (rows == 0) return WQ_OK;
+    WQ_REQUIRE(x && gamma && beta && h_out, "wq_add_layernorm_quant: null pointer");
+    WQ_REQUIRE(delta == nullptr || x_out != nullptr, "wq_add_layernorm_quant: delta needs x_out");
+    WQ_REQUIRE(ca == nullptr || (dtype == WQ_F16 && row_stats != nullptr),
+               "wq_add_layernorm_quant: the int8 outputs need fp16 rows and row_stats");
+    WQ_REQUIRE(ca == nullptr || threshold == 0.0f || col_flags, "wq_add_layernorm_quant: threshold needs col_flags");
+    WQ_REQUIRE(wq_aligned(x, 16) && wq_aligned(h_out, 16) && wq_aligned(gamma, 16) && wq_aligned(beta, 16) &&
+                   (delta == nullptr || (wq_aligned(delta, 16) && wq_aligned(x_out, 16))) &&
+                   (ca == nullptr || wq_aligned(ca, 8)),
+               "wq_add_layernorm_quant: pointers must be 16-byte aligned");
+    const unsigned grid = (unsigned)((rows + kWarps - 1) / kWarps);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == WQ_F16) {
+        k_add_ln_quant<__half><<<grid, kWarps * 32, 0, s>>>(
+            (const __half *)x, (const __half *)delta, (const __half *)gamma, (const __half *)beta, eps, rows,
+            (int)cols, (__half *)x_out, (__half *)h_out, threshold, ca, row_stats, col_flags);
+    } else {
+        k_add_ln_quant<__nv_bfloat16><<<grid, kWarps * 32, 0, s>>>(
+            (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)delta, (const __nv_bfloat16 *)gamma,
+            (const __nv_bfloat16 *)beta, eps, rows, (int)cols, (__nv_bfloat16 *)x_out, (__nv_bfloat16 *)h_out,
+            threshold, nullptr, nullptr, nullptr);
+    }
+    WQ_LAUNCH_CHECK();
+    return WQ_OK;
+}
+
+extern "C" int wq_gelu_quant(const void *x, int dtype, int64_t rows, int64_t cols, void *h_out, float threshold,
+                             int8_t *ca, float *row_stats, int32_t *col_flags, wq_stream_t stream) {
+    WQ_REQUIRE(rows >= 0 && cols > 0, "wq_gelu_quant: bad shape");
+    WQ_REQUIRE(cols % 8 == 0, "wq_gelu_quant: cols must be a multiple of 8 (got %lld)", (long long)cols);
+    WQ_REQUIRE(dtype == WQ_F16 || dtype == WQ_BF16, "wq_gelu_quant: dtype must be f16 or bf16");
+    WQ_REQUIRE(threshold >= 0.0f, "wq_gelu_quant: negative threshold");
+    if (rows == 0) return WQ_OK;
+    WQ_REQUIRE(x && h_out, "wq_gelu_quant: null pointer");
+    WQ_REQUIRE(ca == nullptr || (dtype == WQ_F16 && row_stats != nullptr),
+               "wq_gelu_quant: the int8 outputs need fp16 rows and row_stats");
+    WQ_REQUIRE(ca == nullptr || threshold == 0.0f || col_flags, "wq_gelu_quant: threshold needs col_flags");
+    WQ_REQUIRE(wq_aligned(x, 16) && wq_aligned(h_out, 16) && (ca == nullptr || wq_aligned(ca, 8)),
+               "wq_gelu_quant: pointers must be 16-byte aligned");
+    const unsigned grid = (unsigned)((rows + kWarps - 1) / kWarps);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == WQ_F16) {
+        k_gelu_quant<__half><<<grid, kWarps * 32, 0, s>>>((const __half *)x, rows, cols, (__half *)h_out, threshold,
+                                                          ca, row_stats, col_flags);
+    } else {
+        k_gelu_quant<__nv_bfloat16><<<grid, kWarps * 32, 0, s>>>((const __nv_bfloat16 *)x, rows, cols,
+                                                                 (__nv_bfloat16 *)h_out, threshold, nullptr, nullptr,
+                                                                 nullptr);
+    }
+    WQ_LAUNCH_CHECK();
+    return WQ_OK;
+}

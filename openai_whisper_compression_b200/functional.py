@@ -285,6 +285,85 @@ def linear8bitlt(x: torch.Tensor, cb: torch.Tensor, scb: torch.Tensor, bias: Opt
 
 
 # ----------------------------------------------------------------------------------------------
+# producers fused with the LLM.int8 quantizer (rowops.cu, attn_decode.cu)
+# ----------------------------------------------------------------------------------------------
+def _quant_outputs(rows: int, cols: int, device, threshold: Optional[float]):
+    """(ca, sca, state) buffers for a fused producer; all None when threshold is None (no quantization)."""
+    if threshold is None:
+        return None, None, None
+    ca = torch.empty((rows, cols), dtype=torch.int8, device=device)
+    sca = torch.empty((rows,), dtype=torch.float32, device=device)
+    state = OutlierState.get(device, cols) if threshold > 0.0 else None
+    return ca, sca, state
+
+
+def add_layernorm_quant(x: torch.Tensor, delta: Optional[torch.Tensor], weight: torch.Tensor, bias: torch.Tensor,
+                        eps: float, threshold: Optional[float] = None):
+    """x' = x + delta (delta may be None), h = layer_norm(x') and, with a threshold, the Linear8bitLt row
+    quantization of h -- one launch.  Returns (x', h, (ca, sca, state) | None); shapes follow x."""
+    cols = x.shape[-1]
+    x2 = x.reshape(-1, cols)
+    d2 = None if delta is None else delta.reshape(-1, cols)
+    _need_cuda(x2, d2, weight, bias)
+    rows = x2.shape[0]
+    x_out = torch.empty_like(x2) if d2 is not None else x2
+    h = torch.empty_like(x2)
+    ca, sca, state = _quant_outputs(rows, cols, x.device, threshold)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().wq_add_layernorm_quant(
+            _ptr(x2), _ptr(d2), _DT[x2.dtype], _ptr(weight), _ptr(bias), float(eps), rows, cols,
+            _ptr(x_out) if d2 is not None else None, _ptr(h), float(threshold or 0.0), _ptr(ca), _ptr(sca),
+            _ptr(state.col_flags) if state is not None else None, _stream()), "wq_add_layernorm_quant")
+    STATS.launches += 1
+    quant = None if threshold is None else (ca, sca, state)
+    return x_out.view(x.shape), h.view(x.shape), quant
+
+
+def gelu_quant(x: torch.Tensor, threshold: Optional[float] = None):
+    """h = gelu(x) (erf form) and, with a threshold, the Linear8bitLt row quantization of h -- one launch.
+    Returns (h, (ca, sca, state) | None)."""
+    cols = x.shape[-1]
+    x2 = x.reshape(-1, cols)
+    _need_cuda(x2)
+    rows = x2.shape[0]
+    h = torch.empty_like(x2)
+    ca, sca, state = _quant_outputs(rows, cols, x.device, threshold)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().wq_gelu_quant(_ptr(x2), _DT[x2.dtype], rows, cols, _ptr(h), float(threshold or 0.0),
+                                             _ptr(ca), _ptr(sca),
+                                             _ptr(state.col_flags) if state is not None else None, _stream()),
+                   "wq_gelu_quant")
+    STATS.launches += 1
+    return h.view(x.shape), (None if threshold is None else (ca, sca, state))
+
+
+def self_attn_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scaling: float, k_cache: torch.Tensor,
+                     v_cache: torch.Tensor, pos: torch.Tensor, num_heads: int, threshold: Optional[float] = None):
+    """One decode step of WhisperAttention self-attention: append k/v at `pos` (device int64 scalar) to the
+    [B, t_max, H*64] caches and attend over positions 0..pos.  q/k/v: [B, H*64] rows with a common row
+    stride (column blocks of a fused projection are fine).  Returns (out [B, H*64], (ca, sca, state) | None)."""
+    B, d = q.shape
+    ld = q.stride(0)
+    if not (k.shape == q.shape == v.shape and k.stride(0) == ld == v.stride(0)
+            and q.stride(1) == k.stride(1) == v.stride(1) == 1):
+        raise RuntimeError("self_attn_decode: q, k, v must be [B, H*64] with unit column stride and one row stride")
+    if d != num_heads * 64 or k_cache.shape != v_cache.shape or k_cache.shape[0] != B or k_cache.shape[2] != d:
+        raise RuntimeError("self_attn_decode: caches must be [B, t_max, H*64] (head_dim 64)")
+    if pos.dtype != torch.int64 or not pos.is_cuda:
+        raise RuntimeError("self_attn_decode: pos must be a CUDA int64 scalar tensor")
+    _need_cuda(k_cache, v_cache)
+    out = torch.empty((B, d), dtype=q.dtype, device=q.device)
+    ca, sca, state = _quant_outputs(B, d, q.device, threshold)
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.load().wq_self_attn_decode(
+            _ptr(q), _ptr(k), _ptr(v), ld, _DT[q.dtype], float(scaling), _ptr(k_cache), _ptr(v_cache), B,
+            num_heads, k_cache.shape[1], _ptr(pos), _ptr(out), float(threshold or 0.0), _ptr(ca), _ptr(sca),
+            _ptr(state.col_flags) if state is not None else None, _stream()), "wq_self_attn_decode")
+    STATS.launches += 1
+    return out, (None if threshold is None else (ca, sca, state))
+
+
+# ----------------------------------------------------------------------------------------------
 # optimum-quanto qint8
 # ----------------------------------------------------------------------------------------------
 def quanto_quantize_qint8(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -1,0 +1,181 @@
+"""Fused producers (rowops.cu, attn_decode.cu) through the C ABI.
+
+Bars: the residual add and the int8 row quantization are bit-exact (against torch's fp16 add and against the
+stand-alone quantizer -- itself oracle-checked in test_gpu_kernels.py -- run on the tensor the fused kernel
+wrote); LayerNorm / GELU / attention are floating-point producers compared with torch's own ops: at most one
+fp16 ulp apart for LayerNorm and GELU, 2e-3 absolute for attention (fp32 softmax here, fp16 P in torch's
+flash kernels).
+"""
+import pytest
+import torch
+import torch.nn.functional as TF
+
+pytestmark = pytest.mark.gpu
+
+F = None
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _load():
+    global F
+    from openai_whisper_compression_b200 import functional
+    F = functional
+    yield
+
+
+def _ulp16(ref: torch.Tensor) -> torch.Tensor:
+    """Size of one fp16 ulp at |ref| (normal range), as fp32."""
+    a = ref.float().abs().clamp_min(2.0 ** -14)
+    return torch.exp2(torch.floor(torch.log2(a)) - 10)
+
+
+def _standalone_quant(h: torch.Tensor, threshold: float):
+    """(ca, sca, flags) from the stand-alone quantizer on `h`; leaves the shared flag buffer zeroed."""
+    ca, sca, st = F.int8_vectorwise_quant(h, threshold, finalize=False)
+    flags = None
+    if st is not None:
+        flags = st.col_flags[: h.shape[-1] + 1].clone()
+        st.col_flags.zero_()
+    return ca, sca, flags
+
+
+def _take_flags(quant, cols):
+    st = quant[2]
+    if st is None:
+        return None
+    flags = st.col_flags[: cols + 1].clone()
+    st.col_flags.zero_()
+    return flags
+
+
+def _check_quant(quant, h, threshold):
+    cols = h.shape[-1]
+    got_flags = _take_flags(quant, cols)
+    ca, sca, flags = _standalone_quant(h.reshape(-1, cols), threshold)
+    assert torch.equal(quant[0], ca.reshape(quant[0].shape))
+    assert torch.equal(quant[1], sca)
+    if threshold > 0:
+        assert torch.equal(got_flags, flags)
+    else:
+        assert got_flags is None
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 384), (37, 512), (300, 768), (64, 1280), (9, 2048), (5, 8)])
+@pytest.mark.parametrize("with_delta", [True, False])
+@pytest.mark.parametrize("threshold", [None, 0.0, 6.0])
+def test_add_layernorm_quant(rows, cols, with_delta, threshold):
+    g = torch.Generator(device="cuda").manual_seed(rows * 131 + cols)
+    x = (torch.randn(rows, cols, device="cuda", generator=g) * 1.5).half()
+    delta = (torch.randn(rows, cols, device="cuda", generator=g) * 0.7).half() if with_delta else None
+    w = (1.0 + 0.2 * torch.randn(cols, device="cuda", generator=g)).half()
+    b = (0.1 * torch.randn(cols, device="cuda", generator=g)).half()
+    if threshold:
+        w[:: max(1, cols // 5)] *= 8.0          # a few columns cross the outlier threshold
+    x_in = x.clone()
+    x_new, h, quant = F.add_layernorm_quant(x, delta, w, b, 1e-5, threshold)
+    assert torch.equal(x, x_in)
+    ref_x = x + delta if with_delta else x
+    assert torch.equal(x_new, ref_x)                      # fp16 add, bit-exact
+    ref_h = TF.layer_norm(ref_x, (cols,), w, b, 1e-5)
+    err = (h.float() - ref_h.float()).abs()
+    assert bool((err <= _ulp16(ref_h)).all()), float((err / _ulp16(ref_h)).max())
+    assert (h == ref_h).float().mean().item() > 0.98
+    if threshold is None:
+        assert quant is None
+    else:
+        if threshold and rows * cols > 4000:
+            assert (h.float().abs() >= threshold).any()   # the outlier branch is exercised
+        _check_quant(quant, h, threshold)
+
+
+def test_add_layernorm_bf16_and_errors():
+    x = torch.randn(10, 512, device="cuda").bfloat16()
+    d = torch.randn(10, 512, device="cuda").bfloat16()
+    w = torch.ones(512, device="cuda").bfloat16()
+    b = torch.zeros(512, device="cuda").bfloat16()
+    x_new, h, quant = F.add_layernorm_quant(x, d, w, b, 1e-5)
+    assert quant is None and torch.equal(x_new, x + d)
+    ref = TF.layer_norm(x + d, (512,), w, b, 1e-5)
+    assert (h.float() - ref.float()).abs().max().item() <= 2.0 ** -6
+    with pytest.raises(RuntimeError, match="fp16"):
+        F.add_layernorm_quant(x, d, w, b, 1e-5, threshold=6.0)
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        F.add_layernorm_quant(torch.randn(2, 2056, device="cuda").half(), None,
+                              torch.ones(2056, device="cuda").half(), torch.zeros(2056, device="cuda").half(), 1e-5)
+    with pytest.raises(RuntimeError, match="CPU"):
+        F.add_layernorm_quant(torch.randn(2, 64).half(), None, torch.ones(64).half(), torch.zeros(64).half(), 1e-5)
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1536), (50, 2048), (257, 3072), (33, 5120), (3, 8)])
+@pytest.mark.parametrize("threshold", [None, 0.0, 6.0])
+def test_gelu_quant(rows, cols, threshold):
+    g = torch.Generator(device="cuda").manual_seed(rows * 7 + cols)
+    x = (torch.randn(rows, cols, device="cuda", generator=g) * 3.0).half()
+    h, quant = F.gelu_quant(x, threshold)
+    ref = TF.gelu(x)
+    err = (h.float() - ref.float()).abs()
+    assert bool((err <= _ulp16(ref)).all()), float((err / _ulp16(ref)).max())
+    assert (h == ref).float().mean().item() > 0.999
+    if threshold is None:
+        assert quant is None
+    else:
+        if threshold and rows * cols > 1000:
+            assert (h.float().abs() >= threshold).any()
+        _check_quant(quant, h, threshold)
+
+
+@pytest.mark.parametrize("B,H,t_max,pos", [(3, 6, 64, 0), (5, 8, 128, 17), (2, 20, 448, 447), (64, 8, 128, 64),
+                                           (1, 12, 64, 3)])
+@pytest.mark.parametrize("threshold", [None, 6.0])
+@pytest.mark.parametrize("fused_qkv", [True, False])
+def test_self_attn_decode(B, H, t_max, pos, threshold, fused_qkv):
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + H * 10 + pos)
+    if fused_qkv:
+        qkv = (torch.randn(B, 3 * d, device="cuda", generator=g) * 2.0).half()
+        q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+    else:
+        q, k, v = ((torch.randn(B, d, device="cuda", generator=g) * 2.0).half() for _ in range(3))
+    if threshold:
+        v = v.clone() if not fused_qkv else v
+    kc = (torch.randn(B, t_max, d, device="cuda", generator=g)).half()
+    vc = (torch.randn(B, t_max, d, device="cuda", generator=g) * (8.0 if threshold else 1.0)).half()
+    kc0, vc0 = kc.clone(), vc.clone()
+    pos_t = torch.tensor([pos], dtype=torch.int64, device="cuda")
+    scaling = 0.125
+    out, quant = F.self_attn_decode(q, k, v, scaling, kc, vc, pos_t, H, threshold)
+    # cache append: row `pos` replaced, everything else untouched
+    kc0[:, pos] = k
+    vc0[:, pos] = v
+    assert torch.equal(kc, kc0) and torch.equal(vc, vc0)
+    # reference: HF's arithmetic in fp32 on the same (rounded) operands
+    qs = (q * scaling).float().view(B, H, 1, 64)
+    kk = kc0[:, : pos + 1].float().view(B, pos + 1, H, 64).transpose(1, 2)
+    vv = vc0[:, : pos + 1].float().view(B, pos + 1, H, 64).transpose(1, 2)
+    ref = torch.softmax(qs @ kk.transpose(-1, -2), dim=-1) @ vv
+    ref = ref.transpose(1, 2).reshape(B, d)
+    tol = 2e-3 * max(1.0, float(vv.abs().max()))
+    assert (out.float() - ref).abs().max().item() <= tol
+    if threshold is None:
+        assert quant is None
+    else:
+        _check_quant(quant, out, threshold)
+
+
+def test_self_attn_decode_matches_torch_sdpa_and_argument_checks():
+    B, H, t_max, pos = 4, 8, 64, 20
+    d = H * 64
+    q, k, v = ((torch.randn(B, d, device="cuda")).half() for _ in range(3))
+    kc = torch.randn(B, t_max, d, device="cuda").half()
+    vc = torch.randn(B, t_max, d, device="cuda").half()
+    pos_t = torch.tensor([pos], dtype=torch.int64, device="cuda")
+    out, _ = F.self_attn_decode(q, k, v, 0.125, kc, vc, pos_t, H)
+    qh = (q * 0.125).view(B, 1, H, 64).transpose(1, 2)
+    kh = kc[:, : pos + 1].view(B, pos + 1, H, 64).transpose(1, 2)
+    vh = vc[:, : pos + 1].view(B, pos + 1, H, 64).transpose(1, 2)
+    ref = TF.scaled_dot_product_attention(qh, kh, vh, scale=1.0).transpose(1, 2).reshape(B, d)
+    assert (out.float() - ref.float()).abs().max().item() <= 4e-3
+    with pytest.raises(RuntimeError, match="head_dim 64"):
+        F.self_attn_decode(q, k, v, 0.125, kc, vc, pos_t, 4)
+    with pytest.raises(RuntimeError, match="int64"):
+        F.self_attn_decode(q, k, v, 0.125, kc, vc, pos_t.int(), H)
