@@ -41,6 +41,8 @@ class GraphedGreedy:
         self._orig_sample = None
         self.max_states = 4
         self.host_postprocess = True
+        self.fuse_int8 = True          # producer-fused decode step for all-Linear8bitLt decoders
+        self.own_attention = True      # attn_decode.cu instead of index_copy + mask + SDPA
         self.replays = 0
         self.fallbacks = 0
 
@@ -80,24 +82,34 @@ class GraphedGreedy:
     # ------------------------------------------------------------------------------------------
     def _decoder_step(self, st: _State):
         """One token for every utterance: reads st.tok / st.pos, writes st.logits."""
+        if st.fused is not None:
+            return self._decoder_step_int8(st)
         model = self.model
         dec = model.model.decoder
         B, H, hd, d = st.B, st.H, st.hd, st.d
         pos = st.pos
         x = dec.embed_tokens(st.tok) + dec.embed_positions.weight.index_select(0, pos)
-        st.mask.copy_(st.arange <= pos)
-        mask = st.mask.view(1, 1, 1, -1)
+        if not st.own_attn:
+            st.mask.copy_(st.arange <= pos)
+            mask = st.mask.view(1, 1, 1, -1)
         for li, layer in enumerate(dec.layers):
             sa, ca = layer.self_attn, layer.encoder_attn
             res = x
             h = layer.self_attn_layer_norm(x)
-            q = (sa.q_proj(h) * sa.scaling).view(B, 1, H, hd).transpose(1, 2)
-            k = sa.k_proj(h).view(B, 1, H, hd).transpose(1, 2)
-            v = sa.v_proj(h).view(B, 1, H, hd).transpose(1, 2)
-            st.k[li].index_copy_(2, pos, k)
-            st.v[li].index_copy_(2, pos, v)
-            a = TF.scaled_dot_product_attention(q, st.k[li], st.v[li], attn_mask=mask, scale=1.0)
-            x = res + sa.out_proj(a.transpose(1, 2).reshape(B, 1, d))
+            if st.own_attn:
+                # scaling, cache append and attention over positions 0..pos in one launch (attn_decode.cu)
+                a, _ = F.self_attn_decode(sa.q_proj(h).view(B, d), sa.k_proj(h).view(B, d), sa.v_proj(h).view(B, d),
+                                          sa.scaling, st.k[li], st.v[li], pos, H)
+                a = a.view(B, 1, d)
+            else:
+                q = (sa.q_proj(h) * sa.scaling).view(B, 1, H, hd).transpose(1, 2)
+                k = sa.k_proj(h).view(B, 1, H, hd).transpose(1, 2)
+                v = sa.v_proj(h).view(B, 1, H, hd).transpose(1, 2)
+                st.k[li].index_copy_(2, pos, k)
+                st.v[li].index_copy_(2, pos, v)
+                a = TF.scaled_dot_product_attention(q, st.k[li], st.v[li], attn_mask=mask, scale=1.0)
+                a = a.transpose(1, 2).reshape(B, 1, d)
+            x = res + sa.out_proj(a)
             res = x
             h = layer.encoder_attn_layer_norm(x)
             q = (ca.q_proj(h) * ca.scaling).view(B, 1, H, hd).transpose(1, 2)
@@ -107,7 +119,105 @@ class GraphedGreedy:
             h = layer.final_layer_norm(x)
             x = res + layer.fc2(layer.activation_fn(layer.fc1(h)))
         x = dec.layer_norm(x)
-        st.logits.copy_(model.proj_out(x)[:, -1, :])
+        self._project(st, x.view(B, d))
+
+    def _project(self, st: _State, h: torch.Tensor):
+        """Vocabulary projection of the final hidden rows [B, d] into st.logits."""
+        if st.proj_w is not None:
+            torch.mm(h, st.proj_w.t(), out=st.logits_padded)
+        else:
+            st.logits.copy_(self.model.proj_out(h))
+
+    def _decoder_step_int8(self, st: _State):
+        """The same step when every decoder linear is a bitsandbytes-style Linear8bitLt (fp16): each quantized
+        GEMM is fed by a producer that already wrote its int8 rows (rowops.cu / attn_decode.cu), q/k/v share one
+        GEMM over the concatenated weights, residual adds ride in the next LayerNorm launch.  13 launches per
+        layer instead of ~45; the int8 arithmetic per linear is unchanged (same codes, scales, outlier path)."""
+        dec = self.model.model.decoder
+        B, H, hd, d, thr = st.B, st.H, st.hd, st.d, st.threshold
+        x = dec.embed_tokens(st.tok).view(B, d) + dec.embed_positions.weight.index_select(0, st.pos)
+        delta = None
+
+        def gemm(quant, a, w):
+            ca, sca, flags = quant
+            return F.gemm_llmint8(ca, sca, w.cb, w.scb, w.bias, a if flags is not None else None, flags)
+
+        for li, (layer, fw) in enumerate(zip(dec.layers, st.fused)):
+            ln = layer.self_attn_layer_norm
+            x, h, qt = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, thr)
+            qkv = gemm(qt, h, fw.qkv)
+            a, qt = F.self_attn_decode(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], fw.scaling, st.k[li], st.v[li],
+                                       st.pos, H, thr)
+            delta = gemm(qt, a, fw.o)
+            ln = layer.encoder_attn_layer_norm
+            x, h, qt = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, thr)
+            q = gemm(qt, h, fw.cq)
+            if fw.scaling_pow2:
+                # q * 2^-k is exact in fp16 (outside the subnormal range), so the scale can ride in the SDPA call
+                a = TF.scaled_dot_product_attention(q.view(B, 1, H, hd).transpose(1, 2), st.ck[li].transpose(1, 2),
+                                                    st.cv[li].transpose(1, 2), scale=fw.scaling)
+            else:
+                a = TF.scaled_dot_product_attention((q * fw.scaling).view(B, 1, H, hd).transpose(1, 2),
+                                                    st.ck[li].transpose(1, 2), st.cv[li].transpose(1, 2), scale=1.0)
+            a = a.transpose(1, 2).reshape(B, d)
+            delta = gemm(F.int8_vectorwise_quant(a, thr, finalize=False), a, fw.co)
+            ln = layer.final_layer_norm
+            x, h, qt = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, thr)
+            g, qt = F.gelu_quant(gemm(qt, h, fw.fc1), thr)
+            delta = gemm(qt, g, fw.fc2)
+        ln = dec.layer_norm
+        _, h, _ = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, None)
+        self._project(st, h)
+
+    def _plan_int8(self, dtype):
+        """Per-layer packed weights for _decoder_step_int8, or None when the decoder is not all-Linear8bitLt."""
+        from .bnb import Linear8bitLt
+        if dtype != torch.float16:
+            return None, 0.0
+        cfg = self.model.config
+        if cfg.activation_function != "gelu" or cfg.d_model // cfg.decoder_attention_heads != 64 or cfg.d_model > 2048:
+            return None, 0.0
+        plans, thr = [], None
+
+        def pack(mods):
+            for m in mods:
+                if type(m) is not Linear8bitLt or m.state.has_fp16_weights:
+                    return None
+                if m.weight.CB is not None:
+                    m.init_8bit_state()
+                if m.state.CB is None or not m.state.CB.is_cuda:
+                    return None
+                if m.bias is not None and m.bias.dtype != torch.float16:
+                    m.bias.data = m.bias.data.to(torch.float16)     # what Linear8bitLt.forward does on first use
+            w = _State()
+            w.cb = torch.cat([m.state.CB for m in mods], 0).contiguous() if len(mods) > 1 else mods[0].state.CB
+            w.scb = torch.cat([m.state.SCB for m in mods]).contiguous() if len(mods) > 1 else mods[0].state.SCB
+            if all(m.bias is None for m in mods):
+                w.bias = None
+            else:       # a missing bias (k_proj) is an exact zero: fma(x, c, 0) == x * c
+                w.bias = torch.cat([m.bias.detach().float() if m.bias is not None else
+                                    torch.zeros(m.out_features, dtype=torch.float32, device=w.cb.device)
+                                    for m in mods]).contiguous()
+            w.threshold = float(mods[0].state.threshold)
+            return w if all(float(m.state.threshold) == w.threshold for m in mods) else None
+
+        for layer in self.model.model.decoder.layers:
+            sa, ca = layer.self_attn, layer.encoder_attn
+            fw = _State()
+            fw.qkv, fw.o = pack([sa.q_proj, sa.k_proj, sa.v_proj]), pack([sa.out_proj])
+            fw.cq, fw.co = pack([ca.q_proj]), pack([ca.out_proj])
+            fw.fc1, fw.fc2 = pack([layer.fc1]), pack([layer.fc2])
+            ws = [fw.qkv, fw.o, fw.cq, fw.co, fw.fc1, fw.fc2]
+            if any(w is None for w in ws) or sa.scaling != ca.scaling:
+                return None, 0.0
+            thr = ws[0].threshold if thr is None else thr
+            if any(w.threshold != thr for w in ws) or layer.fc1.out_features % 8 != 0:
+                return None, 0.0
+            fw.scaling = float(sa.scaling)
+            m, _ = __import__("math").frexp(fw.scaling)
+            fw.scaling_pow2 = (m == 0.5)
+            plans.append(fw)
+        return plans, thr
 
     def _get_state(self, B: int, t_max: int, dtype: torch.dtype, device) -> _State:
         key = (B, t_max, dtype)
@@ -127,13 +237,31 @@ class GraphedGreedy:
         st.pos = torch.zeros((1,), dtype=torch.long, device=device)
         st.arange = torch.arange(t_max, device=device)
         st.mask = torch.zeros((t_max,), dtype=torch.bool, device=device)
-        st.k = [torch.zeros((B, st.H, t_max, st.hd), dtype=dtype, device=device) for _ in range(L)]
-        st.v = [torch.zeros((B, st.H, t_max, st.hd), dtype=dtype, device=device) for _ in range(L)]
+        st.fused, st.threshold = self._plan_int8(dtype) if self.fuse_int8 else (None, 0.0)
+        st.own_attn = self.own_attention and st.hd == 64 and dtype in (torch.float16, torch.bfloat16)
+        if st.fused is not None or st.own_attn:
+            kv_shape = (B, t_max, st.d)              # projection layout: one 128-byte row per head and position
+        else:
+            kv_shape = (B, st.H, t_max, st.hd)
+        st.k = [torch.zeros(kv_shape, dtype=dtype, device=device) for _ in range(L)]
+        st.v = [torch.zeros(kv_shape, dtype=dtype, device=device) for _ in range(L)]
         # cross-attention K/V stay in the projection's own [B, S, H, hd] layout: the q_len = 1 SDPA kernel
         # streams them through their strides at the same HBM rate (scripts/attn_layout_bench.py)
         st.ck = [torch.zeros((B, S, st.H, st.hd), dtype=dtype, device=device) for _ in range(L)]
         st.cv = [torch.zeros((B, S, st.H, st.hd), dtype=dtype, device=device) for _ in range(L)]
-        st.logits = torch.zeros((B, self.model.proj_out.out_features), dtype=dtype, device=device)
+        po = self.model.proj_out
+        V = po.out_features
+        st.proj_w = None
+        if type(po) is torch.nn.Linear and po.bias is None and po.weight.dtype == dtype and V % 8 != 0:
+            # an odd vocabulary (51865) leaves cuBLAS its unaligned kernel (124 us at B = 256 against ~20 us):
+            # project onto a copy of the weight padded to a multiple of 8 rows, read the first V logits
+            Vp = -(-V // 8) * 8
+            st.proj_w = torch.zeros((Vp, po.in_features), dtype=dtype, device=device)
+            st.proj_w[:V].copy_(po.weight.detach())
+            st.logits_padded = torch.zeros((B, Vp), dtype=dtype, device=device)
+            st.logits = st.logits_padded[:, :V]
+        else:
+            st.logits = torch.zeros((B, V), dtype=dtype, device=device)
         # warm up on a side stream (lazy inits, autotuning), then capture
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
