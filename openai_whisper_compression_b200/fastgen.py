@@ -25,7 +25,7 @@ from typing import Dict, Tuple
 import torch
 import torch.nn.functional as TF
 
-from . import fastenc
+from . import fastenc, fused
 from . import functional as F
 
 
@@ -138,9 +138,7 @@ class GraphedGreedy:
         x = dec.embed_tokens(st.tok).view(B, d) + dec.embed_positions.weight.index_select(0, st.pos)
         delta = None
 
-        def gemm(quant, a, w):
-            ca, sca, flags = quant
-            return F.gemm_llmint8(ca, sca, w.cb, w.scb, w.bias, a if flags is not None else None, flags)
+        gemm = fused.gemm_int8
 
         for li, (layer, fw) in enumerate(zip(dec.layers, st.fused)):
             ln = layer.self_attn_layer_norm
@@ -171,7 +169,6 @@ class GraphedGreedy:
 
     def _plan_int8(self, dtype):
         """Per-layer packed weights for _decoder_step_int8, or None when the decoder is not all-Linear8bitLt."""
-        from .bnb import Linear8bitLt
         if dtype != torch.float16:
             return None, 0.0
         cfg = self.model.config
@@ -179,27 +176,7 @@ class GraphedGreedy:
             return None, 0.0
         plans, thr = [], None
 
-        def pack(mods):
-            for m in mods:
-                if type(m) is not Linear8bitLt or m.state.has_fp16_weights:
-                    return None
-                if m.weight.CB is not None:
-                    m.init_8bit_state()
-                if m.state.CB is None or not m.state.CB.is_cuda:
-                    return None
-                if m.bias is not None and m.bias.dtype != torch.float16:
-                    m.bias.data = m.bias.data.to(torch.float16)     # what Linear8bitLt.forward does on first use
-            w = _State()
-            w.cb = torch.cat([m.state.CB for m in mods], 0).contiguous() if len(mods) > 1 else mods[0].state.CB
-            w.scb = torch.cat([m.state.SCB for m in mods]).contiguous() if len(mods) > 1 else mods[0].state.SCB
-            if all(m.bias is None for m in mods):
-                w.bias = None
-            else:       # a missing bias (k_proj) is an exact zero: fma(x, c, 0) == x * c
-                w.bias = torch.cat([m.bias.detach().float() if m.bias is not None else
-                                    torch.zeros(m.out_features, dtype=torch.float32, device=w.cb.device)
-                                    for m in mods]).contiguous()
-            w.threshold = float(mods[0].state.threshold)
-            return w if all(float(m.state.threshold) == w.threshold for m in mods) else None
+        pack = fused.pack_int8
 
         for layer in self.model.model.decoder.layers:
             sa, ca = layer.self_attn, layer.encoder_attn
@@ -214,8 +191,7 @@ class GraphedGreedy:
             if any(w.threshold != thr for w in ws) or layer.fc1.out_features % 8 != 0:
                 return None, 0.0
             fw.scaling = float(sa.scaling)
-            m, _ = __import__("math").frexp(fw.scaling)
-            fw.scaling_pow2 = (m == 0.5)
+            fw.scaling_pow2 = fused.is_pow2(fw.scaling)
             plans.append(fw)
         return plans, thr
 

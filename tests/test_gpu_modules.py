@@ -391,7 +391,7 @@ def test_copy_free_encoder_attention_is_bit_identical(pkg, scheme):
     feats = _feats(n=5, frames=3000).half().cuda()       # real geometry: S = 1500, 6 heads x 64
     with torch.no_grad():
         ref = model.model.encoder(feats).last_hidden_state
-        assert fastenc.enable(model) == len(model.model.encoder.layers)
+        assert fastenc.enable(model, fuse_int8=False) == len(model.model.encoder.layers)
         out = model.model.encoder(feats).last_hidden_state
         fastenc.disable(model)
         back = model.model.encoder(feats).last_hidden_state
@@ -460,3 +460,47 @@ def test_fused_int8_decode_step_is_bit_identical_to_module_calls(pkg):
             for li in range(len(dec.layers)):
                 assert torch.equal(st.k[li][:, : j + 1], k2[li][:, : j + 1]), (j, li)     # bit-identical caches
                 assert torch.equal(st.v[li][:, : j + 1], v2[li][:, : j + 1]), (j, li)
+
+
+def test_fused_int8_encoder_layer_is_bit_identical_to_module_calls(pkg):
+    """fastenc's producer-fused WhisperEncoderLayer (LLM.int8): exactly the output of the same layer written with
+    the drop-in modules around the same LayerNorm / GELU kernels, and close to HF's own forward (LayerNorm
+    one-ulp differences pass through the int8 quantizers)."""
+    import torch.nn.functional as TF
+    from openai_whisper_compression_b200 import fastenc, harness, functional as F
+    model = harness.apply_scheme(harness.build_model("tiny", encoder_layers=2, decoder_layers=1), "llm_int8", "cuda")
+    feats = _feats(n=3, frames=3000).half().cuda()
+    enc = model.model.encoder
+
+    def module_layer(layer, x):
+        B, S, d = x.shape
+        sa = layer.self_attn
+        ln = layer.self_attn_layer_norm
+        h = F.add_layernorm_quant(x, None, ln.weight, ln.bias, ln.eps)[1]
+        q, k, v = (p(h).view(B, S, sa.num_heads, 64).transpose(1, 2) for p in (sa.q_proj, sa.k_proj, sa.v_proj))
+        a = TF.scaled_dot_product_attention(q, k, v, scale=sa.scaling).transpose(1, 2).reshape(B, S, d)
+        x = x + sa.out_proj(a)
+        ln = layer.final_layer_norm
+        h = F.add_layernorm_quant(x, None, ln.weight, ln.bias, ln.eps)[1]
+        x = x + layer.fc2(F.gelu_quant(layer.fc1(h))[0])
+        c = torch.finfo(torch.float16).max - 1000
+        return torch.clamp(x, min=-c, max=c)
+
+    with torch.no_grad():
+        hf = enc(feats).last_hidden_state
+        x0 = TF.gelu(enc.conv2(TF.gelu(enc.conv1(feats)))).permute(0, 2, 1) + enc.embed_positions.weight
+        x0 = x0.contiguous()
+        ref = x0
+        for layer in enc.layers:
+            ref = module_layer(layer, ref)
+        fastenc.enable(model)
+        got = x0
+        for layer in enc.layers:
+            got = layer(got, None)
+        assert all(getattr(layer, "_whisperq_plan", None) is not None for layer in enc.layers)
+        full = enc(feats).last_hidden_state
+        fastenc.disable(model)
+    assert torch.equal(got, ref)
+    assert torch.isfinite(full).all()
+    diff = (full.float() - hf.float()).abs()
+    assert diff.max().item() <= 0.15 and diff.mean().item() <= 1e-2, (diff.max().item(), diff.mean().item())
