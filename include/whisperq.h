@@ -223,6 +223,13 @@ int wq_self_attn_decode(const void *q, const void *k, const void *v, int64_t ld,
                         void *out, float threshold, int8_t *ca, float *row_stats, int32_t *col_flags,
                         wq_stream_t stream);
 
+/* Greedy token choice for `rows` utterances: out[r] = argmax_c (mask[c] ? -inf : logits[r*ld + c]),
+ * torch.argmax semantics (first index among equal maxima; NaN is the maximum).  mask: uint8/bool [cols] or
+ * NULL.  Replaces masked_fill + argmax over the [B, vocab] logits between decode steps (the Whisper logits
+ * processors the reference's generate() call installs only write -inf at length-dependent positions). */
+int wq_masked_argmax(const void *logits, int dtype, int64_t rows, int64_t cols, int64_t ld,
+                     const uint8_t *mask, int64_t *out, wq_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * WER / CER tallies -- evaluate.load("wer"/"cer").compute, evaluation.py:110-116
  * ---------------------------------------------------------------------------------------- */

@@ -183,6 +183,66 @@ k_gelu_quant(const T *__restrict__ x, int64_t rows, int64_t cols, T *__restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Greedy token choice: argmax over a row of logits with a per-call suppression mask (Whisper's logits
+// processors only ever write -inf at positions that depend on the current length: SuppressTokens,
+// SuppressTokensAtBegin, Min(New)Length -- transformers generation/logits_process.py).  torch.argmax semantics:
+// first index among equal maxima, NaN counts as the maximum.  One CTA per row.
+// ---------------------------------------------------------------------------------------------
+struct ArgBest {
+    float v;
+    int i;
+};
+__device__ __forceinline__ bool arg_better(float v, int i, const ArgBest &b) {
+    if (b.i < 0) return true;
+    const bool vn = v != v, bn = b.v != b.v;
+    if (vn || bn) return vn && (!bn || i < b.i);
+    return v > b.v || (v == b.v && i < b.i);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_masked_argmax(const T *__restrict__ logits, int64_t ld, int V, const uint8_t *__restrict__ mask,
+                int64_t *__restrict__ out) {
+    const T *row = logits + (int64_t)blockIdx.x * ld;
+    ArgBest best{0.0f, -1};
+    const int V8 = V & ~7;
+    for (int c = threadIdx.x * 8; c < V8; c += 256 * 8) {
+        Vec8<T> a;
+        a.raw = *reinterpret_cast<const uint4 *>(row + c);
+        uint2 m = make_uint2(0u, 0u);
+        if (mask != nullptr) m = *reinterpret_cast<const uint2 *>(mask + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t mb = ((j < 4 ? m.x : m.y) >> (8 * (j & 3))) & 0xffu;
+            const float v = mb ? -INFINITY : to_f32(a.get(j));
+            if (arg_better(v, c + j, best)) best = ArgBest{v, c + j};
+        }
+    }
+    for (int c = V8 + threadIdx.x; c < V; c += 256) {
+        const float v = (mask != nullptr && mask[c]) ? -INFINITY : to_f32(row[c]);
+        if (arg_better(v, c, best)) best = ArgBest{v, c};
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best.v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best.i, o);
+        if (oi >= 0 && arg_better(ov, oi, best)) best = ArgBest{ov, oi};
+    }
+    __shared__ float sv[8];
+    __shared__ int si[8];
+    if ((threadIdx.x & 31) == 0) {
+        sv[threadIdx.x >> 5] = best.v;
+        si[threadIdx.x >> 5] = best.i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (si[w] >= 0 && arg_better(sv[w], si[w], best)) best = ArgBest{sv[w], si[w]};
+        out[blockIdx.x] = best.i;
+    }
+}
+
 }  // namespace
 
 extern "C" int wq_add_layernorm_quant(const void *x, const void *delta, int dtype, const void *gamma,
@@ -244,6 +304,24 @@ extern "C" int wq_gelu_quant(const void *x, int dtype, int64_t rows, int64_t col
                                                                  (__nv_bfloat16 *)h_out, threshold, nullptr, nullptr,
                                                                  nullptr);
     }
+    WQ_LAUNCH_CHECK();
+    return WQ_OK;
+}
+
+extern "C" int wq_masked_argmax(const void *logits, int dtype, int64_t rows, int64_t cols, int64_t ld,
+                                const uint8_t *mask, int64_t *out, wq_stream_t stream) {
+    WQ_REQUIRE(rows >= 0 && cols > 0 && cols < (1ll << 31) && ld >= cols, "wq_masked_argmax: bad shape");
+    WQ_REQUIRE(dtype == WQ_F16 || dtype == WQ_BF16, "wq_masked_argmax: dtype must be f16 or bf16");
+    if (rows == 0) return WQ_OK;
+    WQ_REQUIRE(logits && out, "wq_masked_argmax: null pointer");
+    WQ_REQUIRE(ld % 8 == 0 && wq_aligned(logits, 16) && (mask == nullptr || wq_aligned(mask, 8)),
+               "wq_masked_argmax: logits rows must be 16-byte aligned (ld %% 8 == 0), mask 8-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == WQ_F16)
+        k_masked_argmax<__half><<<(unsigned)rows, 256, 0, s>>>((const __half *)logits, ld, (int)cols, mask, out);
+    else
+        k_masked_argmax<__nv_bfloat16><<<(unsigned)rows, 256, 0, s>>>((const __nv_bfloat16 *)logits, ld, (int)cols,
+                                                                        mask, out);
     WQ_LAUNCH_CHECK();
     return WQ_OK;
 }

@@ -127,6 +127,8 @@ class GraphedGreedy:
             torch.mm(h, st.proj_w.t(), out=st.logits_padded)
         else:
             st.logits.copy_(self.model.proj_out(h))
+        if st.argmax_in_graph:
+            F.masked_argmax(st.logits, st.maskrow, out=st.next)
 
     def _decoder_step_int8(self, st: _State):
         """The same step when every decoder linear is a bitsandbytes-style Linear8bitLt (fp16): each quantized
@@ -227,17 +229,20 @@ class GraphedGreedy:
         st.cv = [torch.zeros((B, S, st.H, st.hd), dtype=dtype, device=device) for _ in range(L)]
         po = self.model.proj_out
         V = po.out_features
+        Vp = -(-V // 8) * 8          # rows of the logits buffer start 16-byte aligned (vector loads, cuBLAS)
+        st.logits_padded = torch.zeros((B, Vp), dtype=dtype, device=device)
+        st.logits = st.logits_padded[:, :V]
         st.proj_w = None
         if type(po) is torch.nn.Linear and po.bias is None and po.weight.dtype == dtype and V % 8 != 0:
-            # an odd vocabulary (51865) leaves cuBLAS its unaligned kernel (124 us at B = 256 against ~20 us):
+            # an odd vocabulary (51865) leaves cuBLAS its unaligned kernel (124 us at B = 256 against ~17 us):
             # project onto a copy of the weight padded to a multiple of 8 rows, read the first V logits
-            Vp = -(-V // 8) * 8
             st.proj_w = torch.zeros((Vp, po.in_features), dtype=dtype, device=device)
             st.proj_w[:V].copy_(po.weight.detach())
-            st.logits_padded = torch.zeros((B, Vp), dtype=dtype, device=device)
-            st.logits = st.logits_padded[:, :V]
-        else:
-            st.logits = torch.zeros((B, V), dtype=dtype, device=device)
+        # greedy choice inside the graph: argmax of the logits under this step's suppression mask
+        st.argmax_in_graph = dtype in (torch.float16, torch.bfloat16)
+        st.maskrow = torch.zeros((V,), dtype=torch.bool, device=device)
+        st.next = torch.zeros((B,), dtype=torch.long, device=device)
+        st.mask_cache = {}
         # warm up on a side stream (lazy inits, autotuning), then capture
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
@@ -253,6 +258,26 @@ class GraphedGreedy:
         st.launches_per_replay = F.STATS.launches - before
         self._states[key] = st
         return st
+
+    @staticmethod
+    def _processor_signature(processors):
+        """Hashable description of mask-only processors (their masks depend on it and on the length only);
+        a fresh object when a processor's attributes are not the expected ones (then nothing is shared
+        between generate calls)."""
+        try:
+            sig = []
+            for p in processors:
+                item = [type(p).__name__]
+                for name in ("suppress_tokens", "begin_suppress_tokens", "begin_index", "prompt_length_to_skip",
+                             "min_new_tokens", "min_length", "eos_token_id"):
+                    if hasattr(p, name):
+                        v = getattr(p, name)
+                        item.append((name, tuple(v.reshape(-1).tolist()) if isinstance(v, torch.Tensor) else
+                                     tuple(v) if isinstance(v, (list, tuple)) else v))
+                sig.append(tuple(item))
+            return tuple(sig)
+        except Exception:
+            return object()
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -312,19 +337,39 @@ class GraphedGreedy:
                         return True
             return False
 
-        def run(tokens, position):
+        # With mask-only processors the greedy choice happens inside the graph (wq_masked_argmax on the fp16
+        # logits under st.maskrow); the mask of a given sequence length is evaluated once and cached.
+        in_graph = maskable and st.argmax_in_graph
+        sig = self._processor_signature(logits_processor) if in_graph else None
+
+        def mask_for(ids):
+            key = (sig, ids.shape[1])
+            m = st.mask_cache.get(key)
+            if m is None:
+                m = torch.isinf(logits_processor(ids[:1], zero_row.clone())).view(-1)
+                if len(st.mask_cache) >= 2048:
+                    st.mask_cache.clear()
+                st.mask_cache[key] = m
+            return m
+
+        def run(tokens, position, ids_after=None):
+            """Feed `tokens` at `position`; ids_after = the sequence whose next token these logits choose."""
             st.tok.copy_(tokens.view(B, 1))
             st.pos.fill_(position)
+            if in_graph and ids_after is not None:
+                st.maskrow.copy_(mask_for(ids_after))
             st.graph.replay()
             self.replays += 1
             F.STATS.launches += st.launches_per_replay
 
         for i in range(P):                       # prompt tokens (normally just <|startoftranscript|>)
-            run(input_ids[:, i], i)
+            run(input_ids[:, i], i, input_ids if i == P - 1 else None)
         cur = P
         while True:
             length = input_ids.shape[1]
-            if maskable:
+            if in_graph:
+                next_tokens = st.next.clone()
+            elif maskable:
                 row = logits_processor(input_ids[:1], zero_row.clone())
                 next_tokens = torch.argmax(st.logits.masked_fill(torch.isinf(row), float("-inf")), dim=-1)
             else:
@@ -342,7 +387,7 @@ class GraphedGreedy:
                 unfinished = unfinished & ~stopping_criteria(input_ids, None)
                 if bool(unfinished.max() == 0):
                     break
-            run(next_tokens, cur)
+            run(next_tokens, cur, input_ids)
             cur += 1
         # WhisperGenerationMixin post-processes every utterance separately (generation_whisper.py,
         # generate_with_fallback / _retrieve_segment: `seq[-1] == pad`, nonzero(), slicing): on device tensors

@@ -363,6 +363,27 @@ def self_attn_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scaling:
     return out, (None if threshold is None else (ca, sca, state))
 
 
+def masked_argmax(logits: torch.Tensor, mask: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """argmax over the last dim of [B, V] fp16/bf16 logits (unit column stride, any 16-byte aligned row
+    stride) with the columns where `mask` (bool [V]) is set treated as -inf; torch.argmax tie/NaN rules."""
+    B, V = logits.shape
+    if logits.stride(1) != 1 or not logits.is_cuda:
+        raise RuntimeError("masked_argmax: logits must be a CUDA [B, V] tensor with unit column stride")
+    if mask is not None:
+        if mask.dtype not in (torch.bool, torch.uint8) or mask.numel() != V:
+            raise RuntimeError("masked_argmax: mask must be bool/uint8 [V]")
+        _need_cuda(mask)
+    if out is None:
+        out = torch.empty((B,), dtype=torch.int64, device=logits.device)
+    with torch.cuda.device(logits.device):
+        ld = logits.stride(0) if B > 1 else -(-V // 8) * 8      # a single row has no meaningful stride
+        _lib.check(_lib.load().wq_masked_argmax(_ptr(logits), _DT[logits.dtype], B, V, ld, _ptr(mask), _ptr(out),
+                                                _stream()), "wq_masked_argmax")
+    STATS.launches += 1
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # optimum-quanto qint8
 # ----------------------------------------------------------------------------------------------

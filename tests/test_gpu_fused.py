@@ -179,3 +179,27 @@ def test_self_attn_decode_matches_torch_sdpa_and_argument_checks():
         F.self_attn_decode(q, k, v, 0.125, kc, vc, pos_t, 4)
     with pytest.raises(RuntimeError, match="int64"):
         F.self_attn_decode(q, k, v, 0.125, kc, vc, pos_t.int(), H)
+
+
+@pytest.mark.parametrize("B,V,ld", [(7, 51865, 51872), (256, 51865, 51872), (3, 1000, 1000), (1, 51866, 51872),
+                                    (5, 13, 16)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_masked_argmax_matches_torch(B, V, ld, dtype):
+    g = torch.Generator(device="cuda").manual_seed(B + V)
+    buf = torch.randn(B, ld, device="cuda", generator=g).to(dtype)
+    logits = buf[:, :V]
+    # ties (coarse values), a masked maximum, NaN rows, a fully masked row set
+    logits[0] = (logits[0] * 2).round() / 2
+    mask = torch.rand(V, device="cuda", generator=g) < 0.3
+    if B > 2:
+        logits[1, V // 2] = float("nan")
+        logits[2, :] = -7.0                                   # all equal -> first unmasked index
+    ref = torch.argmax(logits.float().masked_fill(mask, float("-inf")), dim=-1)
+    got = F.masked_argmax(logits, mask)
+    assert torch.equal(got, ref)
+    assert torch.equal(F.masked_argmax(logits), torch.argmax(logits.float(), dim=-1))
+    all_masked = torch.ones(V, dtype=torch.bool, device="cuda")
+    ref_all = torch.argmax(logits.float().masked_fill(all_masked, float("-inf")), dim=-1)
+    assert torch.equal(F.masked_argmax(logits, all_masked), ref_all)
+    with pytest.raises(RuntimeError):
+        F.masked_argmax(torch.randn(4, 51865, device="cuda").half())      # rows not 16-byte aligned
