@@ -30,6 +30,7 @@ k_self_attn_decode(const T *__restrict__ q, const T *__restrict__ k, const T *__
                    const int64_t *__restrict__ pos_ptr, int H, T *__restrict__ out, float threshold,
                    int8_t *__restrict__ ca, float *__restrict__ row_stats, int32_t *__restrict__ col_flags) {
     extern __shared__ float smem[];          // [H][t_max] scores, then [H*64] output row (fp32 of rounded values)
+    pdl_prologue_done();
     const int b = blockIdx.x;
     const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 3, sub = lane & 7;  // 4 cache rows per warp step, 8 lanes x 8 dims per row
@@ -39,6 +40,15 @@ k_self_attn_decode(const T *__restrict__ q, const T *__restrict__ k, const T *__
     float *sc = smem + (size_t)h * t_max;
     float *orow = smem + (size_t)H * t_max;
 
+    T *kc_b = kc + ((int64_t)b * t_max) * d + h * kHeadDim;
+    T *vc_b = vc + ((int64_t)b * t_max) * d + h * kHeadDim;
+    // the loops below are chains of L2 round trips (17 MB of cache, all L2-resident): pull this head's rows
+    // (one 128-byte line per position) into L1 now, while q is fetched and scaled
+    for (int t = lane; t < pos; t += 32) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(kc_b + (int64_t)t * d));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(vc_b + (int64_t)t * d));
+    }
+
     // q (scaled, rounded as HF's `q_proj(h) * scaling`), this lane's 8 dims
     float q8[8];
     load8(q + (int64_t)b * ld + h * kHeadDim + sub * 8, q8);
@@ -46,8 +56,6 @@ k_self_attn_decode(const T *__restrict__ q, const T *__restrict__ k, const T *__
     for (int j = 0; j < 8; ++j) q8[j] = to_f32(from_f32<T>(q8[j] * scaling));
 
     // append this step's k / v rows (lanes 0-7: k, lanes 8-15: v)
-    T *kc_b = kc + ((int64_t)b * t_max) * d + h * kHeadDim;
-    T *vc_b = vc + ((int64_t)b * t_max) * d + h * kHeadDim;
     if (lane < 8) {
         *reinterpret_cast<uint4 *>(kc_b + (int64_t)pos * d + sub * 8) =
             *reinterpret_cast<const uint4 *>(k + (int64_t)b * ld + h * kHeadDim + sub * 8);
@@ -57,23 +65,31 @@ k_self_attn_decode(const T *__restrict__ q, const T *__restrict__ k, const T *__
     }
     __syncwarp();
 
-    // scores
+    // scores: 16 cache rows per step (4 independent 16-byte loads per lane in flight -- the loop is a chain of
+    // L2 round trips, not bandwidth)
     float mx = -INFINITY;
-    for (int t0 = 0; t0 <= pos; t0 += 4) {
-        const int t = t0 + g;
-        float s = 0.0f;
-        if (t <= pos) {
-            float k8[8];
-            load8(kc_b + (int64_t)t * d + sub * 8, k8);
+    for (int t0 = 0; t0 <= pos; t0 += 16) {
+        uint4 kr[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s = fmaf(q8[j], k8[j], s);
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * 4 + g;
+            kr[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (t <= pos) kr[u] = *reinterpret_cast<const uint4 *>(kc_b + (int64_t)t * d + sub * 8);
         }
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (t <= pos) {
-            if (sub == 0) sc[t] = s;
-            mx = fmaxf(mx, s);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * 4 + g;
+            const T *k8 = reinterpret_cast<const T *>(&kr[u]);
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s = fmaf(q8[j], to_f32(k8[j]), s);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            if (t <= pos) {
+                if (sub == 0) sc[t] = s;
+                mx = fmaxf(mx, s);
+            }
         }
     }
     mx = warp_max(mx);
@@ -91,14 +107,23 @@ k_self_attn_decode(const T *__restrict__ q, const T *__restrict__ k, const T *__
 
     // P V
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int t0 = 0; t0 <= pos; t0 += 4) {
-        const int t = t0 + g;
-        if (t <= pos) {
-            float v8[8];
-            load8(vc_b + (int64_t)t * d + sub * 8, v8);
-            const float p = sc[t];
+    for (int t0 = 0; t0 <= pos; t0 += 16) {
+        uint4 vr[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(p, v8[j], acc[j]);
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * 4 + g;
+            vr[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (t <= pos) vr[u] = *reinterpret_cast<const uint4 *>(vc_b + (int64_t)t * d + sub * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * 4 + g;
+            if (t <= pos) {
+                const T *v8 = reinterpret_cast<const T *>(&vr[u]);
+                const float p = sc[t];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(p, to_f32(v8[j]), acc[j]);
+            }
         }
     }
 #pragma unroll
@@ -172,17 +197,16 @@ extern "C" int wq_self_attn_decode(const void *q, const void *k, const void *v, 
     if (dtype == WQ_F16) {
         auto kern = k_self_attn_decode<__half>;
         if (smem > 48 * 1024) WQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)B, H * 32, smem, s>>>((const __half *)q, (const __half *)k, (const __half *)v, ld, scaling,
-                                               (__half *)k_cache, (__half *)v_cache, t_max, pos, H, (__half *)out,
-                                               threshold, ca, row_stats, col_flags);
+        WQ_LAUNCH_PDL(kern, dim3((unsigned)B), dim3(H * 32), smem, s, (const __half *)q, (const __half *)k,
+                      (const __half *)v, ld, scaling, (__half *)k_cache, (__half *)v_cache, t_max, pos, H, (__half *)out,
+                      threshold, ca, row_stats, col_flags);
     } else {
         auto kern = k_self_attn_decode<__nv_bfloat16>;
         if (smem > 48 * 1024) WQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)B, H * 32, smem, s>>>((const __nv_bfloat16 *)q, (const __nv_bfloat16 *)k,
-                                               (const __nv_bfloat16 *)v, ld, scaling, (__nv_bfloat16 *)k_cache,
-                                               (__nv_bfloat16 *)v_cache, t_max, pos, H, (__nv_bfloat16 *)out,
-                                               threshold, nullptr, nullptr, nullptr);
+        WQ_LAUNCH_PDL(kern, dim3((unsigned)B), dim3(H * 32), smem, s, (const __nv_bfloat16 *)q,
+                      (const __nv_bfloat16 *)k, (const __nv_bfloat16 *)v, ld, scaling, (__nv_bfloat16 *)k_cache,
+                      (__nv_bfloat16 *)v_cache, t_max, pos, H, (__nv_bfloat16 *)out, threshold, (int8_t *)nullptr,
+                      (float *)nullptr, (int32_t *)nullptr);
     }
-    WQ_LAUNCH_CHECK();
     return WQ_OK;
 }

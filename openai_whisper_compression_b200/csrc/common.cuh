@@ -55,6 +55,45 @@ static inline bool wq_aligned(const void *p, size_t a) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A decode step is ~80 short kernels back to back; with this launch
+// attribute a kernel's CTAs are scheduled (launch latency, barrier/TMEM set-up, descriptor prefetch) while its
+// stream predecessor is still draining.  Contract for every kernel launched through wq_launch_pdl: call
+// pdl_prologue_done() before the first access to global memory -- it releases this grid's own dependents and then
+// blocks until the predecessor grid has completed and its writes are visible (a no-op without a programmatic
+// predecessor).  Works under stream capture (the edge becomes a programmatic graph dependency).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_prologue_done() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t wq_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                        cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+#define WQ_LAUNCH_PDL(...)                                                              \
+    do {                                                                                \
+        cudaError_t _e = wq_launch_pdl(__VA_ARGS__);                                    \
+        if (_e != cudaSuccess) {                                                        \
+            wq_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,       \
+                         cudaGetErrorString(_e));                                       \
+            return WQ_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);

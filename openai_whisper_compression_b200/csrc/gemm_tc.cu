@@ -405,6 +405,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_prologue_done();      // everything above touched only smem / TMEM / kernel parameters
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
@@ -688,8 +689,7 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cud
     const int total = args.tiles_m * args.tiles_n;
     const int grid = total < wq_sm_count() ? total : wq_sm_count();
 
-    kfn<<<grid, num_threads<BN, BMODE>(), L::TOTAL, stream>>>(ma, mb, my, args);
-    WQ_LAUNCH_CHECK();
+    WQ_LAUNCH_PDL(kfn, dim3(grid), dim3(num_threads<BN, BMODE>()), (size_t)L::TOTAL, stream, ma, mb, my, args);
     return WQ_OK;
 }
 

@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_quant_i8_rowwise_bnb(const __half *__restrict__ a, int64_t rows, int64_t cols, float threshold,
                        int8_t *__restrict__ out, float *__restrict__ row_stats,
                        int32_t *__restrict__ col_flags, int vec_ok) {
+    pdl_prologue_done();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -582,9 +583,8 @@ extern "C" int wq_quant_i8_rowwise_bnb(const void *a_f16, int64_t rows, int64_t 
     WQ_REQUIRE(threshold == 0.0f || col_flags, "wq_quant_i8_rowwise_bnb: threshold needs col_flags");
     const int vec_ok = (cols % 8 == 0) && wq_aligned(a_f16, 16) && wq_aligned(out, 8);
     const unsigned grid = (unsigned)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
-    k_quant_i8_rowwise_bnb<<<grid, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(
-        (const __half *)a_f16, rows, cols, threshold, out, row_stats, col_flags, vec_ok);
-    WQ_LAUNCH_CHECK();
+    WQ_LAUNCH_PDL(k_quant_i8_rowwise_bnb, dim3(grid), dim3(kWarpsPerCta * 32), 0, (cudaStream_t)stream,
+                  (const __half *)a_f16, rows, cols, threshold, out, row_stats, col_flags, vec_ok);
     return WQ_OK;
 }
 

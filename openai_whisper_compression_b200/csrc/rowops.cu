@@ -60,6 +60,7 @@ k_add_ln_quant(const T *x, const T *__restrict__ delta, const T *__restrict__ ga
                const T *__restrict__ beta, float eps, int64_t rows, int cols, T *x_out /* may alias x */,
                T *__restrict__ h_out, float threshold, int8_t *__restrict__ ca, float *__restrict__ row_stats,
                int32_t *__restrict__ col_flags) {
+    pdl_prologue_done();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -67,6 +68,15 @@ k_add_ln_quant(const T *x, const T *__restrict__ delta, const T *__restrict__ ga
     const bool sparse = threshold > 0.0f;
 
     float v[kMaxChunks][8];
+    Vec8<T> gam[kMaxChunks], bet[kMaxChunks];     // fetched up front: not a second L2 round trip after the statistics
+#pragma unroll
+    for (int i = 0; i < kMaxChunks; ++i) {
+        const int c = i * 256 + lane * 8;
+        if (c < cols) {
+            gam[i].raw = *reinterpret_cast<const uint4 *>(gamma + c);
+            bet[i].raw = *reinterpret_cast<const uint4 *>(beta + c);
+        }
+    }
     float sum = 0.0f;
 #pragma unroll
     for (int i = 0; i < kMaxChunks; ++i) {
@@ -107,13 +117,11 @@ k_add_ln_quant(const T *x, const T *__restrict__ delta, const T *__restrict__ ga
     for (int i = 0; i < kMaxChunks; ++i) {
         const int c = i * 256 + lane * 8;
         if (c < cols) {
-            Vec8<T> g, b, h;
-            g.raw = *reinterpret_cast<const uint4 *>(gamma + c);
-            b.raw = *reinterpret_cast<const uint4 *>(beta + c);
+            Vec8<T> h;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 // torch's layer_norm kernel: gamma * (rstd * (x - mean)) + beta in fp32, rounded once
-                const T r = from_f32<T>(to_f32(g.get(j)) * (rstd * (v[i][j] - mean)) + to_f32(b.get(j)));
+                const T r = from_f32<T>(to_f32(gam[i].get(j)) * (rstd * (v[i][j] - mean)) + to_f32(bet[i].get(j)));
                 h.set(j, r);
                 v[i][j] = to_f32(r);
                 am = absmax_step(am, v[i][j], sparse, threshold);
@@ -144,33 +152,46 @@ k_add_ln_quant(const T *x, const T *__restrict__ delta, const T *__restrict__ ga
 // h = gelu(x) (torch approximate='none': x * 0.5 * (1 + erf(x / sqrt(2))) in fp32); optional int8 row
 // quantization of h.  Two passes over the row (the second re-reads the lane's own stores); cols % 8 == 0.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int G>      // G warps share a row (G = 4 for decode-sized calls: rows are few, columns many)
 __global__ void __launch_bounds__(kWarps * 32)
 k_gelu_quant(const T *__restrict__ x, int64_t rows, int64_t cols, T *__restrict__ h_out, float threshold,
              int8_t *__restrict__ ca, float *__restrict__ row_stats, int32_t *__restrict__ col_flags) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    __shared__ float s_am[kWarps];
+    pdl_prologue_done();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * (kWarps / G) + warp / G;
+    const int part = warp % G;
+    const bool live = row < rows;
     const int64_t base = row * cols;
     const bool sparse = threshold > 0.0f;
     float am = 0.0f;
-    for (int64_t c = lane * 8; c < cols; c += 256) {
-        Vec8<T> a, h;
-        a.raw = *reinterpret_cast<const uint4 *>(x + base + c);
+    if (live) {
+        for (int64_t c = (part * 32 + lane) * 8; c < cols; c += 256 * G) {
+            Vec8<T> a, h;
+            a.raw = *reinterpret_cast<const uint4 *>(x + base + c);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float f = to_f32(a.get(j));
-            const T r = from_f32<T>(f * 0.5f * (1.0f + erff(f * 0.70710678118654752440f)));
-            h.set(j, r);
-            am = absmax_step(am, to_f32(r), sparse, threshold);
+            for (int j = 0; j < 8; ++j) {
+                const float f = to_f32(a.get(j));
+                const T r = from_f32<T>(f * 0.5f * (1.0f + erff(f * 0.70710678118654752440f)));
+                h.set(j, r);
+                am = absmax_step(am, to_f32(r), sparse, threshold);
+            }
+            *reinterpret_cast<uint4 *>(h_out + base + c) = h.raw;
         }
-        *reinterpret_cast<uint4 *>(h_out + base + c) = h.raw;
     }
     if (ca == nullptr) return;
     am = warp_max(am);
-    if (lane == 0) row_stats[row] = am;
+    if (G > 1) {
+        if (lane == 0) s_am[warp] = am;
+        __syncthreads();
+        am = 0.0f;
+#pragma unroll
+        for (int w = 0; w < G; ++w) am = fmaxf(am, s_am[(warp / G) * G + w]);
+    }
+    if (!live) return;
+    if (lane == 0 && part == 0) row_stats[row] = am;
     const float scale = __fdiv_rn(127.0f, am);
-    for (int64_t c = lane * 8; c < cols; c += 256) {
+    for (int64_t c = (part * 32 + lane) * 8; c < cols; c += 256 * G) {
         Vec8<T> h;
         h.raw = *reinterpret_cast<const uint4 *>(h_out + base + c);     // this lane's own store
         uint32_t lo = 0, hi = 0;
@@ -191,23 +212,25 @@ k_gelu_quant(const T *__restrict__ x, int64_t rows, int64_t cols, T *__restrict_
 // ---------------------------------------------------------------------------------------------
 struct ArgBest {
     float v;
-    int i;
+    int i;      // INT_MAX = nothing seen yet
 };
-__device__ __forceinline__ bool arg_better(float v, int i, const ArgBest &b) {
-    if (b.i < 0) return true;
-    const bool vn = v != v, bn = b.v != b.v;
-    if (vn || bn) return vn && (!bn || i < b.i);
-    return v > b.v || (v == b.v && i < b.i);
+__device__ __forceinline__ void arg_merge(ArgBest &b, int &nan_i, float ov, int oi, int onan) {
+    if (oi != 0x7fffffff && (b.i == 0x7fffffff || ov > b.v || (ov == b.v && oi < b.i))) b = ArgBest{ov, oi};
+    nan_i = min(nan_i, onan);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_masked_argmax(const T *__restrict__ logits, int64_t ld, int V, const uint8_t *__restrict__ mask,
                 int64_t *__restrict__ out) {
+    pdl_prologue_done();
     const T *row = logits + (int64_t)blockIdx.x * ld;
-    ArgBest best{0.0f, -1};
+    // each thread scans its columns in increasing order, so a strict `>` keeps the first maximum; NaNs are
+    // tracked on the side (torch: NaN is the maximum, first one wins)
+    ArgBest best{-INFINITY, 0x7fffffff};
+    int nan_i = 0x7fffffff;
     const int V8 = V & ~7;
-    for (int c = threadIdx.x * 8; c < V8; c += 256 * 8) {
+    for (int c = threadIdx.x * 8; c < V8; c += 512 * 8) {
         Vec8<T> a;
         a.raw = *reinterpret_cast<const uint4 *>(row + c);
         uint2 m = make_uint2(0u, 0u);
@@ -216,30 +239,33 @@ k_masked_argmax(const T *__restrict__ logits, int64_t ld, int V, const uint8_t *
         for (int j = 0; j < 8; ++j) {
             const uint32_t mb = ((j < 4 ? m.x : m.y) >> (8 * (j & 3))) & 0xffu;
             const float v = mb ? -INFINITY : to_f32(a.get(j));
-            if (arg_better(v, c + j, best)) best = ArgBest{v, c + j};
+            if (v != v) nan_i = min(nan_i, c + j);
+            else if (v > best.v || best.i == 0x7fffffff) best = ArgBest{v, c + j};
         }
     }
-    for (int c = V8 + threadIdx.x; c < V; c += 256) {
+    for (int c = V8 + threadIdx.x; c < V; c += 512) {
         const float v = (mask != nullptr && mask[c]) ? -INFINITY : to_f32(row[c]);
-        if (arg_better(v, c, best)) best = ArgBest{v, c};
+        if (v != v) nan_i = min(nan_i, c);
+        else if (v > best.v || best.i == 0x7fffffff) best = ArgBest{v, c};
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best.v, o);
         const int oi = __shfl_xor_sync(0xffffffffu, best.i, o);
-        if (oi >= 0 && arg_better(ov, oi, best)) best = ArgBest{ov, oi};
+        const int on = __shfl_xor_sync(0xffffffffu, nan_i, o);
+        arg_merge(best, nan_i, ov, oi, on);
     }
-    __shared__ float sv[8];
-    __shared__ int si[8];
+    __shared__ float sv[16];
+    __shared__ int si[16], sn[16];
     if ((threadIdx.x & 31) == 0) {
         sv[threadIdx.x >> 5] = best.v;
         si[threadIdx.x >> 5] = best.i;
+        sn[threadIdx.x >> 5] = nan_i;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w)
-            if (si[w] >= 0 && arg_better(sv[w], si[w], best)) best = ArgBest{sv[w], si[w]};
-        out[blockIdx.x] = best.i;
+        for (int w = 1; w < 16; ++w) arg_merge(best, nan_i, sv[w], si[w], sn[w]);
+        out[blockIdx.x] = nan_i != 0x7fffffff ? nan_i : best.i;
     }
 }
 
@@ -268,16 +294,15 @@ extern "C" int wq_add_layernorm_quant(const void *x, const void *delta, int dtyp
     const unsigned grid = (unsigned)((rows + kWarps - 1) / kWarps);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == WQ_F16) {
-        k_add_ln_quant<__half><<<grid, kWarps * 32, 0, s>>>(
-            (const __half *)x, (const __half *)delta, (const __half *)gamma, (const __half *)beta, eps, rows,
-            (int)cols, (__half *)x_out, (__half *)h_out, threshold, ca, row_stats, col_flags);
+        WQ_LAUNCH_PDL(k_add_ln_quant<__half>, dim3(grid), dim3(kWarps * 32), 0, s, (const __half *)x,
+                      (const __half *)delta, (const __half *)gamma, (const __half *)beta, eps, rows, (int)cols,
+                      (__half *)x_out, (__half *)h_out, threshold, ca, row_stats, col_flags);
     } else {
-        k_add_ln_quant<__nv_bfloat16><<<grid, kWarps * 32, 0, s>>>(
-            (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)delta, (const __nv_bfloat16 *)gamma,
-            (const __nv_bfloat16 *)beta, eps, rows, (int)cols, (__nv_bfloat16 *)x_out, (__nv_bfloat16 *)h_out,
-            threshold, nullptr, nullptr, nullptr);
+        WQ_LAUNCH_PDL(k_add_ln_quant<__nv_bfloat16>, dim3(grid), dim3(kWarps * 32), 0, s, (const __nv_bfloat16 *)x,
+                      (const __nv_bfloat16 *)delta, (const __nv_bfloat16 *)gamma, (const __nv_bfloat16 *)beta, eps,
+                      rows, (int)cols, (__nv_bfloat16 *)x_out, (__nv_bfloat16 *)h_out, threshold, (int8_t *)nullptr,
+                      (float *)nullptr, (int32_t *)nullptr);
     }
-    WQ_LAUNCH_CHECK();
     return WQ_OK;
 }
 
@@ -294,17 +319,19 @@ extern "C" int wq_gelu_quant(const void *x, int dtype, int64_t rows, int64_t col
     WQ_REQUIRE(ca == nullptr || threshold == 0.0f || col_flags, "wq_gelu_quant: threshold needs col_flags");
     WQ_REQUIRE(wq_aligned(x, 16) && wq_aligned(h_out, 16) && (ca == nullptr || wq_aligned(ca, 8)),
                "wq_gelu_quant: pointers must be 16-byte aligned");
-    const unsigned grid = (unsigned)((rows + kWarps - 1) / kWarps);
     cudaStream_t s = (cudaStream_t)stream;
+    const bool split = rows <= 4096 && cols >= 1024;     // few long rows: 4 warps per row
+    const int rows_per_cta = split ? kWarps / 4 : kWarps;
+    const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
     if (dtype == WQ_F16) {
-        k_gelu_quant<__half><<<grid, kWarps * 32, 0, s>>>((const __half *)x, rows, cols, (__half *)h_out, threshold,
-                                                          ca, row_stats, col_flags);
+        auto kern = split ? k_gelu_quant<__half, 4> : k_gelu_quant<__half, 1>;
+        WQ_LAUNCH_PDL(kern, dim3(grid), dim3(kWarps * 32), 0, s, (const __half *)x, rows, cols, (__half *)h_out,
+                      threshold, ca, row_stats, col_flags);
     } else {
-        k_gelu_quant<__nv_bfloat16><<<grid, kWarps * 32, 0, s>>>((const __nv_bfloat16 *)x, rows, cols,
-                                                                 (__nv_bfloat16 *)h_out, threshold, nullptr, nullptr,
-                                                                 nullptr);
+        auto kern = split ? k_gelu_quant<__nv_bfloat16, 4> : k_gelu_quant<__nv_bfloat16, 1>;
+        WQ_LAUNCH_PDL(kern, dim3(grid), dim3(kWarps * 32), 0, s, (const __nv_bfloat16 *)x, rows, cols,
+                      (__nv_bfloat16 *)h_out, threshold, (int8_t *)nullptr, (float *)nullptr, (int32_t *)nullptr);
     }
-    WQ_LAUNCH_CHECK();
     return WQ_OK;
 }
 
@@ -318,10 +345,10 @@ extern "C" int wq_masked_argmax(const void *logits, int dtype, int64_t rows, int
                "wq_masked_argmax: logits rows must be 16-byte aligned (ld %% 8 == 0), mask 8-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == WQ_F16)
-        k_masked_argmax<__half><<<(unsigned)rows, 256, 0, s>>>((const __half *)logits, ld, (int)cols, mask, out);
+        WQ_LAUNCH_PDL(k_masked_argmax<__half>, dim3((unsigned)rows), dim3(512), 0, s, (const __half *)logits, ld,
+                      (int)cols, mask, out);
     else
-        k_masked_argmax<__nv_bfloat16><<<(unsigned)rows, 256, 0, s>>>((const __nv_bfloat16 *)logits, ld, (int)cols,
-                                                                        mask, out);
-    WQ_LAUNCH_CHECK();
+        WQ_LAUNCH_PDL(k_masked_argmax<__nv_bfloat16>, dim3((unsigned)rows), dim3(512), 0, s,
+                      (const __nv_bfloat16 *)logits, ld, (int)cols, mask, out);
     return WQ_OK;
 }

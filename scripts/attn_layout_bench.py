@@ -33,3 +33,10 @@ for chunk in (32, 64, 128):
     us, _ = t(chunked)
     print(f"encoder B={B} strided in chunks of {chunk}: {us:.0f} us")
 o_pre = torch.empty(B, S, H, D, device=dev, dtype=torch.half)
+# cross-attention K/V of all decoder layers as column blocks of ONE fused projection [B, S, L*2*d]
+L = 6
+big = torch.randn(B, S, 2 * L * H * D, device=dev, dtype=torch.half)
+kb = big[:, :, 0:H * D].view(B, S, H, D).transpose(1, 2)
+vb = big[:, :, H * D:2 * H * D].view(B, S, H, D).transpose(1, 2)
+us_b, _ = t(lambda: TF.scaled_dot_product_attention(q1s, kb, vb, scale=1.0), 20)
+print(f"decode cross B={B}: K/V as column blocks of a [B,S,{2*L*H*D}] buffer: {us_b:.0f} us ({gb/us_b*1e6:.0f} GB/s)")
