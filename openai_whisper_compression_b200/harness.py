@@ -116,11 +116,22 @@ class StubProcessor:
     def __call__(self, audio, sampling_rate=16000, return_tensors="pt", **kw):
         return self.feature_extractor(audio, sampling_rate=sampling_rate, return_tensors=return_tensors, **kw)
 
+    _words: List[str] = []
+
+    def _table(self, n: int) -> List[str]:
+        if len(self._words) < n:
+            StubProcessor._words = [f"t{i}" for i in range(max(n, 51866))]
+        return self._words
+
     def decode(self, ids, **kw) -> str:
-        return " ".join(f"t{int(i)}" for i in (ids.tolist() if hasattr(ids, "tolist") else ids))
+        ids = ids.tolist() if hasattr(ids, "tolist") else list(ids)
+        words = self._table(max(ids, default=0) + 1)
+        return " ".join([words[i] for i in ids])
 
     def batch_decode(self, ids, **kw) -> List[str]:
-        return [self.decode(r) for r in ids]
+        rows = ids.tolist() if hasattr(ids, "tolist") else [list(r) for r in ids]
+        words = self._table(max((max(r, default=0) for r in rows), default=0) + 1)
+        return [" ".join([words[i] for i in r]) for r in rows]
 
 
 @torch.no_grad()

@@ -9,6 +9,7 @@ over NCCL.
 """
 from __future__ import annotations
 
+from itertools import chain
 from typing import List, Sequence
 
 import numpy as np
@@ -17,42 +18,49 @@ import torch
 from . import functional as F
 
 
-def _pack(seqs):
-    """list of int32 arrays -> (concatenated ids, int64 offsets [P+1])"""
-    off = np.zeros(len(seqs) + 1, dtype=np.int64)
-    np.cumsum([len(s) for s in seqs], out=off[1:])
-    flat = np.concatenate(seqs).astype(np.int32, copy=False) if len(seqs) else np.zeros((0,), np.int32)
-    return flat, off
-
-
-def _codepoints(text: str) -> np.ndarray:
-    return np.frombuffer(text.encode("utf-32-le"), dtype=np.uint32).astype(np.int32)
+def _host_pack(references: Sequence[str], predictions: Sequence[str]):
+    """Host side of a tally: 2P sequence pairs -- P (reference, hypothesis) word-id pairs, then P code-point
+    pairs -- as (ids int32 [ref ids..., hyp ids...], offsets int64 [ref offsets (2P+1), hyp offsets (2P+1)],
+    number of reference ids).  Word ids index one vocabulary for the whole batch (they only need to be
+    consistent within a pair).  Written for the host cost to stay small next to a 150 ms GPU step: one pass of
+    dict look-ups over the words, one utf-32 encode of all the text."""
+    P = len(references)
+    rw = [r.split() for r in references]
+    hw = [h.split() for h in predictions]
+    vocab = {}
+    sd = vocab.setdefault
+    n_rw = sum(map(len, rw))
+    words = np.array([sd(w, len(vocab)) for w in chain(chain.from_iterable(rw), chain.from_iterable(hw))],
+                     dtype=np.int32)
+    chars = np.frombuffer("".join(chain(references, predictions)).encode("utf-32-le"), dtype=np.int32)
+    n_rc = sum(map(len, references))
+    ref_len = np.fromiter(chain(map(len, rw), map(len, references)), dtype=np.int64, count=2 * P)
+    hyp_len = np.fromiter(chain(map(len, hw), map(len, predictions)), dtype=np.int64, count=2 * P)
+    if max(int(ref_len.max(initial=0)), int(hyp_len.max(initial=0))) > 4096:
+        raise ValueError("sequence longer than 4096 ids")
+    ids = np.concatenate([words[:n_rw], chars[:n_rc], words[n_rw:], chars[n_rc:]])
+    off = np.zeros(2 * (2 * P + 1), dtype=np.int64)
+    np.cumsum(ref_len, out=off[1:2 * P + 1])
+    np.cumsum(hyp_len, out=off[2 * P + 2:])
+    return ids, off, n_rw + n_rc, n_rw, n_rc
 
 
 def tally_on_device(references: Sequence[str], predictions: Sequence[str], device) -> torch.Tensor:
-    """int64[4] tally on `device`; word ids are per-pair vocab indices, chars are code points."""
+    """int64[4] tally on `device`; word ids are per-batch vocab indices, chars are code points.  One edit-distance
+    launch over the 2P pairs, two host->device copies."""
     if len(references) != len(predictions):
         raise ValueError("references and predictions differ in length")
     dev = torch.device(device)
-    if len(references) == 0:
+    P = len(references)
+    if P == 0:
         return torch.zeros(4, dtype=torch.int64, device=dev)
-    rw, hw, rc, hc = [], [], [], []
-    vocab = {}                      # one id space for the whole batch (ids only need to be consistent)
-    for ref, hyp in zip(references, predictions):
-        rw.append(np.fromiter((vocab.setdefault(w, len(vocab)) for w in ref.split()), dtype=np.int32))
-        hw.append(np.fromiter((vocab.setdefault(w, len(vocab)) for w in hyp.split()), dtype=np.int32))
-        rc.append(_codepoints(ref))
-        hc.append(_codepoints(hyp))
-    out = torch.zeros(4, dtype=torch.int64, device=dev)
-    for slot, (rs, hs) in enumerate(((rw, hw), (rc, hc))):
-        r, ro = _pack(rs)
-        h, ho = _pack(hs)
-        if max(max((len(s) for s in rs), default=0), max((len(s) for s in hs), default=0)) > 4096:
-            raise ValueError("sequence longer than 4096 ids")
-        d = F.edit_distance(torch.from_numpy(r).to(dev), torch.from_numpy(ro).to(dev),
-                            torch.from_numpy(h).to(dev), torch.from_numpy(ho).to(dev))
-        out[2 * slot] = d.sum()
-        out[2 * slot + 1] = int(ro[-1])
+    ids, off, n_ref, n_rw, n_rc = _host_pack(references, predictions)
+    ids_d = torch.from_numpy(ids).to(dev)
+    off_d = torch.from_numpy(off).to(dev)
+    d = F.edit_distance(ids_d[:n_ref], off_d[:2 * P + 1], ids_d[n_ref:], off_d[2 * P + 1:])
+    errs = d.view(2, P).sum(1)
+    out = torch.tensor([0, n_rw, 0, n_rc], dtype=torch.int64).to(dev)
+    out[0::2] = errs
     return out
 
 

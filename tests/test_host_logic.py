@@ -176,3 +176,27 @@ def test_tally_all_reduce_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_tally_host_pack_layout_matches_oracle_distances():
+    """tally._host_pack: 2P pairs (words then code points) in one id array + one offset array; the distances
+    the oracle computes from the packed layout equal those of the plain per-pair definition."""
+    import oracle
+    from openai_whisper_compression_b200 import tally
+    refs = ["the quick brown fox", "", "jumps over  the lazy dog", "ünïcödé wörds here", "same same"]
+    hyps = ["the quick brown box", "spurious", "jump over the dog", "unicode words here", "same same"]
+    ids, off, n_ref, n_rw, n_rc = tally._host_pack(refs, hyps)
+    P = len(refs)
+    assert n_rw == sum(len(r.split()) for r in refs) and n_rc == sum(len(r) for r in refs)
+    assert n_ref == n_rw + n_rc and off.shape == (2 * (2 * P + 1),)
+    ref_ids, hyp_ids = ids[:n_ref], ids[n_ref:]
+    ro, ho = off[:2 * P + 1], off[2 * P + 1:]
+    assert ro[0] == 0 and ho[0] == 0 and ro[-1] == n_ref and ho[-1] == len(hyp_ids)
+    for p in range(P):
+        vocab = {}
+        want_w = oracle.edit_distance([vocab.setdefault(w, len(vocab)) for w in refs[p].split()],
+                                      [vocab.setdefault(w, len(vocab)) for w in hyps[p].split()])
+        want_c = oracle.edit_distance([ord(c) for c in refs[p]], [ord(c) for c in hyps[p]])
+        got_w = oracle.edit_distance(list(ref_ids[ro[p]:ro[p + 1]]), list(hyp_ids[ho[p]:ho[p + 1]]))
+        got_c = oracle.edit_distance(list(ref_ids[ro[P + p]:ro[P + p + 1]]), list(hyp_ids[ho[P + p]:ho[P + p + 1]]))
+        assert (got_w, got_c) == (want_w, want_c)
