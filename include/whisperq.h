@@ -141,6 +141,14 @@ int wq_gemm_llmint8(const int8_t *ca, const float *sca, const int8_t *cb, const 
                     const float *bias, void *y_f16, int64_t M, int64_t N, int64_t K,
                     const void *a_f16, int32_t *col_flags, wq_stream_t stream);
 
+/* Same GEMM when several Linear8bitLt layers consume ONE quantized activation (HF Whisper projects the
+ * encoder output through k_proj / v_proj of every decoder layer -- WhisperAttention.forward, cross-attention
+ * branch -- and bitsandbytes would re-quantize it for each): keep_flags != 0 leaves col_flags set for the next
+ * consumer; the last consumer passes 0 (== wq_gemm_llmint8) and clears them. */
+int wq_gemm_llmint8_shared(const int8_t *ca, const float *sca, const int8_t *cb, const float *scb,
+                           const float *bias, void *y_f16, int64_t M, int64_t N, int64_t K,
+                           const void *a_f16, int32_t *col_flags, int keep_flags, wq_stream_t stream);
+
 /* The same Linear8bitLt forward for decode-shaped calls (M <= 64 rows, 64*K + K + 272 <= 200 KiB):
  * activation quantization (threshold rule), int8 products (dp4a), int8_mm_dequant and the outlier
  * side product in ONE launch; bit-identical to wq_quant_i8_rowwise_bnb + wq_gemm_llmint8.

@@ -32,6 +32,8 @@ _PROTOS = {
     "wq_quant_i8_tensor_torch": [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_quant_act_u8_tensor": [c_ptr, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_gemm_llmint8": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
+    "wq_gemm_llmint8_shared": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_int,
+                               c_ptr],
     "wq_linear_llmint8_small": [c_ptr, c_i64, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     "wq_gemm_w8a16": [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],
     "wq_gemm_w4a16": [c_ptr, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],

@@ -61,6 +61,7 @@ struct GemmArgs {
     const int8_t *ca, *cb;
     const __half *a16;
     int32_t *flags;          // [K + 2]: per-column flags, "any", completion counter
+    int keep_flags;          // 1: leave the flags set (another GEMM consumes the same quantized rows next)
 };
 
 template <int BMODE> constexpr bool is_nibble() { return BMODE == B_4BIT || BMODE == B_U4; }
@@ -580,7 +581,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     if (warp == 1) tmem_dealloc(tmem_base, ACC_STAGES * ACC_COLS);
     if constexpr (EPI == EPI_LLMINT8) {
         // outlier flags are self-cleaning: the last CTA to finish clears them for the next call
-        if (args.flags != nullptr && args.flags[args.K] != 0) {
+        if (args.flags != nullptr && !args.keep_flags && args.flags[args.K] != 0) {
             int *s_last = reinterpret_cast<int *>(tmem_holder) + 1;   // spare word next to the TMEM handle
             if (threadIdx.x == 0) {
                 __threadfence();
@@ -711,6 +712,12 @@ int check_common(const char *fn, int64_t M, int64_t N, int64_t K) {
 extern "C" int wq_gemm_llmint8(const int8_t *ca, const float *sca, const int8_t *cb, const float *scb,
                                const float *bias, void *y_f16, int64_t M, int64_t N, int64_t K, const void *a_f16,
                                int32_t *col_flags, wq_stream_t stream) {
+    return wq_gemm_llmint8_shared(ca, sca, cb, scb, bias, y_f16, M, N, K, a_f16, col_flags, 0, stream);
+}
+
+extern "C" int wq_gemm_llmint8_shared(const int8_t *ca, const float *sca, const int8_t *cb, const float *scb,
+                                      const float *bias, void *y_f16, int64_t M, int64_t N, int64_t K,
+                                      const void *a_f16, int32_t *col_flags, int keep_flags, wq_stream_t stream) {
     int rc = check_common("wq_gemm_llmint8", M, N, K);
     if (rc != WQ_OK) return rc;
     if (M == 0 || N == 0) return WQ_OK;
@@ -724,6 +731,7 @@ extern "C" int wq_gemm_llmint8(const int8_t *ca, const float *sca, const int8_t 
     args.num_kb = (int)((K + 127) / 128);
     args.row_scale = sca; args.col_scale = scb; args.bias = bias; args.out = y_f16;
     args.ca = ca; args.cb = cb; args.a16 = (const __half *)a_f16; args.flags = col_flags;
+    args.keep_flags = keep_flags ? 1 : 0;
     CUtensorMap ma, mb;
     rc = make_map_2d(&ma, ca, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, BM, 128, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;

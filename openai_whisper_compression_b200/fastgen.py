@@ -185,8 +185,9 @@ class GraphedGreedy:
             fw = _State()
             fw.qkv, fw.o = pack([sa.q_proj, sa.k_proj, sa.v_proj]), pack([sa.out_proj])
             fw.cq, fw.co = pack([ca.q_proj]), pack([ca.out_proj])
+            fw.ckv = pack([ca.k_proj, ca.v_proj])
             fw.fc1, fw.fc2 = pack([layer.fc1]), pack([layer.fc2])
-            ws = [fw.qkv, fw.o, fw.cq, fw.co, fw.fc1, fw.fc2]
+            ws = [fw.qkv, fw.o, fw.cq, fw.co, fw.ckv, fw.fc1, fw.fc2]
             if any(w is None for w in ws) or sa.scaling != ca.scaling:
                 return None, 0.0
             thr = ws[0].threshold if thr is None else thr
@@ -225,8 +226,11 @@ class GraphedGreedy:
         st.v = [torch.zeros(kv_shape, dtype=dtype, device=device) for _ in range(L)]
         # cross-attention K/V stay in the projection's own [B, S, H, hd] layout: the q_len = 1 SDPA kernel
         # streams them through their strides at the same HBM rate (scripts/attn_layout_bench.py)
-        st.ck = [torch.zeros((B, S, st.H, st.hd), dtype=dtype, device=device) for _ in range(L)]
-        st.cv = [torch.zeros((B, S, st.H, st.hd), dtype=dtype, device=device) for _ in range(L)]
+        # (a layer's K and V are the two column blocks of one [B, S, 2d] buffer, so that an all-int8 decoder can fill
+        # both with one GEMM over [Wk; Wv])
+        st.ckv = [torch.zeros((B, S, 2 * st.d), dtype=dtype, device=device) for _ in range(L)]
+        st.ck = [t[:, :, :st.d].view(B, S, st.H, st.hd) for t in st.ckv]
+        st.cv = [t[:, :, st.d:].view(B, S, st.H, st.hd) for t in st.ckv]
         po = self.model.proj_out
         V = po.out_features
         Vp = -(-V // 8) * 8          # rows of the logits buffer start 16-byte aligned (vector loads, cuBLAS)
@@ -303,10 +307,19 @@ class GraphedGreedy:
 
         # cross-attention keys / values once per call (encoder-shaped GEMMs)
         S = enc.shape[1]
-        for li, layer in enumerate(model.model.decoder.layers):
-            ca = layer.encoder_attn
-            st.ck[li].copy_(ca.k_proj(enc).view(B, S, st.H, st.hd))
-            st.cv[li].copy_(ca.v_proj(enc).view(B, S, st.H, st.hd))
+        layers = model.model.decoder.layers
+        if st.fused is not None and enc.is_contiguous():
+            # all-Linear8bitLt decoder: the encoder output is quantized ONCE (bitsandbytes would do it in each of
+            # the 2L projections) and every layer's [Wk; Wv] GEMM writes straight into its K|V buffer
+            enc2 = enc.view(B * S, st.d)
+            qt = F.int8_vectorwise_quant(enc2, st.threshold, finalize=False)
+            for li, fw in enumerate(st.fused):
+                fused.gemm_int8(qt, enc2, fw.ckv, out=st.ckv[li], keep_flags=li + 1 < len(layers))
+        else:
+            for li, layer in enumerate(layers):
+                ca = layer.encoder_attn
+                st.ck[li].copy_(ca.k_proj(enc).view(B, S, st.H, st.hd))
+                st.cv[li].copy_(ca.v_proj(enc).view(B, S, st.H, st.hd))
 
         pad_token_id = generation_config._pad_token_tensor
         has_eos = any(hasattr(c, "eos_token_id") for c in stopping_criteria)

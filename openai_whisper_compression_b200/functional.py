@@ -237,23 +237,32 @@ def int8_vectorwise_quant(a: torch.Tensor, threshold: float = 0.0, state: Option
 
 def gemm_llmint8(ca: torch.Tensor, sca: torch.Tensor, cb: torch.Tensor, scb: torch.Tensor,
                  bias: Optional[torch.Tensor] = None, a_f16: Optional[torch.Tensor] = None,
-                 state: Optional[OutlierState] = None) -> torch.Tensor:
+                 state: Optional[OutlierState] = None, out: Optional[torch.Tensor] = None,
+                 keep_flags: bool = False) -> torch.Tensor:
     """int8_linear_matmul + int8_mm_dequant (+ mixed-precision outlier decomposition when `state`
-    carries raw flags from int8_vectorwise_quant(..., finalize=False)), one kernel; fp16 [M, N]."""
+    carries raw flags from int8_vectorwise_quant(..., finalize=False)), one kernel; fp16 [M, N].
+    out: optional contiguous fp16 [M, N] destination.  keep_flags: leave the outlier flags set because
+    another GEMM consumes the same quantized rows next (the last consumer clears them)."""
     ca2 = ca.reshape(-1, ca.shape[-1])
     _need_cuda(ca2, sca, cb, scb, bias, a_f16)
     M, K = ca2.shape
     N = cb.shape[0]
-    y = torch.empty((M, N), dtype=torch.float16, device=ca.device)
+    if out is None:
+        y = torch.empty((M, N), dtype=torch.float16, device=ca.device)
+    else:
+        if out.dtype != torch.float16 or out.numel() != M * N or not out.is_contiguous() or not out.is_cuda:
+            raise RuntimeError("gemm_llmint8: out must be a contiguous CUDA fp16 tensor with M*N elements")
+        y = out.view(M, N)
     if bias is not None and bias.dtype != torch.float32:
         if bias.dtype != torch.float16:
             raise RuntimeError("gemm_llmint8: bias must be fp16 (or its exact fp32 widening)")
         bias = bias.float()          # exact; modules pass a cached fp32 copy instead
     with torch.cuda.device(ca.device), _Timed("llmint8", M, N, K):
-        _lib.check(_lib.load().wq_gemm_llmint8(
+        _lib.check(_lib.load().wq_gemm_llmint8_shared(
             _ptr(ca2), _ptr(sca), _ptr(cb), _ptr(scb), _ptr(bias), _ptr(y), M, N, K,
             _ptr(a_f16) if state is not None else None,
-            _ptr(state.col_flags) if state is not None else None, _stream()), "wq_gemm_llmint8")
+            _ptr(state.col_flags) if state is not None else None, 1 if keep_flags else 0, _stream()),
+            "wq_gemm_llmint8")
     STATS.launches += 1
     return y
 

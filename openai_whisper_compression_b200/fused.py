@@ -49,8 +49,10 @@ def pack_int8(mods: Sequence[torch.nn.Module]) -> Optional[PackedInt8]:
     return w if all(float(m.state.threshold) == w.threshold for m in mods) else None
 
 
-def gemm_int8(quant, a: torch.Tensor, w: PackedInt8) -> torch.Tensor:
+def gemm_int8(quant, a: torch.Tensor, w: PackedInt8, out: Optional[torch.Tensor] = None,
+              keep_flags: bool = False) -> torch.Tensor:
     """Linear8bitLt's GEMM on rows that are already quantized: quant = (CA, SCA, outlier state) from a fused
     producer, `a` the fp16 rows they were made from (read only for outlier columns)."""
     ca, sca, state = quant
-    return F.gemm_llmint8(ca, sca, w.cb, w.scb, w.bias, a if state is not None else None, state)
+    return F.gemm_llmint8(ca, sca, w.cb, w.scb, w.bias, a if state is not None else None, state, out=out,
+                          keep_flags=keep_flags)

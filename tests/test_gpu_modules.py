@@ -409,6 +409,10 @@ def test_fused_int8_decode_step_is_bit_identical_to_module_calls(pkg):
     import torch.nn.functional as TF
     from openai_whisper_compression_b200 import fastgen, harness, functional as F
     model = harness.apply_scheme(harness.build_model("tiny", **REAL2), "llm_int8", "cuda")
+    with torch.no_grad():        # a few loud channels per LayerNorm, so that the outlier decomposition is in play
+        for m in model.modules():
+            if isinstance(m, torch.nn.LayerNorm):
+                m.weight[::41] *= 6.0
     feats = _feats(n=6, frames=3000).half().cuda()
     eng = fastgen.enable(model)
     T = 12
@@ -444,6 +448,15 @@ def test_fused_int8_decode_step_is_bit_identical_to_module_calls(pkg):
     start = torch.full((B, 1), model.config.decoder_start_token_id, dtype=ids.dtype, device="cuda")
     full = ids if ids.shape[1] == T + 1 else torch.cat([start, ids], 1)
     with torch.no_grad():
+        # cross-attention K/V: one shared quantization of the encoder output + [Wk; Wv] GEMMs (flags kept between
+        # consumers) == every k_proj / v_proj module quantizing it again
+        enc_out = model.model.encoder(feats).last_hidden_state
+        assert (enc_out.float().abs() >= 6.0).any()          # outlier columns are in play
+        for li, layer in enumerate(dec.layers):
+            assert torch.equal(st.ck[li].reshape(B, -1, d), layer.encoder_attn.k_proj(enc_out))
+            assert torch.equal(st.cv[li].reshape(B, -1, d), layer.encoder_attn.v_proj(enc_out))
+        from openai_whisper_compression_b200.functional import OutlierState
+        assert int(OutlierState.get(enc_out.device, d).col_flags.abs().sum()) == 0      # last consumer cleared them
         for j in range(T):
             st.tok.copy_(full[:, j:j + 1])
             st.pos.fill_(j)
