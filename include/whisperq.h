@@ -231,6 +231,17 @@ int wq_self_attn_decode(const void *q, const void *k, const void *v, int64_t ld,
                         void *out, float threshold, int8_t *ca, float *row_stats, int32_t *col_flags,
                         wq_stream_t stream);
 
+/* Decoder cross-attention for one new token per utterance (WhisperAttention.forward, cross-attention branch
+ * with cached K/V, q_len = 1): out[b] = softmax((q[b] * scaling) K[b]^T) V[b] per head over S encoder positions,
+ * fp32 running softmax.  q: [B, H*64] rows `ldq` elements apart, multiplied by `scaling` and rounded to `dtype`
+ * first (as HF does).  k, v: [B, S, H*64] with rows `ld` elements apart (a layer's K and V may be the two column
+ * blocks of one [B, S, 2*H*64] projection).  out: [B, H*64] contiguous.  HBM-bound: 2*S*H*64*sizeof(dtype) bytes
+ * per utterance.  head_dim is 64.  Optional int8 row quantization of out (ca != NULL, as above); it then needs
+ * row_counters: device int32[B], zero before the first call (the kernel leaves it zero). */
+int wq_cross_attn_decode(const void *q, int64_t ldq, int dtype, float scaling, const void *k, const void *v,
+                         int64_t ld, int64_t B, int64_t S, int H, void *out, float threshold, int8_t *ca,
+                         float *row_stats, int32_t *col_flags, int32_t *row_counters, wq_stream_t stream);
+
 /* Greedy token choice for `rows` utterances: out[r] = argmax_c (mask[c] ? -inf : logits[r*ld + c]),
  * torch.argmax semantics (first index among equal maxima; NaN is the maximum).  mask: uint8/bool [cols] or
  * NULL.  Replaces masked_fill + argmax over the [B, vocab] logits between decode steps (the Whisper logits

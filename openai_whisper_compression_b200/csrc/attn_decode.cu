@@ -30,7 +30,7 @@ k_self_attn_decode(const T *__restrict__ q, const T *__restrict__ k, const T *__
                    const int64_t *__restrict__ pos_ptr, int H, T *__restrict__ out, float threshold,
                    int8_t *__restrict__ ca, float *__restrict__ row_stats, int32_t *__restrict__ col_flags) {
     extern __shared__ float smem[];          // [H][t_max] scores, then [H*64] output row (fp32 of rounded values)
-    pdl_prologue_done();
+    pdl_wait();
     const int b = blockIdx.x;
     const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 3, sub = lane & 7;  // 4 cache rows per warp step, 8 lanes x 8 dims per row
@@ -126,6 +126,7 @@ k_self_attn_decode(const T *__restrict__ q, const T *__restrict__ k, const T *__
             }
         }
     }
+    pdl_trigger();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
@@ -207,6 +208,219 @@ extern "C" int wq_self_attn_decode(const void *q, const void *k, const void *v, 
                       (const __nv_bfloat16 *)k, (const __nv_bfloat16 *)v, ld, scaling, (__nv_bfloat16 *)k_cache,
                       (__nv_bfloat16 *)v_cache, t_max, pos, H, (__nv_bfloat16 *)out, threshold, (int8_t *)nullptr,
                       (float *)nullptr, (int32_t *)nullptr);
+    }
+    return WQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoder cross-attention for one new token per utterance: softmax(q K^T) V over the S = 1500 encoder positions.
+// This is the largest single cost of a decode step and pure HBM streaming: per utterance and layer the fp16 K and V
+// projections of the encoder output (2 x S x d x 2 bytes; 3 MB at d = 512) are read once and nothing else moves.
+// K and V stay where the k_proj / v_proj GEMM wrote them ([B, S, *] rows, `ld` elements apart; a layer's K and V
+// may be column blocks of one buffer).  CTA per (head, utterance); its 4 warps interleave over the positions, 8
+// lanes per 128-byte row, 4 rows per warp instruction, 4 instructions of K and of V in flight per lane; flash-decoding
+// style running max / sum per lane group, merged across groups (shuffles) and warps (smem) at the end.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kXWarps = 4;
+constexpr int kXUnroll = 4;
+
+struct Partial {
+    float m, l, acc[8];
+};
+
+__device__ __forceinline__ void partial_merge(Partial &a, float om, float ol, const float (&oacc)[8]) {
+    const float m = fmaxf(a.m, om);
+    const float ca = (a.m == -INFINITY) ? 0.0f : exp2f(a.m - m);
+    const float cb = (om == -INFINITY) ? 0.0f : exp2f(om - m);
+    a.l = a.l * ca + ol * cb;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a.acc[j] = a.acc[j] * ca + oacc[j] * cb;
+    a.m = m;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kXWarps * 32)
+k_cross_attn_decode(const T *__restrict__ q, int64_t ldq, float scaling, const T *__restrict__ kmat,
+                    const T *__restrict__ vmat, int64_t ld, int S, int H, T *out, float threshold,
+                    int8_t *__restrict__ ca, float *__restrict__ row_stats, int32_t *__restrict__ col_flags,
+                    int32_t *__restrict__ row_counters) {
+    __shared__ float s_part[kXWarps][8][10];      // per warp: 8 dim-groups x (m, l, acc[8])
+    __shared__ float s_red[kXWarps];
+    __shared__ int s_last;
+    pdl_wait();
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 3, sub = lane & 7;
+    const int d = H * kHeadDim;
+    constexpr float kLog2e = 1.4426950408889634f;
+
+    float q8[8];
+    load8(q + (int64_t)b * ldq + h * kHeadDim + sub * 8, q8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q8[j] = to_f32(from_f32<T>(q8[j] * scaling)) * kLog2e;   // scores in log2 units
+
+    const T *kb = kmat + (int64_t)b * S * ld + h * kHeadDim + sub * 8;
+    const T *vb = vmat + (int64_t)b * S * ld + h * kHeadDim + sub * 8;
+    Partial p;
+    p.m = -INFINITY;
+    p.l = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p.acc[j] = 0.0f;
+
+    constexpr int ROWS_PER_IT = kXWarps * 4;
+    constexpr int STEP = ROWS_PER_IT * kXUnroll;
+    uint4 kr[kXUnroll], vr[kXUnroll], kn[kXUnroll], vn[kXUnroll];
+    auto fetch = [&](int t0, uint4 (&kk)[kXUnroll], uint4 (&vv)[kXUnroll]) {
+#pragma unroll
+        for (int u = 0; u < kXUnroll; ++u) {
+            const int t = t0 + u * ROWS_PER_IT;
+            kk[u] = make_uint4(0u, 0u, 0u, 0u);
+            vv[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (t < S) {
+                kk[u] = __ldg(reinterpret_cast<const uint4 *>(kb + (int64_t)t * ld));
+                vv[u] = __ldg(reinterpret_cast<const uint4 *>(vb + (int64_t)t * ld));
+            }
+        }
+    };
+    int t0 = warp * 4 + g;
+    fetch(t0, kr, vr);
+    // the trip count must be warp-uniform (full-mask shuffles inside): bound the loop on the block start, rows past
+    // S are masked per lane
+    for (int tb = 0; tb < S; tb += STEP, t0 += STEP) {
+        fetch(t0 + STEP, kn, vn);          // next block's rows are in flight while this block is reduced
+#pragma unroll
+        for (int u = 0; u < kXUnroll; ++u) {
+            const int t = t0 + u * ROWS_PER_IT;
+            const T *k8 = reinterpret_cast<const T *>(&kr[u]);
+            const T *v8 = reinterpret_cast<const T *>(&vr[u]);
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s = fmaf(q8[j], to_f32(k8[j]), s);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            if (t < S) {
+                const float m = fmaxf(p.m, s);
+                const float corr = exp2f(p.m - m);          // exp2f(-inf) == 0 on the first row
+                const float e = exp2f(s - m);
+                p.l = p.l * corr + e;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) p.acc[j] = fmaf(e, to_f32(v8[j]), p.acc[j] * corr);
+                p.m = m;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kXUnroll; ++u) {
+            kr[u] = kn[u];
+            vr[u] = vn[u];
+        }
+    }
+    pdl_trigger();       // the streaming part is over: the successor's CTAs may take their seats
+    // merge the 4 lane groups of the warp (same dims, different rows)
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, p.m, o);
+        const float ol = __shfl_xor_sync(0xffffffffu, p.l, o);
+        float oacc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) oacc[j] = __shfl_xor_sync(0xffffffffu, p.acc[j], o);
+        partial_merge(p, om, ol, oacc);
+    }
+    if (g == 0) {
+        s_part[warp][sub][0] = p.m;
+        s_part[warp][sub][1] = p.l;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_part[warp][sub][2 + j] = p.acc[j];
+    }
+    __syncthreads();
+    if (warp == 0 && g == 0) {
+#pragma unroll
+        for (int w = 1; w < kXWarps; ++w) {
+            float oacc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) oacc[j] = s_part[w][sub][2 + j];
+            partial_merge(p, s_part[w][sub][0], s_part[w][sub][1], oacc);
+        }
+        const float inv = 1.0f / p.l;
+        uint4 raw;
+        T *o8 = reinterpret_cast<T *>(&raw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o8[j] = from_f32<T>(p.acc[j] * inv);
+        *reinterpret_cast<uint4 *>(out + (int64_t)b * d + h * kHeadDim + sub * 8) = raw;
+    }
+    if (ca == nullptr) return;
+
+    // LLM.int8 row quantization of out[b, :] by the last of this utterance's H head-CTAs to finish
+    // (int8_vectorwise_quant on the rounded values; the counter resets itself for the next launch)
+    if (threadIdx.x < 8) __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&row_counters[b], 1) == H - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const bool sparse = threshold > 0.0f;
+    const T *orow = out + (int64_t)b * d;
+    float am = 0.0f;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        const float x = fabsf(to_f32(__ldcg(orow + c)));
+        if (!sparse || x < threshold) am = fmaxf(am, x);
+    }
+    am = warp_max(am);
+    if (lane == 0) s_red[warp] = am;
+    __syncthreads();
+    am = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kXWarps; ++w) am = fmaxf(am, s_red[w]);
+    if (threadIdx.x == 0) {
+        row_stats[b] = am;
+        row_counters[b] = 0;
+    }
+    const float scale = __fdiv_rn(127.0f, am);
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        const float x = to_f32(__ldcg(orow + c));
+        int qv;
+        if (sparse && !(fabsf(x) < threshold)) {
+            qv = 0;
+            col_flags[c] = 1;
+            col_flags[d] = 1;
+        } else {
+            qv = __float2int_rn(__fmul_rn(x, scale));
+        }
+        ca[(int64_t)b * d + c] = (int8_t)qv;
+    }
+}
+
+}  // namespace
+
+extern "C" int wq_cross_attn_decode(const void *q, int64_t ldq, int dtype, float scaling, const void *k, const void *v,
+                                    int64_t ld, int64_t B, int64_t S, int H, void *out, float threshold, int8_t *ca,
+                                    float *row_stats, int32_t *col_flags, int32_t *row_counters,
+                                    wq_stream_t stream) {
+    WQ_REQUIRE(B >= 0 && B <= 65535 && S >= 1 && S < (1 << 30) && H >= 1 && H <= 65535,
+               "wq_cross_attn_decode: bad shape");
+    WQ_REQUIRE(dtype == WQ_F16 || dtype == WQ_BF16, "wq_cross_attn_decode: dtype must be f16 or bf16");
+    if (B == 0) return WQ_OK;
+    WQ_REQUIRE(q && k && v && out, "wq_cross_attn_decode: null pointer");
+    WQ_REQUIRE(ld % 8 == 0 && ld >= (int64_t)H * kHeadDim && ldq % 8 == 0 && ldq >= (int64_t)H * kHeadDim,
+               "wq_cross_attn_decode: bad row stride");
+    WQ_REQUIRE(wq_aligned(q, 16) && wq_aligned(k, 16) && wq_aligned(v, 16) && wq_aligned(out, 16),
+               "wq_cross_attn_decode: pointers must be 16-byte aligned");
+    WQ_REQUIRE(threshold >= 0.0f, "wq_cross_attn_decode: negative threshold");
+    WQ_REQUIRE(ca == nullptr || (dtype == WQ_F16 && row_stats != nullptr && row_counters != nullptr),
+               "wq_cross_attn_decode: the int8 outputs need fp16 rows, row_stats and row_counters");
+    WQ_REQUIRE(ca == nullptr || threshold == 0.0f || col_flags, "wq_cross_attn_decode: threshold needs col_flags");
+    cudaStream_t s = (cudaStream_t)stream;
+    const dim3 grid((unsigned)H, (unsigned)B);
+    if (dtype == WQ_F16) {
+        WQ_LAUNCH_PDL(k_cross_attn_decode<__half>, grid, dim3(kXWarps * 32), 0, s, (const __half *)q, ldq, scaling,
+                      (const __half *)k, (const __half *)v, ld, (int)S, H, (__half *)out, threshold, ca, row_stats,
+                      col_flags, row_counters);
+    } else {
+        WQ_LAUNCH_PDL(k_cross_attn_decode<__nv_bfloat16>, grid, dim3(kXWarps * 32), 0, s, (const __nv_bfloat16 *)q, ldq,
+                      scaling, (const __nv_bfloat16 *)k, (const __nv_bfloat16 *)v, ld, (int)S, H, (__nv_bfloat16 *)out,
+                      0.0f, (int8_t *)nullptr, (float *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr);
     }
     return WQ_OK;
 }

@@ -57,14 +57,19 @@ static inline bool wq_aligned(const void *p, size_t a) {
 // ----------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL).  A decode step is ~80 short kernels back to back; with this launch
 // attribute a kernel's CTAs are scheduled (launch latency, barrier/TMEM set-up, descriptor prefetch) while its
-// stream predecessor is still draining.  Contract for every kernel launched through wq_launch_pdl: call
-// pdl_prologue_done() before the first access to global memory -- it releases this grid's own dependents and then
-// blocks until the predecessor grid has completed and its writes are visible (a no-op without a programmatic
-// predecessor).  Works under stream capture (the edge becomes a programmatic graph dependency).
+// stream predecessor is still draining.  Contract for every kernel launched through wq_launch_pdl: call pdl_wait()
+// before the first access to global memory -- it blocks until the predecessor grid has completed and its writes
+// are visible (a no-op without a programmatic predecessor) -- and pdl_trigger() once, AFTER the wait: the
+// successor may then be scheduled.  Triggering only after the wait keeps the look-ahead at one kernel; triggering
+// at kernel entry lets the whole downstream chain of a CUDA graph pile onto the SMs (each parked CTA holds
+// registers, threads and shared memory) and cost the HBM-bound attention kernel a quarter of its bandwidth.
+// Works under stream capture (the edge becomes a programmatic graph dependency).
 // ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue_done() {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_wait();
+    pdl_trigger();
 }
 
 template <typename... KArgs, typename... Args>

@@ -19,6 +19,7 @@ logits can differ in the last fp16 bits (tests compare tokens with HF's loop).
 """
 from __future__ import annotations
 
+import os
 import types
 from typing import Dict, Tuple
 
@@ -43,6 +44,11 @@ class GraphedGreedy:
         self.host_postprocess = True
         self.fuse_int8 = True          # producer-fused decode step for all-Linear8bitLt decoders
         self.own_attention = True      # attn_decode.cu instead of index_copy + mask + SDPA
+        # cross-attention at decode time: "own" (attn_decode.cu), "cudnn" (torch SDPA) or "auto".  Both stream K/V at
+        # the HBM rate (scripts/cross_attn_bench.py: 6.7 TB/s at B = 256; own 5.3 vs 4.4 TB/s at B = 64); inside the
+        # step graph the own kernel's 128-thread CTAs leave a longer tail once heads x utterances exceed ~1.4 waves,
+        # so "auto" keeps cuDNN for those shapes (1135 vs 1190 us per step at B = 256, whisper-base)
+        self.cross_attention = os.environ.get("WQ_CROSS_ATTN", "auto")
         self.replays = 0
         self.fallbacks = 0
 
@@ -112,9 +118,16 @@ class GraphedGreedy:
             x = res + sa.out_proj(a)
             res = x
             h = layer.encoder_attn_layer_norm(x)
-            q = (ca.q_proj(h) * ca.scaling).view(B, 1, H, hd).transpose(1, 2)
-            a = TF.scaled_dot_product_attention(q, st.ck[li].transpose(1, 2), st.cv[li].transpose(1, 2), scale=1.0)
-            x = res + ca.out_proj(a.transpose(1, 2).reshape(B, 1, d))
+            if st.own_attn and st.own_cross:
+                a, _ = F.cross_attn_decode(ca.q_proj(h).view(B, d), st.ckv[li][:, :, :d], st.ckv[li][:, :, d:],
+                                           ca.scaling, H)
+                a = a.view(B, 1, d)
+            else:
+                q = (ca.q_proj(h) * ca.scaling).view(B, 1, H, hd).transpose(1, 2)
+                a = TF.scaled_dot_product_attention(q, st.ck[li].transpose(1, 2), st.cv[li].transpose(1, 2),
+                                                    scale=1.0)
+                a = a.transpose(1, 2).reshape(B, 1, d)
+            x = res + ca.out_proj(a)
             res = x
             h = layer.final_layer_norm(x)
             x = res + layer.fc2(layer.activation_fn(layer.fc1(h)))
@@ -152,15 +165,20 @@ class GraphedGreedy:
             ln = layer.encoder_attn_layer_norm
             x, h, qt = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, thr)
             q = gemm(qt, h, fw.cq)
-            if fw.scaling_pow2:
-                # q * 2^-k is exact in fp16 (outside the subnormal range), so the scale can ride in the SDPA call
-                a = TF.scaled_dot_product_attention(q.view(B, 1, H, hd).transpose(1, 2), st.ck[li].transpose(1, 2),
-                                                    st.cv[li].transpose(1, 2), scale=fw.scaling)
+            if st.own_cross:
+                # q scaling, the pass over the 1500 cached encoder positions and out_proj's quantization: one launch
+                a, qt = F.cross_attn_decode(q, st.ckv[li][:, :, :d], st.ckv[li][:, :, d:], fw.scaling, H, thr)
             else:
-                a = TF.scaled_dot_product_attention((q * fw.scaling).view(B, 1, H, hd).transpose(1, 2),
-                                                    st.ck[li].transpose(1, 2), st.cv[li].transpose(1, 2), scale=1.0)
-            a = a.transpose(1, 2).reshape(B, d)
-            delta = gemm(F.int8_vectorwise_quant(a, thr, finalize=False), a, fw.co)
+                if fw.scaling_pow2:     # q * 2^-k is exact in fp16, so the scale can ride in the SDPA call
+                    a = TF.scaled_dot_product_attention(q.view(B, 1, H, hd).transpose(1, 2),
+                                                        st.ck[li].transpose(1, 2), st.cv[li].transpose(1, 2),
+                                                        scale=fw.scaling)
+                else:
+                    a = TF.scaled_dot_product_attention((q * fw.scaling).view(B, 1, H, hd).transpose(1, 2),
+                                                        st.ck[li].transpose(1, 2), st.cv[li].transpose(1, 2), scale=1.0)
+                a = a.transpose(1, 2).reshape(B, d)
+                qt = F.int8_vectorwise_quant(a, thr, finalize=False)
+            delta = gemm(qt, a, fw.co)
             ln = layer.final_layer_norm
             x, h, qt = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, thr)
             g, qt = F.gelu_quant(gemm(qt, h, fw.fc1), thr)
@@ -218,6 +236,7 @@ class GraphedGreedy:
         st.mask = torch.zeros((t_max,), dtype=torch.bool, device=device)
         st.fused, st.threshold = self._plan_int8(dtype) if self.fuse_int8 else (None, 0.0)
         st.own_attn = self.own_attention and st.hd == 64 and dtype in (torch.float16, torch.bfloat16)
+        st.own_cross = self.cross_attention == "own" or (self.cross_attention == "auto" and B * st.H <= 1024)
         if st.fused is not None or st.own_attn:
             kv_shape = (B, t_max, st.d)              # projection layout: one 128-byte row per head and position
         else:

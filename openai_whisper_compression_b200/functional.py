@@ -372,6 +372,43 @@ def self_attn_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scaling:
     return out, (None if threshold is None else (ca, sca, state))
 
 
+_ROW_COUNTERS = {}
+
+
+def _row_counters(device, rows: int) -> torch.Tensor:
+    """Zeroed int32 scratch (self-resetting inside the kernels that use it), one per device, grown on demand."""
+    t = _ROW_COUNTERS.get(device)
+    if t is None or t.numel() < rows:
+        t = _ROW_COUNTERS[device] = torch.zeros((max(rows, 1024),), dtype=torch.int32, device=device)
+    return t
+
+
+def cross_attn_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scaling: float, num_heads: int,
+                      threshold: Optional[float] = None):
+    """One decode step of WhisperAttention cross-attention over cached encoder K/V.  q: [B, H*64] (unit column
+    stride); k, v: [B, S, H*64] views with unit column stride, dense in S (stride(0) == S * stride(1)) and one
+    common row stride.  Returns (out [B, H*64], (ca, sca, state) | None) like the other fused producers."""
+    B, d = q.shape
+    if k.shape != v.shape or k.dim() != 3 or k.shape[0] != B or k.shape[2] != d or d != num_heads * 64:
+        raise RuntimeError("cross_attn_decode: k, v must be [B, S, H*64] (head_dim 64) matching q [B, H*64]")
+    S, ld = k.shape[1], k.stride(1)
+    if not (q.stride(1) == 1 and k.stride(2) == 1 and v.stride(2) == 1 and v.stride(1) == ld
+            and k.stride(0) == S * ld and v.stride(0) == S * ld):
+        raise RuntimeError("cross_attn_decode: unsupported strides")
+    if not (q.is_cuda and k.is_cuda and v.is_cuda):
+        raise RuntimeError("cross_attn_decode: CUDA tensors only (no CPU fallback)")
+    out = torch.empty((B, d), dtype=q.dtype, device=q.device)
+    ca, sca, state = _quant_outputs(B, d, q.device, threshold)
+    counters = _row_counters(q.device, B) if threshold is not None else None
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.load().wq_cross_attn_decode(
+            _ptr(q), q.stride(0) if B > 1 else d, _DT[q.dtype], float(scaling), _ptr(k), _ptr(v), ld, B, S, num_heads,
+            _ptr(out), float(threshold or 0.0), _ptr(ca), _ptr(sca),
+            _ptr(state.col_flags) if state is not None else None, _ptr(counters), _stream()), "wq_cross_attn_decode")
+    STATS.launches += 1
+    return out, (None if threshold is None else (ca, sca, state))
+
+
 def masked_argmax(logits: torch.Tensor, mask: Optional[torch.Tensor] = None,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """argmax over the last dim of [B, V] fp16/bf16 logits (unit column stride, any 16-byte aligned row

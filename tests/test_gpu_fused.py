@@ -203,3 +203,53 @@ def test_masked_argmax_matches_torch(B, V, ld, dtype):
     assert torch.equal(F.masked_argmax(logits, all_masked), ref_all)
     with pytest.raises(RuntimeError):
         F.masked_argmax(torch.randn(4, 51865, device="cuda").half())      # rows not 16-byte aligned
+
+
+@pytest.mark.parametrize("B,H,S", [(3, 6, 1500), (70, 8, 1500), (2, 20, 1500), (5, 12, 37), (1, 8, 1)])
+@pytest.mark.parametrize("threshold", [None, 6.0])
+@pytest.mark.parametrize("kv_fused", [True, False])
+def test_cross_attn_decode(B, H, S, threshold, kv_fused):
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + H + S)
+    q = (torch.randn(B, d, device="cuda", generator=g) * 2.0).half()
+    scale_v = 8.0 if threshold else 1.0
+    if kv_fused:
+        kv = torch.randn(B, S, 2 * d, device="cuda", generator=g).half()
+        kv[:, :, d:] *= scale_v
+        k, v = kv[:, :, :d], kv[:, :, d:]
+    else:
+        k = torch.randn(B, S, d, device="cuda", generator=g).half()
+        v = (torch.randn(B, S, d, device="cuda", generator=g) * scale_v).half()
+    if threshold:
+        k[:, 0] *= 4.0          # a peaked softmax keeps some outputs above the outlier threshold
+    out, quant = F.cross_attn_decode(q, k, v, 0.125, H, threshold)
+    qs = (q * 0.125).float().view(B, H, 1, 64)
+    kk = k.float().reshape(B, S, H, 64).transpose(1, 2)
+    vv = v.float().reshape(B, S, H, 64).transpose(1, 2)
+    ref = (torch.softmax(qs @ kk.transpose(-1, -2), dim=-1) @ vv).transpose(1, 2).reshape(B, d)
+    assert (out.float() - ref).abs().max().item() <= 2e-3 * max(1.0, float(vv.abs().max()))
+    if threshold is None:
+        assert quant is None
+    else:
+        _check_quant(quant, out, threshold)
+        assert int(F._row_counters(q.device, B).abs().sum()) == 0        # self-resetting scratch
+        out2, quant2 = F.cross_attn_decode(q, k, v, 0.125, H, threshold)  # and therefore re-usable
+        assert torch.equal(out2, out) and torch.equal(quant2[0], quant[0]) and torch.equal(quant2[1], quant[1])
+        quant2[2].col_flags.zero_()
+
+
+def test_cross_attn_decode_matches_torch_sdpa_bf16_and_errors():
+    B, H, S = 4, 8, 1500
+    d = H * 64
+    q = torch.randn(B, d, device="cuda").bfloat16()
+    k = torch.randn(B, S, d, device="cuda").bfloat16()
+    v = torch.randn(B, S, d, device="cuda").bfloat16()
+    out, _ = F.cross_attn_decode(q, k, v, 0.125, H)
+    ref = TF.scaled_dot_product_attention((q * 0.125).view(B, 1, H, 64).transpose(1, 2),
+                                          k.view(B, S, H, 64).transpose(1, 2), v.view(B, S, H, 64).transpose(1, 2),
+                                          scale=1.0).transpose(1, 2).reshape(B, d)
+    assert (out.float() - ref.float()).abs().max().item() <= 2e-2
+    with pytest.raises(RuntimeError, match="fp16"):
+        F.cross_attn_decode(q, k, v, 0.125, H, threshold=6.0)
+    with pytest.raises(RuntimeError, match="strides"):
+        F.cross_attn_decode(q, k.transpose(1, 2).contiguous().transpose(1, 2), v, 0.125, H)

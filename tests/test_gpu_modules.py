@@ -418,7 +418,7 @@ def test_fused_int8_decode_step_is_bit_identical_to_module_calls(pkg):
     T = 12
     ids = harness.greedy_generate(model, feats, T)
     st = next(iter(eng._states.values()))
-    assert st.fused is not None
+    assert st.fused is not None and st.own_cross
     dec = model.model.decoder
     B, H, d = st.B, st.H, st.d
     k2 = [torch.zeros_like(t) for t in st.k]
@@ -434,10 +434,8 @@ def test_fused_int8_decode_step_is_bit_identical_to_module_calls(pkg):
             x = x + sa.out_proj(a)
             ln = layer.encoder_attn_layer_norm
             h = F.add_layernorm_quant(x, None, ln.weight, ln.bias, ln.eps)[1]
-            q = ca.q_proj(h).view(B, 1, H, 64).transpose(1, 2)
-            a = TF.scaled_dot_product_attention(q, st.ck[li].transpose(1, 2), st.cv[li].transpose(1, 2),
-                                                scale=ca.scaling)
-            x = x + ca.out_proj(a.transpose(1, 2).reshape(B, d))
+            a, _ = F.cross_attn_decode(ca.q_proj(h), st.ckv[li][:, :, :d], st.ckv[li][:, :, d:], ca.scaling, H)
+            x = x + ca.out_proj(a)
             ln = layer.final_layer_norm
             h = F.add_layernorm_quant(x, None, ln.weight, ln.bias, ln.eps)[1]
             x = x + layer.fc2(F.gelu_quant(layer.fc1(h))[0])
