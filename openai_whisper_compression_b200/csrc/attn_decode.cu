@@ -223,7 +223,6 @@ extern "C" int wq_self_attn_decode(const void *q, const void *k, const void *v, 
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int kXWarps = 4;
 constexpr int kXUnroll = 4;
 
 struct Partial {
@@ -240,7 +239,7 @@ __device__ __forceinline__ void partial_merge(Partial &a, float om, float ol, co
     a.m = m;
 }
 
-template <typename T>
+template <typename T, int kXWarps>
 __global__ void __launch_bounds__(kXWarps * 32)
 k_cross_attn_decode(const T *__restrict__ q, int64_t ldq, float scaling, const T *__restrict__ kmat,
                     const T *__restrict__ vmat, int64_t ld, int S, int H, T *out, float threshold,
@@ -413,12 +412,13 @@ extern "C" int wq_cross_attn_decode(const void *q, int64_t ldq, int dtype, float
     WQ_REQUIRE(ca == nullptr || threshold == 0.0f || col_flags, "wq_cross_attn_decode: threshold needs col_flags");
     cudaStream_t s = (cudaStream_t)stream;
     const dim3 grid((unsigned)H, (unsigned)B);
+    // 4 warps per CTA; 8 measured the same (scripts/cross_attn_bench.py)
     if (dtype == WQ_F16) {
-        WQ_LAUNCH_PDL(k_cross_attn_decode<__half>, grid, dim3(kXWarps * 32), 0, s, (const __half *)q, ldq, scaling,
+        WQ_LAUNCH_PDL((k_cross_attn_decode<__half, 4>), grid, dim3(128), 0, s, (const __half *)q, ldq, scaling,
                       (const __half *)k, (const __half *)v, ld, (int)S, H, (__half *)out, threshold, ca, row_stats,
                       col_flags, row_counters);
     } else {
-        WQ_LAUNCH_PDL(k_cross_attn_decode<__nv_bfloat16>, grid, dim3(kXWarps * 32), 0, s, (const __nv_bfloat16 *)q, ldq,
+        WQ_LAUNCH_PDL((k_cross_attn_decode<__nv_bfloat16, 4>), grid, dim3(128), 0, s, (const __nv_bfloat16 *)q, ldq,
                       scaling, (const __nv_bfloat16 *)k, (const __nv_bfloat16 *)v, ld, (int)S, H, (__nv_bfloat16 *)out,
                       0.0f, (int8_t *)nullptr, (float *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr);
     }
