@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <cstdlib>
 
 #include "../../include/whisperq.h"
 

@@ -62,32 +62,56 @@ struct GemmArgs {
     const __half *a16;
     int32_t *flags;          // [K + 2]: per-column flags, "any", completion counter
     int keep_flags;          // 1: leave the flags set (another GEMM consumes the same quantized rows next)
+    int prefetch;            // > 0: the producer pulls the A row block it will load `prefetch` tiles later into L2
 };
 
 template <int BMODE> constexpr bool is_nibble() { return BMODE == B_4BIT || BMODE == B_U4; }
 template <int BMODE> constexpr int dq_warps() { return BMODE == B_DIRECT ? 0 : (is_nibble<BMODE>() ? 8 : 4); }
 template <int BN, int BMODE> constexpr int num_threads() { return 32 * (2 + epi_warps<BN, BMODE>() + dq_warps<BMODE>()); }
 
-template <int BN, int STAGES, int BMODE, int OUT_BUFS>
+// WS > 0: weight-stationary schedule (B_DIRECT only).  The CTA keeps its W tile -- all num_kb <= WS k-blocks of BN
+// rows -- resident in shared memory and walks M tiles of ONE n column block, so the ring streams A alone: per
+// 256 x 128 tile with K = 512 the SM pulls 128 KB through L2 instead of 192 KB.
+template <int BN, int STAGES, int BMODE, int OUT_BUFS, int WS = 0>
 struct SmemLayout {
+    static_assert(WS == 0 || BMODE == B_DIRECT, "weight-stationary tiles take W straight from TMA");
     static constexpr int A_BYTES = BM * ROW_BYTES;
     static constexpr int B_BYTES = BN * ROW_BYTES;
+    static constexpr int B_SLOTS = WS > 0 ? WS : STAGES;       // W buffers: one per ring stage, or the resident k-blocks
     static constexpr int P_ROW = BMODE == B_I8 ? 64 : (is_nibble<BMODE>() ? 32 : 0);
     static constexpr int P_BYTES = BN * P_ROW;
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
-    static constexpr int OFF_P = OFF_B + STAGES * B_BYTES;
+    static constexpr int OFF_P = OFF_B + B_SLOTS * B_BYTES;
     static constexpr int EW = epi_warps<BN, BMODE>();
     static constexpr int OFF_OUT = OFF_P + STAGES * P_BYTES;   // EW x OUT_BUFS boxes, 1024-byte aligned
-    static constexpr int OFF_CONST = OFF_OUT + EW * OUT_BUFS * BOX_BYTES;  // float [2][3][BN] per-tile constants
-    static constexpr int OFF_LUT = OFF_CONST + 2 * 3 * BN * 4;                    // float lut[16]
+    static constexpr int CONST_BUFS = WS > 0 ? 1 : 2;          // a weight-stationary CTA never changes columns
+    static constexpr int OFF_CONST = OFF_OUT + EW * OUT_BUFS * BOX_BYTES;  // float [CONST_BUFS][3][BN] per-tile constants
+    static constexpr int OFF_LUT = OFF_CONST + CONST_BUFS * 3 * BN * 4;           // float lut[16]
     static constexpr int OFF_BAR = OFF_LUT + 64;               // uint64 barriers
-    static constexpr int NUM_BARS = 3 * STAGES + 2 * ACC_STAGES;
+    static constexpr int NUM_BARS = 3 * STAGES + 2 * ACC_STAGES + 1;
     static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
     static constexpr int TOTAL = OFF_TMEM + 16 + 1024;         // + slack for manual 1024-B alignment
-    static constexpr int TX_BYTES = A_BYTES + (BMODE == B_DIRECT ? B_BYTES : P_BYTES);
+    static constexpr int TX_BYTES = A_BYTES + (WS > 0 ? 0 : (BMODE == B_DIRECT ? B_BYTES : P_BYTES));
     static_assert(TOTAL <= 232448, "shared memory budget exceeded");
 };
+
+// i-th tile of this CTA -> (m tile, n tile); false past the CTA's last tile.  Default: tiles round-robin over the
+// grid, n fastest (the CTAs sharing an A row-block run together).  Weight-stationary: CTA c owns column block
+// c % tiles_n and every (gridDim / tiles_n)-th row block; the tiles_n CTAs of one row block still run together.
+template <int WS>
+__device__ __forceinline__ bool tile_at(const GemmArgs &args, int i, int &mt, int &nt) {
+    if constexpr (WS > 0) {
+        nt = (int)blockIdx.x % args.tiles_n;
+        mt = (int)blockIdx.x / args.tiles_n + i * ((int)gridDim.x / args.tiles_n);
+        return mt < args.tiles_m;
+    } else {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        nt = tile % args.tiles_n;
+        mt = tile / args.tiles_n;
+        return tile < args.tiles_m * args.tiles_n;
+    }
+}
 
 template <typename OutT> __device__ __forceinline__ uint32_t pack2(float a, float b);
 template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
@@ -227,10 +251,10 @@ __device__ __noinline__ void llmint8_outlier_chunk(const GemmArgs &args, const f
 }
 
 // Body of one epilogue warp: drains its 32-row slab of every tile this CTA owns.
-template <int BN, int EW, int EPI, typename OutT, int OUT_BUFS, bool TMA_STORE>
+template <int BN, int EW, int EPI, typename OutT, int OUT_BUFS, bool TMA_STORE, int WS>
 __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtensorMap *map_y, uint8_t *boxes,
                                               float *s_const, uint64_t *bar_tmem_full, uint64_t *bar_tmem_empty,
-                                              uint32_t tmem_base, int warp, int lane, int total_tiles) {
+                                              uint32_t tmem_base, int warp, int lane) {
     constexpr int ACC_COLS = 2 * BN;
     constexpr int BOX_COLS = 128 / (int)sizeof(OutT);   // columns per TMA-store box (64 or 32)
     constexpr int CSPLIT = EW / 8;                      // warps sharing a 32-row slab split its columns
@@ -249,8 +273,9 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
         dyn_zp = (int)args.qparams[1];
     }
     uint32_t t = 0, nstore = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-        const int n0 = (tile % args.tiles_n) * BN, m0 = (tile / args.tiles_n) * BM;
+    int mt, nt;
+    for (; tile_at<WS>(args, (int)t, mt, nt); ++t) {
+        const int n0 = nt * BN, m0 = mt * BM;
         const uint32_t as = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1;
         const int mrow0 = m0 + h * BMH + q * 32;  // first row of this warp's 32-row slab
         const int m = mrow0 + lane;
@@ -259,9 +284,10 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
         float rs = 1.0f;
         if constexpr (EPI == EPI_LLMINT8) rs = row_ok ? __ldg(args.row_scale + m) : 0.0f;
         // stage this tile's per-column constants once (the 8 epilogue warps share them); two
-        // buffers, so a warp that runs ahead never overwrites constants still in use
-        float *sc = s_const + (t & 1) * 3 * BN;
-        {
+        // buffers, so a warp that runs ahead never overwrites constants still in use (weight-stationary
+        // CTAs keep their column block: staged once)
+        float *sc = s_const + (WS > 0 ? 0 : (t & 1) * 3 * BN);
+        if (WS == 0 || t == 0) {
             const float *bias = reinterpret_cast<const float *>(args.bias);
             for (int i = (warp - 2) * 32 + lane; i < 3 * BN; i += EW * 32) {
                 const int which = i / BN;
@@ -352,11 +378,11 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
     __syncwarp();
 }
 
-template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT, int OUT_BUFS>
+template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT, int OUT_BUFS, int WS>
 __global__ void __launch_bounds__(num_threads<BN, BMODE>(), 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ CUtensorMap map_y, const GemmArgs args) {
-    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS>;
+    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS>;
     static_assert(BN == 64 || BN == 128, "BN must be 64 or 128 (2 halves x 2 stages x BN <= 512 TMEM columns)");
     constexpr bool kIntKind = (AKIND == A_S8 || AKIND == A_U8);
     constexpr int A_ELEMS_PER_ROW = kIntKind ? 128 : 64;  // elements of K per 128-byte row
@@ -372,6 +398,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     uint64_t *bar_bready = bars + 2 * STAGES;
     uint64_t *bar_tmem_full = bars + 3 * STAGES;
     uint64_t *bar_tmem_empty = bars + 3 * STAGES + ACC_STAGES;
+    uint64_t *bar_w = bars + 3 * STAGES + 2 * ACC_STAGES;     // weight-stationary: the resident W tile has landed
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + L::OFF_TMEM);
     float *s_lut = reinterpret_cast<float *>(smem + L::OFF_LUT);
 
@@ -393,6 +420,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             mbar_init(&bar_tmem_full[a], 1);
             mbar_init(&bar_tmem_empty[a], EW);
         }
+        mbar_init(bar_w, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -412,15 +440,33 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         // ---------------- TMA producer ----------------
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n0 = (tile % args.tiles_n) * BN, m0 = (tile / args.tiles_n) * BM;
+            int mt, nt;
+            if constexpr (WS > 0) {
+                if (tile_at<WS>(args, 0, mt, nt)) {      // the CTA's W tile, once: num_kb boxes of BN rows x 128 B
+                    mbar_arrive_expect_tx(bar_w, (uint32_t)num_kb * L::B_BYTES);
+                    for (int kb = 0; kb < num_kb; ++kb)
+                        tma_load_2d(smem + L::OFF_B + kb * L::B_BYTES, &map_b, bar_w, kb * 128, nt * BN);
+                }
+            }
+            for (int i = 0; tile_at<WS>(args, i, mt, nt); ++i) {
+                const int n0 = nt * BN, m0 = mt * BM;
+                // A streams from HBM with ~1.5 us of loaded latency and the ring holds < 1 tile: ask L2 for the row
+                // block this CTA reaches `prefetch` tiles from now (one of the tiles_n CTAs sharing it does)
+                int pf_m0 = -1;
+                if (args.prefetch > 0) {
+                    int pmt, pnt;
+                    if (tile_at<WS>(args, i + args.prefetch, pmt, pnt) && pmt % args.tiles_n == pnt) pf_m0 = pmt * BM;
+                }
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&bar_empty[s], ph ^ 1);
                     mbar_arrive_expect_tx(&bar_full[s], L::TX_BYTES);
                     tma_load_2d(smem + L::OFF_A + s * L::A_BYTES, &map_a, &bar_full[s], kb * A_ELEMS_PER_ROW, m0);
-                    if constexpr (BMODE == B_DIRECT)
+                    if (pf_m0 >= 0) tma_prefetch_2d(&map_a, kb * A_ELEMS_PER_ROW, pf_m0);
+                    if constexpr (WS > 0)
+                        (void)n0;
+                    else if constexpr (BMODE == B_DIRECT)
                         tma_load_2d(smem + L::OFF_B + s * L::B_BYTES, &map_b, &bar_full[s], kb * 128, n0);
                     else
                         tma_load_2d(smem + L::OFF_P + s * L::P_BYTES, &map_b, &bar_full[s], kb * L::P_ROW, n0);
@@ -436,9 +482,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                          : make_idesc(kAccF32, AKIND == A_F16 ? kFmtF16 : kFmtBF16,
                                       AKIND == A_F16 ? kFmtF16 : kFmtBF16, BMH, BN);
             uint32_t it = 0, t = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-                const int m0 = (tile / args.tiles_n) * BM;
+            int mt, nt;
+            for (; tile_at<WS>(args, (int)t, mt, nt); ++t) {
+                const int m0 = mt * BM;
                 const bool two_halves = m0 + BMH < args.M;   // second 128 rows hold real data
+                if constexpr (WS > 0) {
+                    if (t == 0) mbar_wait(bar_w, 0);
+                }
                 const uint32_t as = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1;
                 mbar_wait(&bar_tmem_empty[as], aph ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
@@ -451,7 +501,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     tc_fence_after();
                     const uint64_t adesc0 = make_smem_desc_sw128(smem + L::OFF_A + s * L::A_BYTES);
                     const uint64_t adesc1 = make_smem_desc_sw128(smem + L::OFF_A + s * L::A_BYTES + BMH * ROW_BYTES);
-                    const uint64_t bdesc = make_smem_desc_sw128(smem + L::OFF_B + s * L::B_BYTES);
+                    const uint64_t bdesc = make_smem_desc_sw128(smem + L::OFF_B + (WS > 0 ? kb : s) * L::B_BYTES);
 #pragma unroll
                     for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
                         const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
@@ -474,9 +524,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         uint8_t *boxes = smem + L::OFF_OUT + (warp - 2) * OUT_BUFS * BOX_BYTES;   // private staging of this warp
         float *s_const = reinterpret_cast<float *>(smem + L::OFF_CONST);
         if (args.tma_store)
-            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, true>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane, total_tiles);
+            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, true, WS>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane);
         else
-            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, false>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane, total_tiles);
+            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, false, WS>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane);
     } else {
         // ---------------- weight expansion (W8A16 / W4A16): warps 10.. ----------------
         const int t = threadIdx.x - 32 * (2 + EW);
@@ -648,12 +698,13 @@ template <int BN, int BMODE> constexpr int pick_out_bufs() {
 }
 
 // deepest smem ring that fits next to the epilogue staging boxes
-template <int BN, int BMODE, int OUT_BUFS>
+template <int BN, int BMODE, int OUT_BUFS, int WS>
 constexpr int pick_stages() {
     int best = 2;
     for (int st = 2; st <= 6; ++st) {
-        const int stage = BM * ROW_BYTES + BN * ROW_BYTES + BN * (BMODE == B_I8 ? 64 : (is_nibble<BMODE>() ? 32 : 0));
-        const int total = st * stage + epi_warps<BN, BMODE>() * OUT_BUFS * BOX_BYTES + 2 * 3 * BN * 4 + 64 + (3 * st + 2 * ACC_STAGES) * 8 + 16 + 1024;
+        const int stage = BM * ROW_BYTES + (WS > 0 ? 0 : BN * ROW_BYTES) + BN * (BMODE == B_I8 ? 64 : (is_nibble<BMODE>() ? 32 : 0));
+        const int total = st * stage + WS * BN * ROW_BYTES + epi_warps<BN, BMODE>() * OUT_BUFS * BOX_BYTES +
+                          (WS > 0 ? 1 : 2) * 3 * BN * 4 + 64 + (3 * st + 2 * ACC_STAGES + 1) * 8 + 16 + 1024;
         if (total <= 232448) best = st;
     }
     return best;
@@ -664,12 +715,12 @@ template <> CUtensorMapDataType out_dtype_enum<float>() { return CU_TENSOR_MAP_D
 template <> CUtensorMapDataType out_dtype_enum<__half>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT16; }
 template <> CUtensorMapDataType out_dtype_enum<__nv_bfloat16>() { return CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
 
-template <int BN, int AKIND, int BMODE, int EPI, typename OutT>
+template <int BN, int AKIND, int BMODE, int EPI, typename OutT, int WS = 0>
 int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cudaStream_t stream) {
     constexpr int OUT_BUFS = pick_out_bufs<BN, BMODE>();
-    constexpr int STAGES = pick_stages<BN, BMODE, OUT_BUFS>();
-    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS>;
-    auto kfn = k_gemm_tc<BN, STAGES, AKIND, BMODE, EPI, OutT, OUT_BUFS>;
+    constexpr int STAGES = pick_stages<BN, BMODE, OUT_BUFS, WS>();
+    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS>;
+    auto kfn = k_gemm_tc<BN, STAGES, AKIND, BMODE, EPI, OutT, OUT_BUFS, WS>;
     static bool configured = false;
     if (!configured) {
         WQ_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -688,7 +739,8 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cud
         my = ma;  // unused
     }
     const int total = args.tiles_m * args.tiles_n;
-    const int grid = total < wq_sm_count() ? total : wq_sm_count();
+    int grid = total < wq_sm_count() ? total : wq_sm_count();
+    if (WS > 0) grid = (wq_sm_count() / args.tiles_n) * args.tiles_n;   // whole groups of tiles_n CTAs (use_ws())
 
     WQ_LAUNCH_PDL(kfn, dim3(grid), dim3(num_threads<BN, BMODE>()), (size_t)L::TOTAL, stream, ma, mb, my, args);
     return WQ_OK;
@@ -698,6 +750,26 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cud
 bool use_narrow_tile(int64_t M, int64_t N) {
     const int64_t tiles128 = ((M + BM - 1) / BM) * ((N + 127) / 128);  // BM = 256
     return tiles128 < wq_sm_count();
+}
+
+// Weight-stationary schedule for the int8 x int8 schemes: K fits the resident W tile (<= kWS k-blocks of 128),
+// every SM group has several row blocks to walk, and the column blocks divide the grid into whole groups.
+constexpr int kWS = 4;
+// L2 prefetch distance (tiles) of the weight-stationary schedule.  Measured on B200, M = 384000, K = 512
+// (scripts/gemm_ws_bench.py): N = 512: 144 us round-robin -> 130 us stationary -> 118 us with the prefetch;
+// N = 2048: 456 -> 448 -> 422 us.  A deeper ring instead (4 stages, single store buffers) gave 126 / 447 us.
+constexpr int kWSPrefetch = 2;
+bool ws_enabled() {     // WQ_GEMM_WS=0: round-robin tiles everywhere (A/B measurements, scripts/gemm_ws_bench.py)
+    static const bool on = [] {
+        const char *e = getenv("WQ_GEMM_WS");
+        return e == nullptr || e[0] != '0';
+    }();
+    return on;
+}
+bool use_ws(int64_t M, int64_t N, int64_t K) {
+    const int64_t tiles_n = (N + 127) / 128, tiles_m = (M + BM - 1) / BM, kb = (K + 127) / 128;
+    const int64_t sms = wq_sm_count();
+    return ws_enabled() && kb <= kWS && tiles_n <= sms && tiles_m >= 4 * (sms / tiles_n);
 }
 
 int check_common(const char *fn, int64_t M, int64_t N, int64_t K) {
@@ -742,6 +814,10 @@ extern "C" int wq_gemm_llmint8_shared(const int8_t *ca, const float *sca, const 
     }
     rc = make_map_2d(&mb, cb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
+    if (use_ws(M, N, K)) {
+        args.prefetch = kWSPrefetch;
+        return launch_gemm<128, A_S8, B_DIRECT, EPI_LLMINT8, __half, kWS>(ma, mb, args, s);
+    }
     return launch_gemm<128, A_S8, B_DIRECT, EPI_LLMINT8, __half>(ma, mb, args, s);
 }
 
@@ -769,6 +845,10 @@ extern "C" int wq_gemm_dyn_i8(const uint8_t *xq, const float *qparams, const int
     }
     rc = make_map_2d(&mb, wq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
+    if (use_ws(M, N, K)) {
+        args.prefetch = kWSPrefetch;
+        return launch_gemm<128, A_U8, B_DIRECT, EPI_DYN, float, kWS>(ma, mb, args, s);
+    }
     return launch_gemm<128, A_U8, B_DIRECT, EPI_DYN, float>(ma, mb, args, s);
 }
 

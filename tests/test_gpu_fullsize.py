@@ -96,3 +96,49 @@ def test_logmel_full_batch_matches_oracle_on_sampled_utterances(F):
         np.testing.assert_allclose(out[i], ref, rtol=0, atol=1e-4)
     # per-utterance normalisation: max(x) - min(x) <= 8/4 everywhere
     assert float((out.max(axis=(1, 2)) - out.min(axis=(1, 2))).max()) <= 2.0 + 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# weight-stationary schedule of the int8 x int8 GEMM (gemm_tc.cu, WS > 0): taken for K <= 512 and many row
+# blocks; the same rows in chunks of 4096 take the round-robin schedule, and both must agree bit for bit
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(40001, 600, 384), (96000, 512, 512), (37900, 1536, 512)])
+def test_llmint8_weight_stationary_equals_round_robin_with_outliers(F, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g).half()
+    x[::1000, 3] = 9.0            # outlier entries in every 4096-row chunk, same columns
+    x[7::1000, K - 2] = -12.5
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    bias = (torch.randn(N, device="cuda", generator=g) * 0.1).half()
+    cb, scb, _ = F.int8_vectorwise_quant(W, 0.0)
+    y = F.linear8bitlt(x, cb, scb, bias, 6.0)
+    parts = [F.linear8bitlt(x[r:r + 4096].contiguous(), cb, scb, bias, 6.0) for r in range(0, M, 4096)]
+    assert torch.equal(y, torch.cat(parts, 0))
+    # and against the torch-op emulation of the reference formula (fp16 addmm of the outlier term: one rounding)
+    from tests.emulation import EmuLinear8bitLt
+    lin = torch.nn.Linear(K, N).cuda()
+    lin.weight.data, lin.bias.data = W.float(), bias.float()
+    rows = slice(M - 3000, M)
+    ref = EmuLinear8bitLt(lin, 6.0)(x[rows]).float()
+    # the emulation sees only these rows: same outlier columns as the full call (planted in every 1000 rows)
+    err = (y[rows].float() - ref).abs() / ref.abs().clamp_min(1.0)
+    assert err.max().item() <= 2 ** -9
+
+
+def test_torch_dynamic_weight_stationary_equals_round_robin(F):
+    M, N, K = 40001, 600, 384
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(M, K, device="cuda", generator=g) * 2
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.02
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    q, scale, wsum = F.torch_quantize_weight(w)
+    xq, qparams = F.torch_quantize_activation(x)
+    y = F.gemm_dyn_i8(xq, qparams, q, scale, wsum, bias)
+    parts = [F.gemm_dyn_i8(xq[r:r + 4096].contiguous(), qparams, q, scale, wsum, bias) for r in range(0, M, 4096)]
+    assert torch.equal(y, torch.cat(parts, 0))
+    # exact integer identity on the last rows
+    rows = slice(M - 2000, M)
+    acc = xq[rows].double() @ q.double().t()          # exact integers
+    zp = float(qparams[1].item())
+    ref = ((acc - zp * wsum.double()[None, :]).float() * (qparams[0] * scale).float()) + bias[None, :]
+    assert torch.equal(y[rows], ref)
