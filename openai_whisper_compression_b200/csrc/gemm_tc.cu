@@ -72,11 +72,19 @@ template <int BN, int BMODE> constexpr int num_threads() { return 32 * (2 + epi_
 // WS > 0: weight-stationary schedule (B_DIRECT only).  The CTA keeps its W tile -- all num_kb <= WS k-blocks of BN
 // rows -- resident in shared memory and walks M tiles of ONE n column block, so the ring streams A alone: per
 // 256 x 128 tile with K = 512 the SM pulls 128 KB through L2 instead of 192 KB.
-template <int BN, int STAGES, int BMODE, int OUT_BUFS, int WS = 0>
+//
+// COLS = 1: the tile is 128 rows x 2*BN columns and ONE tcgen05.mma per k-step covers it (M = 128, N = 256) instead
+// of two M = 128, N = 128 instructions on two row halves.  An N = 128 instruction reads 4 KB of A and 4 KB of W from
+// shared memory for 64 cycles of tensor work -- 128 B/clk, all the SM's shared-memory bandwidth, and the pipe ran
+// ~45 % active; at N = 256 it is 12 KB per 128 cycles.  The two accumulator "halves" are then column halves.
+template <int BN, int STAGES, int BMODE, int OUT_BUFS, int WS = 0, int COLS = 0>
 struct SmemLayout {
     static_assert(WS == 0 || BMODE == B_DIRECT, "weight-stationary tiles take W straight from TMA");
-    static constexpr int A_BYTES = BM * ROW_BYTES;
-    static constexpr int B_BYTES = BN * ROW_BYTES;
+    static_assert(COLS == 0 || (BMODE == B_DIRECT && BN == 128), "column-split tiles: int8 x int8 schemes, 2 x 128 columns");
+    static constexpr int BMT = COLS ? BMH : BM;                // tile rows
+    static constexpr int BNT = COLS ? 2 * BN : BN;             // tile columns
+    static constexpr int A_BYTES = BMT * ROW_BYTES;
+    static constexpr int B_BYTES = BNT * ROW_BYTES;
     static constexpr int B_SLOTS = WS > 0 ? WS : STAGES;       // W buffers: one per ring stage, or the resident k-blocks
     static constexpr int P_ROW = BMODE == B_I8 ? 64 : (is_nibble<BMODE>() ? 32 : 0);
     static constexpr int P_BYTES = BN * P_ROW;
@@ -86,8 +94,8 @@ struct SmemLayout {
     static constexpr int EW = epi_warps<BN, BMODE>();
     static constexpr int OFF_OUT = OFF_P + STAGES * P_BYTES;   // EW x OUT_BUFS boxes, 1024-byte aligned
     static constexpr int CONST_BUFS = WS > 0 ? 1 : 2;          // a weight-stationary CTA never changes columns
-    static constexpr int OFF_CONST = OFF_OUT + EW * OUT_BUFS * BOX_BYTES;  // float [CONST_BUFS][3][BN] per-tile constants
-    static constexpr int OFF_LUT = OFF_CONST + CONST_BUFS * 3 * BN * 4;           // float lut[16]
+    static constexpr int OFF_CONST = OFF_OUT + EW * OUT_BUFS * BOX_BYTES;  // float [CONST_BUFS][3][BNT] per-tile constants
+    static constexpr int OFF_LUT = OFF_CONST + CONST_BUFS * 3 * BNT * 4;          // float lut[16]
     static constexpr int OFF_BAR = OFF_LUT + 64;               // uint64 barriers
     static constexpr int NUM_BARS = 3 * STAGES + 2 * ACC_STAGES + 1;
     static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
@@ -251,17 +259,18 @@ __device__ __noinline__ void llmint8_outlier_chunk(const GemmArgs &args, const f
 }
 
 // Body of one epilogue warp: drains its 32-row slab of every tile this CTA owns.
-template <int BN, int EW, int EPI, typename OutT, int OUT_BUFS, bool TMA_STORE, int WS>
+template <int BN, int EW, int EPI, typename OutT, int OUT_BUFS, bool TMA_STORE, int WS, int COLS>
 __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtensorMap *map_y, uint8_t *boxes,
                                               float *s_const, uint64_t *bar_tmem_full, uint64_t *bar_tmem_empty,
                                               uint32_t tmem_base, int warp, int lane) {
     constexpr int ACC_COLS = 2 * BN;
+    constexpr int BMT = COLS ? BMH : BM, BNT = COLS ? 2 * BN : BN;   // tile rows / columns
     constexpr int BOX_COLS = 128 / (int)sizeof(OutT);   // columns per TMA-store box (64 or 32)
     constexpr int CSPLIT = EW / 8;                      // warps sharing a 32-row slab split its columns
     constexpr int N_BOX = BN / BOX_COLS / CSPLIT;       // boxes per warp per tile
     constexpr int NCH = BOX_COLS / 32;                  // tcgen05.ld chunks per box (2 or 1)
     const int grp = (warp - 2) >> 2;
-    const int h = grp & 1;                              // 128-row half of the tile
+    const int h = grp & 1;                              // 128-row half of the tile (COLS: 128-column half)
     const int bx0 = (grp >> 1) * N_BOX;                 // first box (column range) of this warp
     const int q = warp & 3;                             // TMEM lane quarter this warp may access
     const bool vec_ok = ((size_t)args.N * sizeof(OutT)) % 16 == 0;
@@ -275,23 +284,25 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
     uint32_t t = 0, nstore = 0;
     int mt, nt;
     for (; tile_at<WS>(args, (int)t, mt, nt); ++t) {
-        const int n0 = nt * BN, m0 = mt * BM;
+        const int n0 = nt * BNT, m0 = mt * BMT;
         const uint32_t as = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1;
-        const int mrow0 = m0 + h * BMH + q * 32;  // first row of this warp's 32-row slab
+        const int mrow0 = m0 + (COLS ? 0 : h * BMH) + q * 32;  // first row of this warp's 32-row slab
+        const int ch0 = COLS ? h * BN : 0;        // first tile column of this warp's half
+        const int nh0 = n0 + ch0;                 // ... as a column of Y
         const int m = mrow0 + lane;
         const bool row_ok = m < args.M;
-        const bool slab_ok = mrow0 < args.M;      // warp-uniform
+        const bool slab_ok = mrow0 < args.M && nh0 < args.N;      // warp-uniform
         float rs = 1.0f;
         if constexpr (EPI == EPI_LLMINT8) rs = row_ok ? __ldg(args.row_scale + m) : 0.0f;
         // stage this tile's per-column constants once (the 8 epilogue warps share them); two
         // buffers, so a warp that runs ahead never overwrites constants still in use (weight-stationary
         // CTAs keep their column block: staged once)
-        float *sc = s_const + (WS > 0 ? 0 : (t & 1) * 3 * BN);
+        float *sc = s_const + (WS > 0 ? 0 : (t & 1) * 3 * BNT);
         if (WS == 0 || t == 0) {
             const float *bias = reinterpret_cast<const float *>(args.bias);
-            for (int i = (warp - 2) * 32 + lane; i < 3 * BN; i += EW * 32) {
-                const int which = i / BN;
-                const int n = min(n0 + (i - which * BN), args.N - 1);
+            for (int i = (warp - 2) * 32 + lane; i < 3 * BNT; i += EW * 32) {
+                const int which = i / BNT;
+                const int n = min(n0 + (i - which * BNT), args.N - 1);
                 float val = 0.0f;
                 if (which == 0) {
                     if constexpr (EPI == EPI_LLMINT8 || EPI == EPI_W8A16) val = __ldg(args.col_scale + n);
@@ -325,8 +336,8 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
 #pragma unroll 1
                         for (int cc = 0; cc < NCH; ++cc) {
                             const int col0 = bx * BOX_COLS + cc * 32;
-                            llmint8_outlier_chunk<BN, OutT, TMA_STORE>(args, sc, tmem_row + col0, n0 + col0, col0, m, row_ok,
-                                                                       rs, box, cc, lane, row_ptr, vec_ok);
+                            llmint8_outlier_chunk<BNT, OutT, TMA_STORE>(args, sc, tmem_row + col0, nh0 + col0, ch0 + col0, m,
+                                                                        row_ok, rs, box, cc, lane, row_ptr, vec_ok);
                         }
                     }
                 }
@@ -339,8 +350,8 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
                             tmem_ld_32x32(tmem_row + col0, r);
                             tmem_ld_wait();
                             float v[32];
-                            epi_chunk<BN, EPI>(r, v, sc, col0, rs, dyn_s, dyn_zp);
-                            emit_chunk<OutT, TMA_STORE>(v, box, cc, lane, row_ptr, n0 + col0, args.N, row_ok, vec_ok);
+                            epi_chunk<BNT, EPI>(r, v, sc, ch0 + col0, rs, dyn_s, dyn_zp);
+                            emit_chunk<OutT, TMA_STORE>(v, box, cc, lane, row_ptr, nh0 + col0, args.N, row_ok, vec_ok);
                         }
                     } else {
                         uint32_t r[NCH][32];
@@ -351,8 +362,8 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
                         for (int cc = 0; cc < NCH; ++cc) {
                             const int col0 = bx * BOX_COLS + cc * 32;   // column inside the tile
                             float v[32];
-                            epi_chunk<BN, EPI>(r[cc], v, sc, col0, rs, dyn_s, dyn_zp);
-                            emit_chunk<OutT, TMA_STORE>(v, box, cc, lane, row_ptr, n0 + col0, args.N, row_ok, vec_ok);
+                            epi_chunk<BNT, EPI>(r[cc], v, sc, ch0 + col0, rs, dyn_s, dyn_zp);
+                            emit_chunk<OutT, TMA_STORE>(v, box, cc, lane, row_ptr, nh0 + col0, args.N, row_ok, vec_ok);
                         }
                     }
                 }
@@ -360,7 +371,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(map_y, box, n0 + bx * BOX_COLS, mrow0);
+                        tma_store_2d(map_y, box, nh0 + bx * BOX_COLS, mrow0);
                         tma_store_commit();
                     }
                     ++nstore;
@@ -378,11 +389,12 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
     __syncwarp();
 }
 
-template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT, int OUT_BUFS, int WS>
+template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT, int OUT_BUFS, int WS, int COLS>
 __global__ void __launch_bounds__(num_threads<BN, BMODE>(), 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ CUtensorMap map_y, const GemmArgs args) {
-    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS>;
+    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS, COLS>;
+    constexpr int BMT = L::BMT, BNT = L::BNT;
     static_assert(BN == 64 || BN == 128, "BN must be 64 or 128 (2 halves x 2 stages x BN <= 512 TMEM columns)");
     constexpr bool kIntKind = (AKIND == A_S8 || AKIND == A_U8);
     constexpr int A_ELEMS_PER_ROW = kIntKind ? 128 : 64;  // elements of K per 128-byte row
@@ -445,17 +457,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 if (tile_at<WS>(args, 0, mt, nt)) {      // the CTA's W tile, once: num_kb boxes of BN rows x 128 B
                     mbar_arrive_expect_tx(bar_w, (uint32_t)num_kb * L::B_BYTES);
                     for (int kb = 0; kb < num_kb; ++kb)
-                        tma_load_2d(smem + L::OFF_B + kb * L::B_BYTES, &map_b, bar_w, kb * 128, nt * BN);
+                        tma_load_2d(smem + L::OFF_B + kb * L::B_BYTES, &map_b, bar_w, kb * 128, nt * BNT);
                 }
             }
             for (int i = 0; tile_at<WS>(args, i, mt, nt); ++i) {
-                const int n0 = nt * BN, m0 = mt * BM;
+                const int n0 = nt * BNT, m0 = mt * BMT;
                 // A streams from HBM with ~1.5 us of loaded latency and the ring holds < 1 tile: ask L2 for the row
                 // block this CTA reaches `prefetch` tiles from now (one of the tiles_n CTAs sharing it does)
                 int pf_m0 = -1;
                 if (args.prefetch > 0) {
                     int pmt, pnt;
-                    if (tile_at<WS>(args, i + args.prefetch, pmt, pnt) && pmt % args.tiles_n == pnt) pf_m0 = pmt * BM;
+                    if (tile_at<WS>(args, i + args.prefetch, pmt, pnt) && pmt % args.tiles_n == pnt) pf_m0 = pmt * BMT;
                 }
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
@@ -478,14 +490,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             constexpr uint32_t idesc =
-                kIntKind ? make_idesc(kAccS32, AKIND == A_S8 ? kFmtS8 : kFmtU8, kFmtS8, BMH, BN)
+                kIntKind ? make_idesc(kAccS32, AKIND == A_S8 ? kFmtS8 : kFmtU8, kFmtS8, BMH, BNT)
                          : make_idesc(kAccF32, AKIND == A_F16 ? kFmtF16 : kFmtBF16,
                                       AKIND == A_F16 ? kFmtF16 : kFmtBF16, BMH, BN);
             uint32_t it = 0, t = 0;
             int mt, nt;
             for (; tile_at<WS>(args, (int)t, mt, nt); ++t) {
-                const int m0 = mt * BM;
-                const bool two_halves = m0 + BMH < args.M;   // second 128 rows hold real data
+                const int m0 = mt * BMT;
+                const bool two_halves = COLS == 0 && m0 + BMH < args.M;   // second 128 rows hold real data
                 if constexpr (WS > 0) {
                     if (t == 0) mbar_wait(bar_w, 0);
                 }
@@ -524,9 +536,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         uint8_t *boxes = smem + L::OFF_OUT + (warp - 2) * OUT_BUFS * BOX_BYTES;   // private staging of this warp
         float *s_const = reinterpret_cast<float *>(smem + L::OFF_CONST);
         if (args.tma_store)
-            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, true, WS>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane);
+            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, true, WS, COLS>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane);
         else
-            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, false, WS>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane);
+            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, false, WS, COLS>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane);
     } else {
         // ---------------- weight expansion (W8A16 / W4A16): warps 10.. ----------------
         const int t = threadIdx.x - 32 * (2 + EW);
@@ -698,13 +710,14 @@ template <int BN, int BMODE> constexpr int pick_out_bufs() {
 }
 
 // deepest smem ring that fits next to the epilogue staging boxes
-template <int BN, int BMODE, int OUT_BUFS, int WS>
+template <int BN, int BMODE, int OUT_BUFS, int WS, int COLS>
 constexpr int pick_stages() {
     int best = 2;
     for (int st = 2; st <= 6; ++st) {
-        const int stage = BM * ROW_BYTES + (WS > 0 ? 0 : BN * ROW_BYTES) + BN * (BMODE == B_I8 ? 64 : (is_nibble<BMODE>() ? 32 : 0));
-        const int total = st * stage + WS * BN * ROW_BYTES + epi_warps<BN, BMODE>() * OUT_BUFS * BOX_BYTES +
-                          (WS > 0 ? 1 : 2) * 3 * BN * 4 + 64 + (3 * st + 2 * ACC_STAGES + 1) * 8 + 16 + 1024;
+        const int bmt = COLS ? BMH : BM, bnt = COLS ? 2 * BN : BN;
+        const int stage = bmt * ROW_BYTES + (WS > 0 ? 0 : bnt * ROW_BYTES) + BN * (BMODE == B_I8 ? 64 : (is_nibble<BMODE>() ? 32 : 0));
+        const int total = st * stage + WS * bnt * ROW_BYTES + epi_warps<BN, BMODE>() * OUT_BUFS * BOX_BYTES +
+                          (WS > 0 ? 1 : 2) * 3 * bnt * 4 + 64 + (3 * st + 2 * ACC_STAGES + 1) * 8 + 16 + 1024;
         if (total <= 232448) best = st;
     }
     return best;
@@ -715,19 +728,20 @@ template <> CUtensorMapDataType out_dtype_enum<float>() { return CU_TENSOR_MAP_D
 template <> CUtensorMapDataType out_dtype_enum<__half>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT16; }
 template <> CUtensorMapDataType out_dtype_enum<__nv_bfloat16>() { return CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
 
-template <int BN, int AKIND, int BMODE, int EPI, typename OutT, int WS = 0>
+template <int BN, int AKIND, int BMODE, int EPI, typename OutT, int WS = 0, int COLS = 0>
 int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cudaStream_t stream) {
-    constexpr int OUT_BUFS = pick_out_bufs<BN, BMODE>();
-    constexpr int STAGES = pick_stages<BN, BMODE, OUT_BUFS, WS>();
-    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS>;
-    auto kfn = k_gemm_tc<BN, STAGES, AKIND, BMODE, EPI, OutT, OUT_BUFS, WS>;
+    // a resident 256-row W tile (128 KB) leaves room for single store buffers only
+    constexpr int OUT_BUFS = (WS > 0 && COLS) ? 1 : pick_out_bufs<BN, BMODE>();
+    constexpr int STAGES = pick_stages<BN, BMODE, OUT_BUFS, WS, COLS>();
+    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS, COLS>;
+    auto kfn = k_gemm_tc<BN, STAGES, AKIND, BMODE, EPI, OutT, OUT_BUFS, WS, COLS>;
     static bool configured = false;
     if (!configured) {
         WQ_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
     }
-    args.tiles_m = (args.M + BM - 1) / BM;
-    args.tiles_n = (args.N + BN - 1) / BN;
+    args.tiles_m = (args.M + L::BMT - 1) / L::BMT;
+    args.tiles_n = (args.N + L::BNT - 1) / L::BNT;
     // TMA store needs a 16-byte-aligned row pitch; otherwise the epilogue stores directly
     args.tma_store = (((size_t)args.N * sizeof(OutT)) % 16 == 0 && wq_aligned(args.out, 16)) ? 1 : 0;
     CUtensorMap my;
@@ -766,10 +780,52 @@ bool ws_enabled() {     // WQ_GEMM_WS=0: round-robin tiles everywhere (A/B measu
     }();
     return on;
 }
-bool use_ws(int64_t M, int64_t N, int64_t K) {
-    const int64_t tiles_n = (N + 127) / 128, tiles_m = (M + BM - 1) / BM, kb = (K + 127) / 128;
+bool use_ws(int64_t M, int64_t N, int64_t K, bool cols) {
+    const int64_t bmt = cols ? BMH : BM, bnt = cols ? 256 : 128;
+    const int64_t tiles_n = (N + bnt - 1) / bnt, tiles_m = (M + bmt - 1) / bmt, kb = (K + 127) / 128;
     const int64_t sms = wq_sm_count();
     return ws_enabled() && kb <= kWS && tiles_n <= sms && tiles_m >= 4 * (sms / tiles_n);
+}
+// 128 x 256 tiles with one N = 256 MMA per k-step (COLS) for the int8 x int8 schemes: when the call is not
+// decode-shaped and the 256-wide column blocks add no padding over 128-wide ones.  Measured on B200 at M = 384000
+// (scripts/gemm_ws_bench.py, COLS vs 256 x 128 tiles): K = 2048, N = 512: 347 vs 368 us; K = 512 (both
+// weight-stationary): N = 2048: 413 vs 421, N = 1536: 320 vs 331, N = 1024: 224 vs 220, N = 512: 132 vs 118 us -- the
+// resident 256-row W tile leaves the A ring 48 KB, so narrow weight-stationary calls keep the 256 x 128 tile.
+// WQ_GEMM_COLS=0 disables (A/B).
+bool use_cols(int64_t M, int64_t N, int64_t K) {
+    static const bool on = [] {
+        const char *e = getenv("WQ_GEMM_COLS");
+        return e == nullptr || e[0] != '0';
+    }();
+    if (!on || use_narrow_tile(M, N) || ((N + 127) / 128) % 2 != 0) return false;
+    return !(use_ws(M, N, K, false) && N < 1536);
+}
+
+// tensor maps + launch of the int8 x int8 schemes (LLM.int8, torch dynamic): tile shape and schedule by shape
+template <int AKIND, int EPI, typename OutT>
+int launch_i8(const void *a, const void *b, GemmArgs args, cudaStream_t s) {
+    const int64_t M = args.M, N = args.N, K = args.K;
+    const bool narrow = use_narrow_tile(M, N), cols = use_cols(M, N, K);
+    CUtensorMap ma, mb;
+    int rc = make_map_2d(&ma, a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, cols ? BMH : BM, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != WQ_OK) return rc;
+    rc = make_map_2d(&mb, b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, narrow ? 64 : (cols ? 256 : 128), 128,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != WQ_OK) return rc;
+    if (narrow) return launch_gemm<64, AKIND, B_DIRECT, EPI, OutT>(ma, mb, args, s);
+    const bool ws = use_ws(M, N, K, cols);
+    if (cols) {
+        if (ws) {
+            args.prefetch = 2 * kWSPrefetch;        // 128-row tiles: same look-ahead in rows
+            return launch_gemm<128, AKIND, B_DIRECT, EPI, OutT, kWS, 1>(ma, mb, args, s);
+        }
+        return launch_gemm<128, AKIND, B_DIRECT, EPI, OutT, 0, 1>(ma, mb, args, s);
+    }
+    if (ws) {
+        args.prefetch = kWSPrefetch;
+        return launch_gemm<128, AKIND, B_DIRECT, EPI, OutT, kWS>(ma, mb, args, s);
+    }
+    return launch_gemm<128, AKIND, B_DIRECT, EPI, OutT>(ma, mb, args, s);
 }
 
 int check_common(const char *fn, int64_t M, int64_t N, int64_t K) {
@@ -804,21 +860,7 @@ extern "C" int wq_gemm_llmint8_shared(const int8_t *ca, const float *sca, const 
     args.row_scale = sca; args.col_scale = scb; args.bias = bias; args.out = y_f16;
     args.ca = ca; args.cb = cb; args.a16 = (const __half *)a_f16; args.flags = col_flags;
     args.keep_flags = keep_flags ? 1 : 0;
-    CUtensorMap ma, mb;
-    rc = make_map_2d(&ma, ca, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, BM, 128, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc != WQ_OK) return rc;
-    if (use_narrow_tile(M, N)) {
-        rc = make_map_2d(&mb, cb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc != WQ_OK) return rc;
-        return launch_gemm<64, A_S8, B_DIRECT, EPI_LLMINT8, __half>(ma, mb, args, s);
-    }
-    rc = make_map_2d(&mb, cb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc != WQ_OK) return rc;
-    if (use_ws(M, N, K)) {
-        args.prefetch = kWSPrefetch;
-        return launch_gemm<128, A_S8, B_DIRECT, EPI_LLMINT8, __half, kWS>(ma, mb, args, s);
-    }
-    return launch_gemm<128, A_S8, B_DIRECT, EPI_LLMINT8, __half>(ma, mb, args, s);
+    return launch_i8<A_S8, EPI_LLMINT8, __half>(ca, cb, args, s);
 }
 
 extern "C" int wq_gemm_dyn_i8(const uint8_t *xq, const float *qparams, const int8_t *wq, const float *w_scale,
@@ -835,21 +877,7 @@ extern "C" int wq_gemm_dyn_i8(const uint8_t *xq, const float *qparams, const int
     args.M = (int)M; args.N = (int)N; args.K = (int)K;
     args.num_kb = (int)((K + 127) / 128);
     args.qparams = qparams; args.w_scale = w_scale; args.wsum = wsum; args.bias = bias; args.out = y;
-    CUtensorMap ma, mb;
-    rc = make_map_2d(&ma, xq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, BM, 128, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc != WQ_OK) return rc;
-    if (use_narrow_tile(M, N)) {
-        rc = make_map_2d(&mb, wq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc != WQ_OK) return rc;
-        return launch_gemm<64, A_U8, B_DIRECT, EPI_DYN, float>(ma, mb, args, s);
-    }
-    rc = make_map_2d(&mb, wq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc != WQ_OK) return rc;
-    if (use_ws(M, N, K)) {
-        args.prefetch = kWSPrefetch;
-        return launch_gemm<128, A_U8, B_DIRECT, EPI_DYN, float, kWS>(ma, mb, args, s);
-    }
-    return launch_gemm<128, A_U8, B_DIRECT, EPI_DYN, float>(ma, mb, args, s);
+    return launch_i8<A_U8, EPI_DYN, float>(xq, wq, args, s);
 }
 
 namespace {

@@ -54,7 +54,8 @@ template <typename T> struct Vec8 {
 // ---------------------------------------------------------------------------------------------
 // x' = x + delta ; h = LayerNorm(x') ; optional int8 row quantization of h.  cols % 8 == 0, cols <= 2048.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int CH>      // CH x 256 columns held in registers (sized to the row: 147 registers at CH = 8
+                                   // left one CTA per SM and 0.25 of the HBM rate on d_model = 512 rows)
 __global__ void __launch_bounds__(kWarps * 32)
 k_add_ln_quant(const T *x, const T *__restrict__ delta, const T *__restrict__ gamma,
                const T *__restrict__ beta, float eps, int64_t rows, int cols, T *x_out /* may alias x */,
@@ -67,10 +68,10 @@ k_add_ln_quant(const T *x, const T *__restrict__ delta, const T *__restrict__ ga
     const int64_t base = row * cols;
     const bool sparse = threshold > 0.0f;
 
-    float v[kMaxChunks][8];
-    Vec8<T> gam[kMaxChunks], bet[kMaxChunks];     // fetched up front: not a second L2 round trip after the statistics
+    float v[CH][8];
+    Vec8<T> gam[CH], bet[CH];     // fetched up front: not a second L2 round trip after the statistics
 #pragma unroll
-    for (int i = 0; i < kMaxChunks; ++i) {
+    for (int i = 0; i < CH; ++i) {
         const int c = i * 256 + lane * 8;
         if (c < cols) {
             gam[i].raw = *reinterpret_cast<const uint4 *>(gamma + c);
@@ -79,7 +80,7 @@ k_add_ln_quant(const T *x, const T *__restrict__ delta, const T *__restrict__ ga
     }
     float sum = 0.0f;
 #pragma unroll
-    for (int i = 0; i < kMaxChunks; ++i) {
+    for (int i = 0; i < CH; ++i) {
         const int c = i * 256 + lane * 8;
         if (c < cols) {
             Vec8<T> a;
@@ -101,7 +102,7 @@ k_add_ln_quant(const T *x, const T *__restrict__ delta, const T *__restrict__ ga
     const float mean = warp_sum_f32(sum) / (float)cols;
     float m2 = 0.0f;
 #pragma unroll
-    for (int i = 0; i < kMaxChunks; ++i) {
+    for (int i = 0; i < CH; ++i) {
         if (i * 256 + lane * 8 < cols) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -114,7 +115,7 @@ k_add_ln_quant(const T *x, const T *__restrict__ delta, const T *__restrict__ ga
 
     float am = 0.0f;
 #pragma unroll
-    for (int i = 0; i < kMaxChunks; ++i) {
+    for (int i = 0; i < CH; ++i) {
         const int c = i * 256 + lane * 8;
         if (c < cols) {
             Vec8<T> h;
@@ -134,7 +135,7 @@ k_add_ln_quant(const T *x, const T *__restrict__ delta, const T *__restrict__ ga
     if (lane == 0) row_stats[row] = am;
     const float scale = __fdiv_rn(127.0f, am);
 #pragma unroll
-    for (int i = 0; i < kMaxChunks; ++i) {
+    for (int i = 0; i < CH; ++i) {
         const int c = i * 256 + lane * 8;
         if (c < cols) {
             uint32_t lo = 0, hi = 0;
@@ -146,6 +147,11 @@ k_add_ln_quant(const T *x, const T *__restrict__ delta, const T *__restrict__ ga
             *reinterpret_cast<uint2 *>(ca + base + c) = make_uint2(lo, hi);
         }
     }
+}
+
+// gelu(x) as torch computes it for approximate='none': x * 0.5 * (1 + erf(x / sqrt(2))) in fp32, rounded to T.
+template <typename T> __device__ __forceinline__ T gelu_erf(float f) {
+    return from_f32<T>(f * 0.5f * (1.0f + erff(f * 0.70710678118654752440f)));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -171,8 +177,7 @@ k_gelu_quant(const T *__restrict__ x, int64_t rows, int64_t cols, T *__restrict_
             a.raw = *reinterpret_cast<const uint4 *>(x + base + c);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float f = to_f32(a.get(j));
-                const T r = from_f32<T>(f * 0.5f * (1.0f + erff(f * 0.70710678118654752440f)));
+                const T r = gelu_erf<T>(to_f32(a.get(j)));
                 h.set(j, r);
                 am = absmax_step(am, to_f32(r), sparse, threshold);
             }
@@ -201,6 +206,82 @@ k_gelu_quant(const T *__restrict__ x, int64_t rows, int64_t cols, T *__restrict_
             if (j < 4) lo |= q << (8 * j); else hi |= q << (8 * (j - 4));
         }
         *reinterpret_cast<uint2 *>(ca + base + c) = make_uint2(lo, hi);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same for encoder-sized fp16 calls (rows >= 4096, cols <= 2048), through a table.  An fp16 GELU is a function
+// of 65536 bit patterns: k_gelu_table_fill evaluates gelu_erf<__half> once per pattern into a 128 KB device table,
+// every CTA of k_gelu_quant_lut copies it into shared memory and then replaces ~40 fp32 instructions per element
+// (erff) by one 2-byte shared-memory load -- bit-identical by construction, and the kernel goes from
+// instruction-bound (1.19 ms per 384000 x 2048 on B200) to the HBM stream it is (2 B read, 3 B written per element).
+// Persistent CTAs of 16 warps, one warp per row, the row's 8 x 16-byte chunks are loaded up front and converted in place.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLutWarps = 16;
+constexpr int kLutEntries = 65536;
+__device__ __half g_gelu_table[kLutEntries];
+
+__global__ void k_gelu_table_fill() {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (unsigned)kLutEntries) g_gelu_table[i] = gelu_erf<__half>(__half2float(__ushort_as_half((unsigned short)i)));
+}
+
+__global__ void __launch_bounds__(kLutWarps * 32, 1)
+k_gelu_quant_lut(const __half *__restrict__ x, int64_t rows, int cols, __half *__restrict__ h_out, float threshold,
+                 int8_t *__restrict__ ca, float *__restrict__ row_stats, int32_t *__restrict__ col_flags) {
+    extern __shared__ __align__(16) unsigned short s_lut[];
+    {   // the table does not depend on the predecessor kernel: copied before the PDL wait
+        const uint4 *src = reinterpret_cast<const uint4 *>(g_gelu_table);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+        for (int i = threadIdx.x; i < kLutEntries * 2 / 16; i += kLutWarps * 32) dst[i] = src[i];
+    }
+    __syncthreads();
+    pdl_prologue_done();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool sparse = threshold > 0.0f;
+    for (int64_t row = (int64_t)blockIdx.x * kLutWarps + warp; row < rows; row += (int64_t)gridDim.x * kLutWarps) {
+        const int64_t base = row * cols;
+        uint4 v[kMaxChunks];
+#pragma unroll
+        for (int i = 0; i < kMaxChunks; ++i) {
+            const int c = i * 256 + lane * 8;
+            if (c < cols) v[i] = __ldcs(reinterpret_cast<const uint4 *>(x + base + c));     // streamed once
+        }
+        float am = 0.0f;
+#pragma unroll
+        for (int i = 0; i < kMaxChunks; ++i) {
+            const int c = i * 256 + lane * 8;
+            if (c < cols) {
+                uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t lo = s_lut[w[j] & 0xffffu], hi = s_lut[w[j] >> 16];
+                    am = absmax_step(am, __half2float(__ushort_as_half((unsigned short)lo)), sparse, threshold);
+                    am = absmax_step(am, __half2float(__ushort_as_half((unsigned short)hi)), sparse, threshold);
+                    w[j] = lo | (hi << 16);
+                }
+                v[i] = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4 *>(h_out + base + c) = v[i];
+            }
+        }
+        if (ca == nullptr) continue;
+        am = warp_max(am);
+        if (lane == 0) row_stats[row] = am;
+        const float scale = __fdiv_rn(127.0f, am);
+#pragma unroll
+        for (int i = 0; i < kMaxChunks; ++i) {
+            const int c = i * 256 + lane * 8;
+            if (c < cols) {
+                const __half *h8 = reinterpret_cast<const __half *>(&v[i]);
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t q = quant_elem(__half2float(h8[j]), scale, sparse, threshold, col_flags, c + j, cols);
+                    if (j < 4) lo |= q << (8 * j); else hi |= q << (8 * (j - 4));
+                }
+                *reinterpret_cast<uint2 *>(ca + base + c) = make_uint2(lo, hi);
+            }
+        }
     }
 }
 
@@ -293,16 +374,28 @@ extern "C" int wq_add_layernorm_quant(const void *x, const void *delta, int dtyp
                "wq_add_layernorm_quant: pointers must be 16-byte aligned");
     const unsigned grid = (unsigned)((rows + kWarps - 1) / kWarps);
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == WQ_F16) {
-        WQ_LAUNCH_PDL(k_add_ln_quant<__half>, dim3(grid), dim3(kWarps * 32), 0, s, (const __half *)x,
-                      (const __half *)delta, (const __half *)gamma, (const __half *)beta, eps, rows, (int)cols,
-                      (__half *)x_out, (__half *)h_out, threshold, ca, row_stats, col_flags);
-    } else {
-        WQ_LAUNCH_PDL(k_add_ln_quant<__nv_bfloat16>, dim3(grid), dim3(kWarps * 32), 0, s, (const __nv_bfloat16 *)x,
-                      (const __nv_bfloat16 *)delta, (const __nv_bfloat16 *)gamma, (const __nv_bfloat16 *)beta, eps,
-                      rows, (int)cols, (__nv_bfloat16 *)x_out, (__nv_bfloat16 *)h_out, threshold, (int8_t *)nullptr,
-                      (float *)nullptr, (int32_t *)nullptr);
+    const int chunks = (int)((cols + 255) / 256);
+#define WQ_LN_CASE(CH)                                                                                                 \
+    if (chunks <= CH) {                                                                                                \
+        if (dtype == WQ_F16) {                                                                                         \
+            WQ_LAUNCH_PDL((k_add_ln_quant<__half, CH>), dim3(grid), dim3(kWarps * 32), 0, s, (const __half *)x,        \
+                          (const __half *)delta, (const __half *)gamma, (const __half *)beta, eps, rows, (int)cols,    \
+                          (__half *)x_out, (__half *)h_out, threshold, ca, row_stats, col_flags);                      \
+        } else {                                                                                                       \
+            WQ_LAUNCH_PDL((k_add_ln_quant<__nv_bfloat16, CH>), dim3(grid), dim3(kWarps * 32), 0, s,                    \
+                          (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)delta, (const __nv_bfloat16 *)gamma,        \
+                          (const __nv_bfloat16 *)beta, eps, rows, (int)cols, (__nv_bfloat16 *)x_out,                   \
+                          (__nv_bfloat16 *)h_out, threshold, (int8_t *)nullptr, (float *)nullptr, (int32_t *)nullptr); \
+        }                                                                                                              \
+        return WQ_OK;                                                                                                  \
     }
+    WQ_LN_CASE(2)
+    WQ_LN_CASE(3)
+    WQ_LN_CASE(4)
+    WQ_LN_CASE(5)
+    WQ_LN_CASE(6)
+    WQ_LN_CASE(8)
+#undef WQ_LN_CASE
     return WQ_OK;
 }
 
@@ -320,6 +413,39 @@ extern "C" int wq_gelu_quant(const void *x, int dtype, int64_t rows, int64_t col
     WQ_REQUIRE(wq_aligned(x, 16) && wq_aligned(h_out, 16) && (ca == nullptr || wq_aligned(ca, 8)),
                "wq_gelu_quant: pointers must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == WQ_F16 && rows >= 4096 && cols <= 256 * kMaxChunks) {
+        // table path (k_gelu_quant_lut).  The table of a device is filled on first use, synchronously; a first use
+        // under stream capture (no synchronisation allowed) takes the erff kernel below instead.
+        static bool ready[64] = {};
+        static bool configured = false;
+        int dev = 0;
+        WQ_CUDA(cudaGetDevice(&dev));
+        bool ok = dev >= 0 && dev < 64;
+        if (ok && !ready[dev]) {
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            WQ_CUDA(cudaStreamIsCapturing(s, &cap));
+            if (cap == cudaStreamCaptureStatusNone) {
+                k_gelu_table_fill<<<kLutEntries / 256, 256, 0, s>>>();
+                WQ_LAUNCH_CHECK();
+                WQ_CUDA(cudaStreamSynchronize(s));
+                ready[dev] = true;
+            } else {
+                ok = false;
+            }
+        }
+        if (ok) {
+            if (!configured) {
+                WQ_CUDA(cudaFuncSetAttribute(k_gelu_quant_lut, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kLutEntries * 2));
+                configured = true;
+            }
+            const int64_t want = (rows + kLutWarps - 1) / kLutWarps;
+            const unsigned grid = (unsigned)(want < wq_sm_count() ? want : wq_sm_count());
+            WQ_LAUNCH_PDL(k_gelu_quant_lut, dim3(grid), dim3(kLutWarps * 32), (size_t)kLutEntries * 2, s,
+                          (const __half *)x, rows, (int)cols, (__half *)h_out, threshold, ca, row_stats, col_flags);
+            return WQ_OK;
+        }
+    }
     const bool split = rows <= 4096 && cols >= 1024;     // few long rows: 4 warps per row
     const int rows_per_cta = split ? kWarps / 4 : kWarps;
     const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);

@@ -102,7 +102,8 @@ def test_logmel_full_batch_matches_oracle_on_sampled_utterances(F):
 # weight-stationary schedule of the int8 x int8 GEMM (gemm_tc.cu, WS > 0): taken for K <= 512 and many row
 # blocks; the same rows in chunks of 4096 take the round-robin schedule, and both must agree bit for bit
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("M,N,K", [(40001, 600, 384), (96000, 512, 512), (37900, 1536, 512)])
+@pytest.mark.parametrize("M,N,K", [(40001, 600, 384), (96000, 512, 512), (37900, 1536, 512), (40001, 1000, 512),
+                                   (40001, 1704, 512)])
 def test_llmint8_weight_stationary_equals_round_robin_with_outliers(F, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     x = torch.randn(M, K, device="cuda", generator=g).half()

@@ -124,6 +124,38 @@ def test_gelu_quant(rows, cols, threshold):
         _check_quant(quant, h, threshold)
 
 
+@pytest.mark.parametrize("rows,cols", [(4096, 2048), (5003, 1000), (6000, 384), (4100, 8)])
+@pytest.mark.parametrize("threshold", [None, 0.0, 6.0])
+def test_gelu_quant_table_path_is_bit_identical_to_erf_path(rows, cols, threshold):
+    """Encoder-sized fp16 calls (rows >= 4096, cols <= 2048) take the 65536-entry table kernel; the same rows in
+    chunks of 1000 take the erff kernel.  Same values, codes, row statistics and outlier flags, bit for bit --
+    including every special input (inf, nan, -0, subnormals)."""
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    x = (torch.randn(rows, cols, device="cuda", generator=g) * 3.0).half()
+    special = torch.tensor([float("inf"), float("-inf"), float("nan"), -0.0, 6e-8, -6e-8, 65504.0, -65504.0],
+                           device="cuda").half()
+    x[5, :8] = special
+    h, quant = F.gelu_quant(x, threshold)
+    flags = None
+    if threshold:
+        st = quant[2]
+        flags = st.col_flags[: cols + 1].clone()
+        st.col_flags.zero_()
+    parts = [F.gelu_quant(x[r:r + 1000].contiguous(), threshold) for r in range(0, rows, 1000)]
+    h_ref = torch.cat([p[0] for p in parts], 0)
+    assert torch.equal(h.view(torch.int16), h_ref.view(torch.int16))
+    if threshold is None:
+        assert quant is None
+        return
+    assert torch.equal(quant[0], torch.cat([p[1][0] for p in parts], 0))
+    assert torch.equal(quant[1].view(torch.int32), torch.cat([p[1][1] for p in parts], 0).view(torch.int32))
+    if threshold:
+        st = parts[0][1][2]
+        assert torch.equal(flags, st.col_flags[: cols + 1])
+        st.col_flags.zero_()
+        assert int(flags[cols].item()) == 1
+
+
 @pytest.mark.parametrize("B,H,t_max,pos", [(3, 6, 64, 0), (5, 8, 128, 17), (2, 20, 448, 447), (64, 8, 128, 64),
                                            (1, 12, 64, 3)])
 @pytest.mark.parametrize("threshold", [None, 6.0])
