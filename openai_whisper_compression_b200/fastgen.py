@@ -34,6 +34,27 @@ class _State:
     pass
 
 
+class _FastReturn(Exception):
+    """Carries the finished token ids out of HF's generate stack (see GraphedGreedy._maybe_unwind)."""
+
+    def __init__(self, sequences: torch.Tensor):
+        super().__init__("whisperq fast return")
+        self.sequences = sequences
+
+
+# keyword arguments of WhisperGenerationMixin.generate that must keep their defaults for the short post-processing
+# (generation_whisper.py:383-412); everything else in **kwargs must be one of _PLAIN_KWARGS
+_WHISPER_DEFAULTS = {"generation_config": None, "logits_processor": None, "stopping_criteria": None,
+                     "prefix_allowed_tokens_fn": None, "synced_gpus": False, "return_timestamps": None,
+                     "prompt_ids": None, "prompt_condition_type": None, "condition_on_prev_tokens": None,
+                     "temperature": None, "compression_ratio_threshold": None, "logprob_threshold": None,
+                     "no_speech_threshold": None, "num_segment_frames": None, "attention_mask": None,
+                     "return_token_timestamps": None, "return_segments": False, "return_dict_in_generate": None,
+                     "force_unique_generate_call": None, "monitor_progress": None}
+_PLAIN_KWARGS = {"input_features", "task", "language", "is_multilingual", "time_precision", "time_precision_features",
+                 "do_sample", "num_beams", "max_new_tokens", "min_new_tokens", "max_length", "min_length", "use_cache"}
+
+
 class GraphedGreedy:
     def __init__(self, model, len_bucket: int = 64):
         self.model = model
@@ -49,8 +70,15 @@ class GraphedGreedy:
         # step graph the own kernel's 128-thread CTAs leave a longer tail once heads x utterances exceed ~1.4 waves,
         # so "auto" keeps cuDNN for those shapes (1135 vs 1190 us per step at B = 256, whisper-base)
         self.cross_attention = os.environ.get("WQ_CROSS_ATTN", "auto")
+        # HF walks the finished batch utterance by utterance (generate_with_fallback, _retrieve_segment,
+        # _pad_to_max_length: ~30 tiny tensor ops each, 12.5 ms at B = 256 with the GPU idle).  For the plain call
+        # transcribe_batch makes (data_utils.py:152) that walk only strips trailing pad/eos tokens and re-pads:
+        # done here in a few batched ops, same result (tests/test_host_logic.py)
+        self.fast_post = os.environ.get("WQ_FAST_POST", "1") != "0"
+        self._unwind = False
         self.replays = 0
         self.fallbacks = 0
+        self.fast_returns = 0
 
     # ------------------------------------------------------------------------------------------
     def install(self):
@@ -64,7 +92,14 @@ class GraphedGreedy:
                 return model_self._whisperq_fastgen._sample(input_ids, **kwargs)
 
             def generate(model_self, *args, **kwargs):
-                out = base.generate(model_self, *args, **kwargs)
+                eng = model_self._whisperq_fastgen
+                eng._unwind = eng.fast_post and eng._plain_call(args, kwargs)
+                try:
+                    out = base.generate(model_self, *args, **kwargs)
+                except _FastReturn as done:
+                    out = done.sequences
+                finally:
+                    eng._unwind = False
                 # the fast loop hands HF's per-utterance post-processing host-resident token ids (see
                 # _sample); the caller gets them back where HF would have put them
                 if isinstance(out, torch.Tensor) and out.device != model_self.device:
@@ -84,6 +119,71 @@ class GraphedGreedy:
             self._orig_sample = None
             del self.model._whisperq_fastgen
             fastenc.disable(self.model)
+
+    # ------------------------------------------------------------------------------------------
+    def _plain_call(self, args, kwargs) -> bool:
+        """True when `model.generate(*args, **kwargs)` is the plain short-form call whose post-processing in
+        WhisperGenerationMixin.generate reduces to stripping trailing pad/eos tokens: one <= 30 s window, no
+        timestamps / prompts / temperature fallback / thresholds / dict outputs.  Anything else keeps HF's path."""
+        if len(args) > 1:
+            return False
+        feats = args[0] if args else kwargs.get("input_features")
+        cfg = self.model.config
+        if not isinstance(feats, torch.Tensor) or feats.dim() != 3 or feats.shape[-1] > 2 * cfg.max_source_positions:
+            return False
+        for k, v in kwargs.items():
+            if k in _WHISPER_DEFAULTS:
+                if not (v is _WHISPER_DEFAULTS[k] or v == _WHISPER_DEFAULTS[k]):
+                    return False
+            elif k not in _PLAIN_KWARGS:
+                return False
+        gc = self.model.generation_config
+        for name in ("return_timestamps", "return_dict_in_generate", "condition_on_prev_tokens",
+                     "compression_ratio_threshold", "logprob_threshold", "no_speech_threshold",
+                     "force_unique_generate_call", "output_scores", "output_logits", "output_attentions",
+                     "output_hidden_states"):
+            if getattr(gc, name, None):
+                return False
+        return (getattr(gc, "num_return_sequences", 1) or 1) == 1
+
+    def _maybe_unwind(self, sequences: torch.Tensor, prompt_len: int, generation_config) -> None:
+        """HF's post-processing of a finished plain call (generate_with_fallback :1063-1096, _retrieve_segment's
+        no-timestamp branch :2051-2075, _pad_to_max_length :182-230 of generation_whisper.py), batched: drop the
+        decoder prompt; a row ending in pad loses as many trailing tokens as it holds pads (one fewer when pad ==
+        eos); a row then ending in eos loses it; rows are right-padded with pad to the longest.  Raises
+        _FastReturn (caught by the `generate` override) when that is all HF would do; returns otherwise."""
+        if not self._unwind or sequences.dim() != 2:
+            return
+        pad, eos = generation_config.pad_token_id, generation_config.eos_token_id
+        if isinstance(pad, torch.Tensor):
+            pad = pad.item() if pad.numel() == 1 else None
+        if isinstance(eos, (list, tuple)):
+            eos = eos[0] if len(eos) == 1 else None
+        if isinstance(eos, torch.Tensor):
+            eos = eos.item() if eos.numel() == 1 else None
+        if not isinstance(pad, int) or not isinstance(eos, int):
+            return
+        seq = sequences.cpu()
+        tok = seq[:, prompt_len:]
+        B, T = tok.shape
+        if T == 0:
+            return
+        ts_begin = (generation_config.no_timestamps_token_id + 1 if hasattr(generation_config, "no_timestamps_token_id")
+                    else self.model.config.vocab_size + 1)
+        if bool((tok >= ts_begin).any()):
+            return                                  # timestamp tokens: HF cuts segments, keep its path
+        n_pad = (tok == pad).sum(1)
+        cut = torch.where(tok[:, -1] == pad, n_pad - (1 if pad == eos else 0), torch.zeros_like(n_pad))
+        length = T - cut
+        if bool((length <= 0).any()):
+            return                                  # HF would index an empty row: let it
+        last = tok.gather(1, (length - 1).view(B, 1)).view(B)
+        length = length - (last == eos).long()
+        width = int(length.max())
+        keep = torch.arange(width).view(1, width) < length.view(B, 1)
+        out = torch.where(keep, tok[:, :width], torch.full((), pad, dtype=tok.dtype))
+        self.fast_returns += 1
+        raise _FastReturn(out.contiguous())
 
     # ------------------------------------------------------------------------------------------
     def _decoder_step(self, st: _State):
@@ -315,9 +415,12 @@ class GraphedGreedy:
                     and generation_config.max_length <= model.config.max_target_positions)
         if not eligible:
             self.fallbacks += 1
-            return self._orig_sample(input_ids, logits_processor=logits_processor,
-                                     stopping_criteria=stopping_criteria, generation_config=generation_config,
-                                     synced_gpus=synced_gpus, streamer=streamer, **model_kwargs)
+            out = self._orig_sample(input_ids, logits_processor=logits_processor,
+                                    stopping_criteria=stopping_criteria, generation_config=generation_config,
+                                    synced_gpus=synced_gpus, streamer=streamer, **model_kwargs)
+            if isinstance(out, torch.Tensor):
+                self._maybe_unwind(out, input_ids.shape[1], generation_config)
+            return out
         enc = enc_out[0] if not hasattr(enc_out, "last_hidden_state") else enc_out.last_hidden_state
         B, P = input_ids.shape
         t_max = -(-int(generation_config.max_length) // self.len_bucket) * self.len_bucket
@@ -426,7 +529,11 @@ class GraphedGreedy:
         # that is ~4 blocking syncs per utterance, ~45 ms at B = 256 -- as long as 25 decode steps.  The ids
         # are read back once here (HF's own dict path does the same with .cpu()) and HF's loops run on
         # the host copy; `generate` above returns the final tensor to the model's device.
-        return input_ids.cpu() if self.host_postprocess else input_ids
+        if not self.host_postprocess:
+            return input_ids
+        ids = input_ids.cpu()
+        self._maybe_unwind(ids, P, generation_config)
+        return ids
 
 
 def enable(model, len_bucket: int = 64) -> GraphedGreedy:
