@@ -106,9 +106,27 @@ class GraphedGreedy:
                     out = out.to(model_self.device)
                 return out
 
+            # HF prepares every 30 s window with per-utterance Python loops over device tensors
+            # (generation_whisper.py:1813-1849); on the first pass of a short-form batch they change nothing
+            def _maybe_reduce_batch(input_features, seek, max_frames, cur_bsz, batch_idx_map):
+                if (isinstance(seek, torch.Tensor) and isinstance(max_frames, torch.Tensor) and seek.shape == max_frames.shape
+                        and len(batch_idx_map) >= cur_bsz and not bool((seek >= max_frames).any())):
+                    return input_features, cur_bsz, [batch_idx_map[i] for i in range(cur_bsz)]   # nobody is finished
+                return base._maybe_reduce_batch(input_features, seek, max_frames, cur_bsz, batch_idx_map)
+
+            def _get_input_segment(input_features, seek, seek_num_frames, num_segment_frames, cur_bsz, batch_idx_map):
+                if (isinstance(input_features, torch.Tensor) and input_features.dim() == 3
+                        and input_features.shape[0] == cur_bsz and input_features.shape[-1] == num_segment_frames
+                        and isinstance(seek, torch.Tensor) and isinstance(seek_num_frames, torch.Tensor)
+                        and not bool((seek != 0).any()) and bool((seek_num_frames >= num_segment_frames).all())):
+                    return input_features           # every slice [0 : >= length] is the whole window: cat == input
+                return base._get_input_segment(input_features, seek, seek_num_frames, num_segment_frames, cur_bsz,
+                                               batch_idx_map)
+
             self._base_cls = base
-            self.model.__class__ = type(base.__name__, (base,), {"_sample": _sample, "generate": generate,
-                                                                 "__module__": base.__module__})
+            self.model.__class__ = type(base.__name__, (base,), {
+                "_sample": _sample, "generate": generate, "_maybe_reduce_batch": staticmethod(_maybe_reduce_batch),
+                "_get_input_segment": staticmethod(_get_input_segment), "__module__": base.__module__})
             self.model._whisperq_fastgen = self
             fastenc.enable(self.model)       # copy-free encoder self-attention (same arithmetic)
         return self

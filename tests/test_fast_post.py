@@ -102,3 +102,50 @@ def test_fast_post_leaves_timestamp_tokens_and_non_plain_calls_to_hf(rig):
     assert not eng._plain_call((feats,), {"temperature": (0.0, 0.2)})
     assert not eng._plain_call((torch.zeros(2, 80, 6000),), {})
     assert eng._plain_call((feats,), {"do_sample": False, "num_beams": 1, "max_new_tokens": 4, "language": "en"})
+
+
+def test_window_preparation_shortcuts_equal_hf(rig):
+    """The subclass's _maybe_reduce_batch / _get_input_segment against HF's static methods: identical results when
+    the shortcut applies (first pass of a short-form batch) and when it does not (exhausted or seeked utterances,
+    short windows)."""
+    model, eng, feats = rig
+    base, cls = eng._base_cls, type(model)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(6, 4, 3000, generator=g)
+    full = torch.full((6,), 3000, dtype=torch.long)
+    cases = [(torch.zeros(6, dtype=torch.long), full.clone()),                       # first pass
+             (torch.tensor([0, 3000, 0, 0, 3000, 0]), full.clone()),                 # two exhausted
+             (torch.tensor([0, 0, 1200, 0, 0, 0]), full.clone())]                    # one seeked
+    for seek, max_frames in cases:
+        bmap = list(range(6))
+        ref = base._maybe_reduce_batch(x, seek, max_frames, 6, bmap)
+        got = cls._maybe_reduce_batch(x, seek, max_frames, 6, bmap)
+        assert torch.equal(got[0], ref[0]) and got[1] == ref[1] and got[2] == ref[2]
+        xf, bsz, bmap2 = ref
+        n = (max_frames - seek).clamp(max=3000)
+        ref_seg = base._get_input_segment(xf, seek, n, 3000, bsz, bmap2)
+        got_seg = cls._get_input_segment(xf, seek, n, 3000, bsz, bmap2)
+        assert got_seg.shape == ref_seg.shape and torch.equal(got_seg, ref_seg)
+    # windows shorter than 3000 frames are padded by HF: not the shortcut's case
+    short = torch.randn(3, 4, 1000, generator=g)
+    z = torch.zeros(3, dtype=torch.long)
+    n = torch.full((3,), 1000, dtype=torch.long)
+    assert torch.equal(cls._get_input_segment(short, z, n, 3000, 3, [0, 1, 2]),
+                       base._get_input_segment(short, z, n, 3000, 3, [0, 1, 2]))
+
+
+def test_generate_with_all_host_shortcuts_equals_pristine_hf_on_cpu():
+    """Whole `model.generate` on the CPU (HF's own decode loop): the untouched HF class against the same model after
+    fastgen.enable (window shortcuts + batched post-processing active).  Same ids."""
+    torch.manual_seed(1)
+    model = harness.build_model("tiny", encoder_layers=1, decoder_layers=1).eval()
+    feats = torch.randn(3, model.config.num_mel_bins, 3000) * 0.3
+    ref = harness.greedy_generate(model, feats, 5)
+    ref_free = model.generate(feats, do_sample=False, num_beams=1, max_new_tokens=6)   # eos allowed
+    eng = fastgen.enable(model)
+    got = harness.greedy_generate(model, feats, 5)
+    got_free = model.generate(feats, do_sample=False, num_beams=1, max_new_tokens=6)
+    assert eng.fast_returns == 2
+    assert torch.equal(got, ref) and torch.equal(got_free, ref_free)
+    eng.uninstall()
+    assert torch.equal(harness.greedy_generate(model, feats, 5), ref)
