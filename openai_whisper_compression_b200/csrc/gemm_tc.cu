@@ -2,8 +2,15 @@
 //
 //   Y[M,N] = epilogue( A[M,K] . W[N,K]^T )
 //
-// Persistent kernel: one CTA per SM walks 256 x BN output tiles (two 128-row UMMA halves; n fastest, so the CTAs that
-// share an A row-block run together and hit L2).  Warp roles:
+// Persistent kernel: one CTA per SM walks output tiles.  Tile shape and schedule are template parameters picked per
+// call (launch_i8 / launch_gemm; measurements in DESIGN.md section 3.1):
+//   256 x BN, two row halves      two M = 128, N = BN MMAs per k-step share one W tile (BN = 128, or 64 for
+//                                 decode-shaped calls); every scheme
+//   128 x 256, two column halves  (COLS) one M = 128, N = 256 MMA per k-step; int8 x int8 schemes
+//   round-robin                   tiles n-fastest over the grid: the CTAs sharing an A row-block run together (L2)
+//   weight-stationary             (WS) K <= 512, int8 x int8: the CTA's W tile stays in shared memory, the ring streams
+//                                 A alone and the producer prefetches the A row block of a later tile into L2
+// Warp roles:
 //   warp 0      TMA producer: A tile (and the W tile, or the PACKED W tile) -> shared memory ring
 //   warp 1      TMEM allocation + single-thread tcgen05.mma issue into a 2-deep TMEM accumulator ring
 //   warps 2..9  epilogue (2 halves x 4 TMEM lane quarters): tcgen05.ld the accumulator (one TMEM lane
