@@ -107,6 +107,14 @@ int wq_quant_i8_rowwise_quanto(const void *w, int w_dtype, int64_t N, int64_t K,
 int wq_quant_u4_group_quanto(const void *w, int w_dtype, int64_t N, int64_t K, int group,
                              uint8_t *packed, float *scale, float *shift, wq_stream_t stream);
 
+/* The same quantizer for weights=qint2 or qint4 (bits = 2 | 4) -- quantize(model, weights=qint2),
+ * quantization/evaluation_scripts/dynamic_evaluation_int2.py:158-160: scale = (max - min) / (2^bits - 1),
+ * q = clamp(rint((w + shift) / scale), 0, 2^bits - 1).  2-bit codes are stored in the SAME container as 4-bit
+ * ones (one code per nibble, high nibble first), so wq_gemm_u4a16 consumes them unchanged; the arithmetic is
+ * quanto's qint2, the storage is 4 bits per weight (quanto packs four codes per byte). */
+int wq_quant_ubits_group_quanto(const void *w, int w_dtype, int64_t N, int64_t K, int group, int bits,
+                                uint8_t *packed, float *scale, float *shift, wq_stream_t stream);
+
 /* torch.quantization.quantize_dynamic weight observer + quantize_per_tensor --
  * model_utils.py:131-134, pruning+quantization/pytorch_implementation.py:657-665.
  * scale = max(-min, max) / 127.5 (>= FLT_EPSILON), q = clamp(nearbyint(w * (1/scale))).

@@ -29,6 +29,7 @@ _PROTOS = {
     "wq_outlier_columns": [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_quant_i8_rowwise_quanto": [c_ptr, c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
     "wq_quant_u4_group_quanto": [c_ptr, c_int, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
+    "wq_quant_ubits_group_quanto": [c_ptr, c_int, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_quant_i8_tensor_torch": [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_quant_act_u8_tensor": [c_ptr, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_gemm_llmint8": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr],

@@ -365,8 +365,8 @@ k_dequant_absmax_blockwise8(const uint8_t *__restrict__ q, const float *__restri
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_quant_u4_group_quanto(const T *__restrict__ w, int64_t n_groups, int group, uint8_t *__restrict__ packed,
-                        float *__restrict__ scale, float *__restrict__ shift) {
+k_quant_u4_group_quanto(const T *__restrict__ w, int64_t n_groups, int group, float qmax,
+                        uint8_t *__restrict__ packed, float *__restrict__ scale, float *__restrict__ shift) {
     const int lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     if (g >= n_groups) return;
@@ -379,20 +379,20 @@ k_quant_u4_group_quanto(const T *__restrict__ w, int64_t n_groups, int group, ui
     }
     mn = warp_min(mn);
     mx = warp_max(mx);
-    const float s = __fdiv_rn(__fsub_rn(mx, mn), 15.0f);   // (rmax - rmin) / (qmax - qmin)
+    const float s = __fdiv_rn(__fsub_rn(mx, mn), qmax);    // (rmax - rmin) / (qmax - qmin): 15 (qint4) or 3 (qint2)
     const float sh = -mn;                                   // shift = -rmin
     if (lane == 0) {
         scale[g] = s;
         shift[g] = sh;
     }
-    // q = clamp(round((w + shift) / scale), 0, 15); two codes per byte, first in the high nibble
+    // q = clamp(round((w + shift) / scale), 0, qmax); two codes per byte, first in the high nibble
     for (int i = lane * 2; i < group; i += 64) {
         uint32_t c[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             float r = rintf(__fdiv_rn(__fadd_rn(to_f32(pw[i + j]), sh), s));
             if (r != r) r = 0.0f;                           // constant group: 0 / 0
-            r = fminf(fmaxf(r, 0.0f), 15.0f);
+            r = fminf(fmaxf(r, 0.0f), qmax);
             c[j] = (uint32_t)(int)r;
         }
         packed[(g * group + i) >> 1] = (uint8_t)((c[0] << 4) | c[1]);
@@ -668,6 +668,13 @@ extern "C" int wq_quant_act_u8_tensor(const void *x, int x_dtype, int64_t n, uin
 
 extern "C" int wq_quant_u4_group_quanto(const void *w, int w_dtype, int64_t N, int64_t K, int group, uint8_t *packed,
                                         float *scale, float *shift, wq_stream_t stream) {
+    return wq_quant_ubits_group_quanto(w, w_dtype, N, K, group, 4, packed, scale, shift, stream);
+}
+
+extern "C" int wq_quant_ubits_group_quanto(const void *w, int w_dtype, int64_t N, int64_t K, int group, int bits,
+                                           uint8_t *packed, float *scale, float *shift, wq_stream_t stream) {
+    WQ_REQUIRE(bits == 2 || bits == 4, "wq_quant_ubits_group_quanto: bits must be 2 or 4 (got %d)", bits);
+    const float qmax = (float)((1 << bits) - 1);
     WQ_REQUIRE(N >= 0 && K >= 0, "wq_quant_u4_group_quanto: negative shape");
     WQ_REQUIRE(group >= 2 && group % 2 == 0 && (K == 0 || K % group == 0),
                "wq_quant_u4_group_quanto: group %d must be even and divide K=%lld", group, (long long)K);
@@ -678,13 +685,13 @@ extern "C" int wq_quant_u4_group_quanto(const void *w, int w_dtype, int64_t N, i
     cudaStream_t s = (cudaStream_t)stream;
     switch (w_dtype) {
         case WQ_F32:
-            k_quant_u4_group_quanto<float><<<grid, kWarpsPerCta * 32, 0, s>>>((const float *)w, n_groups, group, packed, scale, shift);
+            k_quant_u4_group_quanto<float><<<grid, kWarpsPerCta * 32, 0, s>>>((const float *)w, n_groups, group, qmax, packed, scale, shift);
             break;
         case WQ_F16:
-            k_quant_u4_group_quanto<__half><<<grid, kWarpsPerCta * 32, 0, s>>>((const __half *)w, n_groups, group, packed, scale, shift);
+            k_quant_u4_group_quanto<__half><<<grid, kWarpsPerCta * 32, 0, s>>>((const __half *)w, n_groups, group, qmax, packed, scale, shift);
             break;
         case WQ_BF16:
-            k_quant_u4_group_quanto<__nv_bfloat16><<<grid, kWarpsPerCta * 32, 0, s>>>((const __nv_bfloat16 *)w, n_groups, group, packed, scale, shift);
+            k_quant_u4_group_quanto<__nv_bfloat16><<<grid, kWarpsPerCta * 32, 0, s>>>((const __nv_bfloat16 *)w, n_groups, group, qmax, packed, scale, shift);
             break;
         default:
             WQ_REQUIRE(false, "wq_quant_u4_group_quanto: bad dtype %d", w_dtype);

@@ -473,9 +473,12 @@ def quanto_group_size(in_features: int) -> int:
     return in_features
 
 
-def quanto_quantize_qint4(w: torch.Tensor, group: Optional[int] = None):
+def quanto_quantize_qint4(w: torch.Tensor, group: Optional[int] = None, bits: int = 4):
     """quanto MaxOptimizer + AffineQuantizer: (packed uint8 [N, K/2], scale f32 [N, K/g],
-    shift f32 [N, K/g], group)."""
+    shift f32 [N, K/g], group).  bits = 2 gives quanto's qint2 codes (0..3) in the same one-code-per-nibble
+    container, so gemm_u4a16 consumes either."""
+    if bits not in (2, 4):
+        raise ValueError("bits must be 2 or 4")
     w = w.contiguous()
     _need_cuda(w)
     N, K = w.shape
@@ -484,8 +487,9 @@ def quanto_quantize_qint4(w: torch.Tensor, group: Optional[int] = None):
     scale = torch.empty((N, K // g), dtype=torch.float32, device=w.device)
     shift = torch.empty((N, K // g), dtype=torch.float32, device=w.device)
     with torch.cuda.device(w.device):
-        _lib.check(_lib.load().wq_quant_u4_group_quanto(_ptr(w), _DT[w.dtype], N, K, g, _ptr(packed), _ptr(scale),
-                                                        _ptr(shift), _stream()), "wq_quant_u4_group_quanto")
+        _lib.check(_lib.load().wq_quant_ubits_group_quanto(_ptr(w), _DT[w.dtype], N, K, g, bits, _ptr(packed),
+                                                           _ptr(scale), _ptr(shift), _stream()),
+                   "wq_quant_ubits_group_quanto")
     STATS.launches += 1
     return packed, scale, shift, g
 

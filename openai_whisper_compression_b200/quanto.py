@@ -5,13 +5,14 @@ pruning+quantization/quanto_implementation.py:648-670).
 
 Implemented on the sm_100a library: weights-only ``qint8`` (per-output-channel absmax / 127,
 ``torch.round`` half-to-even, W8A16 fused GEMM) and weights-only ``qint4`` (group-wise affine uint4,
-MaxOptimizer: scale = (max - min) / 15, float shift = -min; fused W4A16 GEMM).  ``quantize`` swaps every ``nn.Linear`` (incl.
+MaxOptimizer: scale = (max - min) / 15, float shift = -min; fused W4A16 GEMM) and ``qint2`` (the same with
+three levels above zero; the 2-bit codes are kept one per nibble in the qint4 container, so the arithmetic is quanto's
+and the storage is 4 bits per weight).  ``quantize`` swaps every ``nn.Linear`` (incl.
 ``proj_out``) for ``QLinear``; ``freeze`` fixes the integer weights.  The reference quantizes a
 CPU model and moves it to the device afterwards (model_utils.py:126-137): ``freeze`` on a CPU
 module records the request and the integer codes are produced by the CUDA kernel the moment the
 module reaches a CUDA device -- there is no CPU arithmetic path.  Not implemented yet (SURVEY.md
-section 8f rank 2, raise NotImplementedError): qint2 / qfloat8 weights, activation quantization +
-Calibration.
+section 8f rank 2, raise NotImplementedError): qfloat8 weights, activation quantization + Calibration.
 """
 from __future__ import annotations
 
@@ -57,11 +58,11 @@ class QLinear(nn.Linear):
         if activations is not None:
             raise NotImplementedError("quanto activation quantization (static, Calibration) is outside the "
                                       "built hot path (SURVEY.md section 8f rank 2)")
-        if weights is not None and getattr(weights, "name", None) not in ("qint8", "qint4"):
-            raise NotImplementedError(f"quanto weights={weights} is not implemented yet; qint8 and qint4 are "
-                                      "(SURVEY.md section 8f rank 2)")
-        if weights is not None and weights.name == "qint4" and in_features % 64 != 0:
-            raise NotImplementedError("qint4 weights need in_features % 64 == 0 in the fused GEMM")
+        if weights is not None and getattr(weights, "name", None) not in ("qint8", "qint4", "qint2"):
+            raise NotImplementedError(f"quanto weights={weights} is not implemented yet; qint8, qint4 and qint2 "
+                                      "are (SURVEY.md section 8f rank 2)")
+        if weights is not None and weights.name in ("qint4", "qint2") and in_features % 64 != 0:
+            raise NotImplementedError("qint4 / qint2 weights need in_features % 64 == 0 in the fused GEMM")
         self.weight_qtype = weights
         self.activation_qtype = activations
         self.optimizer = optimizer
@@ -98,8 +99,9 @@ class QLinear(nn.Linear):
 
     def _quantize_now(self):
         w = self.weight.data
-        if self.weight_qtype.name == "qint4":
-            q, scale, self._wshift, self._group = F.quanto_quantize_qint4(w)
+        if self.weight_qtype.name in ("qint4", "qint2"):
+            # qint2 codes (0..3) live in the qint4 container (one code per nibble): same fused GEMM
+            q, scale, self._wshift, self._group = F.quanto_quantize_qint4(w, bits=self.weight_qtype.bits)
         else:
             q, scale = F.quanto_quantize_qint8(w)
         self._wq, self._wscale = q, scale

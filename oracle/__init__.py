@@ -243,16 +243,16 @@ def quanto_group_size(in_features: int) -> int:
     return in_features
 
 
-def quanto_qint4(w: np.ndarray, group: Optional[int] = None):
-    """(codes uint8 [N, K] one per element, scale f32 [N, K/g], shift f32 [N, K/g], group)."""
+def quanto_qint4(w: np.ndarray, group: Optional[int] = None, bits: int = 4):
+    """(codes uint8 [N, K] one per element, scale f32 [N, K/g], shift f32 [N, K/g], group); bits = 2: qint2."""
     wf = _f32(w)
     N, K = wf.shape
     g = group or quanto_group_size(K)
     q = np.zeros((N, K), dtype=np.uint8)
     scale = np.zeros((N, K // g), dtype=np.float32)
     shift = np.zeros((N, K // g), dtype=np.float32)
-    lib().orc_quanto_qint4(_p(wf), ctypes.c_int64(N), ctypes.c_int64(K), ctypes.c_int(g), _p(q), _p(scale),
-                           _p(shift))
+    lib().orc_quanto_qbits(_p(wf), ctypes.c_int64(N), ctypes.c_int64(K), ctypes.c_int(g), ctypes.c_int(bits), _p(q),
+                           _p(scale), _p(shift))
     return q, scale, shift, g
 
 

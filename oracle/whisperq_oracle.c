@@ -289,8 +289,17 @@ void orc_quanto_qint8(const float *w, int64_t N, int64_t K, int8_t *q, float *sc
  * consecutive in-features of one output channel: scale = (max - min) / 15,
  * shift = -min, q = clamp(round_half_even((w + shift) / scale), 0, 15).
  * q holds one code per element (unpacked). */
+void orc_quanto_qbits(const float *w, int64_t N, int64_t K, int group, int bits, uint8_t *q,
+                      float *scale, float *shift);
 void orc_quanto_qint4(const float *w, int64_t N, int64_t K, int group, uint8_t *q,
                       float *scale, float *shift) {
+    orc_quanto_qbits(w, N, K, group, 4, q, scale, shift);
+}
+
+/* the same for qint2 / qint4: qmax = 2^bits - 1 levels above 0 */
+void orc_quanto_qbits(const float *w, int64_t N, int64_t K, int group, int bits, uint8_t *q,
+                      float *scale, float *shift) {
+    const float qmax = (float)((1 << bits) - 1);
     int64_t ng = K / group;
     for (int64_t n = 0; n < N; ++n)
         for (int64_t g = 0; g < ng; ++g) {
@@ -300,14 +309,14 @@ void orc_quanto_qint4(const float *w, int64_t N, int64_t K, int group, uint8_t *
                 if (p[i] < mn) mn = p[i];
                 if (p[i] > mx) mx = p[i];
             }
-            float s = (mx - mn) / 15.0f, sh = -mn;
+            float s = (mx - mn) / qmax, sh = -mn;
             scale[n * ng + g] = s;
             shift[n * ng + g] = sh;
             for (int i = 0; i < group; ++i) {
                 float r = rintf((p[i] + sh) / s);
                 if (r != r) r = 0.0f;
                 if (r < 0.0f) r = 0.0f;
-                if (r > 15.0f) r = 15.0f;
+                if (r > qmax) r = qmax;
                 q[n * K + g * group + i] = (uint8_t)r;
             }
         }

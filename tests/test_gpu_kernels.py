@@ -330,6 +330,28 @@ def test_llmint8_small_m_kernel_bit_identical_to_tensor_core_path(M, N, K, outli
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
 @pytest.mark.parametrize("N,K", [(48, 64), (130, 384), (33, 1280), (5, 160)])
+def test_quanto_qint2_codes_bit_exact_and_gemm(dtype, N, K):
+    """qint2 (quantization/evaluation_scripts/dynamic_evaluation_int2.py:158-160): codes 0..3 in the qint4
+    container, bit-exact vs the oracle; the fused GEMM consumes them unchanged."""
+    rng = np.random.RandomState(N * 3 + K)
+    w = (rng.randn(N, K) * 0.05).astype(np.float32)
+    wt = dev(w).to(dtype)
+    packed, scale, shift, g = F.quanto_quantize_qint4(wt, bits=2)
+    q_ref, s_ref, sh_ref, g_ref = oracle.quanto_qint4(wt.float().cpu().numpy(), bits=2)
+    assert g == g_ref and int(q_ref.max()) <= 3
+    np.testing.assert_array_equal(scale.cpu().numpy(), s_ref)
+    np.testing.assert_array_equal(shift.cpu().numpy(), sh_ref)
+    np.testing.assert_array_equal(packed.cpu().numpy(), oracle.quanto_qint4_pack(q_ref))
+    if K % 64 == 0:
+        x = dev((rng.randn(9, K) * 0.5).astype(np.float32)).half()
+        y = F.gemm_u4a16(x, packed, scale, shift, g, None, out_dtype=torch.float32).cpu().numpy()
+        wd = torch.from_numpy(oracle.quanto_qint4_dequant(q_ref, s_ref, sh_ref, g)).half().double().numpy()
+        ref = x.double().cpu().numpy() @ wd.T
+        assert np.abs(y - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("N,K", [(48, 64), (130, 384), (33, 1280), (5, 160)])
 def test_quanto_qint4_codes_bit_exact(dtype, N, K):
     rng = np.random.RandomState(N * K)
     w = (rng.randn(N, K) * 0.02).astype(np.float32)

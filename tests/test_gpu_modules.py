@@ -352,6 +352,31 @@ def test_quanto_int4_model_flow(pkg):
     assert ids.shape[0] == 4
 
 
+def test_quanto_int2_model_flow(pkg):
+    """dynamic_evaluation_int2.py:158-160: quantize(model, weights=qint2) + freeze, then .to(device): every linear
+    becomes a qint2 QLinear (codes 0..3 from the quantizer of the oracle), forward = dequantise-then-matmul."""
+    from openai_whisper_compression_b200 import harness, quanto
+    model = harness.build_model("tiny", **MICRO)
+    quanto.quantize(model, weights=quanto.qint2)
+    quanto.freeze(model)
+    model = model.to("cuda")
+    qs = [m for m in model.modules() if isinstance(m, quanto.QLinear)]
+    assert len(qs) == 33 and all(m.frozen and m.weight_qtype.name == "qint2" for m in qs)
+    fc1 = model.model.decoder.layers[0].fc1
+    ref = harness.build_model("tiny", **MICRO).model.decoder.layers[0].fc1
+    q_ref, s_ref, sh_ref, g = oracle.quanto_qint4(ref.weight.detach().numpy(), bits=2)
+    sd = fc1.state_dict()
+    np.testing.assert_array_equal(sd["weight._data"].cpu().numpy(), oracle.quanto_qint4_pack(q_ref))
+    assert int(q_ref.max()) == 3
+    x = torch.randn(3, 5, 64)
+    y = fc1(x.cuda()).cpu().numpy()
+    wd = oracle.quanto_qint4_dequant(q_ref, s_ref, sh_ref, g).astype(np.float16).astype(np.float64)
+    y_ref = x.half().double().numpy() @ wd.T + ref.bias.detach().double().numpy()
+    assert np.abs(y - y_ref).max() < 1e-3
+    ids = harness.greedy_generate(model, _feats().cuda(), 6)
+    assert ids.shape[0] == 4
+
+
 def test_graphed_greedy_early_stop_paths_match_hf(pkg):
     """min_new_tokens < max_new_tokens: after the minimum the loop must evaluate HF's stopping
     criteria every step (EOS possible); before it, it may skip the host sync.  Same ids as HF."""

@@ -192,6 +192,24 @@ def test_edit_distance_and_tally():
     assert t[3] == len("the cat sat") + len("a b")
 
 
+def test_quanto_qint2_invariants():
+    """quanto qint2 = the qint4 scheme with three levels above zero."""
+    rng = np.random.RandomState(2)
+    W = (rng.randn(8, 256) * 0.05).astype(np.float32)
+    q, scale, shift, g = oracle.quanto_qint4(W, bits=2)
+    assert g == 128 and q.max() == 3 and q.min() == 0
+    Wg = W.reshape(8, 2, 128)
+    np.testing.assert_array_equal(scale, ((Wg.max(2) - Wg.min(2)) / np.float32(3.0)).astype(np.float32))
+    np.testing.assert_array_equal(shift, -Wg.min(2))
+    qg = q.reshape(8, 2, 128)
+    assert (qg.max(2) == 3).all() and (qg.min(2) == 0).all()       # every group spans the whole code range
+    deq = oracle.quanto_qint4_dequant(q, scale, shift, g)
+    assert np.abs(deq - W).max() <= scale.max() * 0.5 * (1 + 1e-5)
+    # the 4-bit scheme on the same weights resolves 5x finer
+    q4, s4, _, _ = oracle.quanto_qint4(W)
+    np.testing.assert_allclose(scale, s4 * 5.0, rtol=1e-6)
+
+
 def test_quanto_qint4_invariants():
     rng = np.random.RandomState(4)
     W = (rng.randn(16, 384) * 0.02).astype(np.float32)
