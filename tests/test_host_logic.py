@@ -200,3 +200,27 @@ def test_tally_host_pack_layout_matches_oracle_distances():
         got_w = oracle.edit_distance(list(ref_ids[ro[p]:ro[p + 1]]), list(hyp_ids[ho[p]:ho[p + 1]]))
         got_c = oracle.edit_distance(list(ref_ids[ro[P + p]:ro[P + p + 1]]), list(hyp_ids[ho[P + p]:ho[P + p + 1]]))
         assert (got_w, got_c) == (want_w, want_c)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path: torch quantize_dynamic on HF Whisper) on a tiny
+    bounded sample: one JSON line with the keys the driver reads."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--size", "tiny",
+                          "--cpu-sample", "1", "--new-tokens", "3", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "audio-seconds/sec" and line["unit"] == "audio-s/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and line["vs_baseline"] is None
+    # other ranks of a torchrun launch exit quietly
+    env = dict(os.environ, RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
