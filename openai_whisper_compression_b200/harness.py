@@ -128,7 +128,16 @@ class StubProcessor:
         words = self._table(max(ids, default=0) + 1)
         return " ".join([words[i] for i in ids])
 
+    _word_array = None
+
     def batch_decode(self, ids, **kw) -> List[str]:
+        if isinstance(ids, torch.Tensor) and ids.dim() == 2 and ids.numel() > 0:
+            # one fancy-index over an object array of the pseudo-words, then one join per row
+            a = ids.detach().cpu().numpy()
+            words = self._table(int(a.max()) + 1)
+            if StubProcessor._word_array is None or len(StubProcessor._word_array) != len(words):
+                StubProcessor._word_array = np.array(words, dtype=object)
+            return [" ".join(r) for r in StubProcessor._word_array[a]]
         rows = ids.tolist() if hasattr(ids, "tolist") else [list(r) for r in ids]
         words = self._table(max((max(r, default=0) for r in rows), default=0) + 1)
         return [" ".join([words[i] for i in r]) for r in rows]

@@ -9,7 +9,7 @@ over NCCL.
 """
 from __future__ import annotations
 
-from itertools import chain
+from itertools import chain, count
 from typing import List, Sequence
 
 import numpy as np
@@ -27,11 +27,11 @@ def _host_pack(references: Sequence[str], predictions: Sequence[str]):
     P = len(references)
     rw = [r.split() for r in references]
     hw = [h.split() for h in predictions]
-    vocab = {}
-    sd = vocab.setdefault
     n_rw = sum(map(len, rw))
-    words = np.array([sd(w, len(vocab)) for w in chain(chain.from_iterable(rw), chain.from_iterable(hw))],
-                     dtype=np.int32)
+    n_hw = sum(map(len, hw))
+    # id of a word = position of its first occurrence (dict.setdefault driven by map(): no Python-level loop)
+    words = np.fromiter(map({}.setdefault, chain(chain.from_iterable(rw), chain.from_iterable(hw)), count()),
+                        dtype=np.int32, count=n_rw + n_hw)
     chars = np.frombuffer("".join(chain(references, predictions)).encode("utf-32-le"), dtype=np.int32)
     n_rc = sum(map(len, references))
     ref_len = np.fromiter(chain(map(len, rw), map(len, references)), dtype=np.int64, count=2 * P)
