@@ -224,3 +224,15 @@ def test_bench_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=300, cwd=root, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_stub_processor_decode_forms_agree():
+    """StubProcessor.batch_decode: tensor fast path (one fancy index) == list path == per-row decode."""
+    from openai_whisper_compression_b200 import harness
+    p = harness.StubProcessor.__new__(harness.StubProcessor)
+    ids = torch.randint(0, 51865, (7, 5), generator=torch.Generator().manual_seed(0))
+    want = [" ".join(f"t{i}" for i in r) for r in ids.tolist()]
+    assert p.batch_decode(ids) == want and p.batch_decode(ids.tolist()) == want
+    assert [p.decode(r) for r in ids] == want
+    assert p.batch_decode(torch.zeros((0, 4), dtype=torch.long)) == []
+    assert p.batch_decode([[1, 2], [3]]) == ["t1 t2", "t3"]
