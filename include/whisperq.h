@@ -257,6 +257,25 @@ int wq_cross_attn_decode(const void *q, int64_t ldq, int dtype, float scaling, c
 int wq_masked_argmax(const void *logits, int dtype, int64_t rows, int64_t cols, int64_t ld,
                      const uint8_t *mask, int64_t *out, wq_stream_t stream);
 
+/* Unquantized linear on the tcgen05 pipeline, for the vocabulary projection the HF bitsandbytes flows keep in
+ * floating point (`proj_out`: transformers modeling_whisper.py:971,1081; HF get_modules_to_not_convert keeps the
+ * output embedding out of replace_with_bnb_linear, so model_utils.py:112-118 leaves it fp16) with the greedy
+ * choice of GenerationMixin._sample (torch.argmax over the processed logits, reached from data_utils.py:152)
+ * folded into the epilogue.
+ *   y[m, n] = x[m, :] . w[n, :] + bias[n]   fp32 accumulation, rounded once to y_dtype
+ * x: [M, K] of x_dtype (F16 / BF16); w: [N, K] of x_dtype; bias fp32 [N] or NULL; y: [M, N] of y_dtype (= x_dtype
+ * or F32) with a row pitch of ldy elements (0 = N), or NULL when only the arg-max is wanted (the logits then never
+ * reach HBM).  argmax_keys: device uint64 [M], zero on entry, or NULL; every tile folds
+ * key = (order-preserving bits of the rounded y << 32) | (0xFFFFFFFF - n) into keys[m] with atomicMax -- i.e.
+ * torch.argmax's rules: first index among equal maxima, NaN is the maximum; columns with mask[n] != 0 count as -inf
+ * (the Whisper logits processors only ever write -inf at length-dependent positions).  mask: uint8 / bool, 16-byte
+ * aligned, mask_len >= N rounded up to whole 128-column tiles (64 for decode-shaped calls), or NULL.
+ * wq_argmax_finalize turns keys into token ids and zeroes the keys for the next call. */
+int wq_gemm_f16(const void *x, int x_dtype, const void *w, const float *bias, void *y, int y_dtype,
+                int64_t ldy, int64_t M, int64_t N, int64_t K, const uint8_t *mask, int64_t mask_len,
+                unsigned long long *argmax_keys, wq_stream_t stream);
+int wq_argmax_finalize(unsigned long long *keys, int64_t M, int64_t *out, wq_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * WER / CER tallies -- evaluate.load("wer"/"cer").compute, evaluation.py:110-116
  * ---------------------------------------------------------------------------------------- */

@@ -159,7 +159,7 @@ k_self_attn_decode(const T *__restrict__ q, const T *__restrict__ k, const T *__
     am = 0.0f;
     for (int w = 0; w < H; ++w) am = fmaxf(am, s_red[w]);
     if (threadIdx.x == 0) row_stats[b] = am;
-    const float scale = __fdiv_rn(127.0f, am);
+    const float scale = bnb_row_scale(am);
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
         const float x = orow[c];
         int qv;
@@ -217,9 +217,16 @@ extern "C" int wq_self_attn_decode(const void *q, const void *k, const void *v, 
 // This is the largest single cost of a decode step and pure HBM streaming: per utterance and layer the fp16 K and V
 // projections of the encoder output (2 x S x d x 2 bytes; 3 MB at d = 512) are read once and nothing else moves.
 // K and V stay where the k_proj / v_proj GEMM wrote them ([B, S, *] rows, `ld` elements apart; a layer's K and V
-// may be column blocks of one buffer).  CTA per (head, utterance); its 4 warps interleave over the positions, 8
-// lanes per 128-byte row, 4 rows per warp instruction, 4 instructions of K and of V in flight per lane; flash-decoding
-// style running max / sum per lane group, merged across groups (shuffles) and warps (smem) at the end.
+// may be column blocks of one buffer).
+//
+// Persistent kernel: a fixed grid (a small multiple of the SM count, at most one CTA per work item) walks the
+// (utterance, head) work items, heads fastest.  The 8 warps of a CTA interleave over the positions of one item, 8
+// lanes per 128-byte row, 4 rows per warp instruction, 4 instructions of K and of V in flight per lane and the next
+// 4 already requested (256 B per lane outstanding); the first block of the NEXT item is requested before the current
+// item's partial results are merged, so the stream never drains at an item boundary.  Flash-decoding style running
+// max / sum per lane group, merged across groups (shuffles) and warps (shared memory, double-buffered by item
+// parity).  Round 1 launched one 128-thread CTA per item: once heads x utterances exceeded ~1.4 waves (B = 256) the
+// ragged last wave cost 5 % against cuDNN inside the step graph; the item walk has no waves.
 // ---------------------------------------------------------------------------------------------
 namespace {
 
@@ -240,38 +247,28 @@ __device__ __forceinline__ void partial_merge(Partial &a, float om, float ol, co
 }
 
 template <typename T, int kXWarps>
-__global__ void __launch_bounds__(kXWarps * 32)
+__global__ void __launch_bounds__(kXWarps * 32, 2)
 k_cross_attn_decode(const T *__restrict__ q, int64_t ldq, float scaling, const T *__restrict__ kmat,
-                    const T *__restrict__ vmat, int64_t ld, int S, int H, T *out, float threshold,
+                    const T *__restrict__ vmat, int64_t ld, int S, int H, int n_items, T *out, float threshold,
                     int8_t *__restrict__ ca, float *__restrict__ row_stats, int32_t *__restrict__ col_flags,
                     int32_t *__restrict__ row_counters) {
-    __shared__ float s_part[kXWarps][8][10];      // per warp: 8 dim-groups x (m, l, acc[8])
+    __shared__ float s_part[2][kXWarps][8][10];   // per item parity and warp: 8 dim-groups x (m, l, acc[8])
     __shared__ float s_red[kXWarps];
     __shared__ int s_last;
     pdl_wait();
-    const int h = blockIdx.x, b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 3, sub = lane & 7;
     const int d = H * kHeadDim;
     constexpr float kLog2e = 1.4426950408889634f;
-
-    float q8[8];
-    load8(q + (int64_t)b * ldq + h * kHeadDim + sub * 8, q8);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) q8[j] = to_f32(from_f32<T>(q8[j] * scaling)) * kLog2e;   // scores in log2 units
-
-    const T *kb = kmat + (int64_t)b * S * ld + h * kHeadDim + sub * 8;
-    const T *vb = vmat + (int64_t)b * S * ld + h * kHeadDim + sub * 8;
-    Partial p;
-    p.m = -INFINITY;
-    p.l = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) p.acc[j] = 0.0f;
-
     constexpr int ROWS_PER_IT = kXWarps * 4;
     constexpr int STEP = ROWS_PER_IT * kXUnroll;
+    const int t_first = warp * 4 + g;
+
+    int item = (int)blockIdx.x;
+    if (item >= n_items) return;
+
     uint4 kr[kXUnroll], vr[kXUnroll], kn[kXUnroll], vn[kXUnroll];
-    auto fetch = [&](int t0, uint4 (&kk)[kXUnroll], uint4 (&vv)[kXUnroll]) {
+    auto fetch = [&](const T *kb, const T *vb, int t0, uint4 (&kk)[kXUnroll], uint4 (&vv)[kXUnroll]) {
 #pragma unroll
         for (int u = 0; u < kXUnroll; ++u) {
             const int t = t0 + u * ROWS_PER_IT;
@@ -283,112 +280,156 @@ k_cross_attn_decode(const T *__restrict__ q, int64_t ldq, float scaling, const T
             }
         }
     };
-    int t0 = warp * 4 + g;
-    fetch(t0, kr, vr);
-    // the trip count must be warp-uniform (full-mask shuffles inside): bound the loop on the block start, rows past
-    // S are masked per lane
-    for (int tb = 0; tb < S; tb += STEP, t0 += STEP) {
-        fetch(t0 + STEP, kn, vn);          // next block's rows are in flight while this block is reduced
+    auto item_ptrs = [&](int it, const T *&kb, const T *&vb, const T *&qb) {
+        const int b = it / H, h = it - b * H;
+        kb = kmat + (int64_t)b * S * ld + h * kHeadDim + sub * 8;
+        vb = vmat + (int64_t)b * S * ld + h * kHeadDim + sub * 8;
+        qb = q + (int64_t)b * ldq + h * kHeadDim + sub * 8;
+    };
+
+    const T *kb, *vb, *qb;
+    item_ptrs(item, kb, vb, qb);
+    fetch(kb, vb, t_first, kr, vr);
+    float q8[8];
+    load8(qb, q8);
+    int par = 0;
+    for (;; item += (int)gridDim.x, par ^= 1) {
+        const int next = item + (int)gridDim.x;
+        const bool has_next = next < n_items;
+        const T *kbn = kb, *vbn = vb, *qbn = qb;
+        if (has_next) item_ptrs(next, kbn, vbn, qbn);
+        const int b = item / H, h = item - b * H;
 #pragma unroll
-        for (int u = 0; u < kXUnroll; ++u) {
-            const int t = t0 + u * ROWS_PER_IT;
-            const T *k8 = reinterpret_cast<const T *>(&kr[u]);
-            const T *v8 = reinterpret_cast<const T *>(&vr[u]);
-            float s = 0.0f;
+        for (int j = 0; j < 8; ++j) q8[j] = to_f32(from_f32<T>(q8[j] * scaling)) * kLog2e;   // scores in log2 units
+        Partial p;
+        p.m = -INFINITY;
+        p.l = 0.0f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s = fmaf(q8[j], to_f32(k8[j]), s);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (t < S) {
-                const float m = fmaxf(p.m, s);
-                const float corr = exp2f(p.m - m);          // exp2f(-inf) == 0 on the first row
-                const float e = exp2f(s - m);
-                p.l = p.l * corr + e;
+        for (int j = 0; j < 8; ++j) p.acc[j] = 0.0f;
+
+        // the trip count is warp-uniform (full-mask shuffles inside): the loop is bounded on the block start, rows
+        // past S are masked per lane
+        int t0 = t_first;
+        for (int tb = 0; tb < S; tb += STEP, t0 += STEP) {
+            if (tb + STEP < S) fetch(kb, vb, t0 + STEP, kn, vn);          // next block of this item ...
+            else if (has_next) fetch(kbn, vbn, t_first, kn, vn);          // ... or the first block of the next item
 #pragma unroll
-                for (int j = 0; j < 8; ++j) p.acc[j] = fmaf(e, to_f32(v8[j]), p.acc[j] * corr);
-                p.m = m;
+            for (int u = 0; u < kXUnroll; ++u) {
+                const int t = t0 + u * ROWS_PER_IT;
+                const T *k8 = reinterpret_cast<const T *>(&kr[u]);
+                const T *v8 = reinterpret_cast<const T *>(&vr[u]);
+                float s = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s = fmaf(q8[j], to_f32(k8[j]), s);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                if (t < S) {
+                    const float m = fmaxf(p.m, s);
+                    const float corr = exp2f(p.m - m);          // exp2f(-inf) == 0 on the first row
+                    const float e = exp2f(s - m);
+                    p.l = p.l * corr + e;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) p.acc[j] = fmaf(e, to_f32(v8[j]), p.acc[j] * corr);
+                    p.m = m;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kXUnroll; ++u) {
+                kr[u] = kn[u];
+                vr[u] = vn[u];
             }
         }
+        if (has_next) load8(qbn, q8);      // next item's query row (L2) travels while this item is merged
+        else pdl_trigger();                // this CTA's stream is over: the successor's CTAs may take their seats
+        // merge the 4 lane groups of the warp (same dims, different rows)
 #pragma unroll
-        for (int u = 0; u < kXUnroll; ++u) {
-            kr[u] = kn[u];
-            vr[u] = vn[u];
-        }
-    }
-    pdl_trigger();       // the streaming part is over: the successor's CTAs may take their seats
-    // merge the 4 lane groups of the warp (same dims, different rows)
-#pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-        const float om = __shfl_xor_sync(0xffffffffu, p.m, o);
-        const float ol = __shfl_xor_sync(0xffffffffu, p.l, o);
-        float oacc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) oacc[j] = __shfl_xor_sync(0xffffffffu, p.acc[j], o);
-        partial_merge(p, om, ol, oacc);
-    }
-    if (g == 0) {
-        s_part[warp][sub][0] = p.m;
-        s_part[warp][sub][1] = p.l;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s_part[warp][sub][2 + j] = p.acc[j];
-    }
-    __syncthreads();
-    if (warp == 0 && g == 0) {
-#pragma unroll
-        for (int w = 1; w < kXWarps; ++w) {
+        for (int o = 8; o <= 16; o <<= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, p.m, o);
+            const float ol = __shfl_xor_sync(0xffffffffu, p.l, o);
             float oacc[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) oacc[j] = s_part[w][sub][2 + j];
-            partial_merge(p, s_part[w][sub][0], s_part[w][sub][1], oacc);
+            for (int j = 0; j < 8; ++j) oacc[j] = __shfl_xor_sync(0xffffffffu, p.acc[j], o);
+            partial_merge(p, om, ol, oacc);
         }
-        const float inv = 1.0f / p.l;
-        uint4 raw;
-        T *o8 = reinterpret_cast<T *>(&raw);
+        if (g == 0) {
+            s_part[par][warp][sub][0] = p.m;
+            s_part[par][warp][sub][1] = p.l;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o8[j] = from_f32<T>(p.acc[j] * inv);
-        *reinterpret_cast<uint4 *>(out + (int64_t)b * d + h * kHeadDim + sub * 8) = raw;
+            for (int j = 0; j < 8; ++j) s_part[par][warp][sub][2 + j] = p.acc[j];
+        }
+        __syncthreads();
+        if (warp == 0 && g == 0) {
+#pragma unroll
+            for (int w = 1; w < kXWarps; ++w) {
+                float oacc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) oacc[j] = s_part[par][w][sub][2 + j];
+                partial_merge(p, s_part[par][w][sub][0], s_part[par][w][sub][1], oacc);
+            }
+            const float inv = 1.0f / p.l;
+            uint4 raw;
+            T *o8 = reinterpret_cast<T *>(&raw);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o8[j] = from_f32<T>(p.acc[j] * inv);
+            *reinterpret_cast<uint4 *>(out + (int64_t)b * d + h * kHeadDim + sub * 8) = raw;
+        }
+        if (ca != nullptr) {
+            // LLM.int8 row quantization of out[b, :] by the last of this utterance's H head items to finish
+            // (int8_vectorwise_quant on the rounded values; the counter resets itself for the next launch)
+            if (threadIdx.x < 8) __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) s_last = (atomicAdd(&row_counters[b], 1) == H - 1);
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                const bool sparse = threshold > 0.0f;
+                const T *orow = out + (int64_t)b * d;
+                float am = 0.0f;
+                for (int c = threadIdx.x; c < d; c += blockDim.x) {
+                    const float x = fabsf(to_f32(__ldcg(orow + c)));
+                    if (!sparse || x < threshold) am = fmaxf(am, x);
+                }
+                am = warp_max(am);
+                if (lane == 0) s_red[warp] = am;
+                __syncthreads();
+                am = 0.0f;
+#pragma unroll
+                for (int w = 0; w < kXWarps; ++w) am = fmaxf(am, s_red[w]);
+                if (threadIdx.x == 0) {
+                    row_stats[b] = am;
+                    row_counters[b] = 0;
+                }
+                const float scale = bnb_row_scale(am);
+                for (int c = threadIdx.x; c < d; c += blockDim.x) {
+                    const float x = to_f32(__ldcg(orow + c));
+                    int qv;
+                    if (sparse && !(fabsf(x) < threshold)) {
+                        qv = 0;
+                        col_flags[c] = 1;
+                        col_flags[d] = 1;
+                    } else {
+                        qv = __float2int_rn(__fmul_rn(x, scale));
+                    }
+                    ca[(int64_t)b * d + c] = (int8_t)qv;
+                }
+            }
+        }
+        if (!has_next) break;
+        kb = kbn;
+        vb = vbn;
+        qb = qbn;
     }
-    if (ca == nullptr) return;
+}
 
-    // LLM.int8 row quantization of out[b, :] by the last of this utterance's H head-CTAs to finish
-    // (int8_vectorwise_quant on the rounded values; the counter resets itself for the next launch)
-    if (threadIdx.x < 8) __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&row_counters[b], 1) == H - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const bool sparse = threshold > 0.0f;
-    const T *orow = out + (int64_t)b * d;
-    float am = 0.0f;
-    for (int c = threadIdx.x; c < d; c += blockDim.x) {
-        const float x = fabsf(to_f32(__ldcg(orow + c)));
-        if (!sparse || x < threshold) am = fmaxf(am, x);
-    }
-    am = warp_max(am);
-    if (lane == 0) s_red[warp] = am;
-    __syncthreads();
-    am = 0.0f;
-#pragma unroll
-    for (int w = 0; w < kXWarps; ++w) am = fmaxf(am, s_red[w]);
-    if (threadIdx.x == 0) {
-        row_stats[b] = am;
-        row_counters[b] = 0;
-    }
-    const float scale = __fdiv_rn(127.0f, am);
-    for (int c = threadIdx.x; c < d; c += blockDim.x) {
-        const float x = to_f32(__ldcg(orow + c));
-        int qv;
-        if (sparse && !(fabsf(x) < threshold)) {
-            qv = 0;
-            col_flags[c] = 1;
-            col_flags[d] = 1;
-        } else {
-            qv = __float2int_rn(__fmul_rn(x, scale));
-        }
-        ca[(int64_t)b * d + c] = (int8_t)qv;
-    }
+// CTAs per SM of the persistent grid (WQ_XATTN_CTAS = 1 | 2; 2 keeps 128 KB of loads in flight per SM)
+int xattn_ctas_per_sm() {
+    static const int n = [] {
+        const char *e = getenv("WQ_XATTN_CTAS");
+        const int v = e ? atoi(e) : 2;
+        return v < 1 ? 1 : (v > 2 ? 2 : v);
+    }();
+    return n;
 }
 
 }  // namespace
@@ -397,7 +438,7 @@ extern "C" int wq_cross_attn_decode(const void *q, int64_t ldq, int dtype, float
                                     int64_t ld, int64_t B, int64_t S, int H, void *out, float threshold, int8_t *ca,
                                     float *row_stats, int32_t *col_flags, int32_t *row_counters,
                                     wq_stream_t stream) {
-    WQ_REQUIRE(B >= 0 && B <= 65535 && S >= 1 && S < (1 << 30) && H >= 1 && H <= 65535,
+    WQ_REQUIRE(B >= 0 && S >= 1 && S < (1 << 30) && H >= 1 && H <= 65535 && B * H < (1ll << 30),
                "wq_cross_attn_decode: bad shape");
     WQ_REQUIRE(dtype == WQ_F16 || dtype == WQ_BF16, "wq_cross_attn_decode: dtype must be f16 or bf16");
     if (B == 0) return WQ_OK;
@@ -411,16 +452,18 @@ extern "C" int wq_cross_attn_decode(const void *q, int64_t ldq, int dtype, float
                "wq_cross_attn_decode: the int8 outputs need fp16 rows, row_stats and row_counters");
     WQ_REQUIRE(ca == nullptr || threshold == 0.0f || col_flags, "wq_cross_attn_decode: threshold needs col_flags");
     cudaStream_t s = (cudaStream_t)stream;
-    const dim3 grid((unsigned)H, (unsigned)B);
-    // 4 warps per CTA; 8 measured the same (scripts/cross_attn_bench.py)
+    const int n_items = (int)(B * H);
+    const int cap = wq_sm_count() * xattn_ctas_per_sm();
+    const dim3 grid((unsigned)(n_items < cap ? n_items : cap));
     if (dtype == WQ_F16) {
-        WQ_LAUNCH_PDL((k_cross_attn_decode<__half, 4>), grid, dim3(128), 0, s, (const __half *)q, ldq, scaling,
-                      (const __half *)k, (const __half *)v, ld, (int)S, H, (__half *)out, threshold, ca, row_stats,
-                      col_flags, row_counters);
+        WQ_LAUNCH_PDL((k_cross_attn_decode<__half, 8>), grid, dim3(256), 0, s, (const __half *)q, ldq, scaling,
+                      (const __half *)k, (const __half *)v, ld, (int)S, H, n_items, (__half *)out, threshold, ca,
+                      row_stats, col_flags, row_counters);
     } else {
-        WQ_LAUNCH_PDL((k_cross_attn_decode<__nv_bfloat16, 4>), grid, dim3(128), 0, s, (const __nv_bfloat16 *)q, ldq,
-                      scaling, (const __nv_bfloat16 *)k, (const __nv_bfloat16 *)v, ld, (int)S, H, (__nv_bfloat16 *)out,
-                      0.0f, (int8_t *)nullptr, (float *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr);
+        WQ_LAUNCH_PDL((k_cross_attn_decode<__nv_bfloat16, 8>), grid, dim3(256), 0, s, (const __nv_bfloat16 *)q, ldq,
+                      scaling, (const __nv_bfloat16 *)k, (const __nv_bfloat16 *)v, ld, (int)S, H, n_items,
+                      (__nv_bfloat16 *)out, 0.0f, (int8_t *)nullptr, (float *)nullptr, (int32_t *)nullptr,
+                      (int32_t *)nullptr);
     }
     return WQ_OK;
 }

@@ -132,6 +132,13 @@ __device__ __forceinline__ int warp_sum_i32(int v) {
     return v;
 }
 
+// Row scale of bitsandbytes' int8_vectorwise_quant.  Its kernel (csrc/kernels.cu, kInt8VectorQuant) forms 127 / absmax
+// with the approximate-division intrinsic; over all fp16 (absmax, a) pairs that changes 8 734 of 503 856 639 codes
+// against the IEEE quotient (a * scale landing on the other side of a .5 boundary; exhaustive sweep on B200,
+// scripts/bnb_open_points.cu -> tests/golden/fdividef_127_fp16.npz, which lets the CPU oracle reproduce it), so
+// the approximate form is what every LLM.int8 quantizer here uses.  absmax == 0 gives +inf -> NaN codes -> 0.
+__device__ __forceinline__ float bnb_row_scale(float absmax) { return __fdividef(127.0f, absmax); }
+
 // Order-preserving float <-> uint32 map (for atomicMin/atomicMax on floats).
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
     uint32_t u = __float_as_uint(f);

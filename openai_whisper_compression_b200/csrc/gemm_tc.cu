@@ -27,6 +27,8 @@
 //   EPI_DYN      u8 x s8 -> s32, y = (acc - zp*wsum[n]) * (s_x*s_w) + bias[n]          (torch)
 //   EPI_W8A16    f16 x f16(int8) -> f32, y = acc*scale[n] + bias[n]                    (quanto)
 //   EPI_W4A16    f16 x f16(code*absmax) -> f32, y = acc + bias[n]                       (bnb NF4)
+//   EPI_PLAIN    f16 x f16 -> f32, y = acc + bias[n]; W taken straight from TMA (unquantized proj_out), optional
+//                masked arg-max over the rounded outputs folded into the epilogue (greedy token choice)
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -45,7 +47,7 @@ constexpr int BOX_BYTES = 32 * 128;  // one TMA-store box: 32 rows x 128 bytes (
 
 enum AKind { A_F16 = 0, A_BF16 = 1, A_S8 = 2, A_U8 = 3 };
 enum BMode { B_DIRECT = 0, B_I8 = 1, B_4BIT = 2, B_U4 = 3 };   // B_U4: quanto group-wise affine uint4
-enum Epi { EPI_LLMINT8 = 0, EPI_W8A16 = 1, EPI_W4A16 = 2, EPI_DYN = 3 };
+enum Epi { EPI_LLMINT8 = 0, EPI_W8A16 = 1, EPI_W4A16 = 2, EPI_DYN = 3, EPI_PLAIN = 4 };
 
 struct GemmArgs {
     int M, N, K;
@@ -70,7 +72,40 @@ struct GemmArgs {
     int32_t *flags;          // [K + 2]: per-column flags, "any", completion counter
     int keep_flags;          // 1: leave the flags set (another GEMM consumes the same quantized rows next)
     int prefetch;            // > 0: the producer pulls the A row block it will load `prefetch` tiles later into L2
+    int ldy;                 // row pitch of `out` in elements (>= N)
+    // EPI_PLAIN: greedy choice folded into the epilogue.  keys[m] = max over columns of
+    // (order-preserving bits of the ROUNDED output << 32) | (0xFFFFFFFF - n), columns with mask[n] != 0 count as -inf
+    unsigned long long *argmax_keys;
+    const uint8_t *mask;     // [>= tiles_n * tile columns] bytes, or nullptr
+    int no_store;            // 1: the outputs themselves are not written (only the arg-max is wanted)
 };
+
+// Running arg-max of one output row over 32 adjacent columns starting at Y column `n_abs` (a multiple of 32).
+// torch.argmax rules: first index among equal maxima (columns are visited in ascending order, strict >), NaN is the
+// maximum.  The value compared is the output as it would be stored (rounded to OutT).
+template <typename OutT>
+__device__ __forceinline__ void argmax_chunk(const float (&v)[32], const uint8_t *mask, int n_abs, int N,
+                                             uint32_t &best_ord, uint32_t &best_idx) {
+    uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (mask != nullptr) {
+        const uint4 m0 = __ldg(reinterpret_cast<const uint4 *>(mask + n_abs));
+        const uint4 m1 = __ldg(reinterpret_cast<const uint4 *>(mask + n_abs) + 1);
+        mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
+        mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int n = n_abs + j;
+        if (n >= N) break;
+        float f = to_f32(from_f32<OutT>(v[j]));
+        if ((mw[j >> 2] >> (8 * (j & 3))) & 0xffu) f = -INFINITY;
+        const uint32_t ord = (f != f) ? 0xFFFFFFFFu : float_to_ordered(f);
+        if (ord > best_ord) {
+            best_ord = ord;
+            best_idx = (uint32_t)n;
+        }
+    }
+}
 
 template <int BMODE> constexpr bool is_nibble() { return BMODE == B_4BIT || BMODE == B_U4; }
 template <int BMODE> constexpr int dq_warps() { return BMODE == B_DIRECT ? 0 : (is_nibble<BMODE>() ? 8 : 4); }
@@ -280,7 +315,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
     const int h = grp & 1;                              // 128-row half of the tile (COLS: 128-column half)
     const int bx0 = (grp >> 1) * N_BOX;                 // first box (column range) of this warp
     const int q = warp & 3;                             // TMEM lane quarter this warp may access
-    const bool vec_ok = ((size_t)args.N * sizeof(OutT)) % 16 == 0;
+    const bool vec_ok = ((size_t)args.ldy * sizeof(OutT)) % 16 == 0;
     const bool any_outlier = (EPI == EPI_LLMINT8) && args.flags != nullptr && args.flags[args.K] != 0;
     float dyn_s = 0.0f;
     int dyn_zp = 0;
@@ -298,7 +333,9 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
         const int nh0 = n0 + ch0;                 // ... as a column of Y
         const int m = mrow0 + lane;
         const bool row_ok = m < args.M;
+        const bool st_ok = row_ok && !args.no_store;
         const bool slab_ok = mrow0 < args.M && nh0 < args.N;      // warp-uniform
+        uint32_t best_ord = 0u, best_idx = 0xFFFFFFFFu;           // EPI_PLAIN arg-max of this row over the tile
         float rs = 1.0f;
         if constexpr (EPI == EPI_LLMINT8) rs = row_ok ? __ldg(args.row_scale + m) : 0.0f;
         // stage this tile's per-column constants once (the 8 epilogue warps share them); two
@@ -326,7 +363,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
         mbar_wait(&bar_tmem_full[as], aph);
         tc_fence_after();
         if (slab_ok) {
-            OutT *row_ptr = reinterpret_cast<OutT *>(args.out) + (size_t)(row_ok ? m : 0) * args.N;
+            OutT *row_ptr = reinterpret_cast<OutT *>(args.out) + (size_t)(row_ok ? m : 0) * args.ldy;
             const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_COLS + h * BN;
 #pragma unroll 1
             for (int bx = bx0; bx < bx0 + N_BOX; ++bx) {
@@ -358,7 +395,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
                             tmem_ld_wait();
                             float v[32];
                             epi_chunk<BNT, EPI>(r, v, sc, ch0 + col0, rs, dyn_s, dyn_zp);
-                            emit_chunk<OutT, TMA_STORE>(v, box, cc, lane, row_ptr, nh0 + col0, args.N, row_ok, vec_ok);
+                            emit_chunk<OutT, TMA_STORE>(v, box, cc, lane, row_ptr, nh0 + col0, args.N, st_ok, vec_ok);
                         }
                     } else {
                         uint32_t r[NCH][32];
@@ -370,7 +407,11 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
                             const int col0 = bx * BOX_COLS + cc * 32;   // column inside the tile
                             float v[32];
                             epi_chunk<BNT, EPI>(r[cc], v, sc, ch0 + col0, rs, dyn_s, dyn_zp);
-                            emit_chunk<OutT, TMA_STORE>(v, box, cc, lane, row_ptr, nh0 + col0, args.N, row_ok, vec_ok);
+                            if constexpr (EPI == EPI_PLAIN) {
+                                if (args.argmax_keys != nullptr)
+                                    argmax_chunk<OutT>(v, args.mask, nh0 + col0, args.N, best_ord, best_idx);
+                            }
+                            emit_chunk<OutT, TMA_STORE>(v, box, cc, lane, row_ptr, nh0 + col0, args.N, st_ok, vec_ok);
                         }
                     }
                 }
@@ -384,6 +425,10 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
                     ++nstore;
                 }
             }
+        }
+        if constexpr (EPI == EPI_PLAIN) {
+            if (args.argmax_keys != nullptr && row_ok && best_idx != 0xFFFFFFFFu)
+                atomicMax(args.argmax_keys + m, ((unsigned long long)best_ord << 32) | (0xFFFFFFFFu - best_idx));
         }
         // accumulator fully read: hand the TMEM stage back to the MMA warp
         tc_fence_before();
@@ -486,7 +531,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     if constexpr (WS > 0)
                         (void)n0;
                     else if constexpr (BMODE == B_DIRECT)
-                        tma_load_2d(smem + L::OFF_B + s * L::B_BYTES, &map_b, &bar_full[s], kb * 128, n0);
+                        tma_load_2d(smem + L::OFF_B + s * L::B_BYTES, &map_b, &bar_full[s], kb * A_ELEMS_PER_ROW, n0);
                     else
                         tma_load_2d(smem + L::OFF_P + s * L::P_BYTES, &map_b, &bar_full[s], kb * L::P_ROW, n0);
                 }
@@ -691,14 +736,14 @@ EncodeTiledFn get_encode_fn() {
 
 // 2-D row-major matrix [rows, cols] of `elem_bytes`-byte elements, box = [box_rows, box_cols].
 int make_map_2d(CUtensorMap *map, const void *base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows,
-                uint64_t cols, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz) {
+                uint64_t cols, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz, uint64_t pitch_elems = 0) {
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) {
         wq_set_error("cuTensorMapEncodeTiled is not available from the driver");
         return WQ_ERR_CUDA;
     }
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {cols * (uint64_t)elem_bytes};
+    cuuint64_t strides[1] = {(pitch_elems ? pitch_elems : cols) * (uint64_t)elem_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
@@ -749,12 +794,13 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cud
     }
     args.tiles_m = (args.M + L::BMT - 1) / L::BMT;
     args.tiles_n = (args.N + L::BNT - 1) / L::BNT;
+    if (args.ldy == 0) args.ldy = args.N;
     // TMA store needs a 16-byte-aligned row pitch; otherwise the epilogue stores directly
-    args.tma_store = (((size_t)args.N * sizeof(OutT)) % 16 == 0 && wq_aligned(args.out, 16)) ? 1 : 0;
+    args.tma_store = (!args.no_store && ((size_t)args.ldy * sizeof(OutT)) % 16 == 0 && wq_aligned(args.out, 16)) ? 1 : 0;
     CUtensorMap my;
     if (args.tma_store) {
         int rc = make_map_2d(&my, args.out, out_dtype_enum<OutT>(), (int)sizeof(OutT), args.M, args.N, 32,
-                             128 / (int)sizeof(OutT), CU_TENSOR_MAP_SWIZZLE_128B);
+                             128 / (int)sizeof(OutT), CU_TENSOR_MAP_SWIZZLE_128B, (uint64_t)args.ldy);
         if (rc != WQ_OK) return rc;
     } else {
         my = ma;  // unused
@@ -982,4 +1028,62 @@ extern "C" int wq_gemm_u4a16(const void *x, int x_dtype, const uint8_t *packed, 
                      CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc != WQ_OK) return rc;
     return dispatch_a16<B_U4, EPI_W4A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream);
+}
+
+/* Unquantized linear on the same tcgen05 pipeline: y = x @ W^T + bias with W [N, K] in the activation dtype, taken
+ * straight from TMA (no expansion warps).  Serves the vocabulary projection the HF bitsandbytes flows keep in fp16
+ * (proj_out, modeling_whisper.py:971,1081).  With argmax_keys the greedy choice (torch.argmax of the rounded logits
+ * under a suppression mask) is folded into the epilogue; y may then be NULL: the logits never reach HBM. */
+extern "C" int wq_gemm_f16(const void *x, int x_dtype, const void *w, const float *bias, void *y, int y_dtype,
+                           int64_t ldy, int64_t M, int64_t N, int64_t K, const uint8_t *mask, int64_t mask_len,
+                           unsigned long long *argmax_keys, wq_stream_t stream) {
+    int rc = check_common("wq_gemm_f16", M, N, K);
+    if (rc != WQ_OK) return rc;
+    if (M == 0 || N == 0) return WQ_OK;
+    WQ_REQUIRE(x && w, "wq_gemm_f16: null pointer");
+    WQ_REQUIRE(y != nullptr || argmax_keys != nullptr, "wq_gemm_f16: neither an output nor arg-max keys requested");
+    WQ_REQUIRE(K % 8 == 0, "wq_gemm_f16: K=%lld must be a multiple of 8", (long long)K);
+    WQ_REQUIRE(wq_aligned(x, 16) && wq_aligned(w, 16) && (y == nullptr || wq_aligned(y, 16)), "wq_gemm_f16: misaligned buffer");
+    if (ldy == 0) ldy = N;
+    WQ_REQUIRE(ldy >= N && ldy < (1ll << 31), "wq_gemm_f16: bad output pitch %lld", (long long)ldy);
+    GemmArgs args = {};
+    args.M = (int)M; args.N = (int)N; args.K = (int)K;
+    args.num_kb = (int)((K + 63) / 64);
+    args.bias = bias; args.out = y; args.ldy = (int)ldy;
+    args.argmax_keys = argmax_keys; args.mask = mask; args.no_store = y == nullptr ? 1 : 0;
+    const bool narrow = use_narrow_tile(M, N);
+    if (mask != nullptr) {
+        const int64_t bnt = narrow ? 64 : 128;
+        WQ_REQUIRE(argmax_keys != nullptr, "wq_gemm_f16: a mask needs argmax_keys");
+        WQ_REQUIRE(wq_aligned(mask, 16) && mask_len >= ((N + bnt - 1) / bnt) * bnt,
+                   "wq_gemm_f16: mask must be 16-byte aligned and padded to whole %lld-column tiles", (long long)bnt);
+    }
+    const CUtensorMapDataType dt = x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUtensorMap ma, mb;
+    rc = make_map_2d(&ma, x, dt, 2, M, K, BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != WQ_OK) return rc;
+    rc = make_map_2d(&mb, w, dt, 2, N, K, narrow ? 64 : 128, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != WQ_OK) return rc;
+    return dispatch_a16<B_DIRECT, EPI_PLAIN>(ma, mb, args, x_dtype, y == nullptr ? x_dtype : y_dtype, narrow,
+                                             (cudaStream_t)stream);
+}
+
+namespace {
+__global__ void k_argmax_finalize(unsigned long long *keys, int64_t M, int64_t *out) {
+    pdl_prologue_done();
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < M) {
+        out[m] = (int64_t)(0xFFFFFFFFu - (uint32_t)(keys[m] & 0xFFFFFFFFull));
+        keys[m] = 0ull;      // ready for the next projection
+    }
+}
+}  // namespace
+
+/* Token ids from the arg-max keys of wq_gemm_f16 (and reset of the keys): out[m] = column of the maximum. */
+extern "C" int wq_argmax_finalize(unsigned long long *keys, int64_t M, int64_t *out, wq_stream_t stream) {
+    WQ_REQUIRE(M >= 0, "wq_argmax_finalize: bad shape");
+    if (M == 0) return WQ_OK;
+    WQ_REQUIRE(keys && out, "wq_argmax_finalize: null pointer");
+    WQ_LAUNCH_PDL(k_argmax_finalize, dim3((unsigned)((M + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, keys, M, out);
+    return WQ_OK;
 }

@@ -65,7 +65,7 @@ k_llmint8_small(const __half *__restrict__ a, int M, int K, float threshold, con
         }
         am = warp_max(am);
         if (lane == 0) s_sca[m] = am;
-        const float scale = __fdiv_rn(127.0f, am);
+        const float scale = bnb_row_scale(am);
         for (int c = lane * 8; c < K; c += 256) {
             const uint4 raw = *reinterpret_cast<const uint4 *>(pr + c);
             const __half *h = reinterpret_cast<const __half *>(&raw);

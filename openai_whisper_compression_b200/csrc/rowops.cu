@@ -133,7 +133,7 @@ k_add_ln_quant(const T *x, const T *__restrict__ delta, const T *__restrict__ ga
     if (ca == nullptr) return;
     am = warp_max(am);
     if (lane == 0) row_stats[row] = am;
-    const float scale = __fdiv_rn(127.0f, am);
+    const float scale = bnb_row_scale(am);
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
         const int c = i * 256 + lane * 8;
@@ -195,7 +195,7 @@ k_gelu_quant(const T *__restrict__ x, int64_t rows, int64_t cols, T *__restrict_
     }
     if (!live) return;
     if (lane == 0 && part == 0) row_stats[row] = am;
-    const float scale = __fdiv_rn(127.0f, am);
+    const float scale = bnb_row_scale(am);
     for (int64_t c = (part * 32 + lane) * 8; c < cols; c += 256 * G) {
         Vec8<T> h;
         h.raw = *reinterpret_cast<const uint4 *>(h_out + base + c);     // this lane's own store
@@ -267,7 +267,7 @@ k_gelu_quant_lut(const __half *__restrict__ x, int64_t rows, int cols, __half *_
         if (ca == nullptr) continue;
         am = warp_max(am);
         if (lane == 0) row_stats[row] = am;
-        const float scale = __fdiv_rn(127.0f, am);
+        const float scale = bnb_row_scale(am);
 #pragma unroll
         for (int i = 0; i < kMaxChunks; ++i) {
             const int c = i * 256 + lane * 8;

@@ -76,6 +76,9 @@ class GraphedGreedy:
         # done here in a few batched ops, same result (tests/test_host_logic.py)
         self.fast_post = os.environ.get("WQ_FAST_POST", "1") != "0"
         self._unwind = False
+        self.keep_logits = False       # True: the captured step always writes the [B, V] logits (tests, debugging)
+        self.time_loop = False         # bench.py: CUDA events around the token loop of every generate call
+        self.loop_events = []          # (start, end, replays)
         self.replays = 0
         self.fallbacks = 0
         self.fast_returns = 0
@@ -253,13 +256,20 @@ class GraphedGreedy:
         self._project(st, x.view(B, d))
 
     def _project(self, st: _State, h: torch.Tensor):
-        """Vocabulary projection of the final hidden rows [B, d] into st.logits."""
-        if st.proj_w is not None:
-            torch.mm(h, st.proj_w.t(), out=st.logits_padded)
-        else:
-            st.logits.copy_(self.model.proj_out(h))
+        """Vocabulary projection of the final hidden rows [B, d] and the greedy choice under st.maskrow.  An
+        unquantized proj_out (the HF bitsandbytes flows keep it fp16) runs on the tcgen05 GEMM with the arg-max folded
+        into its epilogue: the [B, V] logits are written only when the state was built to keep them."""
+        if st.proj_own:
+            po = self.model.proj_out
+            F.gemm_f16(h, po.weight, st.proj_bias, out=st.logits_padded if st.store_logits else None,
+                       argmax_keys=st.keys if st.argmax_in_graph else None,
+                       mask=st.maskrow if st.argmax_in_graph else None, store=st.store_logits)
+            if st.argmax_in_graph:
+                F.argmax_finalize(st.keys, out=st.next)
+            return
+        st.logits.copy_(self.model.proj_out(h))
         if st.argmax_in_graph:
-            F.masked_argmax(st.logits, st.maskrow, out=st.next)
+            F.masked_argmax(st.logits, st.maskrow[:st.logits.shape[1]], out=st.next)
 
     def _decoder_step_int8(self, st: _State):
         """The same step when every decoder linear is a bitsandbytes-style Linear8bitLt (fp16): each quantized
@@ -334,15 +344,53 @@ class GraphedGreedy:
             plans.append(fw)
         return plans, thr
 
-    def _get_state(self, B: int, t_max: int, dtype: torch.dtype, device) -> _State:
-        key = (B, t_max, dtype)
+    def _fingerprint(self):
+        """Identity of every tensor the captured graphs and packed copies were built from: (data_ptr, version) of
+        the model's parameters and of the quantized state the drop-in modules keep outside their
+        parameters.  In-place updates bump the version, re-quantizing / .to() / load_state_dict(assign) / pruning
+        re-parametrisation change the pointer: either way the cached states are rebuilt."""
+        fp = []
+        for root in (self.model,):          # encoder too: fastenc's per-layer plans hold concatenated copies
+            for p in root.parameters():
+                fp.append((p.data_ptr(), p._version))
+            for m in root.modules():
+                stt = getattr(m, "state", None)
+                for t in (getattr(stt, "CB", None), getattr(stt, "SCB", None), getattr(m, "_wq", None),
+                          getattr(m, "_wscale", None), getattr(m, "_wshift", None)):
+                    if isinstance(t, torch.Tensor):
+                        fp.append((t.data_ptr(), t._version))
+                qs = getattr(getattr(m, "weight", None), "quant_state", None)
+                if qs is not None and isinstance(getattr(qs, "absmax", None), torch.Tensor):
+                    fp.append((qs.absmax.data_ptr(), qs.absmax._version))
+        return hash(tuple(fp))
+
+    def invalidate(self) -> None:
+        """Drop every captured graph / packed weight copy (call after changing weights in a way the fingerprint
+        cannot see, e.g. writing through a raw pointer)."""
+        self._states.clear()
+        for layer in self.model.model.encoder.layers:
+            if hasattr(layer, "_whisperq_plan"):
+                del layer._whisperq_plan
+
+    def step_logits(self, st: _State) -> torch.Tensor:
+        """Raw logits [B, V] of the last replayed step (tests; states built with keep_logits)."""
+        if not st.store_logits:
+            raise RuntimeError("this state was captured without the logits store (set eng.keep_logits = True first)")
+        return st.logits
+
+    def _get_state(self, B: int, t_max: int, dtype: torch.dtype, device, store_logits: bool = True) -> _State:
+        fp = self._fingerprint()
+        key = (B, t_max, dtype, torch.device(device).index, bool(store_logits), self.cross_attention)
         st = self._states.get(key)
-        if st is not None:
+        if st is not None and st.fingerprint == fp:
             return st
+        if st is not None:              # weights changed since capture: everything cached is stale
+            self.invalidate()
         if len(self._states) >= self.max_states:       # static caches are large: keep a few shapes
             self._states.pop(next(iter(self._states)))
         cfg = self.model.config
         st = _State()
+        st.fingerprint = fp
         st.B, st.d = B, cfg.d_model
         st.H = cfg.decoder_attention_heads
         st.hd = st.d // st.H
@@ -354,7 +402,9 @@ class GraphedGreedy:
         st.mask = torch.zeros((t_max,), dtype=torch.bool, device=device)
         st.fused, st.threshold = self._plan_int8(dtype) if self.fuse_int8 else (None, 0.0)
         st.own_attn = self.own_attention and st.hd == 64 and dtype in (torch.float16, torch.bfloat16)
-        st.own_cross = self.cross_attention == "own" or (self.cross_attention == "auto" and B * st.H <= 1024)
+        # decode-time cross-attention: the persistent item-walking kernel of attn_decode.cu for every batch size
+        # ("cudnn" keeps torch SDPA for A/B measurements only)
+        st.own_cross = self.cross_attention != "cudnn"
         if st.fused is not None or st.own_attn:
             kv_shape = (B, t_max, st.d)              # projection layout: one 128-byte row per head and position
         else:
@@ -373,15 +423,16 @@ class GraphedGreedy:
         Vp = -(-V // 8) * 8          # rows of the logits buffer start 16-byte aligned (vector loads, cuBLAS)
         st.logits_padded = torch.zeros((B, Vp), dtype=dtype, device=device)
         st.logits = st.logits_padded[:, :V]
-        st.proj_w = None
-        if type(po) is torch.nn.Linear and po.bias is None and po.weight.dtype == dtype and V % 8 != 0:
-            # an odd vocabulary (51865) leaves cuBLAS its unaligned kernel (124 us at B = 256 against ~17 us):
-            # project onto a copy of the weight padded to a multiple of 8 rows, read the first V logits
-            st.proj_w = torch.zeros((Vp, po.in_features), dtype=dtype, device=device)
-            st.proj_w[:V].copy_(po.weight.detach())
         # greedy choice inside the graph: argmax of the logits under this step's suppression mask
         st.argmax_in_graph = dtype in (torch.float16, torch.bfloat16)
-        st.maskrow = torch.zeros((V,), dtype=torch.bool, device=device)
+        # an unquantized projection (HF bitsandbytes flows: proj_out stays fp16) runs on the library's own GEMM,
+        # straight from the module's weight (any vocabulary size; no padded copy), arg-max in the epilogue
+        st.proj_own = (type(po) is torch.nn.Linear and po.weight.dtype == dtype and po.weight.is_contiguous()
+                       and dtype in (torch.float16, torch.bfloat16) and po.in_features % 8 == 0)
+        st.proj_bias = po.bias.detach().float() if (st.proj_own and po.bias is not None) else None
+        st.store_logits = bool(store_logits) or not (st.proj_own and st.argmax_in_graph)
+        st.keys = torch.zeros((B,), dtype=torch.long, device=device)
+        st.maskrow = torch.zeros((-(-V // 256) * 256,), dtype=torch.bool, device=device)   # whole GEMM tiles
         st.next = torch.zeros((B,), dtype=torch.long, device=device)
         st.mask_cache = {}
         # warm up on a side stream (lazy inits, autotuning), then capture
@@ -420,6 +471,23 @@ class GraphedGreedy:
         except Exception:
             return object()
 
+    @staticmethod
+    def _plain_decoder_inputs(input_ids, model_kwargs) -> bool:
+        """The fast loop feeds token t at position t and attends every earlier position.  HF derives positions from
+        `decoder_attention_mask` when prompts are left-padded (generation_whisper.py: prompt_ids /
+        condition_on_prev_tokens) and accepts explicit position ids / embeddings: any of those keeps HF's loop."""
+        if model_kwargs.get("decoder_position_ids") is not None or model_kwargs.get("decoder_inputs_embeds") is not None:
+            return False
+        m = model_kwargs.get("decoder_attention_mask")
+        if m is not None and not bool((m != 0).all()):
+            return False
+        return True
+
+    @staticmethod
+    def _known_criteria(stopping_criteria) -> bool:
+        from transformers.generation.stopping_criteria import EosTokenCriteria, MaxLengthCriteria
+        return all(type(c) in (EosTokenCriteria, MaxLengthCriteria) for c in (stopping_criteria or []))
+
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def _sample(self, input_ids, logits_processor=None, stopping_criteria=None, generation_config=None,
@@ -430,7 +498,9 @@ class GraphedGreedy:
                     and not generation_config.return_dict_in_generate and streamer is None and not synced_gpus
                     and enc_out is not None and model_kwargs.get("use_cache", True)
                     and generation_config.max_length is not None
-                    and generation_config.max_length <= model.config.max_target_positions)
+                    and generation_config.max_length <= model.config.max_target_positions
+                    and self._plain_decoder_inputs(input_ids, model_kwargs)
+                    and self._known_criteria(stopping_criteria))
         if not eligible:
             self.fallbacks += 1
             out = self._orig_sample(input_ids, logits_processor=logits_processor,
@@ -443,7 +513,19 @@ class GraphedGreedy:
         B, P = input_ids.shape
         t_max = -(-int(generation_config.max_length) // self.len_bucket) * self.len_bucket
         t_max = min(t_max, model.config.max_target_positions)
-        st = self._get_state(B, t_max, enc.dtype, input_ids.device)
+        # Whisper's processors only write -inf at positions that depend on the current LENGTH
+        # (suppress lists, begin-suppress, min-new-tokens): evaluate them on a single zero row
+        # (cost independent of the batch) and apply the resulting mask to the fp16 logits.  argmax
+        # of the masked fp16 logits == argmax of HF's masked fp32 copy (exact widening, same ties).
+        from transformers.generation.logits_process import (MinLengthLogitsProcessor,
+                                                            MinNewTokensLengthLogitsProcessor,
+                                                            SuppressTokensAtBeginLogitsProcessor,
+                                                            SuppressTokensLogitsProcessor)
+        mask_only = (SuppressTokensLogitsProcessor, SuppressTokensAtBeginLogitsProcessor,
+                     MinNewTokensLengthLogitsProcessor, MinLengthLogitsProcessor)
+        maskable = all(type(p) in mask_only for p in logits_processor)
+        # the raw logits are only materialised when something reads them (non-mask processors, tests)
+        st = self._get_state(B, t_max, enc.dtype, input_ids.device, store_logits=self.keep_logits or not maskable)
 
         # cross-attention keys / values once per call (encoder-shaped GEMMs)
         S = enc.shape[1]
@@ -461,22 +543,12 @@ class GraphedGreedy:
                 st.ck[li].copy_(ca.k_proj(enc).view(B, S, st.H, st.hd))
                 st.cv[li].copy_(ca.v_proj(enc).view(B, S, st.H, st.hd))
 
+        V = st.logits.shape[1]
         pad_token_id = generation_config._pad_token_tensor
         has_eos = any(hasattr(c, "eos_token_id") for c in stopping_criteria)
         unfinished = torch.ones(B, dtype=torch.long, device=input_ids.device)
         max_length = int(generation_config.max_length)
 
-        # Whisper's processors only write -inf at positions that depend on the current LENGTH
-        # (suppress lists, begin-suppress, min-new-tokens): evaluate them on a single zero row
-        # (cost independent of the batch) and apply the resulting mask to the fp16 logits.  argmax
-        # of the masked fp16 logits == argmax of HF's masked fp32 copy (exact widening, same ties).
-        from transformers.generation.logits_process import (MinLengthLogitsProcessor,
-                                                            MinNewTokensLengthLogitsProcessor,
-                                                            SuppressTokensAtBeginLogitsProcessor,
-                                                            SuppressTokensLogitsProcessor)
-        mask_only = (SuppressTokensLogitsProcessor, SuppressTokensAtBeginLogitsProcessor,
-                     MinNewTokensLengthLogitsProcessor, MinLengthLogitsProcessor)
-        maskable = all(type(p) in mask_only for p in logits_processor)
         zero_row = torch.zeros((1, st.logits.shape[1]), dtype=torch.float32, device=input_ids.device)
 
         def eos_suppressed(length: int) -> bool:
@@ -510,11 +582,15 @@ class GraphedGreedy:
             st.tok.copy_(tokens.view(B, 1))
             st.pos.fill_(position)
             if in_graph and ids_after is not None:
-                st.maskrow.copy_(mask_for(ids_after))
+                st.maskrow[:V].copy_(mask_for(ids_after))
             st.graph.replay()
             self.replays += 1
             F.STATS.launches += st.launches_per_replay
 
+        replays0 = self.replays
+        if self.time_loop:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         for i in range(P):                       # prompt tokens (normally just <|startoftranscript|>)
             run(input_ids[:, i], i, input_ids if i == P - 1 else None)
         cur = P
@@ -547,6 +623,9 @@ class GraphedGreedy:
         # that is ~4 blocking syncs per utterance, ~45 ms at B = 256 -- as long as 25 decode steps.  The ids
         # are read back once here (HF's own dict path does the same with .cpu()) and HF's loops run on
         # the host copy; `generate` above returns the final tensor to the model's device.
+        if self.time_loop:
+            ev1.record()
+            self.loop_events.append((ev0, ev1, self.replays - replays0))
         if not self.host_postprocess:
             return input_ids
         ids = input_ids.cpu()

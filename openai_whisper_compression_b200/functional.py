@@ -430,6 +430,55 @@ def masked_argmax(logits: torch.Tensor, mask: Optional[torch.Tensor] = None,
     return out
 
 
+def gemm_f16(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None, argmax_keys: Optional[torch.Tensor] = None,
+             mask: Optional[torch.Tensor] = None, store: bool = True) -> Optional[torch.Tensor]:
+    """Unquantized linear y = x @ w.T + bias on the tcgen05 pipeline (the fp16 / bf16 `proj_out` of the HF
+    bitsandbytes flows).  out: optional [M, >= N] destination whose first N columns are written (row stride kept).
+    argmax_keys: uint64-as-int64 [M] zero-initialised keys that receive the masked arg-max of every row (see
+    argmax_finalize); mask: bool / uint8, padded to whole 128-column tiles.  store=False with argmax_keys: the
+    logits are not written at all."""
+    N, K = w.shape
+    x2 = x.reshape(-1, K)
+    _need_cuda(x2, w, bias, argmax_keys, mask)
+    if x2.dtype not in (torch.float16, torch.bfloat16) or w.dtype != x2.dtype:
+        raise RuntimeError("gemm_f16: x and w must both be float16 or bfloat16")
+    M = x2.shape[0]
+    y = None
+    ldy = 0
+    if store:
+        if out is None:
+            y = torch.empty((M, N), dtype=x2.dtype, device=x.device)
+        else:
+            if out.dim() != 2 or out.shape[0] != M or out.shape[1] < N or out.stride(1) != 1 or out.dtype != x2.dtype:
+                raise RuntimeError("gemm_f16: out must be [M, >= N] with unit column stride in the dtype of x")
+            y, ldy = out, (out.stride(0) if M > 1 else out.shape[1])
+    elif argmax_keys is None:
+        raise RuntimeError("gemm_f16: store=False needs argmax_keys")
+    if argmax_keys is not None and (argmax_keys.dtype != torch.int64 or argmax_keys.numel() < M):
+        raise RuntimeError("gemm_f16: argmax_keys must be int64 [M]")
+    if bias is not None and bias.dtype != torch.float32:
+        bias = bias.float()
+    with torch.cuda.device(x.device), _Timed("f16", M, N, K):
+        _lib.check(_lib.load().wq_gemm_f16(_ptr(x2), _DT[x2.dtype], _ptr(w), _ptr(bias), _ptr(y), _DT[x2.dtype], ldy,
+                                           M, N, K, _ptr(mask), 0 if mask is None else mask.numel(),
+                                           _ptr(argmax_keys), _stream()), "wq_gemm_f16")
+    STATS.launches += 1
+    return y
+
+
+def argmax_finalize(keys: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Token ids from the arg-max keys gemm_f16 accumulated; zeroes the keys for the next projection."""
+    _need_cuda(keys, out)
+    M = keys.numel()
+    if out is None:
+        out = torch.empty((M,), dtype=torch.int64, device=keys.device)
+    with torch.cuda.device(keys.device):
+        _lib.check(_lib.load().wq_argmax_finalize(_ptr(keys), M, _ptr(out), _stream()), "wq_argmax_finalize")
+    STATS.launches += 1
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # optimum-quanto qint8
 # ----------------------------------------------------------------------------------------------

@@ -12,7 +12,10 @@ Parity status (see the header of whisperq_oracle.c and DESIGN.md):
   * torch dynamic-int8 and log-mel: pinned against the live torch / HF implementations the
     reference calls (model_utils.py:131-134, data_utils.py:56-58) via tests/golden/.
   * bitsandbytes NF4 / LLM.int8, optimum-quanto qint8: PARITY UNPINNED (libraries absent, the
-    reference holds no golden vectors); restated from SURVEY.md Appendix A.
+    reference holds no golden vectors); restated from SURVEY.md Appendix A.  The open points of A.2 were closed on
+    a B200 in round 2 (scripts/bnb_open_points.cu, profiles/r02_bnb_open_points.json): the approximate division of
+    the row scale DOES change codes, so kernels and oracle now use it (table fixture); mul-then-add and fmaf forms
+    of int8_mm_dequant are the same instruction under nvcc's default -fmad=true.
 """
 from __future__ import annotations
 
@@ -57,6 +60,21 @@ def _f32(a) -> np.ndarray:
 
 
 _QT = {"nf4": 0, "fp4": 1}
+
+_FDIVIDEF = None
+
+
+def fdividef_127_table() -> np.ndarray:
+    """__fdividef(127.0f, h) for every fp16 bit pattern h of a positive finite absmax (float32[65536], index = fp16
+    bits), dumped on a B200 by scripts/bnb_open_points.cu and committed as tests/golden/fdividef_127_fp16.npz:
+    bitsandbytes' int8_vectorwise_quant kernel forms its row scale with that approximate-division intrinsic, which
+    differs from the IEEE quotient for 9 185 of the 31 743 absmax values."""
+    global _FDIVIDEF
+    if _FDIVIDEF is None:
+        path = os.path.join(os.path.dirname(_HERE), "tests", "golden", "fdividef_127_fp16.npz")
+        _FDIVIDEF = np.ascontiguousarray(np.load(path)["table"], dtype=np.float32)
+        assert _FDIVIDEF.shape == (65536,)
+    return _FDIVIDEF
 
 NF4_CODE = np.array([lib().orc_nf4_codebook()[i] for i in range(16)], dtype=np.float32)
 FP4_CODE = np.array([lib().orc_fp4_codebook()[i] for i in range(16)], dtype=np.float32)
@@ -137,8 +155,9 @@ def quantize_absmax_double(absmax: np.ndarray):
 # --------------------------------------------------------------------------------------
 # bitsandbytes LLM.int8
 # --------------------------------------------------------------------------------------
-def int8_vectorwise_quant(a: np.ndarray, threshold: float = 0.0):
-    """bitsandbytes.functional.int8_vectorwise_quant on fp16 input.
+def int8_vectorwise_quant(a: np.ndarray, threshold: float = 0.0, approx_div: bool = True):
+    """bitsandbytes.functional.int8_vectorwise_quant on fp16 input (approx_div: the library's __fdividef row scale,
+    through the committed table; False: the IEEE quotient, kept for the sweep test that counts the difference).
 
     Returns (CA int8 [rows, cols], row_stats f32 [rows], outlier_cols int64 or None)."""
     a16 = np.asarray(a).astype(np.float16)
@@ -148,7 +167,8 @@ def int8_vectorwise_quant(a: np.ndarray, threshold: float = 0.0):
     stats = np.zeros((rows,), dtype=np.float32)
     flags = np.zeros((cols,), dtype=np.uint8)
     lib().orc_bnb_int8_vectorwise_quant(_p(af), ctypes.c_int64(rows), ctypes.c_int64(cols),
-                                        ctypes.c_float(threshold), _p(out), _p(stats), _p(flags))
+                                        ctypes.c_float(threshold), _p(out), _p(stats), _p(flags),
+                                        _p(fdividef_127_table()) if approx_div else None)
     cols_idx = None
     if threshold > 0.0 and flags.any():
         cols_idx = np.nonzero(flags)[0].astype(np.int64)

@@ -171,15 +171,31 @@ void orc_quant_absmax_double(const float *absmax, int64_t n, const float *code, 
 /* bitsandbytes LLM.int8                                      */
 /* ------------------------------------------------------------------------- */
 
+/* fp16 bit pattern of a float that holds an fp16 value exactly (incl. subnormals) */
+static uint16_t half_bits_exact(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    const uint32_t sign = (u >> 16) & 0x8000u, e = (u >> 23) & 0xffu, m = u & 0x7fffffu;
+    if (e == 0) return (uint16_t)sign;                 /* zero (fp32 subnormals are below fp16's range) */
+    if (e == 0xff) return (uint16_t)(sign | 0x7c00u | (m ? 0x200u : 0u));
+    const int he = (int)e - 127 + 15;
+    if (he >= 1) return (uint16_t)(sign | ((uint32_t)he << 10) | (m >> 13));
+    return (uint16_t)(sign | ((m | 0x800000u) >> (126 - (int)e)));
+}
+
 /* int8_vectorwise_quant(A, threshold): per row absmax over entries with
- * |a| < threshold (all entries when threshold == 0), q = rn(a * (127/absmax)),
+ * |a| < threshold (all entries when threshold == 0), q = rn(a * scale),
  * entries with |a| >= threshold stored as 0 and their column flagged.
  * `a` holds fp16 values converted to fp32.  col_flags (may be NULL) is OR-ed.
- * Deviation (documented in DESIGN.md): bitsandbytes forms 127/absmax with
- * div.approx; this uses the IEEE quotient so that a CPU can be bit-exact. */
+ * scale: bitsandbytes forms 127/absmax with __fdividef (approximate division,
+ * csrc/kernels.cu kInt8VectorQuant), which a CPU cannot compute -- but absmax
+ * is an fp16 value, so scale_table[fp16 bits of absmax] (65536 floats dumped
+ * from a B200 by scripts/bnb_open_points.cu, tests/golden/fdividef_127_fp16.npz)
+ * reproduces it exactly.  scale_table == NULL: the IEEE quotient (differs from
+ * the approximate form in 8734 of 5.0e8 fp16 (absmax, a) pairs). */
 void orc_bnb_int8_vectorwise_quant(const float *a, int64_t rows, int64_t cols,
                                    float threshold, int8_t *out, float *row_stats,
-                                   uint8_t *col_flags) {
+                                   uint8_t *col_flags, const float *scale_table) {
     for (int64_t r = 0; r < rows; ++r) {
         const float *row = a + r * cols;
         float am = 0.0f;
@@ -189,7 +205,7 @@ void orc_bnb_int8_vectorwise_quant(const float *a, int64_t rows, int64_t cols,
             if (v > am) am = v;
         }
         row_stats[r] = am;
-        float scale = 127.0f / am;
+        float scale = scale_table ? scale_table[half_bits_exact(am)] : 127.0f / am;
         for (int64_t c = 0; c < cols; ++c) {
             float v = row[c];
             if (threshold > 0.0f && !(fabsf(v) < threshold)) {

@@ -3,8 +3,23 @@ models on the same device / dtype (so that everything except the linear under te
 HF code).  Each follows the oracle's restatement (oracle/whisperq_oracle.c) operation by
 operation; float64 is used where the oracle uses fmaf so that the result is the same fp32 value
 except in exact double-rounding ties."""
+import os
+
+import numpy as np
 import torch
 from torch import nn
+
+_TABLE = {}
+
+
+def bnb_row_scale(absmax: torch.Tensor) -> torch.Tensor:
+    """127 / absmax as bitsandbytes' kernel forms it (__fdividef), through the table dumped on a B200
+    (tests/golden/fdividef_127_fp16.npz); absmax holds fp16 values."""
+    t = _TABLE.get(absmax.device)
+    if t is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fdividef_127_fp16.npz")
+        t = _TABLE[absmax.device] = torch.from_numpy(np.load(path)["table"]).to(absmax.device)
+    return t[absmax.half().view(torch.int16).long() & 0xffff]
 
 
 def _set(model, name, new):
@@ -22,8 +37,7 @@ class EmuLinear8bitLt(nn.Module):
         super().__init__()
         W = lin.weight.detach().half().float()
         self.SCB = W.abs().amax(1)
-        # NB: `127.0 / t` in torch is reciprocal(t) * 127 (two roundings); the kernel/oracle use the IEEE quotient
-        self.CB = torch.nan_to_num(torch.round(W * torch.div(torch.full_like(self.SCB, 127.0), self.SCB)[:, None])).to(torch.int8)
+        self.CB = torch.nan_to_num(torch.round(W * bnb_row_scale(self.SCB)[:, None])).to(torch.int8)
         self.bias = None if lin.bias is None else lin.bias.detach().half()
         self.threshold = threshold
 
@@ -32,7 +46,7 @@ class EmuLinear8bitLt(nn.Module):
         Af = A.float()
         out = Af.abs() >= self.threshold
         am = torch.where(out, torch.zeros_like(Af), Af.abs()).amax(1)
-        CA = torch.nan_to_num(torch.round(Af * torch.div(torch.full_like(am, 127.0), am)[:, None]))
+        CA = torch.nan_to_num(torch.round(Af * bnb_row_scale(am)[:, None]))
         CA = torch.where(out, torch.zeros_like(CA), CA)
         cols = out.any(0)
         CA[:, cols] = 0

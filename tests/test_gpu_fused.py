@@ -237,7 +237,10 @@ def test_masked_argmax_matches_torch(B, V, ld, dtype):
         F.masked_argmax(torch.randn(4, 51865, device="cuda").half())      # rows not 16-byte aligned
 
 
-@pytest.mark.parametrize("B,H,S", [(3, 6, 1500), (70, 8, 1500), (2, 20, 1500), (5, 12, 37), (1, 8, 1)])
+# (300, 8, 333) and (160, 8, 1500): more (utterance, head) items than the persistent grid has CTAs -- every CTA walks
+# several items (prefetch across the item boundary, double-buffered merge scratch)
+@pytest.mark.parametrize("B,H,S", [(3, 6, 1500), (70, 8, 1500), (2, 20, 1500), (5, 12, 37), (1, 8, 1), (300, 8, 333),
+                                   (160, 8, 1500), (97, 20, 129)])
 @pytest.mark.parametrize("threshold", [None, 6.0])
 @pytest.mark.parametrize("kv_fused", [True, False])
 def test_cross_attn_decode(B, H, S, threshold, kv_fused):

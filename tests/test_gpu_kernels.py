@@ -430,3 +430,77 @@ def test_linear4bit_double_quant_module():
     y = m(x.cuda()).float().cpu().numpy()
     y_ref = x.double().numpy() @ wd_ref.astype(np.float64).T + lin.bias.detach().double().numpy()
     assert np.abs(y - y_ref).max() < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: bitsandbytes' approximate row scale, unquantized projection with fused arg-max
+# ------------------------------------------------------------------------------------------------
+def test_int8_row_scale_is_the_approximate_division_of_bitsandbytes():
+    """The fp16 (absmax, a) pairs on which __fdividef(127, absmax) and the IEEE quotient give different int8 codes
+    (exhaustive B200 sweep, profiles/r02_bnb_open_points.json): the quantizer kernel must produce the approximate
+    form's code (what bitsandbytes' kInt8VectorQuant computes), and so must the oracle through its table."""
+    import json
+    import os
+    rep = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles",
+                                      "r02_bnb_open_points.json")))
+    recs = rep["first_mismatches"]
+    rows = np.zeros((len(recs), 16), dtype=np.uint16)
+    for i, r in enumerate(recs):
+        rows[i, 0], rows[i, 1] = r["absmax_bits"], r["a_bits"]
+    a = rows.view(np.float16)
+    ca, stats, _ = F.int8_vectorwise_quant(dev(a), 0.0)
+    got = ca.cpu().numpy()
+    np.testing.assert_array_equal(got[:, 1], np.array([r["q_fdividef"] for r in recs], dtype=np.int8))
+    assert not np.array_equal(got[:, 1], np.array([r["q_ieee"] for r in recs], dtype=np.int8))
+    CA, SCA, _ = oracle.int8_vectorwise_quant(a, 0.0)
+    np.testing.assert_array_equal(got, CA)
+    np.testing.assert_array_equal(stats.cpu().numpy(), SCA)
+    # every fp16 absmax: the kernel's scale is the committed table (row = [absmax, absmax/2 rounded], code differs
+    # wherever the table entry is used)
+    bits = np.arange(1, 0x7c00, dtype=np.uint16)
+    full = np.zeros((bits.size, 16), dtype=np.uint16)
+    full[:, 0] = bits
+    full[:, 1] = (bits.view(np.float16).astype(np.float32) * np.float32(0.5)).astype(np.float16).view(np.uint16)
+    full[:, 2] = (bits.view(np.float16).astype(np.float32) * np.float32(0.75)).astype(np.float16).view(np.uint16)
+    af = full.view(np.float16)
+    ca2, _, _ = F.int8_vectorwise_quant(dev(af), 0.0)
+    CA2, _, _ = oracle.int8_vectorwise_quant(af, 0.0)
+    np.testing.assert_array_equal(ca2.cpu().numpy(), CA2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(256, 51865, 512), (6, 51866, 1280), (300, 1000, 384), (1, 51865, 384), (64, 130, 64)])
+def test_gemm_f16_projection_and_fused_argmax(dtype, M, N, K):
+    """Unquantized proj_out on the tcgen05 pipeline: logits within one output rounding of an fp32 reference, and
+    the arg-max folded into the epilogue == torch.argmax(masked logits) of the logits the SAME kernel stores
+    (bit-exact: same rounded values, first index among ties), with and without storing the logits."""
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(dtype)
+    Vp = -(-N // 256) * 256
+    out = torch.zeros((M, -(-N // 8) * 8), dtype=dtype, device="cuda")
+    mask = torch.zeros((Vp,), dtype=torch.bool, device="cuda")
+    mask[:N] = torch.rand(N, device="cuda", generator=g) < 0.3
+    keys = torch.zeros((M,), dtype=torch.int64, device="cuda")
+    y = F.gemm_f16(x, w, None, out=out, argmax_keys=keys, mask=mask)
+    ref = x.float() @ w.float().t()
+    tol = 2e-3 if dtype == torch.float16 else 1.6e-2
+    assert (y[:, :N].float() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+    tok = F.argmax_finalize(keys)
+    assert int(keys.abs().sum()) == 0                                   # keys reset for the next call
+    want = torch.argmax(y[:, :N].float().masked_fill(mask[:N], float("-inf")), dim=-1)
+    assert torch.equal(tok, want)
+    # ties and a fully masked row
+    x2 = x.clone()
+    x2[0] = 0
+    y2 = F.gemm_f16(x2, w, None, out=out, argmax_keys=keys, mask=mask)
+    tok2 = F.argmax_finalize(keys)
+    assert torch.equal(tok2, torch.argmax(y2[:, :N].float().masked_fill(mask[:N], float("-inf")), dim=-1))
+    # the same without storing the logits, no mask, with a bias
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    F.gemm_f16(x, w, bias, argmax_keys=keys, store=False)
+    tok3 = F.argmax_finalize(keys)
+    y3 = F.gemm_f16(x, w, bias)
+    assert y3.shape == (M, N)
+    assert torch.equal(tok3, torch.argmax(y3.float(), dim=-1))
+    assert (y3.float() - (ref + bias)).abs().max().item() <= tol * max(1.0, ref.abs().max().item())

@@ -289,12 +289,13 @@ def test_graphed_greedy_matches_hf_generate(pkg, scheme, geom):
                          return_dict_in_generate=True, output_logits=True)   # HF loop (fallback criteria)
     ref_ids = harness.greedy_generate(model, feats, T)      # HF's own loop, plain call
     eng = fastgen.enable(model)
+    eng.keep_logits = True          # the captured step also stores the raw logits (compared below)
     ids = harness.greedy_generate(model, feats, T)
     assert eng.replays > 0 and eng.fallbacks == 0
     st = next(iter(eng._states.values()))
     assert st.own_attn == (geom == "real")
     assert (st.fused is not None) == (geom == "real" and scheme == "llm_int8")
-    assert (st.proj_w is not None) == (scheme in ("llm_int8", "fp16", "bnb_nf4"))   # unquantized proj_out
+    assert st.proj_own == (scheme in ("llm_int8", "fp16", "bnb_nf4"))   # unquantized proj_out: own GEMM + arg-max
     assert ids.shape == ref_ids.shape
     logits = torch.stack(ref.logits, 1).float()
     top2 = logits.topk(2, -1).values
@@ -440,6 +441,7 @@ def test_fused_int8_decode_step_is_bit_identical_to_module_calls(pkg):
                 m.weight[::41] *= 6.0
     feats = _feats(n=6, frames=3000).half().cuda()
     eng = fastgen.enable(model)
+    eng.keep_logits = True
     T = 12
     ids = harness.greedy_generate(model, feats, T)
     st = next(iter(eng._states.values()))

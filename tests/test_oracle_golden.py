@@ -244,3 +244,36 @@ def test_dynamic_map_and_nested_absmax_quantization():
         assert q[blk][i] in (0, 255)
         assert deq[blk][i] == np.float32(np.float32(code[q[blk][i]] * a2[b]) + off)
     assert np.abs(deq - absmax).max() <= 0.01 * np.abs(absmax - off).max() + 1e-7
+
+
+def test_fdividef_table_reproduces_the_b200_sweep():
+    """SURVEY A.2 open point "exact reciprocal", closed on a B200 (scripts/bnb_open_points.cu): bitsandbytes' row
+    scale __fdividef(127, absmax) against the IEEE quotient over ALL fp16 (absmax, 0 <= a <= absmax) pairs.  The
+    committed table (tests/golden/fdividef_127_fp16.npz) must reproduce the counts the GPU reported
+    (profiles/r02_bnb_open_points.json): that is what pins the oracle's int8 codes to the approximate form."""
+    import json
+    import os
+    table = oracle.fdividef_127_table()
+    rep = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles",
+                                      "r02_bnb_open_points.json")))
+    vals = np.arange(0, 0x7c00, dtype=np.uint16).view(np.float16).astype(np.float32)
+    ieee = np.zeros(0x7c00, dtype=np.float32)
+    ieee[1:] = np.float32(127.0) / vals[1:]
+    assert int((ieee[1:] != table[1:0x7c00]).sum()) == rep["absmax_values_with_different_scale"] == 9185
+    pairs = mism = 0
+    for hb in range(1, 0x7c00):
+        a = vals[: hb + 1]
+        q1 = np.rint(a * table[hb])
+        q2 = np.rint(a * ieee[hb])
+        pairs += hb + 1
+        mism += int((q1 != q2).sum())
+    assert pairs == rep["fp16_pairs"] and mism == rep["code_mismatches"] == 8734
+    # the listed pairs, through the C oracle: approximate form = GPU's code, IEEE form = the other one
+    for rec in rep["first_mismatches"][:16]:
+        am = np.array([rec["absmax_bits"]], dtype=np.uint16).view(np.float16)[0]
+        a = np.array([rec["a_bits"]], dtype=np.uint16).view(np.float16)[0]
+        row = np.array([[am, a]], dtype=np.float16)
+        assert int(oracle.int8_vectorwise_quant(row, 0.0)[0][0, 1]) == rec["q_fdividef"]
+        assert int(oracle.int8_vectorwise_quant(row, 0.0, approx_div=False)[0][0, 1]) == rec["q_ieee"]
+    # int8_mm_dequant: written as mul-then-add it is contracted to the same FFMA as fmaf (0 mismatches in 2.5e9)
+    assert rep["plain_vs_fmaf_f32_mismatches"] == 0
