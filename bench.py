@@ -335,6 +335,8 @@ def decode_probe(model, eng, peaks, ms_step, T):
     # decode-shaped quantized GEMMs: the six weight matrices of every decoder layer, captured as ONE CUDA graph
     # (the way the step runs them: back to back, programmatic dependent launch) and replayed under events
     if st.fused is not None:
+        B = st.views[0].B           # rows per launch: the step decodes the batch in row groups (one per stream)
+        out["row_groups"] = len(st.views)
         x = torch.randn((B, d), device=q.device, dtype=torch.float16)
         calls = []
         for fw in st.fused:
@@ -365,7 +367,7 @@ def decode_probe(model, eng, peaks, ms_step, T):
         tot_b = sum(w.cb.shape[0] * w.cb.shape[1] + B * w.cb.shape[1] + 2 * B * w.cb.shape[0] for _, _, w in calls)
         tot_t = sum(a.elapsed_time(b) for a, b in ts) / len(ts) * 1e-3
         out["decode_gemm"] = {
-            "kernel": "k_gemm_tc decode-shaped launches (M = utterances per GPU), LLM.int8",
+            "kernel": f"k_gemm_tc decode-shaped launches (M = {B} rows: one row group of the batch), LLM.int8",
             "bound": "hbm", "launches": len(calls), "avg_launch_us": tot_t / len(calls) * 1e6,
             "algorithmic_bytes_per_launch": tot_b / len(calls), "achieved": tot_b / tot_t / 1e9,
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": tot_b / tot_t / 1e9 / peaks["hbm_gbs"],

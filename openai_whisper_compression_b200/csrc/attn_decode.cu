@@ -10,6 +10,8 @@
 // quantization of the [H*64] output row (same arithmetic as k_quant_i8_rowwise_bnb, on the rounded fp16 values).
 // L2-resident, latency-bound: what matters is launch count, not bandwidth.
 #include "common.cuh"
+#include "ptx.cuh"
+#include "tma_host.cuh"
 
 namespace {
 
@@ -246,6 +248,54 @@ __device__ __forceinline__ void partial_merge(Partial &a, float om, float ol, co
     a.m = m;
 }
 
+// LLM.int8 row quantization of out[b, :] by the last of this utterance's H head items to finish
+// (int8_vectorwise_quant on the rounded values; the counter resets itself for the next launch).  Called by the ONE
+// warp that wrote this item's output (lanes with g == 0 hold the stores), so no CTA-wide barrier is needed and the
+// other warps are already streaming the next item (a __syncthreads + fence here cost the persistent kernel a third
+// of its in-graph bandwidth: the fence waits for the CTA's prefetched loads).
+template <typename T>
+__device__ __forceinline__ void quantize_row_if_last(const T *out, int b, int d, int H, int lane, int g, float threshold,
+                                                     int8_t *__restrict__ ca, float *__restrict__ row_stats,
+                                                     int32_t *__restrict__ col_flags, int32_t *__restrict__ row_counters) {
+    if (g == 0) __threadfence();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(&row_counters[b], 1) == H - 1);
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    const bool sparse = threshold > 0.0f;
+    const T *orow = out + (int64_t)b * d;
+    float am = 0.0f;
+    for (int c = lane; c < d; c += 32) {
+        const float x = fabsf(to_f32(__ldcg(orow + c)));
+        if (!sparse || x < threshold) am = fmaxf(am, x);
+    }
+    am = warp_max(am);
+    if (lane == 0) {
+        row_stats[b] = am;
+        row_counters[b] = 0;
+    }
+    const float scale = bnb_row_scale(am);
+    for (int c = lane * 4; c < d; c += 128) {       // d is a multiple of 64: four codes per store
+        uint32_t pk = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float x = to_f32(__ldcg(orow + c + j));
+            int qv;
+            if (sparse && !(fabsf(x) < threshold)) {
+                qv = 0;
+                col_flags[c + j] = 1;
+                col_flags[d] = 1;
+            } else {
+                qv = __float2int_rn(__fmul_rn(x, scale));
+            }
+            pk |= (uint32_t)(qv & 0xff) << (8 * j);
+        }
+        *reinterpret_cast<uint32_t *>(ca + (int64_t)b * d + c) = pk;
+    }
+}
+
 template <typename T, int kXWarps>
 __global__ void __launch_bounds__(kXWarps * 32, 2)
 k_cross_attn_decode(const T *__restrict__ q, int64_t ldq, float scaling, const T *__restrict__ kmat,
@@ -253,8 +303,6 @@ k_cross_attn_decode(const T *__restrict__ q, int64_t ldq, float scaling, const T
                     int8_t *__restrict__ ca, float *__restrict__ row_stats, int32_t *__restrict__ col_flags,
                     int32_t *__restrict__ row_counters) {
     __shared__ float s_part[2][kXWarps][8][10];   // per item parity and warp: 8 dim-groups x (m, l, acc[8])
-    __shared__ float s_red[kXWarps];
-    __shared__ int s_last;
     pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 3, sub = lane & 7;
@@ -374,51 +422,170 @@ k_cross_attn_decode(const T *__restrict__ q, int64_t ldq, float scaling, const T
             for (int j = 0; j < 8; ++j) o8[j] = from_f32<T>(p.acc[j] * inv);
             *reinterpret_cast<uint4 *>(out + (int64_t)b * d + h * kHeadDim + sub * 8) = raw;
         }
-        if (ca != nullptr) {
-            // LLM.int8 row quantization of out[b, :] by the last of this utterance's H head items to finish
-            // (int8_vectorwise_quant on the rounded values; the counter resets itself for the next launch)
-            if (threadIdx.x < 8) __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) s_last = (atomicAdd(&row_counters[b], 1) == H - 1);
-            __syncthreads();
-            if (s_last) {
-                __threadfence();
-                const bool sparse = threshold > 0.0f;
-                const T *orow = out + (int64_t)b * d;
-                float am = 0.0f;
-                for (int c = threadIdx.x; c < d; c += blockDim.x) {
-                    const float x = fabsf(to_f32(__ldcg(orow + c)));
-                    if (!sparse || x < threshold) am = fmaxf(am, x);
-                }
-                am = warp_max(am);
-                if (lane == 0) s_red[warp] = am;
-                __syncthreads();
-                am = 0.0f;
-#pragma unroll
-                for (int w = 0; w < kXWarps; ++w) am = fmaxf(am, s_red[w]);
-                if (threadIdx.x == 0) {
-                    row_stats[b] = am;
-                    row_counters[b] = 0;
-                }
-                const float scale = bnb_row_scale(am);
-                for (int c = threadIdx.x; c < d; c += blockDim.x) {
-                    const float x = to_f32(__ldcg(orow + c));
-                    int qv;
-                    if (sparse && !(fabsf(x) < threshold)) {
-                        qv = 0;
-                        col_flags[c] = 1;
-                        col_flags[d] = 1;
-                    } else {
-                        qv = __float2int_rn(__fmul_rn(x, scale));
-                    }
-                    ca[(int64_t)b * d + c] = (int8_t)qv;
-                }
-            }
-        }
+        if (ca != nullptr && warp == 0)
+            quantize_row_if_last(out, b, d, H, lane, g, threshold, ca, row_stats, col_flags, row_counters);
         if (!has_next) break;
         kb = kbn;
         vb = vbn;
         qb = qbn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same walk with the stream landing in SHARED memory (TMA) instead of registers.
+//
+// The register-fed kernel above needs ~128 KB of loads in flight per SM to run HBM at rate (measured: 64 KB/SM ->
+// 4.6 TB/s, 128 KB/SM -> 6.5 TB/s at ~2 us loaded latency), and with 16-byte loads that is 60 K registers per SM: the
+// SM is full, nothing of another stream can run beside it.  Here one elected thread issues cp.async.bulk.tensor loads
+// of [64 positions x 128 B] boxes of K and of V (one head of one utterance: a dense 2-D box of the [B*S, d] matrix
+// the projection GEMM wrote) into a 6-stage x 16 KB ring -- 96 KB in flight per SM in shared memory -- and four
+// consumer warps fold the landed rows into the running softmax.  160 threads x ~64 registers: the SM keeps > 50 K
+// registers and 130 KB of shared memory free, which is what lets the launch-bound rest of the decode step of the
+// OTHER half-batch (fastgen's second stream: lean GEMM tiles, LayerNorm, self-attention) run under this kernel's
+// HBM stream.  The ring is item-agnostic: the producer runs ahead across (utterance, head) boundaries.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTR = 64;                    // positions per ring stage
+constexpr int kTStages = 6;
+constexpr int kTCW = 4;                    // consumer warps
+constexpr int kTStageBytes = kTR * 128;    // one operand (K or V) of one stage
+constexpr int kTSmem = 2 * kTStages * kTStageBytes + 1024;
+
+template <typename T>
+__global__ void __launch_bounds__((kTCW + 1) * 32, 1)
+k_cross_attn_decode_tma(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                        const T *__restrict__ q, int64_t ldq, float scaling, int S, int H, int n_items, T *out,
+                        float threshold, int8_t *__restrict__ ca, float *__restrict__ row_stats,
+                        int32_t *__restrict__ col_flags, int32_t *__restrict__ row_counters) {
+    using namespace wq;
+    extern __shared__ __align__(1024) uint8_t xs_raw[];
+    uint8_t *xs = xs_raw + ((1024u - (smem_u32(xs_raw) & 1023u)) & 1023u);
+    uint8_t *sK = xs, *sV = xs + kTStages * kTStageBytes;
+    __shared__ uint64_t bar_full[kTStages], bar_empty[kTStages];
+    __shared__ float s_part[2][kTCW][8][10];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 3, sub = lane & 7;
+    const int d = H * kHeadDim;
+    constexpr float kLog2e = 1.4426950408889634f;
+    const int n_blk = (S + kTR - 1) / kTR;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_k);
+        tma_prefetch_desc(&map_v);
+        for (int s = 0; s < kTStages; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], kTCW);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    pdl_wait();
+
+    if (warp == kTCW) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int item = (int)blockIdx.x; item < n_items; item += (int)gridDim.x) {
+                const int b = item / H, h = item - b * H;
+                for (int blk = 0; blk < n_blk; ++blk, ++it) {
+                    const int s = it % kTStages;
+                    mbar_wait(&bar_empty[s], ((it / kTStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bar_full[s], 2 * kTStageBytes);
+                    tma_load_2d(sK + s * kTStageBytes, &map_k, &bar_full[s], h * kHeadDim, b * S + blk * kTR);
+                    tma_load_2d(sV + s * kTStageBytes, &map_v, &bar_full[s], h * kHeadDim, b * S + blk * kTR);
+                }
+            }
+        }
+        __syncwarp();
+        pdl_trigger();
+        return;
+    }
+
+    // ---------------- consumers: warps 0..3, 16 positions of every stage each ----------------
+    uint32_t it = 0;
+    int par = 0;
+    for (int item = (int)blockIdx.x; item < n_items; item += (int)gridDim.x, par ^= 1) {
+        const int b = item / H, h = item - b * H;
+        float q8[8];
+        load8(q + (int64_t)b * ldq + h * kHeadDim + sub * 8, q8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q8[j] = to_f32(from_f32<T>(q8[j] * scaling)) * kLog2e;   // scores in log2 units
+        Partial p;
+        p.m = -INFINITY;
+        p.l = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p.acc[j] = 0.0f;
+        for (int blk = 0; blk < n_blk; ++blk, ++it) {
+            const int s = it % kTStages;
+            mbar_wait(&bar_full[s], (it / kTStages) & 1);
+            const uint8_t *pk = sK + s * kTStageBytes + (warp * 16 + g) * 128 + sub * 16;
+            const uint8_t *pv = sV + s * kTStageBytes + (warp * 16 + g) * 128 + sub * 16;
+            uint4 kr[4], vr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                kr[u] = *reinterpret_cast<const uint4 *>(pk + u * 4 * 128);
+                vr[u] = *reinterpret_cast<const uint4 *>(pv + u * 4 * 128);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[s]);      // this warp's rows of the stage are in registers
+            const int t_base = blk * kTR + warp * 16 + g;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = t_base + u * 4;
+                const T *k8 = reinterpret_cast<const T *>(&kr[u]);
+                const T *v8 = reinterpret_cast<const T *>(&vr[u]);
+                float sc = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sc = fmaf(q8[j], to_f32(k8[j]), sc);
+                sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+                sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+                sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+                if (t < S) {
+                    const float m = fmaxf(p.m, sc);
+                    const float corr = exp2f(p.m - m);          // exp2f(-inf) == 0 on the first row
+                    const float e = exp2f(sc - m);
+                    p.l = p.l * corr + e;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) p.acc[j] = fmaf(e, to_f32(v8[j]), p.acc[j] * corr);
+                    p.m = m;
+                }
+            }
+        }
+        if (item + (int)gridDim.x >= n_items) pdl_trigger();
+        // merge the 4 lane groups of the warp (same dims, different rows)
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, p.m, o);
+            const float ol = __shfl_xor_sync(0xffffffffu, p.l, o);
+            float oacc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) oacc[j] = __shfl_xor_sync(0xffffffffu, p.acc[j], o);
+            partial_merge(p, om, ol, oacc);
+        }
+        if (g == 0) {
+            s_part[par][warp][sub][0] = p.m;
+            s_part[par][warp][sub][1] = p.l;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s_part[par][warp][sub][2 + j] = p.acc[j];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTCW * 32) : "memory");      // the consumer warps only
+        if (warp != 0) continue;
+        if (g == 0) {
+#pragma unroll
+            for (int w = 1; w < kTCW; ++w) {
+                float oacc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) oacc[j] = s_part[par][w][sub][2 + j];
+                partial_merge(p, s_part[par][w][sub][0], s_part[par][w][sub][1], oacc);
+            }
+            const float inv = 1.0f / p.l;
+            uint4 raw;
+            T *o8 = reinterpret_cast<T *>(&raw);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o8[j] = from_f32<T>(p.acc[j] * inv);
+            *reinterpret_cast<uint4 *>(out + (int64_t)b * d + h * kHeadDim + sub * 8) = raw;
+        }
+        if (ca != nullptr)
+            quantize_row_if_last(out, b, d, H, lane, g, threshold, ca, row_stats, col_flags, row_counters);
     }
 }
 
@@ -453,6 +620,39 @@ extern "C" int wq_cross_attn_decode(const void *q, int64_t ldq, int dtype, float
     WQ_REQUIRE(ca == nullptr || threshold == 0.0f || col_flags, "wq_cross_attn_decode: threshold needs col_flags");
     cudaStream_t s = (cudaStream_t)stream;
     const int n_items = (int)(B * H);
+    static const bool use_tma = [] {       // WQ_XATTN=reg: the register-fed kernel (A/B measurements)
+        const char *e = getenv("WQ_XATTN");
+        return e == nullptr || e[0] != 'r';
+    }();
+    if (use_tma && B * S < (1ll << 31)) {
+        // K and V as [B*S, H*64] matrices with a row pitch of ld elements; one box = 64 positions of one head
+        const CUtensorMapDataType dt = dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+        CUtensorMap mk, mv;
+        int rc = make_map_2d(&mk, k, dt, 2, (uint64_t)(B * S), (uint64_t)H * kHeadDim, kTR, kHeadDim,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, (uint64_t)ld);
+        if (rc != WQ_OK) return rc;
+        rc = make_map_2d(&mv, v, dt, 2, (uint64_t)(B * S), (uint64_t)H * kHeadDim, kTR, kHeadDim,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, (uint64_t)ld);
+        if (rc != WQ_OK) return rc;
+        const int cap = wq_sm_count();
+        const dim3 grid((unsigned)(n_items < cap ? n_items : cap));
+        static bool configured = false;
+        if (!configured) {
+            WQ_CUDA(cudaFuncSetAttribute(k_cross_attn_decode_tma<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
+            WQ_CUDA(cudaFuncSetAttribute(k_cross_attn_decode_tma<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
+            configured = true;
+        }
+        if (dtype == WQ_F16) {
+            WQ_LAUNCH_PDL(k_cross_attn_decode_tma<__half>, grid, dim3((kTCW + 1) * 32), (size_t)kTSmem, s, mk, mv,
+                          (const __half *)q, ldq, scaling, (int)S, H, n_items, (__half *)out, threshold, ca, row_stats,
+                          col_flags, row_counters);
+        } else {
+            WQ_LAUNCH_PDL(k_cross_attn_decode_tma<__nv_bfloat16>, grid, dim3((kTCW + 1) * 32), (size_t)kTSmem, s, mk, mv,
+                          (const __nv_bfloat16 *)q, ldq, scaling, (int)S, H, n_items, (__nv_bfloat16 *)out, 0.0f,
+                          (int8_t *)nullptr, (float *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr);
+        }
+        return WQ_OK;
+    }
     const int cap = wq_sm_count() * xattn_ctas_per_sm();
     const dim3 grid((unsigned)(n_items < cap ? n_items : cap));
     if (dtype == WQ_F16) {

@@ -31,6 +31,7 @@
 //                masked arg-max over the rounded outputs folded into the epilogue (greedy token choice)
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tma_host.cuh"
 
 namespace {
 using namespace wq;
@@ -42,7 +43,8 @@ constexpr int UMMA_K_BYTES = 32;   // one tcgen05.mma consumes 32 bytes of K per
 constexpr int ACC_STAGES = 2;      // TMEM accumulator ring (epilogue of tile i overlaps mainloop of i+1)
 // epilogue warps: 2 halves x 4 TMEM lane quarters.  The kernel also supports 16 (two warps split the
 // columns of each 32-row slab); measured slower on B200 (56 vs 46 us at 96000x512x512), so 8 is used.
-template <int BN, int BMODE> constexpr int epi_warps() { return 8; }
+// LEAN tiles (decode-shaped calls with M <= 128: 128 rows, one half) run 4.
+template <int BN, int BMODE, int LEAN = 0> constexpr int epi_warps() { return LEAN ? 4 : 8; }
 constexpr int BOX_BYTES = 32 * 128;  // one TMA-store box: 32 rows x 128 bytes (SWIZZLE_128B)
 
 enum AKind { A_F16 = 0, A_BF16 = 1, A_S8 = 2, A_U8 = 3 };
@@ -109,7 +111,7 @@ __device__ __forceinline__ void argmax_chunk(const float (&v)[32], const uint8_t
 
 template <int BMODE> constexpr bool is_nibble() { return BMODE == B_4BIT || BMODE == B_U4; }
 template <int BMODE> constexpr int dq_warps() { return BMODE == B_DIRECT ? 0 : (is_nibble<BMODE>() ? 8 : 4); }
-template <int BN, int BMODE> constexpr int num_threads() { return 32 * (2 + epi_warps<BN, BMODE>() + dq_warps<BMODE>()); }
+template <int BN, int BMODE, int LEAN = 0> constexpr int num_threads() { return 32 * (2 + epi_warps<BN, BMODE, LEAN>() + dq_warps<BMODE>()); }
 
 // WS > 0: weight-stationary schedule (B_DIRECT only).  The CTA keeps its W tile -- all num_kb <= WS k-blocks of BN
 // rows -- resident in shared memory and walks M tiles of ONE n column block, so the ring streams A alone: per
@@ -119,11 +121,16 @@ template <int BN, int BMODE> constexpr int num_threads() { return 32 * (2 + epi_
 // of two M = 128, N = 128 instructions on two row halves.  An N = 128 instruction reads 4 KB of A and 4 KB of W from
 // shared memory for 64 cycles of tensor work -- 128 B/clk, all the SM's shared-memory bandwidth, and the pipe ran
 // ~45 % active; at N = 256 it is 12 KB per 128 cycles.  The two accumulator "halves" are then column halves.
-template <int BN, int STAGES, int BMODE, int OUT_BUFS, int WS = 0, int COLS = 0>
+//
+// LEAN = 1: the tile is 128 rows (ONE half) x BN columns with 4 epilogue warps -- decode-shaped calls with at most 128
+// rows.  Half the A bytes per stage, 192 threads and ~128 KB of shared memory instead of 320 / 226 KB, so that the CTA
+// fits on an SM next to a resident attention CTA of the other half-batch's stream (fastgen two-stream decode).
+template <int BN, int STAGES, int BMODE, int OUT_BUFS, int WS = 0, int COLS = 0, int LEAN = 0>
 struct SmemLayout {
+    static_assert(LEAN == 0 || (WS == 0 && COLS == 0), "lean tiles: plain round-robin schedule");
     static_assert(WS == 0 || BMODE == B_DIRECT, "weight-stationary tiles take W straight from TMA");
     static_assert(COLS == 0 || (BMODE == B_DIRECT && BN == 128), "column-split tiles: int8 x int8 schemes, 2 x 128 columns");
-    static constexpr int BMT = COLS ? BMH : BM;                // tile rows
+    static constexpr int BMT = (COLS || LEAN) ? BMH : BM;      // tile rows
     static constexpr int BNT = COLS ? 2 * BN : BN;             // tile columns
     static constexpr int A_BYTES = BMT * ROW_BYTES;
     static constexpr int B_BYTES = BNT * ROW_BYTES;
@@ -133,7 +140,7 @@ struct SmemLayout {
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
     static constexpr int OFF_P = OFF_B + B_SLOTS * B_BYTES;
-    static constexpr int EW = epi_warps<BN, BMODE>();
+    static constexpr int EW = epi_warps<BN, BMODE, LEAN>();
     static constexpr int OFF_OUT = OFF_P + STAGES * P_BYTES;   // EW x OUT_BUFS boxes, 1024-byte aligned
     static constexpr int CONST_BUFS = WS > 0 ? 1 : 2;          // a weight-stationary CTA never changes columns
     static constexpr int OFF_CONST = OFF_OUT + EW * OUT_BUFS * BOX_BYTES;  // float [CONST_BUFS][3][BNT] per-tile constants
@@ -301,14 +308,14 @@ __device__ __noinline__ void llmint8_outlier_chunk(const GemmArgs &args, const f
 }
 
 // Body of one epilogue warp: drains its 32-row slab of every tile this CTA owns.
-template <int BN, int EW, int EPI, typename OutT, int OUT_BUFS, bool TMA_STORE, int WS, int COLS>
+template <int BN, int EW, int EPI, typename OutT, int OUT_BUFS, bool TMA_STORE, int WS, int COLS, int LEAN>
 __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtensorMap *map_y, uint8_t *boxes,
                                               float *s_const, uint64_t *bar_tmem_full, uint64_t *bar_tmem_empty,
                                               uint32_t tmem_base, int warp, int lane) {
     constexpr int ACC_COLS = 2 * BN;
-    constexpr int BMT = COLS ? BMH : BM, BNT = COLS ? 2 * BN : BN;   // tile rows / columns
+    constexpr int BMT = (COLS || LEAN) ? BMH : BM, BNT = COLS ? 2 * BN : BN;   // tile rows / columns
     constexpr int BOX_COLS = 128 / (int)sizeof(OutT);   // columns per TMA-store box (64 or 32)
-    constexpr int CSPLIT = EW / 8;                      // warps sharing a 32-row slab split its columns
+    constexpr int CSPLIT = EW >= 8 ? EW / 8 : 1;        // warps sharing a 32-row slab split its columns
     constexpr int N_BOX = BN / BOX_COLS / CSPLIT;       // boxes per warp per tile
     constexpr int NCH = BOX_COLS / 32;                  // tcgen05.ld chunks per box (2 or 1)
     const int grp = (warp - 2) >> 2;
@@ -441,17 +448,17 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
     __syncwarp();
 }
 
-template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT, int OUT_BUFS, int WS, int COLS>
-__global__ void __launch_bounds__(num_threads<BN, BMODE>(), 1)
+template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT, int OUT_BUFS, int WS, int COLS, int LEAN>
+__global__ void __launch_bounds__(num_threads<BN, BMODE, LEAN>(), LEAN ? 2 : 1)   // lean: <= 168 registers
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ CUtensorMap map_y, const GemmArgs args) {
-    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS, COLS>;
+    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS, COLS, LEAN>;
     constexpr int BMT = L::BMT, BNT = L::BNT;
     static_assert(BN == 64 || BN == 128, "BN must be 64 or 128 (2 halves x 2 stages x BN <= 512 TMEM columns)");
     constexpr bool kIntKind = (AKIND == A_S8 || AKIND == A_U8);
     constexpr int A_ELEMS_PER_ROW = kIntKind ? 128 : 64;  // elements of K per 128-byte row
     constexpr int DQ_WARPS = dq_warps<BMODE>();
-    constexpr int EW = epi_warps<BN, BMODE>();
+    constexpr int EW = epi_warps<BN, BMODE, LEAN>();
     constexpr int ACC_COLS = 2 * BN;                      // one accumulator stage: half 0 | half 1
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -549,7 +556,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             int mt, nt;
             for (; tile_at<WS>(args, (int)t, mt, nt); ++t) {
                 const int m0 = mt * BMT;
-                const bool two_halves = COLS == 0 && m0 + BMH < args.M;   // second 128 rows hold real data
+                const bool two_halves = COLS == 0 && LEAN == 0 && m0 + BMH < args.M;   // second 128 rows hold real data
                 if constexpr (WS > 0) {
                     if (t == 0) mbar_wait(bar_w, 0);
                 }
@@ -588,9 +595,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         uint8_t *boxes = smem + L::OFF_OUT + (warp - 2) * OUT_BUFS * BOX_BYTES;   // private staging of this warp
         float *s_const = reinterpret_cast<float *>(smem + L::OFF_CONST);
         if (args.tma_store)
-            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, true, WS, COLS>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane);
+            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, true, WS, COLS, LEAN>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane);
         else
-            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, false, WS, COLS>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane);
+            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, false, WS, COLS, LEAN>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane);
     } else {
         // ---------------- weight expansion (W8A16 / W4A16): warps 10.. ----------------
         const int t = threadIdx.x - 32 * (2 + EW);
@@ -718,59 +725,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------
 // host side: tensor maps + dispatch
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn == nullptr) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-// 2-D row-major matrix [rows, cols] of `elem_bytes`-byte elements, box = [box_rows, box_cols].
-int make_map_2d(CUtensorMap *map, const void *base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows,
-                uint64_t cols, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz, uint64_t pitch_elems = 0) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (fn == nullptr) {
-        wq_set_error("cuTensorMapEncodeTiled is not available from the driver");
-        return WQ_ERR_CUDA;
-    }
-    cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {(pitch_elems ? pitch_elems : cols) * (uint64_t)elem_bytes};
-    cuuint32_t box[2] = {box_cols, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        wq_set_error("cuTensorMapEncodeTiled failed (%d): rows %llu cols %llu elem %d box %ux%u", (int)r,
-                     (unsigned long long)rows, (unsigned long long)cols, elem_bytes, box_rows, box_cols);
-        return WQ_ERR_CUDA;
-    }
-    return WQ_OK;
-}
-
 // TMA-store boxes per epilogue warp (double-buffered when shared memory allows)
 template <int BN, int BMODE> constexpr int pick_out_bufs() {
-    return ((BMODE == B_I8 && BN == 128) || epi_warps<BN, BMODE>() == 16) ? 1 : 2;
+    return (BMODE == B_I8 && BN == 128) ? 1 : 2;
 }
 
 // deepest smem ring that fits next to the epilogue staging boxes
-template <int BN, int BMODE, int OUT_BUFS, int WS, int COLS>
+template <int BN, int BMODE, int OUT_BUFS, int WS, int COLS, int LEAN>
 constexpr int pick_stages() {
     int best = 2;
+    // lean tiles stop at 128 KB: they are meant to share an SM with another stream's resident CTAs
+    const int budget = LEAN ? 131072 : 232448;
     for (int st = 2; st <= 6; ++st) {
-        const int bmt = COLS ? BMH : BM, bnt = COLS ? 2 * BN : BN;
+        const int bmt = (COLS || LEAN) ? BMH : BM, bnt = COLS ? 2 * BN : BN;
         const int stage = bmt * ROW_BYTES + (WS > 0 ? 0 : bnt * ROW_BYTES) + BN * (BMODE == B_I8 ? 64 : (is_nibble<BMODE>() ? 32 : 0));
-        const int total = st * stage + WS * bnt * ROW_BYTES + epi_warps<BN, BMODE>() * OUT_BUFS * BOX_BYTES +
+        const int total = st * stage + WS * bnt * ROW_BYTES + epi_warps<BN, BMODE, LEAN>() * OUT_BUFS * BOX_BYTES +
                           (WS > 0 ? 1 : 2) * 3 * bnt * 4 + 64 + (3 * st + 2 * ACC_STAGES + 1) * 8 + 16 + 1024;
-        if (total <= 232448) best = st;
+        if (total <= budget) best = st;
     }
     return best;
 }
@@ -780,13 +751,13 @@ template <> CUtensorMapDataType out_dtype_enum<float>() { return CU_TENSOR_MAP_D
 template <> CUtensorMapDataType out_dtype_enum<__half>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT16; }
 template <> CUtensorMapDataType out_dtype_enum<__nv_bfloat16>() { return CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
 
-template <int BN, int AKIND, int BMODE, int EPI, typename OutT, int WS = 0, int COLS = 0>
+template <int BN, int AKIND, int BMODE, int EPI, typename OutT, int WS = 0, int COLS = 0, int LEAN = 0>
 int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cudaStream_t stream) {
     // a resident 256-row W tile (128 KB) leaves room for single store buffers only
     constexpr int OUT_BUFS = (WS > 0 && COLS) ? 1 : pick_out_bufs<BN, BMODE>();
-    constexpr int STAGES = pick_stages<BN, BMODE, OUT_BUFS, WS, COLS>();
-    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS, COLS>;
-    auto kfn = k_gemm_tc<BN, STAGES, AKIND, BMODE, EPI, OutT, OUT_BUFS, WS, COLS>;
+    constexpr int STAGES = pick_stages<BN, BMODE, OUT_BUFS, WS, COLS, LEAN>();
+    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS, COLS, LEAN>;
+    auto kfn = k_gemm_tc<BN, STAGES, AKIND, BMODE, EPI, OutT, OUT_BUFS, WS, COLS, LEAN>;
     static bool configured = false;
     if (!configured) {
         WQ_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -809,7 +780,7 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cud
     int grid = total < wq_sm_count() ? total : wq_sm_count();
     if (WS > 0) grid = (wq_sm_count() / args.tiles_n) * args.tiles_n;   // whole groups of tiles_n CTAs (use_ws())
 
-    WQ_LAUNCH_PDL(kfn, dim3(grid), dim3(num_threads<BN, BMODE>()), (size_t)L::TOTAL, stream, ma, mb, my, args);
+    WQ_LAUNCH_PDL(kfn, dim3(grid), dim3(num_threads<BN, BMODE, LEAN>()), (size_t)L::TOTAL, stream, ma, mb, my, args);
     return WQ_OK;
 }
 
@@ -817,6 +788,15 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cud
 bool use_narrow_tile(int64_t M, int64_t N) {
     const int64_t tiles128 = ((M + BM - 1) / BM) * ((N + 127) / 128);  // BM = 256
     return tiles128 < wq_sm_count();
+}
+
+// Lean 128-row tile for decode-shaped calls with at most 128 rows (WQ_GEMM_LEAN=0 disables, A/B measurements).
+bool use_lean_tile(int64_t M) {
+    static const bool on = [] {
+        const char *e = getenv("WQ_GEMM_LEAN");
+        return e == nullptr || e[0] != '0';
+    }();
+    return on && M <= BMH;
 }
 
 // Weight-stationary schedule for the int8 x int8 schemes: K fits the resident W tile (<= kWS k-blocks of 128),
@@ -859,12 +839,14 @@ template <int AKIND, int EPI, typename OutT>
 int launch_i8(const void *a, const void *b, GemmArgs args, cudaStream_t s) {
     const int64_t M = args.M, N = args.N, K = args.K;
     const bool narrow = use_narrow_tile(M, N), cols = use_cols(M, N, K);
+    const bool lean = narrow && use_lean_tile(M);
     CUtensorMap ma, mb;
-    int rc = make_map_2d(&ma, a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, cols ? BMH : BM, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = make_map_2d(&ma, a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, (cols || lean) ? BMH : BM, 128, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
     rc = make_map_2d(&mb, b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, narrow ? 64 : (cols ? 256 : 128), 128,
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
+    if (lean) return launch_gemm<64, AKIND, B_DIRECT, EPI, OutT, 0, 0, 1>(ma, mb, args, s);
     if (narrow) return launch_gemm<64, AKIND, B_DIRECT, EPI, OutT>(ma, mb, args, s);
     const bool ws = use_ws(M, N, K, cols);
     if (cols) {

@@ -77,6 +77,11 @@ class GraphedGreedy:
         self.fast_post = os.environ.get("WQ_FAST_POST", "1") != "0"
         self._unwind = False
         self.keep_logits = False       # True: the captured step always writes the [B, V] logits (tests, debugging)
+        # fused LLM.int8 step: row groups of the batch decoded on as many streams (1 = off).  Per token and layer the
+        # step is a ~75 us chain of short dependent launches followed by a cross-attention pass that streams the
+        # cached K/V at the HBM rate; with 4 groups a group's chain hides under the other groups' streams
+        self.streams = int(os.environ.get("WQ_DECODE_STREAMS", "4"))
+        self.min_rows_per_stream = 32
         self.time_loop = False         # bench.py: CUDA events around the token loop of every generate call
         self.loop_events = []          # (start, end, replays)
         self.replays = 0
@@ -208,9 +213,25 @@ class GraphedGreedy:
 
     # ------------------------------------------------------------------------------------------
     def _decoder_step(self, st: _State):
-        """One token for every utterance: reads st.tok / st.pos, writes st.logits."""
+        """One token for every utterance: reads st.tok / st.pos, writes st.logits / st.next."""
         if st.fused is not None:
-            return self._decoder_step_int8(st)
+            if len(st.views) == 1:
+                return self._decoder_step_int8(st, st.views[0])
+            # several row groups of the batch on as many streams: a group's launch-bound chain (LayerNorm, decode-
+            # shaped GEMMs, self-attention) runs under the HBM-bound cross-attention stream of another group.  Under
+            # capture the fork / join become graph dependencies; each group has its own outlier / counter scratch.
+            cur = torch.cuda.current_stream()
+            for v in st.views[1:]:
+                v.stream.wait_stream(cur)
+            with F.scratch_slot(st.views[0].slot):
+                self._decoder_step_int8(st, st.views[0], project=False)
+            for v in st.views[1:]:
+                with torch.cuda.stream(v.stream), F.scratch_slot(v.slot):
+                    self._decoder_step_int8(st, v, project=False)
+            for v in st.views[1:]:
+                cur.wait_stream(v.stream)
+            # one vocabulary projection for the whole batch (the 53 MB weight is streamed once per token)
+            return self._project(st, st.whole, st.hfinal)
         model = self.model
         dec = model.model.decoder
         B, H, hd, d = st.B, st.H, st.hd, st.d
@@ -253,32 +274,32 @@ class GraphedGreedy:
             h = layer.final_layer_norm(x)
             x = res + layer.fc2(layer.activation_fn(layer.fc1(h)))
         x = dec.layer_norm(x)
-        self._project(st, x.view(B, d))
+        self._project(st, st.whole, x.view(B, d))
 
-    def _project(self, st: _State, h: torch.Tensor):
+    def _project(self, st: _State, v: _State, h: torch.Tensor):
         """Vocabulary projection of the final hidden rows [B, d] and the greedy choice under st.maskrow.  An
         unquantized proj_out (the HF bitsandbytes flows keep it fp16) runs on the tcgen05 GEMM with the arg-max folded
         into its epilogue: the [B, V] logits are written only when the state was built to keep them."""
         if st.proj_own:
             po = self.model.proj_out
-            F.gemm_f16(h, po.weight, st.proj_bias, out=st.logits_padded if st.store_logits else None,
-                       argmax_keys=st.keys if st.argmax_in_graph else None,
+            F.gemm_f16(h, po.weight, st.proj_bias, out=v.logits_padded if st.store_logits else None,
+                       argmax_keys=v.keys if st.argmax_in_graph else None,
                        mask=st.maskrow if st.argmax_in_graph else None, store=st.store_logits)
             if st.argmax_in_graph:
-                F.argmax_finalize(st.keys, out=st.next)
+                F.argmax_finalize(v.keys, out=v.next)
             return
-        st.logits.copy_(self.model.proj_out(h))
+        v.logits.copy_(self.model.proj_out(h))
         if st.argmax_in_graph:
-            F.masked_argmax(st.logits, st.maskrow[:st.logits.shape[1]], out=st.next)
+            F.masked_argmax(v.logits, st.maskrow[:v.logits.shape[1]], out=v.next)
 
-    def _decoder_step_int8(self, st: _State):
+    def _decoder_step_int8(self, st: _State, v: _State, project: bool = True):
         """The same step when every decoder linear is a bitsandbytes-style Linear8bitLt (fp16): each quantized
         GEMM is fed by a producer that already wrote its int8 rows (rowops.cu / attn_decode.cu), q/k/v share one
         GEMM over the concatenated weights, residual adds ride in the next LayerNorm launch.  13 launches per
         layer instead of ~45; the int8 arithmetic per linear is unchanged (same codes, scales, outlier path)."""
         dec = self.model.model.decoder
-        B, H, hd, d, thr = st.B, st.H, st.hd, st.d, st.threshold
-        x = dec.embed_tokens(st.tok).view(B, d) + dec.embed_positions.weight.index_select(0, st.pos)
+        B, H, hd, d, thr = v.B, st.H, st.hd, st.d, st.threshold
+        x = dec.embed_tokens(v.tok).view(B, d) + dec.embed_positions.weight.index_select(0, st.pos)
         delta = None
 
         gemm = fused.gemm_int8
@@ -287,7 +308,7 @@ class GraphedGreedy:
             ln = layer.self_attn_layer_norm
             x, h, qt = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, thr)
             qkv = gemm(qt, h, fw.qkv)
-            a, qt = F.self_attn_decode(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], fw.scaling, st.k[li], st.v[li],
+            a, qt = F.self_attn_decode(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], fw.scaling, v.k[li], v.v[li],
                                        st.pos, H, thr)
             delta = gemm(qt, a, fw.o)
             ln = layer.encoder_attn_layer_norm
@@ -295,15 +316,15 @@ class GraphedGreedy:
             q = gemm(qt, h, fw.cq)
             if st.own_cross:
                 # q scaling, the pass over the 1500 cached encoder positions and out_proj's quantization: one launch
-                a, qt = F.cross_attn_decode(q, st.ckv[li][:, :, :d], st.ckv[li][:, :, d:], fw.scaling, H, thr)
+                a, qt = F.cross_attn_decode(q, v.ckv[li][:, :, :d], v.ckv[li][:, :, d:], fw.scaling, H, thr)
             else:
                 if fw.scaling_pow2:     # q * 2^-k is exact in fp16, so the scale can ride in the SDPA call
                     a = TF.scaled_dot_product_attention(q.view(B, 1, H, hd).transpose(1, 2),
-                                                        st.ck[li].transpose(1, 2), st.cv[li].transpose(1, 2),
+                                                        v.ck[li].transpose(1, 2), v.cv[li].transpose(1, 2),
                                                         scale=fw.scaling)
                 else:
                     a = TF.scaled_dot_product_attention((q * fw.scaling).view(B, 1, H, hd).transpose(1, 2),
-                                                        st.ck[li].transpose(1, 2), st.cv[li].transpose(1, 2), scale=1.0)
+                                                        v.ck[li].transpose(1, 2), v.cv[li].transpose(1, 2), scale=1.0)
                 a = a.transpose(1, 2).reshape(B, d)
                 qt = F.int8_vectorwise_quant(a, thr, finalize=False)
             delta = gemm(qt, a, fw.co)
@@ -312,8 +333,11 @@ class GraphedGreedy:
             g, qt = F.gelu_quant(gemm(qt, h, fw.fc1), thr)
             delta = gemm(qt, g, fw.fc2)
         ln = dec.layer_norm
+        if not project:      # multi-stream step: the groups' final hidden rows meet in one buffer
+            F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, None, h_out=st.hfinal[v.r0:v.r1])
+            return
         _, h, _ = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, None)
-        self._project(st, h)
+        self._project(st, v, h)
 
     def _plan_int8(self, dtype):
         """Per-layer packed weights for _decoder_step_int8, or None when the decoder is not all-Linear8bitLt."""
@@ -380,7 +404,7 @@ class GraphedGreedy:
 
     def _get_state(self, B: int, t_max: int, dtype: torch.dtype, device, store_logits: bool = True) -> _State:
         fp = self._fingerprint()
-        key = (B, t_max, dtype, torch.device(device).index, bool(store_logits), self.cross_attention)
+        key = (B, t_max, dtype, torch.device(device).index, bool(store_logits), self.cross_attention, self.streams)
         st = self._states.get(key)
         if st is not None and st.fingerprint == fp:
             return st
@@ -435,6 +459,26 @@ class GraphedGreedy:
         st.maskrow = torch.zeros((-(-V // 256) * 256,), dtype=torch.bool, device=device)   # whole GEMM tiles
         st.next = torch.zeros((B,), dtype=torch.long, device=device)
         st.mask_cache = {}
+        # row groups of the batch for the multi-stream fused step (one group = the whole batch otherwise)
+        n = self.streams if (st.fused is not None and st.own_attn and st.own_cross) else 1
+        while n > 1 and (B % n != 0 or B // n < self.min_rows_per_stream):
+            n //= 2
+        st.views = []
+        st.hfinal = torch.zeros((B, st.d), dtype=dtype, device=device) if n > 1 else None
+        for i in range(-1, n):
+            r0, r1 = (0, B) if i < 0 else (i * (B // n), (i + 1) * (B // n))
+            v = _State()
+            v.B, v.slot, v.r0, v.r1 = r1 - r0, max(i, 0), r0, r1
+            v.stream = None if i <= 0 else torch.cuda.Stream(device=device)
+            v.tok, v.next, v.keys = st.tok[r0:r1], st.next[r0:r1], st.keys[r0:r1]
+            v.k, v.v = [t[r0:r1] for t in st.k], [t[r0:r1] for t in st.v]
+            v.ckv = [t[r0:r1] for t in st.ckv]
+            v.ck, v.cv = [t[r0:r1] for t in st.ck], [t[r0:r1] for t in st.cv]
+            v.logits_padded, v.logits = st.logits_padded[r0:r1], st.logits[r0:r1]
+            if i < 0:
+                st.whole = v
+            else:
+                st.views.append(v)
         # warm up on a side stream (lazy inits, autotuning), then capture
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))

@@ -179,8 +179,31 @@ def gemm_w4a16(x: torch.Tensor, packed: torch.Tensor, absmax: torch.Tensor, N: i
 # ----------------------------------------------------------------------------------------------
 # bitsandbytes LLM.int8
 # ----------------------------------------------------------------------------------------------
+_SLOT = 0
+
+
+class scratch_slot:
+    """Context manager selecting which copy of the per-device scratch (outlier flags, row counters) the wrappers
+    below hand to the kernels.  The flags are written by a producer kernel and consumed / cleared by the GEMM that
+    follows it on the same stream; two streams working on two half-batches at the same time (fastgen's two-stream
+    decode step) therefore need a copy each."""
+
+    def __init__(self, slot: int):
+        self.slot = int(slot)
+
+    def __enter__(self):
+        global _SLOT
+        self.prev, _SLOT = _SLOT, self.slot
+        return self
+
+    def __exit__(self, *exc):
+        global _SLOT
+        _SLOT = self.prev
+        return False
+
+
 class OutlierState:
-    """Per-device scratch for the outlier bookkeeping (flags are self-cleaning)."""
+    """Per-device (and per scratch slot) buffers for the outlier bookkeeping (flags are self-cleaning)."""
 
     _cache = {}
 
@@ -191,7 +214,7 @@ class OutlierState:
 
     @classmethod
     def get(cls, device: torch.device, cols: int) -> "OutlierState":
-        key = (device.index, cols)
+        key = (device.index, cols, _SLOT)
         st = cls._cache.get(key)
         if st is None:
             st = cls._cache[key] = cls(device, cols)
@@ -307,16 +330,22 @@ def _quant_outputs(rows: int, cols: int, device, threshold: Optional[float]):
 
 
 def add_layernorm_quant(x: torch.Tensor, delta: Optional[torch.Tensor], weight: torch.Tensor, bias: torch.Tensor,
-                        eps: float, threshold: Optional[float] = None):
+                        eps: float, threshold: Optional[float] = None, h_out: Optional[torch.Tensor] = None):
     """x' = x + delta (delta may be None), h = layer_norm(x') and, with a threshold, the Linear8bitLt row
-    quantization of h -- one launch.  Returns (x', h, (ca, sca, state) | None); shapes follow x."""
+    quantization of h -- one launch.  Returns (x', h, (ca, sca, state) | None); shapes follow x.  h_out: optional
+    contiguous destination for h (same shape and dtype as x)."""
     cols = x.shape[-1]
     x2 = x.reshape(-1, cols)
     d2 = None if delta is None else delta.reshape(-1, cols)
     _need_cuda(x2, d2, weight, bias)
     rows = x2.shape[0]
     x_out = torch.empty_like(x2) if d2 is not None else x2
-    h = torch.empty_like(x2)
+    if h_out is None:
+        h = torch.empty_like(x2)
+    else:
+        if h_out.shape != x2.shape or h_out.dtype != x2.dtype or not h_out.is_contiguous():
+            raise RuntimeError("add_layernorm_quant: h_out must be a contiguous tensor shaped like x")
+        h = h_out
     ca, sca, state = _quant_outputs(rows, cols, x.device, threshold)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().wq_add_layernorm_quant(
@@ -373,13 +402,17 @@ def self_attn_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scaling:
 
 
 _ROW_COUNTERS = {}
+_ROW_COUNTERS_KEEP = []      # outgrown buffers stay alive: captured CUDA graphs may still point at them
 
 
 def _row_counters(device, rows: int) -> torch.Tensor:
     """Zeroed int32 scratch (self-resetting inside the kernels that use it), one per device, grown on demand."""
-    t = _ROW_COUNTERS.get(device)
+    key = (device, _SLOT)
+    t = _ROW_COUNTERS.get(key)
     if t is None or t.numel() < rows:
-        t = _ROW_COUNTERS[device] = torch.zeros((max(rows, 1024),), dtype=torch.int32, device=device)
+        if t is not None:
+            _ROW_COUNTERS_KEEP.append(t)
+        t = _ROW_COUNTERS[key] = torch.zeros((max(rows, 1024),), dtype=torch.int32, device=device)
     return t
 
 

@@ -53,14 +53,19 @@ def _prefix_until_indecisive(logits, tol):
     return torch.where(decisive.all(1), decisive.shape[1], (~decisive).float().argmax(1)), decisive
 
 
-def _check_fast_vs_hf(H, model, feats, T, tol, mean_tol, expect_fused=None, cross=None):
-    """fastgen (graph replay, fused step where available) vs HF's loop on the same modules."""
+def _check_fast_vs_hf(H, model, feats, T, rel_tol, rel_mean, expect_fused=None, cross=None, streams=None):
+    """fastgen (graph replay, fused step where available) vs HF's loop on the same modules.  Tolerances are relative
+    to the largest |logit| of HF's run (random-init logits are O(2..4), growing with the width of the model)."""
     from openai_whisper_compression_b200 import fastgen
     hf_seq, hf_logits = _hf_loop(model, feats, T)
+    scale = max(1.0, hf_logits.abs().max().item())
+    tol, mean_tol = rel_tol * scale, rel_mean * scale
     ref_ids = H.greedy_generate(model, feats, T)
     eng = fastgen.enable(model)
     if cross is not None:
         eng.cross_attention = cross
+    if streams is not None:
+        eng.streams = streams
     ids = H.greedy_generate(model, feats, T)
     assert eng.replays > 0 and eng.fallbacks == 0
     # the same call with the logits store captured into the step (the bench branch keeps only the argmax)
@@ -103,14 +108,16 @@ def _check_fast_vs_hf(H, model, feats, T, tol, mean_tol, expect_fused=None, cros
 # ------------------------------------------------------------------------------------------------------------
 # C2 -- the bench branch: whisper-base, all 6 + 6 layers, LLM.int8 (threshold 6.0, HF load_in_8bit flow)
 # ------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,cross", [(144, "auto"), (24, "auto"), (136, "cudnn")])
-def test_config2_base_llmint8_bench_branch_matches_hf_loop(H, B, cross):
+@pytest.mark.parametrize("B,cross,streams", [(144, "own", 4), (144, "own", 1), (128, "own", 2), (24, "own", 4),
+                                             (136, "cudnn", 1)])
+def test_config2_base_llmint8_bench_branch_matches_hf_loop(H, B, cross, streams):
     """bench.py's default workload at heads x utterances > 1024 (144 x 8 = 1152): the producer-fused int8 decode
-    step with the decode-attention kernels, q|k|v fused GEMM, in-graph projection + argmax.  Tolerance: 6e-2 abs
-    on logits of scale ~2.5 (one-ulp LayerNorm differences pass through the int8 quantizers of 12 layers), mean 1e-2."""
+    step -- row groups of the batch on 4 streams (bench default), 2 streams, or one --, TMA-fed cross-attention, fused
+    q|k|v GEMM, lean decode tiles, projection with the arg-max in its epilogue.  Tolerance: 3 % of the logit scale
+    (~2.4 -> 7e-2 abs: one-ulp LayerNorm differences pass through the int8 quantizers of 12 layers), mean 0.5 %."""
     model = H.apply_scheme(H.build_model("base"), "llm_int8", "cuda")
     feats = _bench_features(H, B, 80, True)
-    _check_fast_vs_hf(H, model, feats, 16, 6e-2, 1e-2, expect_fused=True, cross=cross)
+    _check_fast_vs_hf(H, model, feats, 16, 3e-2, 5e-3, expect_fused=True, cross=cross, streams=streams)
 
 
 def test_config2_base_llmint8_modules_match_emulation(H):
@@ -163,7 +170,7 @@ def test_config3_small_nf4_full_depth(H):
     ours = H.apply_scheme(H.build_model("small"), "bnb_nf4", "cuda")
     feats = _bench_features(H, 6, 80, True)
     T = 16
-    _check_fast_vs_hf(H, ours, feats, T, 3e-2, 3e-3)
+    _check_fast_vs_hf(H, ours, feats, T, 1e-2, 1e-3)
     ref = _emulate_dequant(H, ours, H.build_model("small").half().cuda())
     ids_ref, log_ref = _hf_loop(ref, feats, T)
     with torch.no_grad():
@@ -221,7 +228,7 @@ def test_config4_medium_pruned_quanto_int8_fp32_flow(H):
     assert d.max().item() < 2e-2 and d.mean().item() < 2e-3
     _, decisive = _prefix_until_indecisive(lb, 4e-2)
     assert torch.equal(la.argmax(-1)[decisive], lb.argmax(-1)[decisive])
-    _check_fast_vs_hf(H, ours, feats, T, 2e-2, 2e-3)
+    _check_fast_vs_hf(H, ours, feats, T, 1e-2, 1e-3)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -255,5 +262,5 @@ def test_config5_large_v3_geometry(H, scheme):
     assert d.max().item() <= tol
     _, decisive = _prefix_until_indecisive(lb, 2 * tol)
     assert torch.equal(la.argmax(-1)[decisive], lb.argmax(-1)[decisive])
-    _check_fast_vs_hf(H, ours, feats, T, 6e-2 if half else 2e-2, 1e-2 if half else 2e-3,
+    _check_fast_vs_hf(H, ours, feats, T, 3e-2 if half else 1e-2, 5e-3 if half else 1e-3,
                       expect_fused=True if half else None)
