@@ -310,13 +310,17 @@ def decode_probe(model, eng, peaks, ms_step, T):
     S = st.ckv[0].shape[1]
     elt = st.ckv[0].element_size()
     q = torch.randn((B, d), device=st.ckv[0].device, dtype=st.ckv[0].dtype)
+    # as in the fused step: the kernel also writes the int8 rows of its output for out_proj
+    thr_probe = st.threshold if (st.fused is not None and q.dtype == torch.float16) else None
     ts = []
     for rep in range(2):
         for li in range(len(st.ckv)):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            F.cross_attn_decode(q, st.ckv[li][:, :, :d], st.ckv[li][:, :, d:], 0.125, H, None)
+            _, qx = F.cross_attn_decode(q, st.ckv[li][:, :, :d], st.ckv[li][:, :, d:], 0.125, H, thr_probe)
             e1.record()
+            if qx is not None and qx[2] is not None:
+                qx[2].col_flags.zero_()      # no GEMM consumes (and clears) the outlier flags here
             if rep:
                 ts.append((e0, e1))
     torch.cuda.synchronize()

@@ -248,6 +248,53 @@ __device__ __forceinline__ void partial_merge(Partial &a, float om, float ol, co
     a.m = m;
 }
 
+// Fold kXUnroll landed (k, v) 16-byte row chunks into the running softmax of this lane group in ONE update: the
+// four scores are independent chains (8 FMAs + 3 shuffles each, interleaved by the compiler), then a single
+// max / rescale and four independent exponentials.  Row by row the update is a serial chain of ~250 cycles per row
+// (max -> exp2 -> rescale), which left a warp latency-bound; block-wise it is ~200 cycles per FOUR rows.  valid[u]:
+// the row exists (positions past S are masked).
+template <typename T>
+__device__ __forceinline__ void fold_rows(Partial &p, const float (&q8)[8], const uint4 (&kr)[kXUnroll],
+                                          const uint4 (&vr)[kXUnroll], const bool (&valid)[kXUnroll]) {
+    float sc[kXUnroll];
+#pragma unroll
+    for (int u = 0; u < kXUnroll; ++u) {
+        const T *k8 = reinterpret_cast<const T *>(&kr[u]);
+        float s = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s = fmaf(q8[j], to_f32(k8[j]), s);
+        sc[u] = s;
+    }
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < kXUnroll; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], o);
+    }
+    float m = p.m;
+#pragma unroll
+    for (int u = 0; u < kXUnroll; ++u) {
+        if (!valid[u]) sc[u] = -INFINITY;
+        m = fmaxf(m, sc[u]);
+    }
+    if (m == -INFINITY) return;                       // nothing seen yet and nothing valid here
+    const float corr = exp2f(p.m - m);                // exp2f(-inf) == 0 on the first rows
+    float e[kXUnroll], l = p.l * corr;
+#pragma unroll
+    for (int u = 0; u < kXUnroll; ++u) {
+        e[u] = exp2f(sc[u] - m);                      // masked rows: exp2f(-inf) == 0
+        l += e[u];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float a = p.acc[j] * corr;
+#pragma unroll
+        for (int u = 0; u < kXUnroll; ++u) a = fmaf(e[u], to_f32(reinterpret_cast<const T *>(&vr[u])[j]), a);
+        p.acc[j] = a;
+    }
+    p.l = l;
+    p.m = m;
+}
+
 // LLM.int8 row quantization of out[b, :] by the last of this utterance's H head items to finish
 // (int8_vectorwise_quant on the rounded values; the counter resets itself for the next launch).  Called by the ONE
 // warp that wrote this item's output (lanes with g == 0 hold the stores), so no CTA-wide barrier is needed and the
@@ -361,27 +408,10 @@ k_cross_attn_decode(const T *__restrict__ q, int64_t ldq, float scaling, const T
         for (int tb = 0; tb < S; tb += STEP, t0 += STEP) {
             if (tb + STEP < S) fetch(kb, vb, t0 + STEP, kn, vn);          // next block of this item ...
             else if (has_next) fetch(kbn, vbn, t_first, kn, vn);          // ... or the first block of the next item
+            bool valid[kXUnroll];
 #pragma unroll
-            for (int u = 0; u < kXUnroll; ++u) {
-                const int t = t0 + u * ROWS_PER_IT;
-                const T *k8 = reinterpret_cast<const T *>(&kr[u]);
-                const T *v8 = reinterpret_cast<const T *>(&vr[u]);
-                float s = 0.0f;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) s = fmaf(q8[j], to_f32(k8[j]), s);
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                if (t < S) {
-                    const float m = fmaxf(p.m, s);
-                    const float corr = exp2f(p.m - m);          // exp2f(-inf) == 0 on the first row
-                    const float e = exp2f(s - m);
-                    p.l = p.l * corr + e;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) p.acc[j] = fmaf(e, to_f32(v8[j]), p.acc[j] * corr);
-                    p.m = m;
-                }
-            }
+            for (int u = 0; u < kXUnroll; ++u) valid[u] = t0 + u * ROWS_PER_IT < S;
+            fold_rows<T>(p, q8, kr, vr, valid);
 #pragma unroll
             for (int u = 0; u < kXUnroll; ++u) {
                 kr[u] = kn[u];
@@ -444,24 +474,28 @@ k_cross_attn_decode(const T *__restrict__ q, int64_t ldq, float scaling, const T
 // OTHER half-batch (fastgen's second stream: lean GEMM tiles, LayerNorm, self-attention) run under this kernel's
 // HBM stream.  The ring is item-agnostic: the producer runs ahead across (utterance, head) boundaries.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTR = 64;                    // positions per ring stage
-constexpr int kTStages = 6;
-constexpr int kTCW = 4;                    // consumer warps
-constexpr int kTStageBytes = kTR * 128;    // one operand (K or V) of one stage
-constexpr int kTSmem = 2 * kTStages * kTStageBytes + 1024;
+constexpr int kTMaxStages = 12;
+constexpr int kTStageBytes = 64 * 128;     // one operand (K or V) of one 64-position stage
 
-template <typename T>
-__global__ void __launch_bounds__((kTCW + 1) * 32, 1)
+// kTCW consumer warps; a stage holds 16 * kTCW positions (one TMA box of K, one of V).  Warp kTCW is the TMA producer,
+// warp kTCW + 1 the finisher: the cross-CTA bookkeeping of the optional int8 row quantization (fence, counter, and
+// for the utterance's last head the quantization itself) costs ~5 us of pure memory latency per item; on a streaming
+// warp that stalls the whole ring (measured: 123 -> 215 us per launch), on its own warp it is free.
+template <typename T, int kTCW>
+__global__ void __launch_bounds__((kTCW + 2) * 32, 2)
 k_cross_attn_decode_tma(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
-                        const T *__restrict__ q, int64_t ldq, float scaling, int S, int H, int n_items, T *out,
+                        int kTStages, const T *__restrict__ q, int64_t ldq, float scaling, int S, int H, int n_items, T *out,
                         float threshold, int8_t *__restrict__ ca, float *__restrict__ row_stats,
                         int32_t *__restrict__ col_flags, int32_t *__restrict__ row_counters) {
     using namespace wq;
     extern __shared__ __align__(1024) uint8_t xs_raw[];
     uint8_t *xs = xs_raw + ((1024u - (smem_u32(xs_raw) & 1023u)) & 1023u);
-    uint8_t *sK = xs, *sV = xs + kTStages * kTStageBytes;
-    __shared__ uint64_t bar_full[kTStages], bar_empty[kTStages];
+    constexpr int kTR = 16 * kTCW;                      // positions per stage
+    constexpr int kOpBytes = kTR * 128;                 // bytes of K (or V) per stage
+    uint8_t *sK = xs, *sV = xs + kTStages * kOpBytes;
+    __shared__ uint64_t bar_full[kTMaxStages], bar_empty[kTMaxStages];
     __shared__ float s_part[2][kTCW][8][10];
+    __shared__ volatile int s_done;                     // items whose output rows warp 0 has written
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 3, sub = lane & 7;
     const int d = H * kHeadDim;
@@ -476,10 +510,23 @@ k_cross_attn_decode_tma(const __grid_constant__ CUtensorMap map_k, const __grid_
             mbar_init(&bar_empty[s], kTCW);
         }
         fence_mbar_init();
+        s_done = 0;
     }
     __syncthreads();
     pdl_wait();
 
+    if (warp == kTCW + 1) {
+        // ---------------- finisher ----------------
+        pdl_trigger();
+        if (ca == nullptr) return;
+        int handled = 0;
+        for (int item = (int)blockIdx.x; item < n_items; item += (int)gridDim.x, ++handled) {
+            while (s_done <= handled) __nanosleep(200);
+            __syncwarp();
+            quantize_row_if_last(out, item / H, d, H, lane, 0, threshold, ca, row_stats, col_flags, row_counters);
+        }
+        return;
+    }
     if (warp == kTCW) {
         // ---------------- producer ----------------
         if (lane == 0) {
@@ -489,9 +536,9 @@ k_cross_attn_decode_tma(const __grid_constant__ CUtensorMap map_k, const __grid_
                 for (int blk = 0; blk < n_blk; ++blk, ++it) {
                     const int s = it % kTStages;
                     mbar_wait(&bar_empty[s], ((it / kTStages) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&bar_full[s], 2 * kTStageBytes);
-                    tma_load_2d(sK + s * kTStageBytes, &map_k, &bar_full[s], h * kHeadDim, b * S + blk * kTR);
-                    tma_load_2d(sV + s * kTStageBytes, &map_v, &bar_full[s], h * kHeadDim, b * S + blk * kTR);
+                    mbar_arrive_expect_tx(&bar_full[s], 2 * kOpBytes);
+                    tma_load_2d(sK + s * kOpBytes, &map_k, &bar_full[s], h * kHeadDim, b * S + blk * kTR);
+                    tma_load_2d(sV + s * kOpBytes, &map_v, &bar_full[s], h * kHeadDim, b * S + blk * kTR);
                 }
             }
         }
@@ -517,38 +564,22 @@ k_cross_attn_decode_tma(const __grid_constant__ CUtensorMap map_k, const __grid_
         for (int blk = 0; blk < n_blk; ++blk, ++it) {
             const int s = it % kTStages;
             mbar_wait(&bar_full[s], (it / kTStages) & 1);
-            const uint8_t *pk = sK + s * kTStageBytes + (warp * 16 + g) * 128 + sub * 16;
-            const uint8_t *pv = sV + s * kTStageBytes + (warp * 16 + g) * 128 + sub * 16;
-            uint4 kr[4], vr[4];
+            const uint8_t *pk = sK + s * kOpBytes + (warp * 16 + g) * 128 + sub * 16;
+            const uint8_t *pv = sV + s * kOpBytes + (warp * 16 + g) * 128 + sub * 16;
+            static_assert(kXUnroll == 4, "a consumer warp takes 16 positions of a stage: 4 lane groups x 4 rows");
+            uint4 kr[kXUnroll], vr[kXUnroll];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kXUnroll; ++u) {
                 kr[u] = *reinterpret_cast<const uint4 *>(pk + u * 4 * 128);
                 vr[u] = *reinterpret_cast<const uint4 *>(pv + u * 4 * 128);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[s]);      // this warp's rows of the stage are in registers
             const int t_base = blk * kTR + warp * 16 + g;
+            bool valid[kXUnroll];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int t = t_base + u * 4;
-                const T *k8 = reinterpret_cast<const T *>(&kr[u]);
-                const T *v8 = reinterpret_cast<const T *>(&vr[u]);
-                float sc = 0.0f;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) sc = fmaf(q8[j], to_f32(k8[j]), sc);
-                sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-                sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-                sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-                if (t < S) {
-                    const float m = fmaxf(p.m, sc);
-                    const float corr = exp2f(p.m - m);          // exp2f(-inf) == 0 on the first row
-                    const float e = exp2f(sc - m);
-                    p.l = p.l * corr + e;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) p.acc[j] = fmaf(e, to_f32(v8[j]), p.acc[j] * corr);
-                    p.m = m;
-                }
-            }
+            for (int u = 0; u < kXUnroll; ++u) valid[u] = t_base + u * 4 < S;
+            fold_rows<T>(p, q8, kr, vr, valid);
         }
         if (item + (int)gridDim.x >= n_items) pdl_trigger();
         // merge the 4 lane groups of the warp (same dims, different rows)
@@ -584,8 +615,11 @@ k_cross_attn_decode_tma(const __grid_constant__ CUtensorMap map_k, const __grid_
             for (int j = 0; j < 8; ++j) o8[j] = from_f32<T>(p.acc[j] * inv);
             *reinterpret_cast<uint4 *>(out + (int64_t)b * d + h * kHeadDim + sub * 8) = raw;
         }
-        if (ca != nullptr)
-            quantize_row_if_last(out, b, d, H, lane, g, threshold, ca, row_stats, col_flags, row_counters);
+        if (ca != nullptr) {        // hand the item to the finisher warp: stores first, then the count
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) s_done = s_done + 1;
+        }
     }
 }
 
@@ -625,32 +659,57 @@ extern "C" int wq_cross_attn_decode(const void *q, int64_t ldq, int dtype, float
         return e == nullptr || e[0] != 'r';
     }();
     if (use_tma && B * S < (1ll << 31)) {
-        // K and V as [B*S, H*64] matrices with a row pitch of ld elements; one box = 64 positions of one head
+        // K and V as [B*S, H*64] matrices with a row pitch of ld elements; one box = 16 * CW positions of one head
+        static const int cw = [] { const char *e = getenv("WQ_XATTN_CW"); return (e && atoi(e) == 4) ? 4 : 8; }();
+        static const int stages = [] {
+            const char *e = getenv("WQ_XATTN_STAGES");
+            const int v = e ? atoi(e) : 3;
+            return v < 2 ? 2 : (v > kTMaxStages ? kTMaxStages : v);
+        }();
+        static const CUtensorMapL2promotion promo = [] {
+            const char *e = getenv("WQ_XATTN_PROMO");
+            const int v = e ? atoi(e) : 256;
+            return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
+                   (v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+        }();
+        const int box_rows = 16 * cw;
+        int nst = stages;
+        while (nst > 2 && 2 * nst * box_rows * 128 + 1024 > 200 * 1024) --nst;
+        // WQ_XATTN_SMEM_KB pads the request (116 KB = at most one CTA of this kernel per SM, still room for a lean GEMM
+        // tile of another row group; measured slower than letting two row groups' streams share an SM: 118 vs 111 ms)
+        static const int pad_kb = [] { const char *e = getenv("WQ_XATTN_SMEM_KB"); return e ? atoi(e) : 0; }();
+        size_t smem = (size_t)2 * nst * box_rows * 128 + 1024;
+        if (smem < (size_t)pad_kb * 1024) smem = (size_t)pad_kb * 1024;
+        if (smem > 201 * 1024) smem = 201 * 1024;
         const CUtensorMapDataType dt = dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
         CUtensorMap mk, mv;
-        int rc = make_map_2d(&mk, k, dt, 2, (uint64_t)(B * S), (uint64_t)H * kHeadDim, kTR, kHeadDim,
-                             CU_TENSOR_MAP_SWIZZLE_NONE, (uint64_t)ld);
+        int rc = make_map_2d(&mk, k, dt, 2, (uint64_t)(B * S), (uint64_t)H * kHeadDim, box_rows, kHeadDim,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, (uint64_t)ld, promo);
         if (rc != WQ_OK) return rc;
-        rc = make_map_2d(&mv, v, dt, 2, (uint64_t)(B * S), (uint64_t)H * kHeadDim, kTR, kHeadDim,
-                         CU_TENSOR_MAP_SWIZZLE_NONE, (uint64_t)ld);
+        rc = make_map_2d(&mv, v, dt, 2, (uint64_t)(B * S), (uint64_t)H * kHeadDim, box_rows, kHeadDim,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, (uint64_t)ld, promo);
         if (rc != WQ_OK) return rc;
         const int cap = wq_sm_count();
         const dim3 grid((unsigned)(n_items < cap ? n_items : cap));
         static bool configured = false;
         if (!configured) {
-            WQ_CUDA(cudaFuncSetAttribute(k_cross_attn_decode_tma<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
-            WQ_CUDA(cudaFuncSetAttribute(k_cross_attn_decode_tma<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
+            WQ_CUDA(cudaFuncSetAttribute(k_cross_attn_decode_tma<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+            WQ_CUDA(cudaFuncSetAttribute(k_cross_attn_decode_tma<__half, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+            WQ_CUDA(cudaFuncSetAttribute(k_cross_attn_decode_tma<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+            WQ_CUDA(cudaFuncSetAttribute(k_cross_attn_decode_tma<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
             configured = true;
         }
+#define WQ_XT_LAUNCH(T, CW, CA, RS, CF, RC, THR)                                                                        \
+        WQ_LAUNCH_PDL((k_cross_attn_decode_tma<T, CW>), grid, dim3((CW + 2) * 32), smem, s, mk, mv, nst, (const T *)q, ldq,  \
+                      scaling, (int)S, H, n_items, (T *)out, THR, CA, RS, CF, RC)
         if (dtype == WQ_F16) {
-            WQ_LAUNCH_PDL(k_cross_attn_decode_tma<__half>, grid, dim3((kTCW + 1) * 32), (size_t)kTSmem, s, mk, mv,
-                          (const __half *)q, ldq, scaling, (int)S, H, n_items, (__half *)out, threshold, ca, row_stats,
-                          col_flags, row_counters);
+            if (cw == 8) WQ_XT_LAUNCH(__half, 8, ca, row_stats, col_flags, row_counters, threshold);
+            else WQ_XT_LAUNCH(__half, 4, ca, row_stats, col_flags, row_counters, threshold);
         } else {
-            WQ_LAUNCH_PDL(k_cross_attn_decode_tma<__nv_bfloat16>, grid, dim3((kTCW + 1) * 32), (size_t)kTSmem, s, mk, mv,
-                          (const __nv_bfloat16 *)q, ldq, scaling, (int)S, H, n_items, (__nv_bfloat16 *)out, 0.0f,
-                          (int8_t *)nullptr, (float *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr);
+            if (cw == 8) WQ_XT_LAUNCH(__nv_bfloat16, 8, (int8_t *)nullptr, (float *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, 0.0f);
+            else WQ_XT_LAUNCH(__nv_bfloat16, 4, (int8_t *)nullptr, (float *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, 0.0f);
         }
+#undef WQ_XT_LAUNCH
         return WQ_OK;
     }
     const int cap = wq_sm_count() * xattn_ctas_per_sm();

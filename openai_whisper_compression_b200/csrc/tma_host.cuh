@@ -26,7 +26,8 @@ inline EncodeTiledFn get_encode_fn() {
 
 // 2-D row-major matrix [rows, cols] of `elem_bytes`-byte elements, box = [box_rows, box_cols].
 inline int make_map_2d(CUtensorMap *map, const void *base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows,
-                uint64_t cols, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz, uint64_t pitch_elems = 0) {
+                uint64_t cols, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz, uint64_t pitch_elems = 0,
+                CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) {
         wq_set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -37,7 +38,7 @@ inline int make_map_2d(CUtensorMap *map, const void *base, CUtensorMapDataType d
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         wq_set_error("cuTensorMapEncodeTiled failed (%d): rows %llu cols %llu elem %d box %ux%u", (int)r,
                      (unsigned long long)rows, (unsigned long long)cols, elem_bytes, box_rows, box_cols);

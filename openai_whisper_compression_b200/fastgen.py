@@ -82,6 +82,9 @@ class GraphedGreedy:
         # cached K/V at the HBM rate; with 4 groups a group's chain hides under the other groups' streams
         self.streams = int(os.environ.get("WQ_DECODE_STREAMS", "4"))
         self.min_rows_per_stream = 32
+        # out_proj's int8 rows written by the cross-attention kernel itself (its finisher warp) or by a separate
+        # quantizer launch (WQ_CROSS_QUANT_INLINE=0)
+        self.cross_quant_inline = os.environ.get("WQ_CROSS_QUANT_INLINE", "1") != "0"
         self.time_loop = False         # bench.py: CUDA events around the token loop of every generate call
         self.loop_events = []          # (start, end, replays)
         self.replays = 0
@@ -316,7 +319,11 @@ class GraphedGreedy:
             q = gemm(qt, h, fw.cq)
             if st.own_cross:
                 # q scaling, the pass over the 1500 cached encoder positions and out_proj's quantization: one launch
-                a, qt = F.cross_attn_decode(q, v.ckv[li][:, :, :d], v.ckv[li][:, :, d:], fw.scaling, H, thr)
+                if self.cross_quant_inline:
+                    a, qt = F.cross_attn_decode(q, v.ckv[li][:, :, :d], v.ckv[li][:, :, d:], fw.scaling, H, thr)
+                else:       # the row quantization as a launch of its own (no cross-CTA completion tail in the stream)
+                    a, _ = F.cross_attn_decode(q, v.ckv[li][:, :, :d], v.ckv[li][:, :, d:], fw.scaling, H, None)
+                    qt = F.int8_vectorwise_quant(a, thr, finalize=False)
             else:
                 if fw.scaling_pow2:     # q * 2^-k is exact in fp16, so the scale can ride in the SDPA call
                     a = TF.scaled_dot_product_attention(q.view(B, 1, H, hd).transpose(1, 2),
@@ -404,7 +411,8 @@ class GraphedGreedy:
 
     def _get_state(self, B: int, t_max: int, dtype: torch.dtype, device, store_logits: bool = True) -> _State:
         fp = self._fingerprint()
-        key = (B, t_max, dtype, torch.device(device).index, bool(store_logits), self.cross_attention, self.streams)
+        key = (B, t_max, dtype, torch.device(device).index, bool(store_logits), self.cross_attention, self.streams,
+               self.cross_quant_inline)
         st = self._states.get(key)
         if st is not None and st.fingerprint == fp:
             return st
