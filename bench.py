@@ -211,11 +211,11 @@ def workload_config(size, scheme, prune, batch, new_tokens, gpus, hf_loop, defau
 # ------------------------------------------------------------------------------------------------
 # roofline helpers
 # ------------------------------------------------------------------------------------------------
-_W_BYTES = {"llmint8": 1.0, "dyn_i8": 1.0, "w8a16": 1.0, "w4a16": 0.5 + 4.0 / 64, "u4a16": 0.5 + 8.0 / 128, "f16": 2.0}
+_W_BYTES = {"llmint8": 1.0, "dyn_i8": 1.0, "w8a16": 1.0, "wf8a16": 1.0, "w8a8": 1.0, "w4a16": 0.5 + 4.0 / 64, "u4a16": 0.5 + 8.0 / 128, "f16": 2.0}
 
 
 def gemm_algorithmic(kind, M, N, K):
-    a_bytes = 1 if kind in ("llmint8", "dyn_i8") else 2
+    a_bytes = 1 if kind in ("llmint8", "dyn_i8", "w8a8") else 2
     o_bytes = 4 if kind == "dyn_i8" else 2
     return M * K * a_bytes + N * K * _W_BYTES[kind] + M * N * o_bytes + 4 * (M + N), 2.0 * M * N * K
 
@@ -341,24 +341,25 @@ def decode_probe(model, eng, peaks, ms_step, T):
     if st.fused is not None:
         B = st.views[0].B           # rows per launch: the step decodes the batch in row groups (one per stream)
         out["row_groups"] = len(st.views)
-        x = torch.randn((B, d), device=q.device, dtype=torch.float16)
+        kind = st.fused[0].qkv.kind
         calls = []
         for fw in st.fused:
             for name in ("qkv", "o", "cq", "co", "fc1", "fc2"):
                 w = getattr(fw, name)
-                a = x if w.cb.shape[1] == d else torch.randn((B, w.cb.shape[1]), device=q.device, dtype=torch.float16)
-                calls.append((F.int8_vectorwise_quant(a, st.threshold, finalize=False), a, w))
+                a = torch.randn((B, w.in_features), device=q.device, dtype=q.dtype)
+                qt = F.int8_vectorwise_quant(a, st.threshold, finalize=False) if kind == "int8" else None
+                calls.append((qt, a, w))
         side = torch.cuda.Stream(device=q.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for qt, a, w in calls:
-                fused.gemm_int8(qt, a, w)
+                fused.gemm(qt, a, w)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             for qt, a, w in calls:
-                fused.gemm_int8(qt, a, w)
+                fused.gemm(qt, a, w)
         ts = []
         for rep in range(6):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -368,16 +369,19 @@ def decode_probe(model, eng, peaks, ms_step, T):
             if rep:
                 ts.append((e0, e1))
         torch.cuda.synchronize()
-        tot_b = sum(w.cb.shape[0] * w.cb.shape[1] + B * w.cb.shape[1] + 2 * B * w.cb.shape[0] for _, _, w in calls)
+        wb = _W_BYTES[{"int8": "llmint8"}.get(kind, kind)]
+        ab = 1 if kind == "int8" else 2
+        tot_b = sum(w.out_features * w.in_features * wb + B * w.in_features * ab + 2 * B * w.out_features
+                    for _, _, w in calls)
         tot_t = sum(a.elapsed_time(b) for a, b in ts) / len(ts) * 1e-3
         out["decode_gemm"] = {
-            "kernel": f"k_gemm_tc decode-shaped launches (M = {B} rows: one row group of the batch), LLM.int8",
+            "kernel": f"k_gemm_tc decode-shaped launches (M = {B} rows: one row group of the batch), {kind}",
             "bound": "hbm", "launches": len(calls), "avg_launch_us": tot_t / len(calls) * 1e6,
             "algorithmic_bytes_per_launch": tot_b / len(calls), "achieved": tot_b / tot_t / 1e9,
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": tot_b / tot_t / 1e9 / peaks["hbm_gbs"],
             "how": "all decoder weight matrices of the model back to back in one CUDA graph, events around the replay",
-            "note": "whisper-base decoder weights are 22 MB in all (L2-resident): these launches are latency-bound, "
-                    "not bandwidth-bound (DESIGN.md section 3.1)"}
+            "note": "the decoder weights of the Whisper sizes are L2-resident or a few us of HBM time per token: these "
+                    "launches are latency-bound, not bandwidth-bound (DESIGN.md section 3.1)"}
     return out
 
 

@@ -188,6 +188,27 @@ int wq_gemm_u4a16(const void *x, int x_dtype, const uint8_t *packed, const float
                   const float *shift, int group, const float *bias, void *y, int y_dtype, int64_t M,
                   int64_t N, int64_t K, wq_stream_t stream);
 
+/* optimum-quanto float8 weights and static activation quantization (quantize(model, weights=..., activations=...)
+ * inside `with Calibration():`, model_utils.py:152-214 apply_static_quantization; quantization.py:53-86).
+ *
+ * wq_quant_f8_rowwise_quanto: weights=qfloat8 (e4m3fn), AbsmaxOptimizer per output channel:
+ *   scale[n] = max|W[n,:]| / 448, q = e4m3(W / scale) (round to nearest even, as torch's .to(float8_e4m3fn)).
+ * wq_gemm_wf8a16: QLinear.forward for those weights, y = matmul(x, Wq.to(x.dtype).t()) * scale + bias.
+ * wq_quant_act_static: quantize_activation(x, qtype, scale) with a calibrated per-tensor scale (device fp32[1]):
+ *   qtype 0 (qint8) code = clamp(rint(x / s), -128, 127); qtype 1 (qfloat8 e4m3) code = e4m3(x / s).  Optional
+ *   outputs: codes_i8 (qint8 only), grid_f16 (the code value as fp16, exact), deq (code * s in the dtype of x =
+ *   ActivationQBytesTensor.dequantize()).
+ * wq_gemm_w8a8: qint8 weights x qint8 activations (quanto qbytes_int_mm):
+ *   y = float(int32(xq . wq^T)) * out_scale[n] + bias[n] with out_scale[n] = input_scale * weight_scale[n]. */
+int wq_quant_f8_rowwise_quanto(const void *w, int w_dtype, int64_t N, int64_t K, uint8_t *q, float *scale,
+                               wq_stream_t stream);
+int wq_gemm_wf8a16(const void *x, int x_dtype, const uint8_t *wq, const float *scale, const float *bias,
+                   void *y, int y_dtype, int64_t M, int64_t N, int64_t K, wq_stream_t stream);
+int wq_quant_act_static(const void *x, int x_dtype, int64_t n, const float *scale, int qtype,
+                        int8_t *codes_i8, void *grid_f16, void *deq, wq_stream_t stream);
+int wq_gemm_w8a8(const int8_t *xq, const int8_t *wq, const float *out_scale, const float *bias, void *y,
+                 int y_dtype, int64_t M, int64_t N, int64_t K, wq_stream_t stream);
+
 /* torch.ao.nn.quantized.dynamic.Linear.forward GPU twin (quantized::linear_dynamic):
  *   y[m,n] = float(acc[m,n] - zp * wsum[n]) * (s_x * s_w) + bias[n], fp32
  * xq uint8 [M, K]; qparams device float[2] = {s_x, zp}; wq int8 [N, K]; w_scale device fp32[1];
@@ -275,6 +296,14 @@ int wq_gemm_f16(const void *x, int x_dtype, const void *w, const float *bias, vo
                 int64_t ldy, int64_t M, int64_t N, int64_t K, const uint8_t *mask, int64_t mask_len,
                 unsigned long long *argmax_keys, wq_stream_t stream);
 int wq_argmax_finalize(unsigned long long *keys, int64_t M, int64_t *out, wq_stream_t stream);
+
+/* Sparse checkpoint -> dense fp32 tensor on the device: the reference's loaders rebuild
+ * every pruned tensor on the host with `dense[indices] = values` (pruning/final_pruning_script/
+ * global_storing_as sparse.py:468-471; torch COO tensors in pruning+quantization/bnb_implementation.py:406-441).
+ * out[0..n_out) is zero-filled, then out[idx0[i] * cols + idx1[i]] = vals[i] (idx1 == NULL: idx0 are flat indices).
+ * idx_bytes: 4 (int32) or 8 (int64).  err_flag: device int, set to 1 when an index falls outside [0, n_out). */
+int wq_scatter_dense_f32(const void *idx0, const void *idx1, int idx_bytes, int64_t cols, const float *vals,
+                         int64_t nnz, float *out, int64_t n_out, int *err_flag, wq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * WER / CER tallies -- evaluate.load("wer"/"cer").compute, evaluation.py:110-116

@@ -48,6 +48,11 @@ _PROTOS = {
     "wq_cross_attn_decode": [c_ptr, c_i64, c_int, c_f32, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_ptr, c_f32,
                              c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_masked_argmax": [c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
+    "wq_quant_f8_rowwise_quanto": [c_ptr, c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
+    "wq_gemm_wf8a16": [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],
+    "wq_quant_act_static": [c_ptr, c_int, c_i64, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
+    "wq_gemm_w8a8": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],
+    "wq_scatter_dense_f32": [c_ptr, c_ptr, c_int, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr],
     "wq_gemm_f16": [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_ptr],
     "wq_argmax_finalize": [c_ptr, c_i64, c_ptr, c_ptr],
     "wq_logmel": [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_int, c_ptr, c_int, c_ptr, c_ptr],

@@ -48,8 +48,9 @@ template <int BN, int BMODE, int LEAN = 0> constexpr int epi_warps() { return LE
 constexpr int BOX_BYTES = 32 * 128;  // one TMA-store box: 32 rows x 128 bytes (SWIZZLE_128B)
 
 enum AKind { A_F16 = 0, A_BF16 = 1, A_S8 = 2, A_U8 = 3 };
-enum BMode { B_DIRECT = 0, B_I8 = 1, B_4BIT = 2, B_U4 = 3 };   // B_U4: quanto group-wise affine uint4
-enum Epi { EPI_LLMINT8 = 0, EPI_W8A16 = 1, EPI_W4A16 = 2, EPI_DYN = 3, EPI_PLAIN = 4 };
+enum BMode { B_DIRECT = 0, B_I8 = 1, B_4BIT = 2, B_U4 = 3, B_F8 = 4 };   // B_U4: quanto group-wise affine uint4; B_F8: e4m3 codes
+template <int BMODE> constexpr bool is_byte() { return BMODE == B_I8 || BMODE == B_F8; }
+enum Epi { EPI_LLMINT8 = 0, EPI_W8A16 = 1, EPI_W4A16 = 2, EPI_DYN = 3, EPI_PLAIN = 4, EPI_W8A8 = 5 };
 
 struct GemmArgs {
     int M, N, K;
@@ -135,7 +136,7 @@ struct SmemLayout {
     static constexpr int A_BYTES = BMT * ROW_BYTES;
     static constexpr int B_BYTES = BNT * ROW_BYTES;
     static constexpr int B_SLOTS = WS > 0 ? WS : STAGES;       // W buffers: one per ring stage, or the resident k-blocks
-    static constexpr int P_ROW = BMODE == B_I8 ? 64 : (is_nibble<BMODE>() ? 32 : 0);
+    static constexpr int P_ROW = is_byte<BMODE>() ? 64 : (is_nibble<BMODE>() ? 32 : 0);
     static constexpr int P_BYTES = BN * P_ROW;
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
@@ -199,6 +200,9 @@ __device__ __forceinline__ void epi_pair(uint32_t r0, uint32_t r1, float cs0, fl
     } else if constexpr (EPI == EPI_W8A16) {
         v0 = __fadd_rn(__fmul_rn(__uint_as_float(r0), cs0), b0);
         v1 = __fadd_rn(__fmul_rn(__uint_as_float(r1), cs1), b1);
+    } else if constexpr (EPI == EPI_W8A8) {     // quanto qbytes_int_mm: int32 * (s_in * s_w[n]) in fp32, then + bias
+        v0 = __fadd_rn(__fmul_rn((float)(int)r0, cs0), b0);
+        v1 = __fadd_rn(__fmul_rn((float)(int)r1, cs1), b1);
     } else {
         v0 = __fadd_rn(__uint_as_float(r0), b0);
         v1 = __fadd_rn(__uint_as_float(r1), b1);
@@ -356,7 +360,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
                 const int n = min(n0 + (i - which * BNT), args.N - 1);
                 float val = 0.0f;
                 if (which == 0) {
-                    if constexpr (EPI == EPI_LLMINT8 || EPI == EPI_W8A16) val = __ldg(args.col_scale + n);
+                    if constexpr (EPI == EPI_LLMINT8 || EPI == EPI_W8A16 || EPI == EPI_W8A8) val = __ldg(args.col_scale + n);
                 } else if (which == 1) {
                     if (bias != nullptr) val = __ldg(bias + n);
                 } else {
@@ -449,7 +453,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
 }
 
 template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT, int OUT_BUFS, int WS, int COLS, int LEAN>
-__global__ void __launch_bounds__(num_threads<BN, BMODE, LEAN>(), LEAN ? 2 : 1)   // lean: <= 168 registers
+__global__ void __launch_bounds__(num_threads<BN, BMODE, LEAN>(), (LEAN && BMODE == B_DIRECT) ? 2 : 1)   // lean int8: <= 168 registers
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ CUtensorMap map_y, const GemmArgs args) {
     using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS, COLS, LEAN>;
@@ -601,7 +605,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     } else {
         // ---------------- weight expansion (W8A16 / W4A16): warps 10.. ----------------
         const int t = threadIdx.x - 32 * (2 + EW);
-        if constexpr (BMODE == B_I8) {
+        if constexpr (is_byte<BMODE>()) {
             const int qd = t & 3, row0 = t >> 2;      // 128 threads: 4 per row, 32 rows per pass
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -619,7 +623,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                         uint32_t o[8];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            if constexpr (AKIND == A_F16) {
+                            if constexpr (BMODE == B_F8) {
+                                // e4m3 -> fp16 is exact (3 mantissa bits, exponents inside fp16's range); bf16 likewise
+                                uint32_t lo, hi;
+                                asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(lo) : "h"((unsigned short)(w[j] & 0xffffu)));
+                                asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(hi) : "h"((unsigned short)(w[j] >> 16)));
+                                if constexpr (AKIND == A_F16) {
+                                    o[2 * j] = lo;
+                                    o[2 * j + 1] = hi;
+                                } else {
+                                    const float2 fl = __half22float2(*reinterpret_cast<__half2 *>(&lo));
+                                    const float2 fh = __half22float2(*reinterpret_cast<__half2 *>(&hi));
+                                    o[2 * j] = pack2<__nv_bfloat16>(fl.x, fl.y);
+                                    o[2 * j + 1] = pack2<__nv_bfloat16>(fh.x, fh.y);
+                                }
+                            } else if constexpr (AKIND == A_F16) {
                                 // s8 -> fp16 exactly: (1024 + (s ^ 0x80)) - 1152
                                 const uint32_t x = w[j] ^ 0x80808080u;
                                 uint32_t lo = __byte_perm(x, 0x64646464u, 0x4140);
@@ -727,7 +745,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------
 // TMA-store boxes per epilogue warp (double-buffered when shared memory allows)
 template <int BN, int BMODE> constexpr int pick_out_bufs() {
-    return (BMODE == B_I8 && BN == 128) ? 1 : 2;
+    return (is_byte<BMODE>() && BN == 128) ? 1 : 2;
 }
 
 // deepest smem ring that fits next to the epilogue staging boxes
@@ -738,7 +756,7 @@ constexpr int pick_stages() {
     const int budget = LEAN ? 131072 : 232448;
     for (int st = 2; st <= 6; ++st) {
         const int bmt = (COLS || LEAN) ? BMH : BM, bnt = COLS ? 2 * BN : BN;
-        const int stage = bmt * ROW_BYTES + (WS > 0 ? 0 : bnt * ROW_BYTES) + BN * (BMODE == B_I8 ? 64 : (is_nibble<BMODE>() ? 32 : 0));
+        const int stage = bmt * ROW_BYTES + (WS > 0 ? 0 : bnt * ROW_BYTES) + BN * (is_byte<BMODE>() ? 64 : (is_nibble<BMODE>() ? 32 : 0));
         const int total = st * stage + WS * bnt * ROW_BYTES + epi_warps<BN, BMODE, LEAN>() * OUT_BUFS * BOX_BYTES +
                           (WS > 0 ? 1 : 2) * 3 * bnt * 4 + 64 + (3 * st + 2 * ACC_STAGES + 1) * 8 + 16 + 1024;
         if (total <= budget) best = st;
@@ -919,16 +937,18 @@ namespace {
 
 template <int BMODE, int EPI>
 int dispatch_a16(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &args, int x_dtype, int y_dtype,
-                 bool narrow, cudaStream_t s) {
+                 bool narrow, cudaStream_t s, bool lean = false) {
 #define WQ_CASE(BN, AK, OT) return launch_gemm<BN, AK, BMODE, EPI, OT>(ma, mb, args, s)
+#define WQ_LEAN(AK, OT) return launch_gemm<64, AK, BMODE, EPI, OT, 0, 0, 1>(ma, mb, args, s)
     if (x_dtype == WQ_F16) {
-        if (y_dtype == WQ_F16) { if (narrow) WQ_CASE(64, A_F16, __half); else WQ_CASE(128, A_F16, __half); }
+        if (y_dtype == WQ_F16) { if (lean) WQ_LEAN(A_F16, __half); if (narrow) WQ_CASE(64, A_F16, __half); else WQ_CASE(128, A_F16, __half); }
         if (y_dtype == WQ_F32) { if (narrow) WQ_CASE(64, A_F16, float); else WQ_CASE(128, A_F16, float); }
     } else if (x_dtype == WQ_BF16) {
-        if (y_dtype == WQ_BF16) { if (narrow) WQ_CASE(64, A_BF16, __nv_bfloat16); else WQ_CASE(128, A_BF16, __nv_bfloat16); }
+        if (y_dtype == WQ_BF16) { if (lean) WQ_LEAN(A_BF16, __nv_bfloat16); if (narrow) WQ_CASE(64, A_BF16, __nv_bfloat16); else WQ_CASE(128, A_BF16, __nv_bfloat16); }
         if (y_dtype == WQ_F32) { if (narrow) WQ_CASE(64, A_BF16, float); else WQ_CASE(128, A_BF16, float); }
     }
 #undef WQ_CASE
+#undef WQ_LEAN
     wq_set_error("unsupported dtype combination x=%d y=%d (x: F16/BF16, y: same as x or F32)", x_dtype, y_dtype);
     return WQ_ERR_INVALID;
 }
@@ -948,14 +968,15 @@ extern "C" int wq_gemm_w8a16(const void *x, int x_dtype, const int8_t *wq, const
     args.num_kb = (int)((K + 63) / 64);
     args.col_scale = scale; args.bias = bias; args.out = y;
     const bool narrow = use_narrow_tile(M, N);
+    const bool lean = narrow && use_lean_tile(M) && y_dtype == x_dtype;    // decode-shaped calls, <= 128 rows
     CUtensorMap ma, mb;
     rc = make_map_2d(&ma, x, x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                     M, K, BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+                     M, K, lean ? BMH : BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
     rc = make_map_2d(&mb, wq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, narrow ? 64 : 128, 64,
                      CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc != WQ_OK) return rc;
-    return dispatch_a16<B_I8, EPI_W8A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream);
+    return dispatch_a16<B_I8, EPI_W8A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream, lean);
 }
 
 extern "C" int wq_gemm_w4a16(const void *x, int x_dtype, const uint8_t *packed, const float *absmax, int quant_type,
@@ -974,14 +995,15 @@ extern "C" int wq_gemm_w4a16(const void *x, int x_dtype, const uint8_t *packed, 
     args.absmax = absmax; args.absmax_ld = (int)(K / 64);
     args.bias = bias; args.out = y; args.quant_type = quant_type;
     const bool narrow = use_narrow_tile(M, N);
+    const bool lean = narrow && use_lean_tile(M) && y_dtype == x_dtype;    // decode-shaped calls, <= 128 rows
     CUtensorMap ma, mb;
     rc = make_map_2d(&ma, x, x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                     M, K, BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+                     M, K, lean ? BMH : BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
     rc = make_map_2d(&mb, packed, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K / 2, narrow ? 64 : 128, 32,
                      CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc != WQ_OK) return rc;
-    return dispatch_a16<B_4BIT, EPI_W4A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream);
+    return dispatch_a16<B_4BIT, EPI_W4A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream, lean);
 }
 
 /* quanto QLinear.forward with weights=qint4 (group-wise affine uint4, MaxOptimizer):
@@ -1002,14 +1024,15 @@ extern "C" int wq_gemm_u4a16(const void *x, int x_dtype, const uint8_t *packed, 
     args.absmax = scale; args.shift = shift; args.group = group; args.absmax_ld = (int)(K / group);
     args.bias = bias; args.out = y;
     const bool narrow = use_narrow_tile(M, N);
+    const bool lean = narrow && use_lean_tile(M) && y_dtype == x_dtype;    // decode-shaped calls, <= 128 rows
     CUtensorMap ma, mb;
     rc = make_map_2d(&ma, x, x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                     M, K, BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+                     M, K, lean ? BMH : BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
     rc = make_map_2d(&mb, packed, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K / 2, narrow ? 64 : 128, 32,
                      CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc != WQ_OK) return rc;
-    return dispatch_a16<B_U4, EPI_W4A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream);
+    return dispatch_a16<B_U4, EPI_W4A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream, lean);
 }
 
 /* Unquantized linear on the same tcgen05 pipeline: y = x @ W^T + bias with W [N, K] in the activation dtype, taken
@@ -1068,4 +1091,54 @@ extern "C" int wq_argmax_finalize(unsigned long long *keys, int64_t M, int64_t *
     WQ_REQUIRE(keys && out, "wq_argmax_finalize: null pointer");
     WQ_LAUNCH_PDL(k_argmax_finalize, dim3((unsigned)((M + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, keys, M, out);
     return WQ_OK;
+}
+
+
+/* quanto QLinear.forward with weights=qfloat8 (e4m3fn codes, per-output-channel scale):
+ * y = matmul(x, Wq.to(x.dtype).t()) * scale + bias -- the same pipeline as wq_gemm_w8a16, the packed byte tile is
+ * expanded e4m3 -> fp16 / bf16 (exact) by the expansion warps. */
+extern "C" int wq_gemm_wf8a16(const void *x, int x_dtype, const uint8_t *wq, const float *scale, const float *bias,
+                              void *y, int y_dtype, int64_t M, int64_t N, int64_t K, wq_stream_t stream) {
+    int rc = check_common("wq_gemm_wf8a16", M, N, K);
+    if (rc != WQ_OK) return rc;
+    if (M == 0 || N == 0) return WQ_OK;
+    WQ_REQUIRE(x && wq && scale && y, "wq_gemm_wf8a16: null pointer");
+    WQ_REQUIRE(K % 16 == 0, "wq_gemm_wf8a16: K=%lld must be a multiple of 16", (long long)K);
+    WQ_REQUIRE(wq_aligned(x, 16) && wq_aligned(wq, 16) && wq_aligned(y, 16), "wq_gemm_wf8a16: misaligned buffer");
+    GemmArgs args = {};
+    args.M = (int)M; args.N = (int)N; args.K = (int)K;
+    args.num_kb = (int)((K + 63) / 64);
+    args.col_scale = scale; args.bias = bias; args.out = y;
+    const bool narrow = use_narrow_tile(M, N);
+    CUtensorMap ma, mb;
+    rc = make_map_2d(&ma, x, x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     M, K, BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != WQ_OK) return rc;
+    rc = make_map_2d(&mb, wq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, narrow ? 64 : 128, 64, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != WQ_OK) return rc;
+    return dispatch_a16<B_F8, EPI_W8A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream);
+}
+
+/* quanto QLinear.forward with qint8 weights AND statically quantized qint8 activations (quantize(model, weights=qint8,
+ * activations=qint8) + Calibration, model_utils.py:152-214): qbytes_int_mm, i.e.
+ *   y = float(int32(xq . wq^T)) * out_scale[n] + bias[n],   out_scale[n] = input_scale * weight_scale[n]
+ * on the kind::i8 tensor-core path.  xq int8 [M, K]; wq int8 [N, K]; out_scale, bias fp32 [N]; y of y_dtype. */
+extern "C" int wq_gemm_w8a8(const int8_t *xq, const int8_t *wq, const float *out_scale, const float *bias, void *y,
+                            int y_dtype, int64_t M, int64_t N, int64_t K, wq_stream_t stream) {
+    int rc = check_common("wq_gemm_w8a8", M, N, K);
+    if (rc != WQ_OK) return rc;
+    if (M == 0 || N == 0) return WQ_OK;
+    WQ_REQUIRE(xq && wq && out_scale && y, "wq_gemm_w8a8: null pointer");
+    WQ_REQUIRE(K % 16 == 0, "wq_gemm_w8a8: K=%lld must be a multiple of 16", (long long)K);
+    WQ_REQUIRE(wq_aligned(xq, 16) && wq_aligned(wq, 16) && wq_aligned(y, 16), "wq_gemm_w8a8: misaligned buffer");
+    GemmArgs args = {};
+    args.M = (int)M; args.N = (int)N; args.K = (int)K;
+    args.num_kb = (int)((K + 127) / 128);
+    args.col_scale = out_scale; args.bias = bias; args.out = y;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (y_dtype == WQ_F32) return launch_i8<A_S8, EPI_W8A8, float>(xq, wq, args, s);
+    if (y_dtype == WQ_F16) return launch_i8<A_S8, EPI_W8A8, __half>(xq, wq, args, s);
+    if (y_dtype == WQ_BF16) return launch_i8<A_S8, EPI_W8A8, __nv_bfloat16>(xq, wq, args, s);
+    wq_set_error("wq_gemm_w8a8: bad y_dtype %d", y_dtype);
+    return WQ_ERR_INVALID;
 }

@@ -256,10 +256,12 @@ k_quant_i8_rowwise_quanto(const T *__restrict__ w, int64_t N, int64_t K, int8_t 
     float am = 0.0f;
     for (int64_t c = lane; c < K; c += 32) am = fmaxf(am, fabsf(to_f32(pr[c])));
     am = warp_max(am);
-    const float s = __fdiv_rn(am, 127.0f);
+    // torch evaluates `absmax / 127` and `w / scale` on half / bfloat16 tensors in fp32 and rounds each result to the
+    // tensor dtype (opmath); for fp32 weights the two roundings below are no-ops
+    const float s = to_f32(from_f32<T>(__fdiv_rn(am, 127.0f)));
     if (lane == 0) scale[row] = s;
     for (int64_t c = lane; c < K; c += 32) {
-        float r = rintf(__fdiv_rn(to_f32(pr[c]), s));
+        float r = rintf(to_f32(from_f32<T>(__fdiv_rn(to_f32(pr[c]), s))));
         if (r != r) r = 0.0f;
         r = fminf(fmaxf(r, -128.0f), 127.0f);
         q[row * K + c] = (int8_t)(int)r;
@@ -721,6 +723,170 @@ extern "C" int wq_dequant_absmax_double(const uint8_t *q, const float *absmax2, 
     WQ_REQUIRE(q && absmax2 && code256 && offset && absmax_out, "wq_dequant_absmax_double: null pointer");
     k_dequant_absmax_blockwise8<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q, absmax2, code256,
                                                                                               offset, n, absmax_out);
+    WQ_LAUNCH_CHECK();
+    return WQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// optimum-quanto float8 weights and static (calibrated) activation quantization -- round 2
+// (model_utils.py:152-214 apply_static_quantization; quantization.py:53-86 "quanto_*_static*" / float8 configs).
+// ---------------------------------------------------------------------------------------------
+#include <cuda_fp8.h>
+
+namespace {
+
+// float -> e4m3fn code, round to nearest even, as torch's `.to(torch.float8_e4m3fn)` (quanto's SymmetricQuantizer for
+// float qtypes: `(base / scale).to(qtype.dtype)`).  Values beyond +-448 do not occur (scale = absmax / 448) except
+// through rounding of the quotient, where the conversion saturates to +-448 like the saturating cast.
+__device__ __forceinline__ uint8_t f32_to_e4m3(float x) {
+    return (uint8_t)__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3);
+}
+__device__ __forceinline__ float e4m3_to_f32(uint8_t c) {
+    const __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)c, __NV_E4M3);
+    return __half2float(*reinterpret_cast<const __half *>(&h));
+}
+
+// weights = qfloat8 (AbsmaxOptimizer, axis 0): scale[n] = max|W[n,:]| / 448, q = e4m3(W / scale)
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_quant_f8_rowwise_quanto(const T *__restrict__ w, int64_t N, int64_t K, uint8_t *__restrict__ q,
+                          float *__restrict__ scale) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (row >= N) return;
+    const T *pr = w + row * K;
+    float am = 0.0f;
+    for (int64_t c = lane; c < K; c += 32) am = fmaxf(am, fabsf(to_f32(pr[c])));
+    am = warp_max(am);
+    const float s = to_f32(from_f32<T>(__fdiv_rn(am, 448.0f)));       // rounded to the weight dtype (torch opmath)
+    if (lane == 0) scale[row] = s;
+    for (int64_t c = lane; c < K; c += 32) {
+        float r = to_f32(from_f32<T>(__fdiv_rn(to_f32(pr[c]), s)));
+        if (r != r) r = 0.0f;                       // all-zero row: 0 / 0
+        q[row * K + c] = f32_to_e4m3(r);
+    }
+}
+
+// Static activation quantization with a calibrated per-tensor scale (device scalar):
+//   qtype 0 (qint8):   code = clamp(rint(x / s), -128, 127)
+//   qtype 1 (qfloat8): code = e4m3(x / s)
+// Outputs (each optional): codes_i8 (int8 codes; qint8 only -- the A operand of the int8 x int8 GEMM), grid_f16 (the
+// code VALUE as fp16, exact for both types -- the A operand of the weight-expanding GEMMs), deq (code * s in the
+// dtype of x: what quanto's ActivationQBytesTensor.dequantize() hands to the next float op).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_quant_act_static(const T *__restrict__ x, int64_t n, const float *__restrict__ scale_ptr, int qtype,
+                   int8_t *__restrict__ codes_i8, __half *__restrict__ grid_f16, T *__restrict__ deq) {
+    pdl_prologue_done();
+    const float s = *scale_ptr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = to_f32(from_f32<T>(__fdiv_rn(to_f32(x[i]), s)));    // `x / scale` rounded to the dtype of x
+        float g;
+        if (qtype == 0) {
+            g = rintf(v);
+            if (g != g) g = 0.0f;
+            g = fminf(fmaxf(g, -128.0f), 127.0f);
+            if (codes_i8 != nullptr) codes_i8[i] = (int8_t)(int)g;
+        } else {
+            g = e4m3_to_f32(f32_to_e4m3(v != v ? 0.0f : v));
+        }
+        if (grid_f16 != nullptr) grid_f16[i] = __float2half_rn(g);
+        if (deq != nullptr) deq[i] = from_f32<T>(__fmul_rn(g, s));
+    }
+}
+
+}  // namespace
+
+extern "C" int wq_quant_f8_rowwise_quanto(const void *w, int w_dtype, int64_t N, int64_t K, uint8_t *q, float *scale,
+                                          wq_stream_t stream) {
+    WQ_REQUIRE(N >= 0 && K >= 0, "wq_quant_f8_rowwise_quanto: negative shape");
+    if (N == 0) return WQ_OK;
+    WQ_REQUIRE(w && q && scale, "wq_quant_f8_rowwise_quanto: null pointer");
+    const unsigned grid = (unsigned)((N + kWarpsPerCta - 1) / kWarpsPerCta);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (w_dtype) {
+        case WQ_F32: k_quant_f8_rowwise_quanto<float><<<grid, kWarpsPerCta * 32, 0, s>>>((const float *)w, N, K, q, scale); break;
+        case WQ_F16: k_quant_f8_rowwise_quanto<__half><<<grid, kWarpsPerCta * 32, 0, s>>>((const __half *)w, N, K, q, scale); break;
+        case WQ_BF16:
+            k_quant_f8_rowwise_quanto<__nv_bfloat16><<<grid, kWarpsPerCta * 32, 0, s>>>((const __nv_bfloat16 *)w, N, K, q, scale);
+            break;
+        default: WQ_REQUIRE(false, "wq_quant_f8_rowwise_quanto: bad dtype %d", w_dtype);
+    }
+    WQ_LAUNCH_CHECK();
+    return WQ_OK;
+}
+
+extern "C" int wq_quant_act_static(const void *x, int x_dtype, int64_t n, const float *scale, int qtype,
+                                   int8_t *codes_i8, void *grid_f16, void *deq, wq_stream_t stream) {
+    WQ_REQUIRE(n >= 0, "wq_quant_act_static: n < 0");
+    WQ_REQUIRE(qtype == 0 || qtype == 1, "wq_quant_act_static: qtype must be 0 (qint8) or 1 (qfloat8 e4m3)");
+    WQ_REQUIRE(qtype == 0 || codes_i8 == nullptr, "wq_quant_act_static: int8 codes exist for qint8 only");
+    if (n == 0) return WQ_OK;
+    WQ_REQUIRE(x && scale, "wq_quant_act_static: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t want = (n + 255) / 256;
+    const unsigned grid = (unsigned)(want < (int64_t)wq_sm_count() * 16 ? want : (int64_t)wq_sm_count() * 16);
+    switch (x_dtype) {
+        case WQ_F32:
+            WQ_LAUNCH_PDL(k_quant_act_static<float>, dim3(grid), dim3(256), 0, s, (const float *)x, n, scale, qtype, codes_i8,
+                          (__half *)grid_f16, (float *)deq);
+            break;
+        case WQ_F16:
+            WQ_LAUNCH_PDL(k_quant_act_static<__half>, dim3(grid), dim3(256), 0, s, (const __half *)x, n, scale, qtype, codes_i8,
+                          (__half *)grid_f16, (__half *)deq);
+            break;
+        case WQ_BF16:
+            WQ_LAUNCH_PDL(k_quant_act_static<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, (const __nv_bfloat16 *)x, n, scale, qtype,
+                          codes_i8, (__half *)grid_f16, (__nv_bfloat16 *)deq);
+            break;
+        default: WQ_REQUIRE(false, "wq_quant_act_static: bad dtype %d", x_dtype);
+    }
+    return WQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sparse checkpoint -> dense tensor on the device.  The reference stores pruned models
+// as per-tensor (indices, values) pairs (pruning/final_pruning_script/global_storing_as sparse.py:287-407: flat int64
+// indices + values in a zip) or as torch COO tensors (pruning+quantization/bnb_implementation.py:386-486) and rebuilds
+// the dense array on the host (`dense[indices] = values`, :468-471).  Here the indices / values are copied to the GPU
+// as they are and scattered there: out (zero-filled by the caller's memset inside this call) [n_out] fp32,
+// out[idx0[i] * cols + idx1[i]] = vals[i] (idx1 == NULL: flat indices).  Duplicate indices: last writer wins as in numpy
+// is NOT guaranteed; the formats never contain duplicates.
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <typename I>
+__global__ void __launch_bounds__(256)
+k_scatter_f32(const I *__restrict__ idx0, const I *__restrict__ idx1, int64_t cols, const float *__restrict__ vals,
+              int64_t nnz, float *__restrict__ out, int64_t n_out, int *__restrict__ err) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t at = (int64_t)idx0[i];
+        if (idx1 != nullptr) at = at * cols + (int64_t)idx1[i];
+        if (at < 0 || at >= n_out) {
+            *err = 1;            // corrupt file: reported by the host wrapper, never written out of bounds
+            continue;
+        }
+        out[at] = vals[i];
+    }
+}
+}  // namespace
+
+extern "C" int wq_scatter_dense_f32(const void *idx0, const void *idx1, int idx_bytes, int64_t cols, const float *vals,
+                                    int64_t nnz, float *out, int64_t n_out, int *err_flag, wq_stream_t stream) {
+    WQ_REQUIRE(nnz >= 0 && n_out >= 0 && cols >= 0, "wq_scatter_dense_f32: negative extent");
+    WQ_REQUIRE(idx_bytes == 4 || idx_bytes == 8, "wq_scatter_dense_f32: indices must be int32 or int64");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_out > 0) {
+        WQ_REQUIRE(out != nullptr, "wq_scatter_dense_f32: null output");
+        WQ_CUDA(cudaMemsetAsync(out, 0, (size_t)n_out * sizeof(float), s));
+    }
+    if (nnz == 0) return WQ_OK;
+    WQ_REQUIRE(idx0 && vals && err_flag, "wq_scatter_dense_f32: null pointer");
+    const int64_t want = (nnz + 255) / 256;
+    const unsigned grid = (unsigned)(want < (int64_t)wq_sm_count() * 16 ? want : (int64_t)wq_sm_count() * 16);
+    if (idx_bytes == 8)
+        k_scatter_f32<int64_t><<<grid, 256, 0, s>>>((const int64_t *)idx0, (const int64_t *)idx1, cols, vals, nnz, out, n_out, err_flag);
+    else
+        k_scatter_f32<int32_t><<<grid, 256, 0, s>>>((const int32_t *)idx0, (const int32_t *)idx1, cols, vals, nnz, out, n_out, err_flag);
     WQ_LAUNCH_CHECK();
     return WQ_OK;
 }

@@ -47,36 +47,40 @@ def _self_attn_forward(self, hidden_states, key_value_states=None, past_key_valu
 
 
 def _plan_layer_int8(layer):
-    """Packed weights for _layer_forward_int8, or None when the layer is not all-Linear8bitLt / fp16 / GELU."""
+    """Packed weights for _layer_forward_int8, or None when the layer's linears are not all drop-in modules of one
+    scheme fused.pack serves for the layer's dtype (LLM.int8 / fp16; W8A16, NF4 / FP4, qint4 / qint2 with fp16 or bf16)."""
     sa = layer.self_attn
     cfg = sa.config
+    dtype = layer.self_attn_layer_norm.weight.dtype
     if (cfg.activation_function != "gelu" or sa.head_dim != 64 or layer.embed_dim > 2048 or layer.embed_dim % 8
-            or layer.self_attn_layer_norm.weight.dtype != torch.float16):
+            or dtype not in (torch.float16, torch.bfloat16)):
         return None
     plan = types.SimpleNamespace()
-    plan.qkv = fused.pack_int8([sa.q_proj, sa.k_proj, sa.v_proj])
-    plan.o = fused.pack_int8([sa.out_proj])
-    plan.fc1 = fused.pack_int8([layer.fc1])
-    plan.fc2 = fused.pack_int8([layer.fc2])
+    plan.qkv = fused.pack([sa.q_proj, sa.k_proj, sa.v_proj], dtype)
+    plan.o = fused.pack([sa.out_proj], dtype)
+    plan.fc1 = fused.pack([layer.fc1], dtype)
+    plan.fc2 = fused.pack([layer.fc2], dtype)
     ws = [plan.qkv, plan.o, plan.fc1, plan.fc2]
-    if any(w is None for w in ws) or any(w.threshold != ws[0].threshold for w in ws):
+    if any(w is None for w in ws) or any(w.threshold != ws[0].threshold or w.kind != ws[0].kind for w in ws):
         return None
-    plan.threshold = ws[0].threshold
+    plan.dtype = dtype
+    plan.threshold = ws[0].threshold if ws[0].kind == "int8" else None     # None: no int8 rows from the producers
     plan.scaling = float(sa.scaling)
     plan.scaling_pow2 = fused.is_pow2(plan.scaling)
     return plan
 
 
 def _layer_forward_int8(self, hidden_states, attention_mask=None, **kwargs):
-    """WhisperEncoderLayer.forward (modeling_whisper.py:380-414) for an all-Linear8bitLt layer: every quantized
-    GEMM is fed by a producer kernel that wrote its int8 rows (add+LayerNorm+quant, GELU+quant), q/k/v are one
-    GEMM over the concatenated weights, SDPA reads the fused projection through its strides.  Per-linear int8
-    arithmetic is unchanged; LayerNorm/GELU are within one fp16 ulp of torch's (tests/test_gpu_fused.py)."""
+    """WhisperEncoderLayer.forward (modeling_whisper.py:380-414) for a layer whose linears are all drop-in modules of
+    one scheme: q/k/v are one GEMM over the concatenated weights, SDPA reads the fused projection through its strides,
+    the residual add rides in the LayerNorm launch; for LLM.int8 every GEMM is fed by a producer kernel that already
+    wrote its int8 rows (add+LayerNorm+quant, GELU+quant).  Per-linear arithmetic is unchanged; LayerNorm / GELU are
+    within one fp16 ulp of torch's (tests/test_gpu_fused.py)."""
     plan = getattr(self, "_whisperq_plan", False)
     if plan is False:
         plan = self._whisperq_plan = _plan_layer_int8(self)
     if (plan is None or attention_mask is not None or self.training or kwargs.get("output_attentions")
-            or hidden_states.dtype != torch.float16 or not hidden_states.is_cuda
+            or hidden_states.dtype != plan.dtype or not hidden_states.is_cuda
             or self.self_attn.config._attn_implementation != "sdpa"):
         return self._whisperq_hf_forward(hidden_states, attention_mask, **kwargs)
     B, S, d = hidden_states.shape
@@ -84,20 +88,22 @@ def _layer_forward_int8(self, hidden_states, attention_mask=None, **kwargs):
     x = hidden_states.reshape(B * S, d)
     ln = self.self_attn_layer_norm
     _, h, qt = F.add_layernorm_quant(x, None, ln.weight, ln.bias, ln.eps, thr)
-    qkv = fused.gemm_int8(qt, h, plan.qkv)
+    qkv = fused.gemm(qt, h, plan.qkv)
     q, k, v = (qkv[:, i * d:(i + 1) * d].view(B, S, H, 64).transpose(1, 2) for i in range(3))
-    if plan.scaling_pow2:       # q * 2^-k is exact in fp16, so the scale rides in the SDPA call
+    if plan.scaling_pow2:       # q * 2^-k is exact in fp16 / bf16, so the scale rides in the SDPA call
         a = TF.scaled_dot_product_attention(q, k, v, scale=plan.scaling)
     else:
         a = TF.scaled_dot_product_attention(q * plan.scaling, k, v, scale=1.0)
     a = a.transpose(1, 2).reshape(B * S, d)
-    att = fused.gemm_int8(F.int8_vectorwise_quant(a, thr, finalize=False), a, plan.o)
+    att = fused.gemm(F.int8_vectorwise_quant(a, thr, finalize=False) if thr is not None else None, a, plan.o)
     ln = self.final_layer_norm
     x, h, qt = F.add_layernorm_quant(x, att, ln.weight, ln.bias, ln.eps, thr)
-    g, qt = F.gelu_quant(fused.gemm_int8(qt, h, plan.fc1), thr)
-    out = x + fused.gemm_int8(qt, g, plan.fc2)
-    clamp_value = torch.finfo(torch.float16).max - 1000
-    return torch.clamp(out, min=-clamp_value, max=clamp_value).view(B, S, d)
+    g, qt = F.gelu_quant(fused.gemm(qt, h, plan.fc1), thr)
+    out = x + fused.gemm(qt, g, plan.fc2)
+    if out.dtype == torch.float16:      # HF clamps fp16 activations only
+        clamp_value = torch.finfo(torch.float16).max - 1000
+        out = torch.clamp(out, min=-clamp_value, max=clamp_value)
+    return out.view(B, S, d)
 
 
 def _contiguous_stream_hook(module, args, kwargs):

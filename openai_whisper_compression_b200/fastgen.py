@@ -305,7 +305,7 @@ class GraphedGreedy:
         x = dec.embed_tokens(v.tok).view(B, d) + dec.embed_positions.weight.index_select(0, st.pos)
         delta = None
 
-        gemm = fused.gemm_int8
+        gemm = fused.gemm      # LLM.int8: consumes the producer's int8 rows; weight-only schemes: the fp16 / bf16 rows
 
         for li, (layer, fw) in enumerate(zip(dec.layers, st.fused)):
             ln = layer.self_attn_layer_norm
@@ -319,11 +319,11 @@ class GraphedGreedy:
             q = gemm(qt, h, fw.cq)
             if st.own_cross:
                 # q scaling, the pass over the 1500 cached encoder positions and out_proj's quantization: one launch
-                if self.cross_quant_inline:
+                if self.cross_quant_inline or thr is None:
                     a, qt = F.cross_attn_decode(q, v.ckv[li][:, :, :d], v.ckv[li][:, :, d:], fw.scaling, H, thr)
                 else:       # the row quantization as a launch of its own (no cross-CTA completion tail in the stream)
                     a, _ = F.cross_attn_decode(q, v.ckv[li][:, :, :d], v.ckv[li][:, :, d:], fw.scaling, H, None)
-                    qt = F.int8_vectorwise_quant(a, thr, finalize=False)
+                    qt = F.int8_vectorwise_quant(a, thr, finalize=False) if thr is not None else None
             else:
                 if fw.scaling_pow2:     # q * 2^-k is exact in fp16, so the scale can ride in the SDPA call
                     a = TF.scaled_dot_product_attention(q.view(B, 1, H, hd).transpose(1, 2),
@@ -333,7 +333,7 @@ class GraphedGreedy:
                     a = TF.scaled_dot_product_attention((q * fw.scaling).view(B, 1, H, hd).transpose(1, 2),
                                                         v.ck[li].transpose(1, 2), v.cv[li].transpose(1, 2), scale=1.0)
                 a = a.transpose(1, 2).reshape(B, d)
-                qt = F.int8_vectorwise_quant(a, thr, finalize=False)
+                qt = F.int8_vectorwise_quant(a, thr, finalize=False) if thr is not None else None
             delta = gemm(qt, a, fw.co)
             ln = layer.final_layer_norm
             x, h, qt = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, thr)
@@ -347,15 +347,19 @@ class GraphedGreedy:
         self._project(st, v, h)
 
     def _plan_int8(self, dtype):
-        """Per-layer packed weights for _decoder_step_int8, or None when the decoder is not all-Linear8bitLt."""
-        if dtype != torch.float16:
+        """Per-layer packed weights for the fused decode step, or None when the decoder's linears are not all drop-in
+        modules of ONE scheme that fused.pack serves for `dtype` (LLM.int8 with fp16 activations; W8A16 / NF4 / FP4 /
+        qint4 / qint2 with fp16 or bf16 activations).  Returns (plans, threshold): threshold is None for the
+        weight-only schemes (their producers write no int8 rows)."""
+        if dtype not in (torch.float16, torch.bfloat16):
             return None, 0.0
         cfg = self.model.config
         if cfg.activation_function != "gelu" or cfg.d_model // cfg.decoder_attention_heads != 64 or cfg.d_model > 2048:
             return None, 0.0
-        plans, thr = [], None
+        plans, thr, kind = [], None, None
 
-        pack = fused.pack_int8
+        def pack(mods):
+            return fused.pack(mods, dtype)
 
         for layer in self.model.model.decoder.layers:
             sa, ca = layer.self_attn, layer.encoder_attn
@@ -367,13 +371,15 @@ class GraphedGreedy:
             ws = [fw.qkv, fw.o, fw.cq, fw.co, fw.ckv, fw.fc1, fw.fc2]
             if any(w is None for w in ws) or sa.scaling != ca.scaling:
                 return None, 0.0
+            kind = ws[0].kind if kind is None else kind
             thr = ws[0].threshold if thr is None else thr
-            if any(w.threshold != thr for w in ws) or layer.fc1.out_features % 8 != 0:
+            if (any(w.kind != kind or w.threshold != thr for w in ws) or layer.fc1.out_features % 8 != 0
+                    or layer.self_attn_layer_norm.weight.dtype != dtype):
                 return None, 0.0
             fw.scaling = float(sa.scaling)
             fw.scaling_pow2 = fused.is_pow2(fw.scaling)
             plans.append(fw)
-        return plans, thr
+        return plans, (thr if kind == "int8" else None)
 
     def _fingerprint(self):
         """Identity of every tensor the captured graphs and packed copies were built from: (data_ptr, version) of
@@ -384,6 +390,9 @@ class GraphedGreedy:
         for root in (self.model,):          # encoder too: fastenc's per-layer plans hold concatenated copies
             for p in root.parameters():
                 fp.append((p.data_ptr(), p._version))
+            for b in root.buffers():            # calibrated activation scales (quanto input_scale / output_scale)
+                if b.numel() == 1:
+                    fp.append((b.data_ptr(), b._version))
             for m in root.modules():
                 stt = getattr(m, "state", None)
                 for t in (getattr(stt, "CB", None), getattr(stt, "SCB", None), getattr(m, "_wq", None),
@@ -546,7 +555,8 @@ class GraphedGreedy:
                 synced_gpus=False, streamer=None, **model_kwargs):
         model = self.model
         enc_out = model_kwargs.get("encoder_outputs")
-        eligible = (input_ids.is_cuda and not generation_config.do_sample
+        from . import quanto as _quanto
+        eligible = (input_ids.is_cuda and not generation_config.do_sample and not _quanto.calibrating()
                     and not generation_config.return_dict_in_generate and streamer is None and not synced_gpus
                     and enc_out is not None and model_kwargs.get("use_cache", True)
                     and generation_config.max_length is not None
@@ -586,9 +596,9 @@ class GraphedGreedy:
             # all-Linear8bitLt decoder: the encoder output is quantized ONCE (bitsandbytes would do it in each of
             # the 2L projections) and every layer's [Wk; Wv] GEMM writes straight into its K|V buffer
             enc2 = enc.view(B * S, st.d)
-            qt = F.int8_vectorwise_quant(enc2, st.threshold, finalize=False)
+            qt = F.int8_vectorwise_quant(enc2, st.threshold, finalize=False) if st.threshold is not None else None
             for li, fw in enumerate(st.fused):
-                fused.gemm_int8(qt, enc2, fw.ckv, out=st.ckv[li], keep_flags=li + 1 < len(layers))
+                fused.gemm(qt, enc2, fw.ckv, out=st.ckv[li], keep_flags=li + 1 < len(layers))
         else:
             for li, layer in enumerate(layers):
                 ca = layer.encoder_attn

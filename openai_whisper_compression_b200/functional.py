@@ -160,14 +160,23 @@ def dequantize_absmax_double(q: torch.Tensor, absmax2: torch.Tensor, offset: tor
     return out
 
 
+def _dest(out: Optional[torch.Tensor], M: int, N: int, dtype, device, what: str) -> torch.Tensor:
+    """[M, N] destination of a GEMM: a fresh tensor, or the caller's contiguous buffer of M*N elements."""
+    if out is None:
+        return torch.empty((M, N), dtype=dtype, device=device)
+    if out.dtype != dtype or out.numel() != M * N or not out.is_contiguous() or not out.is_cuda:
+        raise RuntimeError(f"{what}: out must be a contiguous CUDA tensor of M*N elements in the output dtype")
+    return out.view(M, N)
+
+
 def gemm_w4a16(x: torch.Tensor, packed: torch.Tensor, absmax: torch.Tensor, N: int, K: int,
                bias: Optional[torch.Tensor] = None, quant_type: str = "nf4",
-               out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+               out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Linear4bit.forward hot path: y = x @ dequantize_4bit(W).T + bias, fused (blocksize 64)."""
     x2 = x.reshape(-1, K).contiguous()
     _need_cuda(x2, packed, absmax, bias)
     out_dtype = out_dtype or x2.dtype
-    y = torch.empty((x2.shape[0], N), dtype=out_dtype, device=x.device)
+    y = _dest(out, x2.shape[0], N, out_dtype, x.device, "gemm_w4a16")
     with torch.cuda.device(x.device), _Timed("w4a16", x2.shape[0], N, K):
         _lib.check(_lib.load().wq_gemm_w4a16(_ptr(x2), _DT[x2.dtype], _ptr(packed), _ptr(absmax), _QT[quant_type],
                                              _ptr(bias), _ptr(y), _DT[out_dtype], x2.shape[0], N, K, _stream()),
@@ -530,18 +539,84 @@ def quanto_quantize_qint8(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def gemm_w8a16(x: torch.Tensor, wq: torch.Tensor, scale: torch.Tensor, bias: Optional[torch.Tensor] = None,
-               out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+               out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """QLinear.forward hot path: y = (x @ Wq.T) * scale + bias with fp32 accumulation."""
     N, K = wq.shape
     x2 = x.reshape(-1, K).contiguous()
     _need_cuda(x2, wq, scale, bias)
     out_dtype = out_dtype or x2.dtype
-    y = torch.empty((x2.shape[0], N), dtype=out_dtype, device=x.device)
+    y = _dest(out, x2.shape[0], N, out_dtype, x.device, "gemm_w8a16")
     with torch.cuda.device(x.device), _Timed("w8a16", x2.shape[0], N, K):
         _lib.check(_lib.load().wq_gemm_w8a16(_ptr(x2), _DT[x2.dtype], _ptr(wq), _ptr(scale), _ptr(bias), _ptr(y),
                                              _DT[out_dtype], x2.shape[0], N, K, _stream()), "wq_gemm_w8a16")
     STATS.launches += 1
     return y.reshape(*x.shape[:-1], N)
+
+
+def quanto_quantize_qfloat8(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """quanto AbsmaxOptimizer + SymmetricQuantizer for weights=qfloat8 (e4m3fn, axis 0): (uint8 codes [N, K], scale
+    f32 [N, 1] = absmax / 448 rounded to the weight dtype)."""
+    w = w.contiguous()
+    _need_cuda(w)
+    N, K = w.shape
+    q = torch.empty((N, K), dtype=torch.uint8, device=w.device)
+    scale = torch.empty((N, 1), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.load().wq_quant_f8_rowwise_quanto(_ptr(w), _DT[w.dtype], N, K, _ptr(q), _ptr(scale), _stream()),
+                   "wq_quant_f8_rowwise_quanto")
+    STATS.launches += 1
+    return q, scale
+
+
+def gemm_wf8a16(x: torch.Tensor, wq: torch.Tensor, scale: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """QLinear.forward with qfloat8 weights: y = (x @ e4m3(Wq).T) * scale + bias with fp32 accumulation."""
+    N, K = wq.shape
+    x2 = x.reshape(-1, K).contiguous()
+    _need_cuda(x2, wq, scale, bias)
+    out_dtype = out_dtype or x2.dtype
+    y = _dest(out, x2.shape[0], N, out_dtype, x.device, "gemm_wf8a16")
+    with torch.cuda.device(x.device), _Timed("wf8a16", x2.shape[0], N, K):
+        _lib.check(_lib.load().wq_gemm_wf8a16(_ptr(x2), _DT[x2.dtype], _ptr(wq), _ptr(scale), _ptr(bias), _ptr(y),
+                                              _DT[out_dtype], x2.shape[0], N, K, _stream()), "wq_gemm_wf8a16")
+    STATS.launches += 1
+    return y.reshape(*x.shape[:-1], N)
+
+
+_ACT_QT = {"qint8": 0, "qfloat8": 1, "qfloat8_e4m3fn": 1}
+
+
+def quant_act_static(x: torch.Tensor, scale: torch.Tensor, qtype: str, codes: bool = False, grid: bool = False,
+                     deq: bool = False):
+    """quanto quantize_activation(x, qtype, scale) with a calibrated per-tensor scale (CUDA fp32 scalar tensor).
+    Returns (int8 codes | None, fp16 code values | None, dequantized x in its own dtype | None)."""
+    x = x.contiguous()
+    _need_cuda(x, scale)
+    if scale.dtype != torch.float32 or scale.numel() != 1:
+        raise RuntimeError("quant_act_static: scale must be a float32 scalar tensor on the device")
+    qt = _ACT_QT[qtype]
+    c = torch.empty(x.shape, dtype=torch.int8, device=x.device) if codes else None
+    g = torch.empty(x.shape, dtype=torch.float16, device=x.device) if grid else None
+    d = torch.empty_like(x) if deq else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().wq_quant_act_static(_ptr(x), _DT[x.dtype], x.numel(), _ptr(scale), qt, _ptr(c), _ptr(g),
+                                                   _ptr(d), _stream()), "wq_quant_act_static")
+    STATS.launches += 1
+    return c, g, d
+
+
+def gemm_w8a8(xq: torch.Tensor, wq: torch.Tensor, out_scale: torch.Tensor, bias: Optional[torch.Tensor] = None,
+              out_dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    """qint8 activations x qint8 weights (quanto qbytes_int_mm): y = float(int32 acc) * out_scale[n] + bias[n]."""
+    N, K = wq.shape
+    x2 = xq.reshape(-1, K)
+    _need_cuda(x2, wq, out_scale, bias)
+    y = torch.empty((x2.shape[0], N), dtype=out_dtype, device=xq.device)
+    with torch.cuda.device(xq.device), _Timed("w8a8", x2.shape[0], N, K):
+        _lib.check(_lib.load().wq_gemm_w8a8(_ptr(x2), _ptr(wq), _ptr(out_scale), _ptr(bias), _ptr(y), _DT[out_dtype],
+                                            x2.shape[0], N, K, _stream()), "wq_gemm_w8a8")
+    STATS.launches += 1
+    return y.reshape(*xq.shape[:-1], N)
 
 
 def quanto_group_size(in_features: int) -> int:
@@ -577,13 +652,14 @@ def quanto_quantize_qint4(w: torch.Tensor, group: Optional[int] = None, bits: in
 
 
 def gemm_u4a16(x: torch.Tensor, packed: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, group: int,
-               bias: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+               bias: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """QLinear.forward with qint4 weights: y = x @ (scale*q - shift).T + bias, fused."""
     N, K = packed.shape[0], packed.shape[1] * 2
     x2 = x.reshape(-1, K).contiguous()
     _need_cuda(x2, packed, scale, shift, bias)
     out_dtype = out_dtype or x2.dtype
-    y = torch.empty((x2.shape[0], N), dtype=out_dtype, device=x.device)
+    y = _dest(out, x2.shape[0], N, out_dtype, x.device, "gemm_u4a16")
     with torch.cuda.device(x.device), _Timed("u4a16", x2.shape[0], N, K):
         _lib.check(_lib.load().wq_gemm_u4a16(_ptr(x2), _DT[x2.dtype], _ptr(packed), _ptr(scale), _ptr(shift), group,
                                              _ptr(bias), _ptr(y), _DT[out_dtype], x2.shape[0], N, K, _stream()),

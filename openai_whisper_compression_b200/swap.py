@@ -109,7 +109,8 @@ def install_shims(force: bool = False) -> dict:
     if force or not _importable("optimum"):
         opt = types.ModuleType("optimum")
         q = types.ModuleType("optimum.quanto")
-        for k in ("Calibration", "freeze", "quantize", "qint2", "qint4", "qint8", "qfloat8", "QLinear", "qtype"):
+        for k in ("Calibration", "freeze", "quantize", "qint2", "qint4", "qint8", "qfloat8", "QLinear", "QLayerNorm",
+                  "qtype"):
             setattr(q, k, getattr(quanto, k))
         opt.quanto = q
         sys.modules["optimum"] = opt

@@ -232,13 +232,51 @@ def linear8bitlt_forward(x: np.ndarray, CB: np.ndarray, SCB: np.ndarray, bias=No
 # --------------------------------------------------------------------------------------
 # optimum-quanto qint8
 # --------------------------------------------------------------------------------------
-def quanto_qint8(w: np.ndarray):
+def quanto_qint8(w: np.ndarray, dtype=np.float32):
+    """quanto AbsmaxOptimizer + SymmetricQuantizer, weights=qint8, axis 0.  dtype float32: the C restatement.  dtype
+    float16: the same two expressions (`absmax / 127`, `round(w / scale)`) as torch evaluates them on half tensors --
+    each in fp32, the result rounded to half (opmath) -- which is what quanto computes for an fp16 model (the
+    reference's static flows, model_utils.py:139-142,185); pinned against live torch in tests/test_oracle_golden.py."""
+    if np.dtype(dtype) == np.float16:
+        w16 = np.asarray(w).astype(np.float16)
+        am = np.abs(w16).max(axis=1).astype(np.float32)
+        s = (am / np.float32(127.0)).astype(np.float16)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            r = (w16.astype(np.float32) / s.astype(np.float32)[:, None]).astype(np.float16).astype(np.float32)
+        r = np.where(np.isnan(r), np.float32(0), np.rint(r))
+        return np.clip(r, -128, 127).astype(np.int8), s.astype(np.float32).reshape(-1, 1)
     wf = _f32(w)
     N, K = wf.shape
     q = np.zeros((N, K), dtype=np.int8)
     scale = np.zeros((N,), dtype=np.float32)
     lib().orc_quanto_qint8(_p(wf), ctypes.c_int64(N), ctypes.c_int64(K), _p(q), _p(scale))
     return q, scale.reshape(N, 1)
+
+
+def quanto_qfloat8(w, dtype="float32"):
+    """quanto weights=qfloat8 (e4m3fn), axis 0: scale = absmax / 448, data = (w / scale).to(float8_e4m3fn), evaluated
+    with torch's own CPU ops in `dtype` (torch IS what quanto calls, so this is the live reference, not a
+    restatement).  Returns (uint8 codes, scale float32 [N, 1])."""
+    import torch
+    t = torch.as_tensor(np.asarray(w, dtype=np.float32)).to(getattr(torch, dtype))
+    s = t.abs().amax(dim=1, keepdim=True) / 448.0
+    q = torch.clamp(torch.nan_to_num(t / s, nan=0.0), -448.0, 448.0).to(torch.float8_e4m3fn)   # SymmetricQuantizer clamps to finfo
+    return q.view(torch.uint8).numpy().copy(), s.float().numpy().copy()
+
+
+def quanto_quantize_activation(x, scale: float, qtype: str, dtype="float16"):
+    """quanto quantize_activation(x, qtype, scale) + dequantize with torch's own CPU ops in `dtype`:
+    qint8: clamp(round(x / scale), -128, 127); qfloat8: (x / scale).to(float8_e4m3fn).  Returns (code values as
+    float32, dequantized tensor = code * scale in `dtype`, as float32)."""
+    import torch
+    dt = getattr(torch, dtype)
+    t = torch.as_tensor(np.asarray(x, dtype=np.float32)).to(dt)
+    s = torch.tensor(scale, dtype=dt)
+    if qtype == "qint8":
+        g = torch.clamp(torch.round(t / s), -128, 127)
+    else:
+        g = torch.clamp(t / s, -448.0, 448.0).to(torch.float8_e4m3fn).to(dt)      # clamp to finfo(e4m3fn), then cast
+    return g.float().numpy(), (g * s).float().numpy()
 
 
 def qlinear_forward(x: np.ndarray, q: np.ndarray, scale: np.ndarray, bias=None) -> np.ndarray:

@@ -147,7 +147,7 @@ def test_quanto_qint8_bit_exact(dtype, N, K):
     w[1] = 0
     wt = dev(w, dtype)
     q, scale = F.quanto_quantize_qint8(wt)
-    q_ref, s_ref = oracle.quanto_qint8(wt.float().cpu().numpy())
+    q_ref, s_ref = oracle.quanto_qint8(wt.float().cpu().numpy(), np.float16 if dtype == torch.float16 else np.float32)
     np.testing.assert_array_equal(scale.cpu().numpy(), s_ref)
     np.testing.assert_array_equal(q.cpu().numpy(), q_ref)
 
@@ -504,3 +504,66 @@ def test_gemm_f16_projection_and_fused_argmax(dtype, M, N, K):
     assert y3.shape == (M, N)
     assert torch.equal(tok3, torch.argmax(y3.float(), dim=-1))
     assert (y3.float() - (ref + bias)).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: optimum-quanto float8 weights and static activation quantization
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,K", [(48, 64), (130, 384), (33, 1280)])
+def test_quanto_qfloat8_codes_bit_exact_and_gemm(dtype, N, K):
+    """weights=qfloat8: codes / scales equal torch's own `(w / (absmax / 448)).to(float8_e4m3fn)` in the weight dtype;
+    the fused GEMM equals dequantize-then-matmul (fp32 accumulate, one output rounding)."""
+    rng = np.random.RandomState(N + K)
+    w = (rng.randn(N, K) * 0.02).astype(np.float32)
+    w[rng.rand(N, K) < 0.4] = 0
+    w[1] = 0
+    wt = dev(w, dtype)
+    q, scale = F.quanto_quantize_qfloat8(wt)
+    q_ref, s_ref = oracle.quanto_qfloat8(wt.float().cpu().numpy(), str(dtype).replace("torch.", ""))
+    np.testing.assert_array_equal(scale.cpu().numpy(), s_ref)
+    np.testing.assert_array_equal(q.cpu().numpy(), q_ref)
+    assert np.all(q.cpu().numpy()[w == 0] & 0x7f == 0)                    # pruned zeros stay (signed) zeros
+    if dtype == torch.float32:
+        return
+    x = torch.randn(70, K, device="cuda").to(dtype)
+    bias = torch.randn(N, device="cuda") * 0.1
+    y = F.gemm_wf8a16(x, q, scale.view(-1), bias)
+    wd = q.view(torch.float8_e4m3fn).float()
+    ref = (x.float() @ wd.t()) * scale.view(1, -1) + bias
+    tol = 2e-3 if dtype == torch.float16 else 1.6e-2
+    assert (y.float() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("qtype", ["qint8", "qfloat8"])
+def test_static_activation_quantization_bit_exact(dtype, qtype):
+    """quantize_activation with a calibrated per-tensor scale: code values and dequantized tensor equal torch's own
+    ops in the same dtype (CPU), incl. saturation and values on rounding ties."""
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(37, 96, generator=g) * 3).to(dtype)
+    x[0, :8] = torch.tensor([0.0, 1e4, -1e4, 0.5, 1.5, 2.5, -0.5, 127.5]).to(dtype)
+    dn = str(dtype).replace("torch.", "")
+    sc = torch.tensor(0.0625 if qtype == "qint8" else 0.01, dtype=dtype)
+    g_ref, d_ref = oracle.quanto_quantize_activation(x.float().numpy(), float(sc), qtype, dn)
+    codes, grid, deq = F.quant_act_static(x.cuda(), sc.float().cuda().view(1), qtype, codes=qtype == "qint8", grid=True,
+                                          deq=True)
+    np.testing.assert_array_equal(grid.float().cpu().numpy(), g_ref)
+    np.testing.assert_array_equal(deq.float().cpu().numpy(), d_ref)
+    if codes is not None:
+        np.testing.assert_array_equal(codes.cpu().numpy().astype(np.float32), g_ref)
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("M,N,K", [(300, 200, 384), (5, 512, 512), (1500, 1536, 512)])
+def test_gemm_w8a8_exact_vs_integer_matmul(out_dtype, M, N, K):
+    """qint8 x qint8 (quanto qbytes_int_mm): float(int32 acc) * out_scale[n] + bias[n] with exact integer sums."""
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    xq = torch.randint(-128, 128, (M, K), device="cuda", generator=g, dtype=torch.int8)
+    wq = torch.randint(-128, 128, (N, K), device="cuda", generator=g, dtype=torch.int8)
+    os_ = torch.rand(N, device="cuda", generator=g) * 1e-3
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    y = F.gemm_w8a8(xq, wq, os_, bias, out_dtype)
+    acc = (xq.double() @ wq.double().t())
+    ref = ((acc.float() * os_[None, :]) + bias[None, :]).to(out_dtype)
+    assert torch.equal(y, ref)

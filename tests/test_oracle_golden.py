@@ -277,3 +277,19 @@ def test_fdividef_table_reproduces_the_b200_sweep():
         assert int(oracle.int8_vectorwise_quant(row, 0.0, approx_div=False)[0][0, 1]) == rec["q_ieee"]
     # int8_mm_dequant: written as mul-then-add it is contracted to the same FFMA as fmaf (0 mismatches in 2.5e9)
     assert rep["plain_vs_fmaf_f32_mismatches"] == 0
+
+
+def test_quanto_fp16_opmath_restatement_matches_live_torch():
+    """oracle.quanto_qint8(dtype=float16) restates `absmax / 127` and `round(w / scale)` as torch evaluates them on
+    half tensors (fp32 math, result rounded to half): pinned against torch's own CPU ops."""
+    import torch
+    rng = np.random.RandomState(3)
+    w = (rng.randn(64, 200) * 0.02).astype(np.float16)
+    w[rng.rand(64, 200) < 0.3] = 0
+    w[5] = 0
+    t = torch.from_numpy(w)
+    s = t.abs().amax(dim=1, keepdim=True) / 127
+    q = torch.clamp(torch.nan_to_num(torch.round(t / s), nan=0.0), -128, 127).to(torch.int8)
+    q_ref, s_ref = oracle.quanto_qint8(w, np.float16)
+    np.testing.assert_array_equal(q.numpy(), q_ref)
+    np.testing.assert_array_equal(s.float().numpy(), s_ref)
