@@ -157,6 +157,16 @@ int wq_gemm_llmint8_shared(const int8_t *ca, const float *sca, const int8_t *cb,
                            const float *bias, void *y_f16, int64_t M, int64_t N, int64_t K,
                            const void *a_f16, int32_t *col_flags, int keep_flags, wq_stream_t stream);
 
+/* The same GEMM with the residual connection of the Whisper layer folded into its epilogue (SURVEY.md section 8f
+ * rank 3): y = clamp(fp16(linear) + residual, -clamp_abs, clamp_abs) -- HF's `hidden_states = residual +
+ * hidden_states` and the fp16 overflow clamp that close WhisperEncoderLayer.forward (modeling_whisper.py:408-414),
+ * evaluated as torch does (the projection rounded to fp16, one fp16 addition, clamp).  residual_f16: [M, N] fp16,
+ * contiguous (may be NULL); clamp_abs 0 = no clamp. */
+int wq_gemm_llmint8_residual(const int8_t *ca, const float *sca, const int8_t *cb, const float *scb,
+                             const float *bias, void *y_f16, int64_t M, int64_t N, int64_t K,
+                             const void *a_f16, int32_t *col_flags, int keep_flags,
+                             const void *residual_f16, float clamp_abs, wq_stream_t stream);
+
 /* The same Linear8bitLt forward for decode-shaped calls (M <= 64 rows, 64*K + K + 272 <= 200 KiB):
  * activation quantization (threshold rule), int8 products (dp4a), int8_mm_dequant and the outlier
  * side product in ONE launch; bit-identical to wq_quant_i8_rowwise_bnb + wq_gemm_llmint8.

@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwhisperq.so")
+# WQ_LIB_PATH: an alternative build of the same library (A/B experiments with compile-time variants)
+LIB_PATH = os.environ.get("WQ_LIB_PATH") or os.path.join(_HERE, "libwhisperq.so")
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int
@@ -35,6 +36,8 @@ _PROTOS = {
     "wq_gemm_llmint8": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
     "wq_gemm_llmint8_shared": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_int,
                                c_ptr],
+    "wq_gemm_llmint8_residual": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_int,
+                                 c_ptr, c_f32, c_ptr],
     "wq_linear_llmint8_small": [c_ptr, c_i64, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     "wq_gemm_w8a16": [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],
     "wq_gemm_w4a16": [c_ptr, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],

@@ -21,6 +21,12 @@ k_edit_distance(const int32_t *__restrict__ ref, const int64_t *__restrict__ ref
         if (threadIdx.x == 0) dist[p] = nr + nh;
         return;
     }
+    if (nr > ED_MAX || nh > ED_MAX || nr < 0 || nh < 0) {
+        // longer than the shared-memory diagonals (and than uint16 distances): never index past them -- the pair
+        // gets the sentinel -1, which every caller must treat as an error (tally.py refuses such input up front)
+        if (threadIdx.x == 0) dist[p] = -1;
+        return;
+    }
     // diagonal d holds D[i][d - i] at index i
     for (int d = 0; d <= nr + nh; ++d) {
         uint16_t *cur = diag[d % 3];

@@ -81,7 +81,34 @@ struct GemmArgs {
     unsigned long long *argmax_keys;
     const uint8_t *mask;     // [>= tiles_n * tile columns] bytes, or nullptr
     int no_store;            // 1: the outputs themselves are not written (only the arg-max is wanted)
+    // fused residual: out = clamp(round(y) + residual) -- HF's `hidden_states = residual + hidden_states` followed by
+    // the fp16 clamp of WhisperEncoderLayer.forward (modeling_whisper.py:408-414), in the epilogue of fc2
+    const void *residual;    // [M, N] of the output dtype, row pitch ldy, or nullptr
+    float clamp_abs;         // > 0: clamp the sum to [-clamp_abs, clamp_abs]
 };
+
+// v = round_to_OutT(v) + residual (the addition HF performs on the rounded projection), optionally clamped.
+template <typename OutT>
+__device__ __forceinline__ void add_residual_chunk(float (&v)[32], const OutT *res_row, int nb, int N, bool row_ok,
+                                                   float clamp_abs) {
+    if (!row_ok) return;
+    if (nb + 32 <= N) {
+        uint4 raw[32 * sizeof(OutT) / 16];
+#pragma unroll
+        for (int j = 0; j < (int)(32 * sizeof(OutT) / 16); ++j) raw[j] = __ldg(reinterpret_cast<const uint4 *>(res_row + nb) + j);
+        const OutT *r = reinterpret_cast<const OutT *>(raw);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(to_f32(from_f32<OutT>(v[j])), to_f32(r[j]));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (nb + j < N) v[j] = __fadd_rn(to_f32(from_f32<OutT>(v[j])), to_f32(res_row[nb + j]));
+    }
+    if (clamp_abs > 0.0f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -clamp_abs), clamp_abs);
+    }
+}
 
 // Running arg-max of one output row over 32 adjacent columns starting at Y column `n_abs` (a multiple of 32).
 // torch.argmax rules: first index among equal maxima (columns are visited in ascending order, strict >), NaN is the
@@ -308,6 +335,9 @@ __device__ __noinline__ void llmint8_outlier_chunk(const GemmArgs &args, const f
     epi_chunk<BN, EPI_LLMINT8>(r, v, sc, col0, rs, 0.0f, 0);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __half2float(__float2half_rn(v[j])) + o[j];   // fp16 addmm
+    if (args.residual != nullptr)
+        add_residual_chunk<OutT>(v, reinterpret_cast<const OutT *>(args.residual) + (size_t)(row_ok ? m : 0) * args.ldy, n_abs,
+                                 args.N, row_ok, args.clamp_abs);
     emit_chunk<OutT, TMA_STORE>(v, box, cc, lane, row_ptr, n_abs, args.N, row_ok, vec_ok);
 }
 
@@ -422,6 +452,9 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
                                 if (args.argmax_keys != nullptr)
                                     argmax_chunk<OutT>(v, args.mask, nh0 + col0, args.N, best_ord, best_idx);
                             }
+                            if (args.residual != nullptr)
+                                add_residual_chunk<OutT>(v, reinterpret_cast<const OutT *>(args.residual) + (size_t)(row_ok ? m : 0) * args.ldy,
+                                                         nh0 + col0, args.N, row_ok, args.clamp_abs);
                             emit_chunk<OutT, TMA_STORE>(v, box, cc, lane, row_ptr, nh0 + col0, args.N, st_ok, vec_ok);
                         }
                     }
@@ -772,7 +805,10 @@ template <> CUtensorMapDataType out_dtype_enum<__nv_bfloat16>() { return CU_TENS
 template <int BN, int AKIND, int BMODE, int EPI, typename OutT, int WS = 0, int COLS = 0, int LEAN = 0>
 int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cudaStream_t stream) {
     // a resident 256-row W tile (128 KB) leaves room for single store buffers only
-    constexpr int OUT_BUFS = (WS > 0 && COLS) ? 1 : pick_out_bufs<BN, BMODE>();
+#ifndef WQ_LEAN_OUT_BUFS
+#define WQ_LEAN_OUT_BUFS 1     /* measured: 109.6 vs 110.7 ms per bench step with double buffers (smaller CTA beside the attention stream) */
+#endif
+    constexpr int OUT_BUFS = (WS > 0 && COLS) ? 1 : (LEAN ? WQ_LEAN_OUT_BUFS : pick_out_bufs<BN, BMODE>());
     constexpr int STAGES = pick_stages<BN, BMODE, OUT_BUFS, WS, COLS, LEAN>();
     using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS, COLS, LEAN>;
     auto kfn = k_gemm_tc<BN, STAGES, AKIND, BMODE, EPI, OutT, OUT_BUFS, WS, COLS, LEAN>;
@@ -899,6 +935,14 @@ extern "C" int wq_gemm_llmint8(const int8_t *ca, const float *sca, const int8_t 
 extern "C" int wq_gemm_llmint8_shared(const int8_t *ca, const float *sca, const int8_t *cb, const float *scb,
                                       const float *bias, void *y_f16, int64_t M, int64_t N, int64_t K,
                                       const void *a_f16, int32_t *col_flags, int keep_flags, wq_stream_t stream) {
+    return wq_gemm_llmint8_residual(ca, sca, cb, scb, bias, y_f16, M, N, K, a_f16, col_flags, keep_flags, nullptr, 0.0f,
+                                    stream);
+}
+
+extern "C" int wq_gemm_llmint8_residual(const int8_t *ca, const float *sca, const int8_t *cb, const float *scb,
+                                        const float *bias, void *y_f16, int64_t M, int64_t N, int64_t K,
+                                        const void *a_f16, int32_t *col_flags, int keep_flags,
+                                        const void *residual_f16, float clamp_abs, wq_stream_t stream) {
     int rc = check_common("wq_gemm_llmint8", M, N, K);
     if (rc != WQ_OK) return rc;
     if (M == 0 || N == 0) return WQ_OK;
@@ -913,6 +957,10 @@ extern "C" int wq_gemm_llmint8_shared(const int8_t *ca, const float *sca, const 
     args.row_scale = sca; args.col_scale = scb; args.bias = bias; args.out = y_f16;
     args.ca = ca; args.cb = cb; args.a16 = (const __half *)a_f16; args.flags = col_flags;
     args.keep_flags = keep_flags ? 1 : 0;
+    WQ_REQUIRE(residual_f16 == nullptr || (wq_aligned(residual_f16, 16) && N % 8 == 0),
+               "wq_gemm_llmint8: the residual needs 16-byte aligned rows (N %% 8 == 0)");
+    WQ_REQUIRE(clamp_abs >= 0.0f, "wq_gemm_llmint8: negative clamp");
+    args.residual = residual_f16; args.clamp_abs = clamp_abs;
     return launch_i8<A_S8, EPI_LLMINT8, __half>(ca, cb, args, s);
 }
 

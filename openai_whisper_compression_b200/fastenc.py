@@ -99,9 +99,13 @@ def _layer_forward_int8(self, hidden_states, attention_mask=None, **kwargs):
     ln = self.final_layer_norm
     x, h, qt = F.add_layernorm_quant(x, att, ln.weight, ln.bias, ln.eps, thr)
     g, qt = F.gelu_quant(fused.gemm(qt, h, plan.fc1), thr)
+    clamp_value = torch.finfo(torch.float16).max - 1000
+    if plan.qkv.kind == "int8":
+        # residual add + fp16 clamp in the fc2 GEMM's epilogue (bit-identical to the two torch kernels they replace)
+        out = fused.gemm_int8(qt, g, plan.fc2, residual=x, clamp_abs=float(clamp_value))
+        return out.view(B, S, d)
     out = x + fused.gemm(qt, g, plan.fc2)
     if out.dtype == torch.float16:      # HF clamps fp16 activations only
-        clamp_value = torch.finfo(torch.float16).max - 1000
         out = torch.clamp(out, min=-clamp_value, max=clamp_value)
     return out.view(B, S, d)
 

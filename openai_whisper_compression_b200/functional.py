@@ -270,11 +270,13 @@ def int8_vectorwise_quant(a: torch.Tensor, threshold: float = 0.0, state: Option
 def gemm_llmint8(ca: torch.Tensor, sca: torch.Tensor, cb: torch.Tensor, scb: torch.Tensor,
                  bias: Optional[torch.Tensor] = None, a_f16: Optional[torch.Tensor] = None,
                  state: Optional[OutlierState] = None, out: Optional[torch.Tensor] = None,
-                 keep_flags: bool = False) -> torch.Tensor:
+                 keep_flags: bool = False, residual: Optional[torch.Tensor] = None,
+                 clamp_abs: float = 0.0) -> torch.Tensor:
     """int8_linear_matmul + int8_mm_dequant (+ mixed-precision outlier decomposition when `state`
     carries raw flags from int8_vectorwise_quant(..., finalize=False)), one kernel; fp16 [M, N].
     out: optional contiguous fp16 [M, N] destination.  keep_flags: leave the outlier flags set because
-    another GEMM consumes the same quantized rows next (the last consumer clears them)."""
+    another GEMM consumes the same quantized rows next (the last consumer clears them).  residual / clamp_abs: the
+    layer's residual connection in the epilogue, y = clamp(fp16(linear) + residual) (fc2 of a Whisper layer)."""
     ca2 = ca.reshape(-1, ca.shape[-1])
     _need_cuda(ca2, sca, cb, scb, bias, a_f16)
     M, K = ca2.shape
@@ -290,11 +292,16 @@ def gemm_llmint8(ca: torch.Tensor, sca: torch.Tensor, cb: torch.Tensor, scb: tor
             raise RuntimeError("gemm_llmint8: bias must be fp16 (or its exact fp32 widening)")
         bias = bias.float()          # exact; modules pass a cached fp32 copy instead
     with torch.cuda.device(ca.device), _Timed("llmint8", M, N, K):
-        _lib.check(_lib.load().wq_gemm_llmint8_shared(
+        if residual is not None:
+            residual = residual.reshape(M, N)
+            _need_cuda(residual)
+            if residual.dtype != torch.float16:
+                raise RuntimeError("gemm_llmint8: the residual must be fp16 [M, N]")
+        _lib.check(_lib.load().wq_gemm_llmint8_residual(
             _ptr(ca2), _ptr(sca), _ptr(cb), _ptr(scb), _ptr(bias), _ptr(y), M, N, K,
             _ptr(a_f16) if state is not None else None,
-            _ptr(state.col_flags) if state is not None else None, 1 if keep_flags else 0, _stream()),
-            "wq_gemm_llmint8")
+            _ptr(state.col_flags) if state is not None else None, 1 if keep_flags else 0, _ptr(residual),
+            float(clamp_abs), _stream()), "wq_gemm_llmint8")
     STATS.launches += 1
     return y
 

@@ -125,12 +125,12 @@ def pack(mods: Sequence[torch.nn.Module], dtype: torch.dtype) -> Optional[Packed
 
 
 def gemm_int8(quant, a: torch.Tensor, w: Packed, out: Optional[torch.Tensor] = None,
-              keep_flags: bool = False) -> torch.Tensor:
+              keep_flags: bool = False, residual: Optional[torch.Tensor] = None, clamp_abs: float = 0.0) -> torch.Tensor:
     """Linear8bitLt's GEMM on rows that are already quantized: quant = (CA, SCA, outlier state) from a fused
     producer, `a` the fp16 rows they were made from (read only for outlier columns)."""
     ca, sca, state = quant
     return F.gemm_llmint8(ca, sca, w.cb, w.scb, w.bias, a if state is not None else None, state, out=out,
-                          keep_flags=keep_flags)
+                          keep_flags=keep_flags, residual=residual, clamp_abs=clamp_abs)
 
 
 def gemm(quant, a: torch.Tensor, w: Packed, out: Optional[torch.Tensor] = None, keep_flags: bool = False) -> torch.Tensor:

@@ -58,7 +58,7 @@ def tally_on_device(references: Sequence[str], predictions: Sequence[str], devic
     ids_d = torch.from_numpy(ids).to(dev)
     off_d = torch.from_numpy(off).to(dev)
     d = F.edit_distance(ids_d[:n_ref], off_d[:2 * P + 1], ids_d[n_ref:], off_d[2 * P + 1:])
-    errs = d.view(2, P).sum(1)
+    errs = d.view(2, P).sum(1)       # (the kernel's -1 sentinel for over-long pairs cannot occur: _host_pack refuses them)
     out = torch.tensor([0, n_rw, 0, n_rc], dtype=torch.int64).to(dev)
     out[0::2] = errs
     return out
@@ -91,10 +91,17 @@ class _Metric:
         self.name = name
 
     def compute(self, references: List[str], predictions: List[str]) -> float:
+        # evaluate's wer / cer hand the strings to jiwer, whose default transforms strip the ends and collapse runs
+        # of white space (wer: then split on spaces; cer: characters of the cleaned string), and jiwer refuses an
+        # empty reference
+        references = [" ".join(str(r).split()) for r in references]
+        predictions = [" ".join(str(p).split()) for p in predictions]
+        if any(len(r) == 0 for r in references):
+            raise ValueError("one or more references are empty strings")
         dev = torch.device("cuda", torch.cuda.current_device())
         t = tally_on_device(references, predictions, dev).tolist()
         num, den = (t[0], t[1]) if self.name == "wer" else (t[2], t[3])
-        return num / max(den, 1)
+        return num / den
 
 
 def load_metric(name: str, *a, **k) -> _Metric:

@@ -267,7 +267,20 @@ def test_tally_matches_oracle(pkg):
     t = tally.tally_on_device(refs, hyps, "cuda").cpu().numpy()
     np.testing.assert_array_equal(t, oracle.wer_cer_tally(refs, hyps))
     m = tally.load_metric("wer")
-    assert abs(m.compute(references=refs, predictions=hyps) - t[0] / t[1]) < 1e-12
+    with pytest.raises(ValueError):                      # jiwer refuses empty references; so does the shim
+        m.compute(references=refs, predictions=hyps)
+    refs2, hyps2 = [r for r in refs if r], [h for r, h in zip(refs, hyps) if r]
+    t2 = oracle.wer_cer_tally(refs2, hyps2)
+    assert abs(m.compute(references=refs2, predictions=hyps2) - t2[0] / t2[1]) < 1e-12
+    # jiwer's default transforms: ends stripped, runs of white space collapsed -- for WER and CER alike
+    messy_r, messy_h = ["  the  cat sat ", "a\tb  c"], ["the cat   sat", " a b c  "]
+    assert m.compute(references=messy_r, predictions=messy_h) == 0.0
+    assert tally.load_metric("cer").compute(references=messy_r, predictions=messy_h) == 0.0
+    # the C ABI guards its shared-memory diagonals: an over-long pair gets the sentinel -1, nothing is overrun
+    from openai_whisper_compression_b200 import functional as F
+    big = torch.zeros(5000, dtype=torch.int32, device="cuda")
+    off = torch.tensor([0, 5000], dtype=torch.int64, device="cuda")
+    assert int(F.edit_distance(big, off, big, off)[0]) == -1
 
 
 REAL2 = dict(encoder_layers=2, decoder_layers=2)      # whisper-tiny geometry (d = 384, 6 heads x 64), 2 + 2 layers
