@@ -215,9 +215,12 @@ _W_BYTES = {"llmint8": 1.0, "dyn_i8": 1.0, "w8a16": 1.0, "wf8a16": 1.0, "w8a8": 
 
 
 def gemm_algorithmic(kind, M, N, K):
+    res = kind.endswith("+res")          # the launch also reads the fp16 residual [M, N] (fused residual add, fc2)
+    kind = kind.replace("+res", "")
     a_bytes = 1 if kind in ("llmint8", "dyn_i8", "w8a8") else 2
     o_bytes = 4 if kind == "dyn_i8" else 2
-    return M * K * a_bytes + N * K * _W_BYTES[kind] + M * N * o_bytes + 4 * (M + N), 2.0 * M * N * K
+    return (M * K * a_bytes + N * K * _W_BYTES[kind] + M * N * o_bytes + 4 * (M + N) + (M * N * 2 if res else 0),
+            2.0 * M * N * K)
 
 
 def encoder_gemm_roofline(records, peaks, ms_dev):
@@ -258,7 +261,7 @@ def encoder_gemm_roofline(records, peaks, ms_dev):
                 break
     gbs = tot_bytes / tot_time / 1e9
     tfs = tot_flops / tot_time / 1e12
-    int8_kind = all(k[0] in ("llmint8", "dyn_i8") for k in by_shape)
+    int8_kind = all(k[0].replace("+res", "") in ("llmint8", "dyn_i8", "w8a8") for k in by_shape)
     # which roof binds: arithmetic intensity of the launches against the measured ridge
     # (int8 tensor peak taken as 2x the measured bf16 peak: same pipe, half the operand bytes)
     tensor_peak = peaks["bf16_tflops"] * (2.0 if int8_kind else 1.0)

@@ -81,7 +81,7 @@ class GraphedGreedy:
         # step is a ~75 us chain of short dependent launches followed by a cross-attention pass that streams the
         # cached K/V at the HBM rate; with 4 groups a group's chain hides under the other groups' streams
         self.streams = int(os.environ.get("WQ_DECODE_STREAMS", "4"))
-        self.min_rows_per_stream = 32
+        self.min_rows_per_stream = int(os.environ.get("WQ_DECODE_MIN_ROWS", "16"))
         # out_proj's int8 rows written by the cross-attention kernel itself (its finisher warp) or by a separate
         # quantizer launch (WQ_CROSS_QUANT_INLINE=0)
         self.cross_quant_inline = os.environ.get("WQ_CROSS_QUANT_INLINE", "1") != "0"

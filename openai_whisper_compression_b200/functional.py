@@ -291,7 +291,7 @@ def gemm_llmint8(ca: torch.Tensor, sca: torch.Tensor, cb: torch.Tensor, scb: tor
         if bias.dtype != torch.float16:
             raise RuntimeError("gemm_llmint8: bias must be fp16 (or its exact fp32 widening)")
         bias = bias.float()          # exact; modules pass a cached fp32 copy instead
-    with torch.cuda.device(ca.device), _Timed("llmint8", M, N, K):
+    with torch.cuda.device(ca.device), _Timed("llmint8+res" if residual is not None else "llmint8", M, N, K):
         if residual is not None:
             residual = residual.reshape(M, N)
             _need_cuda(residual)
