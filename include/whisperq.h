@@ -281,6 +281,56 @@ int wq_cross_attn_decode(const void *q, int64_t ldq, int dtype, float scaling, c
                          int64_t ld, int64_t B, int64_t S, int H, void *out, float threshold, int8_t *ca,
                          float *row_stats, int32_t *col_flags, int32_t *row_counters, wq_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * One persistent kernel for everything a WhisperDecoderLayer (bitsandbytes LLM.int8 linears, fp16) does to ONE new
+ * token per utterance between two cross-attention passes (transformers modeling_whisper.py:458-520, reached from
+ * data_utils.py:152 through generate): `run_after` = cross out_proj + residual, LayerNorm, fc1, GELU, fc2 + residual of
+ * layer `after`; `run_before` = LayerNorm, q|k|v, self-attention over the KV cache (appending this token), out_proj +
+ * residual, LayerNorm, cross q_proj of layer `before`; `run_final` = the decoder's closing LayerNorm.  Phases are
+ * separated by a grid-wide barrier; arithmetic is that of wq_add_layernorm_quant, wq_linear_llmint8_small,
+ * wq_self_attn_decode and wq_gelu_quant, operation by operation (bit-identical results).  At most 64 rows per call.
+ * All pointers are device pointers; q|k|v and [k;v] weights are concatenated along N.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    const int8_t *cb;        /* int8 [N, K] */
+    const float *scb;        /* fp32 [N] row absmax of the weight */
+    const float *bias;       /* fp32 [N] (exact widening of the fp16 bias) or NULL */
+    int N, K;
+} wq_decode_linear;
+
+typedef struct {
+    wq_decode_linear qkv, o, cq, co, fc1, fc2;
+    const void *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;   /* fp16 [d]: self_attn / encoder_attn / final LayerNorm */
+    float eps1, eps2, eps3;
+    void *kcache, *vcache;   /* fp16 [rows, t_max, d] self-attention cache of the rows this call serves */
+} wq_decode_layer;
+
+typedef struct {
+    int M, d, ffn, H, t_max;
+    float threshold, scaling;
+    const int64_t *pos;      /* device scalar: position of the token being decoded */
+    void *x;                 /* fp16 [M, d] residual stream, updated in place */
+    void *h, *att, *qkv, *f1, *g;          /* fp16 scratch: [M, d], [M, d], [M, 3d], [M, ffn], [M, ffn] */
+    int8_t *ca_d, *ca_f;     /* int8 scratch: [3][M, d], [M, ffn] */
+    float *sca;              /* fp32 scratch [4][M] */
+    int32_t *flags;          /* int32 scratch [4][max(d, ffn) + 2] */
+    void *q_out;             /* fp16 [M, d]: query rows for the next cross-attention (run_before) */
+    const void *xa;          /* fp16 [M, d]: cross-attention output (run_after) ... */
+    const int8_t *xa_ca;     /* ... its int8 rows, row absmax and outlier flags (wq_cross_attn_decode) */
+    const float *xa_sca;
+    int32_t *xa_flags;       /* [d + 2] or NULL; cleared after use */
+    const void *lnf_g, *lnf_b;
+    float epsf;
+    void *hfinal;            /* fp16 [M, d] (run_final) */
+    unsigned *bar;           /* uint32 [2], zero before the first call: grid barrier state */
+} wq_decode_args;
+
+/* max_ctas: upper bound of the grid (all CTAs must be resident at once; with g row groups decoding on g streams at the
+ * same time pass at most 296 / g). */
+int wq_decode_fused_llmint8(const wq_decode_layer *after, const wq_decode_layer *before,
+                            const wq_decode_args *args, int run_after, int run_before, int run_final,
+                            int max_ctas, wq_stream_t stream);
+
 /* Greedy token choice for `rows` utterances: out[r] = argmax_c (mask[c] ? -inf : logits[r*ld + c]),
  * torch.argmax semantics (first index among equal maxima; NaN is the maximum).  mask: uint8/bool [cols] or
  * NULL.  Replaces masked_fill + argmax over the [B, vocab] logits between decode steps (the Whisper logits

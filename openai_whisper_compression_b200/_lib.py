@@ -50,6 +50,7 @@ _PROTOS = {
                             c_ptr, c_f32, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_cross_attn_decode": [c_ptr, c_i64, c_int, c_f32, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_ptr, c_f32,
                              c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    "wq_decode_fused_llmint8": [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
     "wq_masked_argmax": [c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
     "wq_quant_f8_rowwise_quanto": [c_ptr, c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
     "wq_gemm_wf8a16": [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],
@@ -62,6 +63,26 @@ _PROTOS = {
     "wq_edit_distance": [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr],
 }
 EXPORTS = tuple(["wq_last_error", *_PROTOS.keys()])
+
+
+class DecodeLinear(ctypes.Structure):       # wq_decode_linear
+    _fields_ = [("cb", c_ptr), ("scb", c_ptr), ("bias", c_ptr), ("N", c_int), ("K", c_int)]
+
+
+class DecodeLayer(ctypes.Structure):        # wq_decode_layer
+    _fields_ = [("qkv", DecodeLinear), ("o", DecodeLinear), ("cq", DecodeLinear), ("co", DecodeLinear),
+                ("fc1", DecodeLinear), ("fc2", DecodeLinear),
+                ("ln1_g", c_ptr), ("ln1_b", c_ptr), ("ln2_g", c_ptr), ("ln2_b", c_ptr), ("ln3_g", c_ptr), ("ln3_b", c_ptr),
+                ("eps1", c_f32), ("eps2", c_f32), ("eps3", c_f32), ("kcache", c_ptr), ("vcache", c_ptr)]
+
+
+class DecodeArgs(ctypes.Structure):         # wq_decode_args
+    _fields_ = [("M", c_int), ("d", c_int), ("ffn", c_int), ("H", c_int), ("t_max", c_int),
+                ("threshold", c_f32), ("scaling", c_f32), ("pos", c_ptr), ("x", c_ptr),
+                ("h", c_ptr), ("att", c_ptr), ("qkv", c_ptr), ("f1", c_ptr), ("g", c_ptr),
+                ("ca_d", c_ptr), ("ca_f", c_ptr), ("sca", c_ptr), ("flags", c_ptr), ("q_out", c_ptr),
+                ("xa", c_ptr), ("xa_ca", c_ptr), ("xa_sca", c_ptr), ("xa_flags", c_ptr),
+                ("lnf_g", c_ptr), ("lnf_b", c_ptr), ("epsf", c_f32), ("hfinal", c_ptr), ("bar", c_ptr)]
 
 _lib = None
 

@@ -26,7 +26,7 @@ from typing import Dict, Tuple
 import torch
 import torch.nn.functional as TF
 
-from . import fastenc, fused
+from . import _lib, fastenc, fused
 from . import functional as F
 
 
@@ -85,6 +85,11 @@ class GraphedGreedy:
         # out_proj's int8 rows written by the cross-attention kernel itself (its finisher warp) or by a separate
         # quantizer launch (WQ_CROSS_QUANT_INLINE=0)
         self.cross_quant_inline = os.environ.get("WQ_CROSS_QUANT_INLINE", "1") != "0"
+        # persistent decoder-layer kernel (decode_fused.cu): one launch between two cross-attention passes instead of
+        # twelve.  Bit-identical to the chain and OFF by default: measured SLOWER (64 rows, whisper-base: 153 us per
+        # launch against ~50 us for the twelve PDL-chained launches it replaces; 146 vs 108 ms per bench step) -- eleven
+        # grid barriers and eleven dependent L2 round trips cost more than programmatic dependent launch already hides
+        self.mega = os.environ.get("WQ_DECODE_FUSED", "0") == "1"
         self.time_loop = False         # bench.py: CUDA events around the token loop of every generate call
         self.loop_events = []          # (start, end, replays)
         self.replays = 0
@@ -218,8 +223,9 @@ class GraphedGreedy:
     def _decoder_step(self, st: _State):
         """One token for every utterance: reads st.tok / st.pos, writes st.logits / st.next."""
         if st.fused is not None:
+            step = self._decoder_step_mega if st.mega else self._decoder_step_int8
             if len(st.views) == 1:
-                return self._decoder_step_int8(st, st.views[0])
+                return step(st, st.views[0])
             # several row groups of the batch on as many streams: a group's launch-bound chain (LayerNorm, decode-
             # shaped GEMMs, self-attention) runs under the HBM-bound cross-attention stream of another group.  Under
             # capture the fork / join become graph dependencies; each group has its own outlier / counter scratch.
@@ -227,10 +233,10 @@ class GraphedGreedy:
             for v in st.views[1:]:
                 v.stream.wait_stream(cur)
             with F.scratch_slot(st.views[0].slot):
-                self._decoder_step_int8(st, st.views[0], project=False)
+                step(st, st.views[0], project=False)
             for v in st.views[1:]:
                 with torch.cuda.stream(v.stream), F.scratch_slot(v.slot):
-                    self._decoder_step_int8(st, v, project=False)
+                    step(st, v, project=False)
             for v in st.views[1:]:
                 cur.wait_stream(v.stream)
             # one vocabulary projection for the whole batch (the 53 MB weight is streamed once per token)
@@ -346,6 +352,85 @@ class GraphedGreedy:
         _, h, _ = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, None)
         self._project(st, v, h)
 
+    # ------------------------------------------------------------------------------------------
+    # persistent decoder-layer kernel (decode_fused.cu): one launch between two cross-attention passes
+    # ------------------------------------------------------------------------------------------
+    def _plan_mega(self, st: _State, dtype) -> bool:
+        """Scratch and weight-pointer tables for the persistent per-layer kernel, per row group; False when it does not
+        apply (LLM.int8 / fp16 only, <= 64 rows per group, d_model <= 1280)."""
+        if (not self.mega or st.fused is None or st.threshold is None or dtype != torch.float16 or not st.own_attn
+                or not st.own_cross or st.d > 1280 or any(v.B > 64 for v in st.views)):
+            return False
+        cfg = self.model.config
+        ffn = cfg.decoder_ffn_dim
+        if ffn % 16 != 0 or st.fused[0].qkv.kind != "int8":
+            return False
+        dec = self.model.model.decoder
+        dev = st.tok.device
+        fl = max(st.d, ffn) + 2
+
+        def lin(w):
+            return _lib.DecodeLinear(w.cb.data_ptr(), w.scb.data_ptr(), 0 if w.bias is None else w.bias.data_ptr(),
+                                     int(w.out_features), int(w.in_features))
+
+        for v in st.views:
+            M, d = v.B, st.d
+            z = lambda *shape, dt=torch.float16: torch.zeros(shape, dtype=dt, device=dev)
+            v.m = _State()
+            v.m.x, v.m.h, v.m.att, v.m.q = z(M, d), z(M, d), z(M, d), z(M, d)
+            v.m.qkv, v.m.f1, v.m.g = z(M, 3 * d), z(M, ffn), z(M, ffn)
+            v.m.ca_d, v.m.ca_f = z(3, M, d, dt=torch.int8), z(M, ffn, dt=torch.int8)
+            v.m.sca, v.m.flags = z(4, M, dt=torch.float32), z(4, fl, dt=torch.int32)
+            v.m.bar = z(2, dt=torch.int32)
+            v.m.hfin = st.hfinal[v.r0:v.r1] if st.hfinal is not None else z(M, d)
+            v.m.layers = []
+            for li, (layer, fw) in enumerate(zip(dec.layers, st.fused)):
+                L = _lib.DecodeLayer()
+                L.qkv, L.o, L.cq, L.co, L.fc1, L.fc2 = lin(fw.qkv), lin(fw.o), lin(fw.cq), lin(fw.co), lin(fw.fc1), lin(fw.fc2)
+                n1, n2, n3 = layer.self_attn_layer_norm, layer.encoder_attn_layer_norm, layer.final_layer_norm
+                L.ln1_g, L.ln1_b, L.eps1 = n1.weight.data_ptr(), n1.bias.data_ptr(), float(n1.eps)
+                L.ln2_g, L.ln2_b, L.eps2 = n2.weight.data_ptr(), n2.bias.data_ptr(), float(n2.eps)
+                L.ln3_g, L.ln3_b, L.eps3 = n3.weight.data_ptr(), n3.bias.data_ptr(), float(n3.eps)
+                L.kcache, L.vcache = v.k[li].data_ptr(), v.v[li].data_ptr()
+                v.m.layers.append(L)
+        st.mega_ctas = max(8, min(128, 280 // len(st.views)))
+        st.mega_ffn = ffn
+        return True
+
+    def _mega_args(self, st: _State, v: _State, xa=None):
+        m, dec = v.m, self.model.model.decoder
+        a = _lib.DecodeArgs()
+        a.M, a.d, a.ffn, a.H, a.t_max = v.B, st.d, st.mega_ffn, st.H, st.k[0].shape[1]
+        a.threshold, a.scaling = float(st.threshold), float(st.fused[0].scaling)
+        a.pos, a.x = st.pos.data_ptr(), m.x.data_ptr()
+        a.h, a.att, a.qkv, a.f1, a.g = (t.data_ptr() for t in (m.h, m.att, m.qkv, m.f1, m.g))
+        a.ca_d, a.ca_f, a.sca, a.flags = m.ca_d.data_ptr(), m.ca_f.data_ptr(), m.sca.data_ptr(), m.flags.data_ptr()
+        a.q_out, a.bar = m.q.data_ptr(), m.bar.data_ptr()
+        if xa is not None:
+            out, (ca, sca, state) = xa
+            a.xa, a.xa_ca, a.xa_sca = out.data_ptr(), ca.data_ptr(), sca.data_ptr()
+            a.xa_flags = 0 if state is None else state.col_flags.data_ptr()
+        ln = dec.layer_norm
+        a.lnf_g, a.lnf_b, a.epsf, a.hfinal = ln.weight.data_ptr(), ln.bias.data_ptr(), float(ln.eps), m.hfin.data_ptr()
+        return a
+
+    def _decoder_step_mega(self, st: _State, v: _State, project: bool = True):
+        """The fused LLM.int8 step with ONE persistent launch between consecutive cross-attention passes (the part of
+        layer l after its cross-attention and the part of layer l + 1 before its own, decode_fused.cu) instead of
+        twelve: L + 1 fused launches and L attention launches per token.  Same arithmetic as _decoder_step_int8."""
+        dec = self.model.model.decoder
+        d, H, thr = st.d, st.H, st.threshold
+        torch.add(dec.embed_tokens(v.tok).view(v.B, d), dec.embed_positions.weight.index_select(0, st.pos), out=v.m.x)
+        layers = v.m.layers
+        xa = None
+        for li in range(len(layers)):
+            F.decode_fused_llmint8(layers[li - 1] if li else None, layers[li], self._mega_args(st, v, xa), li > 0, True,
+                                   False, st.mega_ctas)
+            xa = F.cross_attn_decode(v.m.q, v.ckv[li][:, :, :d], v.ckv[li][:, :, d:], st.fused[li].scaling, H, thr)
+        F.decode_fused_llmint8(layers[-1], None, self._mega_args(st, v, xa), True, False, True, st.mega_ctas)
+        if project:
+            self._project(st, v, v.m.hfin)
+
     def _plan_int8(self, dtype):
         """Per-layer packed weights for the fused decode step, or None when the decoder's linears are not all drop-in
         modules of ONE scheme that fused.pack serves for `dtype` (LLM.int8 with fp16 activations; W8A16 / NF4 / FP4 /
@@ -421,7 +506,7 @@ class GraphedGreedy:
     def _get_state(self, B: int, t_max: int, dtype: torch.dtype, device, store_logits: bool = True) -> _State:
         fp = self._fingerprint()
         key = (B, t_max, dtype, torch.device(device).index, bool(store_logits), self.cross_attention, self.streams,
-               self.cross_quant_inline)
+               self.cross_quant_inline, self.mega, self.min_rows_per_stream)
         st = self._states.get(key)
         if st is not None and st.fingerprint == fp:
             return st
@@ -496,6 +581,7 @@ class GraphedGreedy:
                 st.whole = v
             else:
                 st.views.append(v)
+        st.mega = self._plan_mega(st, dtype)
         # warm up on a side stream (lazy inits, autotuning), then capture
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))

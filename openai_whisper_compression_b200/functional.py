@@ -458,6 +458,19 @@ def cross_attn_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scaling
     return out, (None if threshold is None else (ca, sca, state))
 
 
+def decode_fused_llmint8(after, before, args, run_after: bool, run_before: bool, run_final: bool, max_ctas: int) -> None:
+    """One launch of the persistent decoder-layer kernel (decode_fused.cu).  after / before: _lib.DecodeLayer or None;
+    args: _lib.DecodeArgs (the caller keeps every tensor behind the pointers alive)."""
+    import ctypes
+    dev = torch.cuda.current_device()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().wq_decode_fused_llmint8(
+            None if after is None else ctypes.byref(after), None if before is None else ctypes.byref(before),
+            ctypes.byref(args), int(run_after), int(run_before), int(run_final), int(max_ctas), _stream()),
+            "wq_decode_fused_llmint8")
+    STATS.launches += 1
+
+
 def masked_argmax(logits: torch.Tensor, mask: Optional[torch.Tensor] = None,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """argmax over the last dim of [B, V] fp16/bf16 logits (unit column stride, any 16-byte aligned row

@@ -555,3 +555,41 @@ def test_fused_int8_encoder_layer_is_bit_identical_to_module_calls(pkg):
     assert torch.isfinite(full).all()
     diff = (full.float() - hf.float()).abs()
     assert diff.max().item() <= 0.15 and diff.mean().item() <= 1e-2, (diff.max().item(), diff.mean().item())
+
+
+@pytest.mark.parametrize("B,streams", [(6, 1), (70, 2), (64, 4)])
+def test_persistent_decoder_layer_kernel_is_bit_identical_to_the_launch_chain(pkg, B, streams):
+    """decode_fused.cu (one persistent launch between two cross-attention passes: LayerNorm+quant, int8 GEMMs with
+    dp4a, self-attention over the cache, GELU+quant, residual adds, phases separated by a grid barrier; opt-in, it
+    measured slower than the chain) must give exactly the logits, greedy ids and KV caches of the twelve-launch chain
+    (_decoder_step_int8), with outlier columns in play, for one row group and for several on several streams."""
+    from openai_whisper_compression_b200 import fastgen, harness
+    model = harness.apply_scheme(harness.build_model("tiny", **REAL2), "llm_int8", "cuda")
+    with torch.no_grad():        # loud channels so that the outlier decomposition is exercised in every phase
+        for m in model.modules():
+            if isinstance(m, torch.nn.LayerNorm):
+                m.weight[::41] *= 6.0
+    feats = _feats(n=B, frames=3000).half().cuda()
+    eng = fastgen.enable(model)
+    eng.keep_logits, eng.streams = True, streams
+    T = 10
+    outs = {}
+    for mega in (False, True):
+        eng.mega = mega
+        ids = harness.greedy_generate(model, feats, T)
+        st = [s for s in eng._states.values() if s.mega == mega][-1]
+        assert st.mega == mega and len(st.views) == streams
+        start = torch.full((B, 1), model.config.decoder_start_token_id, dtype=ids.dtype, device="cuda")
+        full = ids if ids.shape[1] == T + 1 else torch.cat([start, ids], 1)
+        logits = []
+        for j in range(T):
+            st.tok.copy_(full[:, j:j + 1])
+            st.pos.fill_(j)
+            st.graph.replay()
+            logits.append(st.logits.clone())
+        outs[mega] = (ids, torch.stack(logits), [k.clone() for k in st.k], [v.clone() for v in st.v])
+    assert torch.equal(outs[True][0], outs[False][0])
+    assert torch.equal(outs[True][1], outs[False][1])
+    for a, b in zip(outs[True][2] + outs[True][3], outs[False][2] + outs[False][3]):
+        assert torch.equal(a[:, :T], b[:, :T])
+    assert (outs[True][1].float().abs() > 0).any()
