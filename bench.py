@@ -515,26 +515,6 @@ def run_config(wl: Workload, K: int, W: int, world: int, rank: int, peaks, with_
         done[0].record(); done[1].record()
         issue_copy(0)
 
-    # The transcript work of step i (ids -> text on the host, WER/CER tally: one edit-distance launch + the all-reduce)
-    # runs on a worker thread while the main thread drives step i + 1 (whose host side mostly waits for the GPU); the
-    # timed region ends only when the last step's tally is back on the host.
-    import concurrent.futures as cf
-    pool = cf.ThreadPoolExecutor(max_workers=1)
-    ids_bufs = [wl.ids_host, torch.empty_like(wl.ids_host).pin_memory()]
-    pending = {"f": None, "t": None}
-
-    def transcript_tally(ids_cpu):
-        torch.cuda.set_device(dev)
-        hyps = wl.proc.batch_decode(ids_cpu)
-        t = tally.all_reduce_tally(tally.tally_on_device(wl.refs, hyps, dev))
-        return t.cpu()
-
-    def e2e_drain():
-        if pending["f"] is not None:
-            pending["t"] = pending["f"].result()
-            pending["f"] = None
-        return pending["t"]
-
     def step_e2e():
         i = e2e_state["i"]
         e2e_state["i"] = i + 1
@@ -543,12 +523,12 @@ def run_config(wl: Workload, K: int, W: int, world: int, rank: int, peaks, with_
         torch.cuda.current_stream().wait_event(ready[i % 2])
         ids = wl.hot_path(bufs[i % 2])
         done[i % 2].record()
-        out = ids_bufs[i % 2][:, :ids.shape[1]]
+        out = wl.ids_host[:, :ids.shape[1]]
         out.copy_(ids, non_blocking=True)                        # D2H of the result
         torch.cuda.current_stream().synchronize()
-        e2e_drain()                                              # step i - 1's tally (finished long ago)
-        pending["f"] = pool.submit(transcript_tally, out)
-        return ids
+        hyps = wl.proc.batch_decode(out)
+        t = tally.all_reduce_tally(tally.tally_on_device(wl.refs, hyps, dev))
+        return ids, t.cpu()
 
     def barrier():
         if world > 1:
@@ -568,7 +548,6 @@ def run_config(wl: Workload, K: int, W: int, world: int, rank: int, peaks, with_
         e2e_begin()
         for _ in range(max(1, min(W, 2))):
             step_e2e()
-        e2e_drain()
     if sampler is not None:
         sampler.start()
 
@@ -601,9 +580,7 @@ def run_config(wl: Workload, K: int, W: int, world: int, rank: int, peaks, with_
         e0.record()
         e2e_begin()                                                  # first copy is inside the timed region
         for _ in range(K):
-            ids = step_e2e()
-        t = e2e_drain()                                              # the last step's transcripts are tallied
-        torch.cuda.synchronize()
+            ids, t = step_e2e()
         e1.record()
         barrier()
         res["ms_e2e"] = max_over_ranks(e0.elapsed_time(e1))
@@ -618,7 +595,6 @@ def run_config(wl: Workload, K: int, W: int, world: int, rank: int, peaks, with_
         tc = token_check(wl, ids, tol)
         if rank == 0:
             res["token_check"] = tc
-    pool.shutdown(wait=True)
     del bufs, flush_buf
     return res
 
@@ -731,9 +707,7 @@ def run_ours(args):
         "e2e": {"value": total_audio / (ms_e2e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": B * N_SAMPLES * 4, "d2h_bytes_per_step": r["d2h_bytes"],
                 "note": "per step: pinned-host audio H2D (prefetched one step ahead on a copy stream), log-mel, "
-                        "model.generate, ids D2H, decode to text, WER/CER tally on the GPU (+ all-reduce); the "
-                        "transcript work of a step runs on a worker thread under the next step, the timed region ends "
-                        "when the last tally is back on the host"},
+                        "model.generate, ids D2H, decode to text, WER/CER tally on the GPU (+ all-reduce)"},
         "gpu_launches": r["launches"], "clocks": clocks, "roofline": roofline,
         "token_check": r.get("token_check"), "tally": r.get("tally"), "extra_configs": extra,
     }

@@ -18,8 +18,8 @@ timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_cr
 timeout 600 ncu --set full --clock-control none -k regex:k_cross_attn_decode_tma -s 30 -c 1 -f -o $O/r02_ncu_xattn_quant python scripts/xattn_tune.py >> $O/r02_ncu_xattn.log 2>&1
 # encoder-shaped GEMMs of one timed step + the projection GEMM with the fused arg-max + lean decode tiles
 timeout 900 ncu --nvtx --nvtx-include "wq_timed/" --set full --clock-control none -k regex:k_gemm_tc -c 31 -f -o $O/r02_ncu_gemm $BENCH > $O/r02_ncu_gemm.log 2>&1
-timeout 900 ncu --nvtx --nvtx-include "wq_timed/" --set full --clock-control none --kernel-name-base demangled -k "regex:k_gemm_tc<128, 3, 0, 0, 4" -c 1 -f -o $O/r02_ncu_proj $BENCH >> $O/r02_ncu_gemm.log 2>&1
-timeout 900 ncu --nvtx --nvtx-include "wq_timed/" --set full --clock-control none --kernel-name-base demangled -k "regex:k_gemm_tc<64, [0-9], 2, 0, 0" -c 6 -f -o $O/r02_ncu_lean $BENCH >> $O/r02_ncu_gemm.log 2>&1
+timeout 900 ncu --nvtx --nvtx-include "wq_timed/" --set full --clock-control none --kernel-name-base demangled -k "regex:k_gemm_tc<.int.128, .int.3, .int.0, .int.0, .int.4" -c 1 -f -o $O/r02_ncu_proj $BENCH >> $O/r02_ncu_gemm.log 2>&1
+timeout 900 ncu --nvtx --nvtx-include "wq_timed/" --set full --clock-control none --kernel-name-base demangled -k "regex:k_gemm_tc<.int.64, .int.[0-9], .int.2, .int.0, .int.0, __half, .int.1, .int.0, .int.0, .int.1" -c 6 -f -o $O/r02_ncu_lean $BENCH >> $O/r02_ncu_gemm.log 2>&1
 for r in r02_ncu_xattn r02_ncu_xattn_quant r02_ncu_gemm r02_ncu_proj r02_ncu_lean; do
     [ -f $O/$r.ncu-rep ] && ncu -i $O/$r.ncu-rep --page raw --csv > $O/${r}_raw.csv 2>/dev/null
 done
