@@ -1,0 +1,762 @@
+#!/usr/bin/env python
+"""bench.py -- audio-seconds/sec of the compressed-Whisper hot path on B200.
+
+Headline workload (BASELINE.json configs[1]): whisper-base, bitsandbytes LLM.int8 (threshold 6.0, HF
+load_in_8bit flow: fp16 model, proj_out kept fp16), log-mel + encoder + greedy decode of B x 30 s
+synthetic utterances per GPU per step (random-init weights, seeded gaussian audio, T new tokens
+with min = max because random weights never emit EOS).  One process per GPU; utterances are
+sharded over ranks (weak scaling: B per GPU fixed); the only collective is the int64[4] WER/CER
+tally all-reduce.
+
+  python bench.py --gpus 1 --steps 5 --warmup 3              # our arm
+  python bench.py --impl reference --gpus 1 --steps 2 --warmup 1   # reference CPU arm
+  torchrun --nproc-per-node N ... bench.py --gpus N ...     # N > 1
+
+Prints ONE JSON line (rank 0).  `value`: inputs (raw audio) already resident in HBM; `e2e`: the
+same step through the drop-in modules with HOST audio buffers (pinned H2D copy inside the timed
+region, token ids read back D2H, transcripts decoded and tallied).  `roofline`: the kernel with the
+largest share of the step (the decode-time cross-attention stream over the cached encoder K/V) with
+`encoder_gemm` (tcgen05 GEMM launches timed live with CUDA events inside the device-timed steps) and
+`decode` (per-token graph time from events inside the timed steps; per-kernel probe) beside it.
+`token_check`: ids of the timed path vs HF's own `_sample` loop over the same modules on the same batch.
+`extra_configs`: the other BASELINE.json configs (C3 small/NF4, C4 medium/pruned/quanto-int8 in the reference's
+fp32 flow -- also strong-scaled at 256 utterances global --, C5 large-v3/int8), a few steps each.
+"""
+from __future__ import annotations
+
+import argparse
+import gc
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.setswitchinterval(float(os.environ.get("WQ_SWITCH", "0.0002")))
+sys.path.insert(0, ROOT)
+
+AUDIO_SECONDS = 30.0
+N_SAMPLES = 480000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", default="base")
+    ap.add_argument("--scheme", default="llm_int8")
+    ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step")
+    ap.add_argument("--new-tokens", type=int, default=64)
+    ap.add_argument("--cpu-sample", type=int, default=8,
+                    help="utterances in the CPU baseline sample (the reference's own CPU batch size, BASELINE config 0)")
+    ap.add_argument("--prune", type=float, default=0.0,
+                    help="global L1 magnitude pruning amount applied before quantization (BASELINE config 4: 0.5)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs sub-records (C3, C4, C5)")
+    ap.add_argument("--no-token-check", action="store_true")
+    ap.add_argument("--extra-steps", type=int, default=2)
+    ap.add_argument("--hf-loop", action="store_true",
+                    help="keep HF's Python decode loop instead of the CUDA-graph replay loop (fastgen)")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        under_load = [x for x in sm if x > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(under_load) if under_load else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference CPU arm / cpu_baseline: the reference's own CPU path (model_utils.py:131-134):
+# torch.quantization.quantize_dynamic(model, {torch.nn.Linear}, dtype=torch.qint8, inplace=True)
+# on HF Whisper, generate-only timing as data_utils.py:151-155 (features precomputed by the HF
+# feature extractor, as the reference does in map_to_feats).
+# ------------------------------------------------------------------------------------------------
+def use_all_host_cores() -> int:
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is ONE process that should use the box
+    (VERDICT round 1, weak 9): give torch's intra-op pool every core this process may run on."""
+    import torch
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
+def cpu_reference_run(size: str, n_utts: int, new_tokens: int, steps: int, warmup: int):
+    import numpy as np
+    import torch
+    from transformers import WhisperFeatureExtractor
+    from openai_whisper_compression_b200 import harness
+
+    cores = use_all_host_cores()
+    model = harness.build_model(size)
+    torch.quantization.quantize_dynamic(model, {torch.nn.Linear}, dtype=torch.qint8, inplace=True)
+    model.eval()
+    fe = WhisperFeatureExtractor(feature_size=harness.WHISPER_SIZES[size]["mels"])
+    audio = [harness.synth_audio(i) for i in range(n_utts)]
+    t0 = time.time()
+    feats = torch.from_numpy(np.concatenate([fe(a, sampling_rate=16000, return_tensors="np").input_features
+                                             for a in audio]))
+    t_mel = time.time() - t0
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.time()
+            ids = harness.greedy_generate(model, feats, new_tokens)
+            dt = time.time() - t0
+            if i >= warmup:
+                times.append(dt)
+    assert ids.shape[0] == n_utts
+    per_step = sum(times) / len(times)
+    return {"audio_s_per_s": n_utts * AUDIO_SECONDS / per_step, "ms_per_step": per_step * 1e3,
+            "logmel_s": t_mel, "cores": cores, "engine": torch.backends.quantized.engine}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.size, args.cpu_sample, args.new_tokens, args.steps, args.warmup)
+    sample = (f"{args.cpu_sample} x 30 s utterances, whisper-{args.size}, torch quantize_dynamic qint8 "
+              f"({r['engine']}), greedy {args.new_tokens} new tokens, generate-only timer (log-mel by HF "
+              f"extractor took {r['logmel_s']:.2f} s, untimed as in the reference), {r['cores']} host threads")
+    line = {
+        "impl": "reference", "metric": "audio-seconds/sec", "value": r["audio_s_per_s"], "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+        "config": dict(workload_config(args.size, args.scheme, args.prune, args.batch, args.new_tokens, args.gpus,
+                                       False, True),
+                       decode_loop="HF _sample (the reference's model.generate), CPU"),
+        "cpu_baseline": {"value": r["audio_s_per_s"], "unit": "audio-s/s", "cores": r["cores"],
+                         "kind": "reference", "sample": sample},
+        "e2e": {"value": r["audio_s_per_s"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(size, scheme, prune, batch, new_tokens, gpus, hf_loop, default):
+    what = "bitsandbytes LLM.int8 (threshold 6.0)" if scheme == "llm_int8" else scheme
+    if prune > 0:
+        what = f"{int(prune * 100)} % global-L1 pruned + {what}"
+    return {"workload": f"whisper-{size} {what} log-mel + encoder + greedy "
+                        f"decode, {batch} x 30 s synthetic utterances per GPU per step, "
+                        f"{new_tokens} new tokens" + (" (BASELINE.json configs[1])" if default else ""),
+            "size": size, "scheme": scheme, "prune": prune, "utterances_per_gpu": batch,
+            "new_tokens": new_tokens, "parallelism": f"utterance-sharded dp{gpus}",
+            "decode_loop": "HF _sample (Python)" if hf_loop else
+                           "model.generate -> CUDA-graph replay per token (fastgen), HF logits processors",
+            "l2": "256 MiB write before every step (inside the timed bracket; < 0.1 % of a step); per-step "
+                  "activations (>= 98 MB per encoder linear) exceed the 126 MB L2 as well"}
+
+
+# ------------------------------------------------------------------------------------------------
+# roofline helpers
+# ------------------------------------------------------------------------------------------------
+_W_BYTES = {"llmint8": 1.0, "dyn_i8": 1.0, "w8a16": 1.0, "wf8a16": 1.0, "w8a8": 1.0, "w4a16": 0.5 + 4.0 / 64, "u4a16": 0.5 + 8.0 / 128, "f16": 2.0}
+
+
+def gemm_algorithmic(kind, M, N, K):
+    res = kind.endswith("+res")          # the launch also reads the fp16 residual [M, N] (fused residual add, fc2)
+    kind = kind.replace("+res", "")
+    a_bytes = 1 if kind in ("llmint8", "dyn_i8", "w8a8") else 2
+    o_bytes = 4 if kind == "dyn_i8" else 2
+    return (M * K * a_bytes + N * K * _W_BYTES[kind] + M * N * o_bytes + 4 * (M + N) + (M * N * 2 if res else 0),
+            2.0 * M * N * K)
+
+
+def encoder_gemm_roofline(records, peaks, ms_dev):
+    """Encoder-shaped GEMM launches (M >= 1024) timed live with CUDA events inside the device-timed steps."""
+    by_shape = {}
+    for kind, M, N, Kd, s, e in records:
+        by_shape.setdefault((kind, M, N, Kd), []).append(s.elapsed_time(e) * 1e-3)
+    if not by_shape:
+        return None
+    tot_bytes = tot_flops = tot_time = 0.0
+    n_launch = 0
+    shapes = []
+    for (kind, M, N, Kd), ts in sorted(by_shape.items()):
+        nbytes, flops = gemm_algorithmic(kind, M, N, Kd)
+        avg = sum(ts) / len(ts)
+        shapes.append({"kind": kind, "M": M, "N": N, "K": Kd, "launches": len(ts), "avg_us": avg * 1e6,
+                       "GBps": nbytes / avg / 1e9, "TFLOPs": flops / avg / 1e12})
+        tot_bytes += nbytes * len(ts)
+        tot_flops += flops * len(ts)
+        tot_time += sum(ts)
+        n_launch += len(ts)
+    traffic = None
+    for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            # DRAM bytes per launch from the committed ncu --set full capture of this command's kernel
+            # (same shapes): launch-weighted average, None when a shape was not captured
+            per = json.load(open(tpath)).get("traffic_bytes_per_launch", {})
+            tot_t = 0.0
+            for sh in shapes:
+                key = f"{sh['M']}x{sh['N']}x{sh['K']}"
+                if key not in per:
+                    tot_t = None
+                    break
+                tot_t += per[key] * sh["launches"]
+            traffic = None if tot_t is None else tot_t / n_launch
+            if traffic is not None:
+                break
+    gbs = tot_bytes / tot_time / 1e9
+    tfs = tot_flops / tot_time / 1e12
+    int8_kind = all(k[0].replace("+res", "") in ("llmint8", "dyn_i8", "w8a8") for k in by_shape)
+    # which roof binds: arithmetic intensity of the launches against the measured ridge
+    # (int8 tensor peak taken as 2x the measured bf16 peak: same pipe, half the operand bytes)
+    tensor_peak = peaks["bf16_tflops"] * (2.0 if int8_kind else 1.0)
+    tensor_unit = "TOP/s" if int8_kind else "TFLOP/s"
+    ridge = tensor_peak * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    intensity = tot_flops / tot_bytes
+    out = {"traffic": traffic,
+           "kernel": "k_gemm_tc (TMA + tcgen05 + TMEM, fused dequant epilogue), encoder-shaped launches (M >= 1024), "
+                     "kinds: " + ",".join(sorted({k[0] for k in by_shape})),
+           "launches_timed": n_launch, "avg_launch_us": tot_time / n_launch * 1e6,
+           "algorithmic_bytes_per_launch": tot_bytes / n_launch, "algorithmic_flops_per_launch": tot_flops / n_launch,
+           "arithmetic_intensity": intensity, "ridge": ridge,
+           "hbm_GBps": gbs, "hbm_frac": gbs / peaks["hbm_gbs"],
+           "tensor_TFLOPs": tfs, "tensor_frac_of_bf16_peak": tfs / peaks["bf16_tflops"],
+           "share_of_step": tot_time * 1e3 / ms_dev, "shapes": shapes}
+    if intensity <= ridge:
+        out.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": gbs / peaks["hbm_gbs"],
+                    "peak_source": peaks["source"] + " (burst copy bandwidth, kernel timed alone by events)"})
+    else:
+        out.update({"bound": "tensor", "achieved": tfs, "peak": tensor_peak, "unit": tensor_unit,
+                    "frac": tfs / tensor_peak,
+                    "peak_source": peaks["source"] + " (burst cuBLAS bf16 GEMM, kernel timed alone by events"
+                                   + ("; x2 for kind::i8 MMAs: same pipe, half the operand bytes" if int8_kind else "") + ")"})
+    return out
+
+
+def decode_probe(model, eng, peaks, ms_step, T):
+    """Per-kernel numbers for the graph-replayed decode step.  Kernels inside a CUDA graph cannot be bracketed by
+    torch events, so (a) the per-token time comes from events around the whole replay loop INSIDE the timed steps
+    (eng.loop_events) and (b) the two kernel families that matter are launched once more, eagerly, on the very
+    buffers of the last timed step, each launch bracketed by CUDA events: the cross-attention stream over every
+    layer's cached K/V (cold: 2 S d 2 B per utterance per layer >> L2 in total) and the decode-shaped quantized
+    GEMMs (M = B rows) of every layer (weights cold after the K/V stream)."""
+    import torch
+    from openai_whisper_compression_b200 import functional as F
+    from openai_whisper_compression_b200 import fused
+    out = {}
+    loops = [s.elapsed_time(e) for s, e, _ in eng.loop_events if s is not None]
+    toks = [n for s, e, n in eng.loop_events if s is not None]
+    if loops:
+        out["per_token_ms"] = sum(loops) / max(1, sum(toks))
+        out["decode_loop_share_of_step"] = (sum(loops) / len(loops)) / ms_step
+        out["per_token_how"] = "CUDA events around the token loop (cross-K/V GEMMs excluded) inside the timed steps"
+    st = next((s for s in eng._states.values()), None)
+    if st is None or not getattr(st, "own_attn", False):
+        return out
+    B, H, d = st.B, st.H, st.d
+    S = st.ckv[0].shape[1]
+    elt = st.ckv[0].element_size()
+    q = torch.randn((B, d), device=st.ckv[0].device, dtype=st.ckv[0].dtype)
+    # as in the fused step: the kernel also writes the int8 rows of its output for out_proj
+    thr_probe = st.threshold if (st.fused is not None and q.dtype == torch.float16) else None
+    ts = []
+    for rep in range(2):
+        for li in range(len(st.ckv)):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _, qx = F.cross_attn_decode(q, st.ckv[li][:, :, :d], st.ckv[li][:, :, d:], 0.125, H, thr_probe)
+            e1.record()
+            if qx is not None and qx[2] is not None:
+                qx[2].col_flags.zero_()      # no GEMM consumes (and clears) the outlier flags here
+            if rep:
+                ts.append((e0, e1))
+    torch.cuda.synchronize()
+    if ts:
+        avg = sum(a.elapsed_time(b) for a, b in ts) / len(ts) * 1e-3
+        nbytes = 2.0 * B * S * d * elt
+        launches_per_step = len(st.ckv) * T
+        out["cross_attention"] = {
+            "kernel": "k_cross_attn_decode (one pass over the cached encoder K/V per layer and token)",
+            "bound": "hbm", "algorithmic_bytes_per_launch": nbytes, "avg_launch_us": avg * 1e6,
+            "achieved": nbytes / avg / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": nbytes / avg / 1e9 / peaks["hbm_gbs"], "launches_per_step": launches_per_step,
+            "share_of_step": launches_per_step * avg * 1e3 / ms_step,
+            "how": "same kernel on the timed step's K/V buffers, launched eagerly after the timed region, CUDA events "
+                   "around each launch, every layer's buffers in turn (cold in L2)"}
+    # decode-shaped quantized GEMMs: the six weight matrices of every decoder layer, captured as ONE CUDA graph
+    # (the way the step runs them: back to back, programmatic dependent launch) and replayed under events
+    if st.fused is not None:
+        B = st.views[0].B           # rows per launch: the step decodes the batch in row groups (one per stream)
+        out["row_groups"] = len(st.views)
+        kind = st.fused[0].qkv.kind
+        calls = []
+        for fw in st.fused:
+            for name in ("qkv", "o", "cq", "co", "fc1", "fc2"):
+                w = getattr(fw, name)
+                a = torch.randn((B, w.in_features), device=q.device, dtype=q.dtype)
+                qt = F.int8_vectorwise_quant(a, st.threshold, finalize=False) if kind == "int8" else None
+                calls.append((qt, a, w))
+        side = torch.cuda.Stream(device=q.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for qt, a, w in calls:
+                fused.gemm(qt, a, w)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for qt, a, w in calls:
+                fused.gemm(qt, a, w)
+        ts = []
+        for rep in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            if rep:
+                ts.append((e0, e1))
+        torch.cuda.synchronize()
+        wb = _W_BYTES[{"int8": "llmint8"}.get(kind, kind)]
+        ab = 1 if kind == "int8" else 2
+        tot_b = sum(w.out_features * w.in_features * wb + B * w.in_features * ab + 2 * B * w.out_features
+                    for _, _, w in calls)
+        tot_t = sum(a.elapsed_time(b) for a, b in ts) / len(ts) * 1e-3
+        out["decode_gemm"] = {
+            "kernel": f"k_gemm_tc decode-shaped launches (M = {B} rows: one row group of the batch), {kind}",
+            "bound": "hbm", "launches": len(calls), "avg_launch_us": tot_t / len(calls) * 1e6,
+            "algorithmic_bytes_per_launch": tot_b / len(calls), "achieved": tot_b / tot_t / 1e9,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": tot_b / tot_t / 1e9 / peaks["hbm_gbs"],
+            "how": "all decoder weight matrices of the model back to back in one CUDA graph, events around the replay",
+            "note": "the decoder weights of the Whisper sizes are L2-resident or a few us of HBM time per token: these "
+                    "launches are latency-bound, not bandwidth-bound (DESIGN.md section 3.1)"}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+class Workload:
+    """One (size, scheme, prune, B, T) configuration on this rank's GPU."""
+
+    def __init__(self, size, scheme, prune, B, T, dev, rank, hf_loop=False, fast_init=False):
+        import torch
+        from openai_whisper_compression_b200 import harness
+        self.size, self.scheme, self.prune, self.B, self.T, self.dev = size, scheme, prune, B, T, dev
+        n_mels = harness.WHISPER_SIZES[size]["mels"]
+        master = harness.build_model(size, device=dev if fast_init else None)
+        if prune > 0:
+            harness.global_l1_prune(master, prune)
+        self.model = harness.apply_scheme(master, scheme, dev)
+        del master
+        self.eng = None
+        if not hf_loop:
+            from openai_whisper_compression_b200 import fastgen
+            self.eng = fastgen.enable(self.model)
+        self.proc = harness.StubProcessor(n_mels, device=dev)
+        self.fe = self.proc.feature_extractor
+        self.half = harness.model_dtype(self.model) == torch.float16
+        utts = [rank * B + i for i in range(B)]
+        self.audio_host = torch.empty((B, N_SAMPLES), dtype=torch.float32).pin_memory()
+        for j, u in enumerate(utts):
+            self.audio_host[j] = torch.from_numpy(harness.synth_audio(u))
+        self.audio_dev = self.audio_host.to(dev)
+        self.refs = [harness.synth_reference(u) for u in utts]
+        self.ids_host = torch.empty((B, T + 8), dtype=torch.int64).pin_memory()
+        self.harness = harness
+
+    def hot_path(self, audio):
+        feats = self.fe.features_from_device_audio(audio)
+        if self.half:
+            feats = feats.half()
+        return self.harness.greedy_generate(self.model, feats, self.T)
+
+    def close(self):
+        import torch
+        if self.eng is not None:
+            self.eng.invalidate()
+            self.eng.uninstall()
+        self.model = self.eng = self.audio_dev = self.audio_host = None
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
+def token_check(wl: "Workload", ids_fast, tol: float):
+    """ids of the timed path vs HF's own `_sample` loop over the same drop-in modules (fastgen / fastenc removed),
+    same batch, same features.  The two paths differ in LayerNorm / attention rounding (<= 1 fp16 ulp), so a greedy
+    path may fork where HF's own top-1 / top-2 logit margin is below the logit tolerance of the parity tests;
+    reported: fraction of identical ids, and whether every utterance's FIRST divergence sits at such a position."""
+    import torch
+    eng = wl.eng
+    out = None
+    if eng is not None:
+        eng.uninstall()
+    try:
+        feats = wl.fe.features_from_device_audio(wl.audio_dev)
+        if wl.half:
+            feats = feats.half()
+        with torch.no_grad():
+            out = wl.model.generate(feats, do_sample=False, num_beams=1, min_new_tokens=wl.T, max_new_tokens=wl.T,
+                                    return_dict_in_generate=True, output_logits=True)
+        seq = out.sequences
+        T = wl.T
+        hf = seq[:, seq.shape[1] - T:]
+        fast = ids_fast[:, ids_fast.shape[1] - T:].to(hf.device)
+        same = (hf == fast)
+        first = torch.where(same.all(1), T, (~same).float().argmax(1))
+        n_div = int((first < T).sum())
+        bad = 0
+        min_margin_at_div = None
+        if n_div:
+            rows = torch.nonzero(first < T).view(-1)
+            for b in rows.tolist():
+                lg = out.logits[int(first[b])][b].float()
+                top2 = lg.topk(2).values
+                m = float(top2[0] - top2[1])
+                min_margin_at_div = m if min_margin_at_div is None else max(min_margin_at_div, m)
+                bad += m > tol
+        verdict = "exact" if n_div == 0 else ("exact-at-decisive-positions" if bad == 0 else "MISMATCH")
+        return {"verdict": verdict, "against": "HF _sample loop over the same drop-in modules (fastgen/fastenc removed), "
+                "same batch", "utterances": int(hf.shape[0]), "tokens": int(hf.numel()),
+                "identical_ids_frac": float(same.float().mean()), "utterances_diverging": n_div,
+                "divergences_at_decisive_positions": int(bad), "largest_hf_margin_at_a_divergence": min_margin_at_div,
+                "margin_tol": tol}
+    finally:
+        del out
+        if eng is not None:
+            eng.install()
+
+
+def run_config(wl: Workload, K: int, W: int, world: int, rank: int, peaks, with_e2e=True, do_token_check=True,
+               sampler=None):
+    import torch
+    import torch.distributed as dist
+    from openai_whisper_compression_b200 import functional as F
+    from openai_whisper_compression_b200 import tally
+
+    dev, B, T = wl.dev, wl.B, wl.T
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        flush_buf.zero_()
+        return wl.hot_path(wl.audio_dev)
+
+    # e2e: every step's audio is copied from pinned host memory inside the timed region; the copy of
+    # step i+1 runs on a side stream while step i computes (two device buffers)
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty_like(wl.audio_dev), torch.empty_like(wl.audio_dev)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"i": 0}
+
+    def issue_copy(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[i % 2])                  # buffer no longer read by step i-2
+            bufs[i % 2].copy_(wl.audio_host, non_blocking=True)  # H2D of step i's inputs
+            ready[i % 2].record(copy_stream)
+
+    def e2e_begin():
+        e2e_state["i"] = 0
+        done[0].record(); done[1].record()
+        issue_copy(0)
+
+    # The transcript work of step i (ids -> text on the host, WER/CER tally: one edit-distance launch + the all-reduce)
+    # runs on a worker thread while the main thread drives step i + 1 (whose host side mostly waits for the GPU); the
+    # timed region ends only when the last step's tally is back on the host.
+    import concurrent.futures as cf
+    pool = cf.ThreadPoolExecutor(max_workers=1)
+    ids_bufs = [wl.ids_host, torch.empty_like(wl.ids_host).pin_memory()]
+    pending = {"f": None, "t": None}
+
+    def transcript_tally(ids_cpu):
+        torch.cuda.set_device(dev)
+        hyps = wl.proc.batch_decode(ids_cpu)
+        t = tally.all_reduce_tally(tally.tally_on_device(wl.refs, hyps, dev))
+        return t.cpu()
+
+    def e2e_drain():
+        if pending["f"] is not None:
+            pending["t"] = pending["f"].result()
+            pending["f"] = None
+        return pending["t"]
+
+    def step_e2e():
+        i = e2e_state["i"]
+        e2e_state["i"] = i + 1
+        flush_buf.zero_()
+        issue_copy(i + 1)                                        # next step's inputs, overlapped
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        ids = wl.hot_path(bufs[i % 2])
+        done[i % 2].record()
+        out = ids_bufs[i % 2][:, :ids.shape[1]]
+        out.copy_(ids, non_blocking=True)                        # D2H of the result
+        torch.cuda.current_stream().synchronize()
+        e2e_drain()                                              # step i - 1's tally (finished long ago)
+        pending["f"] = pool.submit(transcript_tally, out)
+        return ids
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(W):
+        step_device()
+    if with_e2e:
+        e2e_begin()
+        for _ in range(max(1, min(W, 2))):
+            step_e2e()
+        e2e_drain()
+    if sampler is not None:
+        sampler.start()
+
+    # ---- device-resident inputs: `value` (+ live GEMM timing for the roofline) ----
+    F.STATS.reset()
+    F.STATS.profile_min_rows = 1024
+    if wl.eng is not None:
+        wl.eng.loop_events = []
+        wl.eng.time_loop = True
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    torch.cuda.nvtx.range_push("wq_timed")          # ncu --nvtx --nvtx-include "wq_timed/" selects this region
+    for _ in range(K):
+        ids = step_device()
+    torch.cuda.nvtx.range_pop()
+    e1.record()
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    launches = F.STATS.launches
+    records = list(F.STATS.records)
+    F.STATS.profile_min_rows = None
+    if wl.eng is not None:
+        wl.eng.time_loop = False
+
+    res = {"ms_dev": ms_dev, "launches": launches, "ids_shape": list(ids.shape)}
+    # ---- host buffers through the drop-in API: `e2e` ----
+    if with_e2e:
+        barrier()
+        e0.record()
+        e2e_begin()                                                  # first copy is inside the timed region
+        for _ in range(K):
+            ids = step_e2e()
+        t = e2e_drain()                                              # the last step's transcripts are tallied
+        torch.cuda.synchronize()
+        e1.record()
+        barrier()
+        res["ms_e2e"] = max_over_ranks(e0.elapsed_time(e1))
+        res["tally"] = {"WER": tally.rates(t)["WER"], "CER": tally.rates(t)["CER"], "ref_words": int(t[1])}
+        res["d2h_bytes"] = int(ids.shape[1]) * B * 8 + 32
+    if rank == 0:
+        res["encoder_gemm"] = encoder_gemm_roofline(records, peaks, ms_dev)
+        if wl.eng is not None:
+            res["decode"] = decode_probe(wl.model, wl.eng, peaks, ms_dev / K, T)
+    if do_token_check:
+        tol = 0.12 if wl.half else 0.04      # 2 x the teacher-forced logit tolerance of tests/test_gpu_configs.py
+        tc = token_check(wl, ids, tol)
+        if rank == 0:
+            res["token_check"] = tc
+    pool.shutdown(wait=True)
+    del bufs, flush_buf
+    return res
+
+
+def summarize_extra(name, wl, r, K, world, peaks):
+    total_audio = world * wl.B * AUDIO_SECONDS * K
+    enc = r.get("encoder_gemm")
+    out = {"name": name,
+           "config": workload_config(wl.size, wl.scheme, wl.prune, wl.B, wl.T, world, False, False),
+           "value": total_audio / (r["ms_dev"] * 1e-3), "unit": "audio-s/s", "ms_per_step": r["ms_dev"] / K,
+           "steps": K, "gpu_launches": r["launches"], "token_check": r.get("token_check")}
+    if "ms_e2e" in r:
+        out["e2e"] = {"value": total_audio / (r["ms_e2e"] * 1e-3), "unit": "audio-s/s", "ms_per_step": r["ms_e2e"] / K}
+    if enc:
+        out["roofline"] = {k: enc[k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel", "launches_timed",
+                                               "avg_launch_us", "hbm_GBps", "tensor_TFLOPs", "share_of_step")}
+    if r.get("decode"):
+        out["decode"] = r["decode"]
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from openai_whisper_compression_b200 import harness
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+
+    peaks = load_peaks()
+    B, T, K, W = args.batch, args.new_tokens, args.steps, max(args.warmup, 3)
+    default = args.size == "base" and args.scheme == "llm_int8" and args.prune == 0
+    wl = Workload(args.size, args.scheme, args.prune, B, T, dev, rank, hf_loop=args.hf_loop)
+    sampler = ClockSampler(local) if rank == 0 else None
+    r = run_config(wl, K, W, world, rank, peaks, with_e2e=True,
+                   do_token_check=not (args.no_token_check or args.hf_loop), sampler=sampler)
+    clocks = sampler.stop() if rank == 0 else None
+    wl.close()
+
+    extra = []
+    if default and not args.no_extra and not args.hf_loop:
+        Ke = max(1, args.extra_steps)
+        plan = []
+        if world == 1:
+            plan += [("C3 whisper-small bnb NF4 (fp16 compute, HF load_in_4bit flow)", "small", "bnb_nf4", 0.0, 64),
+                     ("C4 whisper-medium 50 % global-L1 pruned + quanto qint8 (reference fp32 flow)", "medium",
+                      "quanto_int8", 0.5, 64),
+                     ("C5 whisper-large-v3 LLM.int8 (fp16 flow), 128 mels", "large-v3", "llm_int8", 0.0, 32)]
+        else:
+            plan += [("C5 whisper-large-v3 LLM.int8, 256 utterances global (strong scaling)", "large-v3", "llm_int8", 0.0,
+                      max(1, 256 // world))]
+        plan += [("C4 strong-scaling point: whisper-medium 50 % pruned + quanto qint8 (fp32 flow), 256 utterances "
+                  "GLOBAL", "medium", "quanto_int8", 0.5, max(1, 256 // world))]
+        for name, size, scheme, prune, Be in plan:
+            try:
+                wle = Workload(size, scheme, prune, Be, T, dev, rank, fast_init=True)
+                re_ = run_config(wle, Ke, 3, world, rank, peaks, with_e2e=False,
+                                 do_token_check=not args.no_token_check and Be <= 64)
+                if rank == 0:
+                    rec = summarize_extra(name, wle, re_, Ke, world, peaks)
+                    if "GLOBAL" in name or "global" in name:
+                        rec["scaling"] = "strong"
+                    extra.append(rec)
+                wle.close()
+            except Exception as ex:      # an extra config must never take the headline line down with it
+                if rank == 0:
+                    extra.append({"name": name, "error": f"{type(ex).__name__}: {ex}"[:300]})
+                if world > 1:
+                    raise
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_audio = world * B * AUDIO_SECONDS * K
+    ms_dev, ms_e2e = r["ms_dev"], r["ms_e2e"]
+    enc = r.get("encoder_gemm")
+    dec = r.get("decode") or {}
+    # headline roofline: the repo kernel with the largest share of the step
+    cands = []
+    if dec.get("cross_attention"):
+        cands.append(dict(dec["cross_attention"], name="cross_attention"))
+    if enc:
+        cands.append(dict(enc, name="encoder_gemm"))
+    roofline = None
+    if cands:
+        top = max(cands, key=lambda c: c.get("share_of_step", 0.0))
+        roofline = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
+                    "frac": top["frac"], "traffic": top.get("traffic"), "kernel": top["kernel"],
+                    "dominant": top["name"], "share_of_step": top.get("share_of_step"),
+                    "algorithmic_bytes_per_launch": top.get("algorithmic_bytes_per_launch"),
+                    "avg_launch_us": top.get("avg_launch_us"),
+                    "peak_source": peaks["source"] + " (MEASURED_PEAKS.json burst copy bandwidth)",
+                    "encoder_gemm": enc, "decode": dec}
+    line = {
+        "metric": "audio-seconds/sec", "value": total_audio / (ms_dev * 1e-3), "unit": "audio-s/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+        "config": workload_config(args.size, args.scheme, args.prune, B, T, world, args.hf_loop, default),
+        "e2e": {"value": total_audio / (ms_e2e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": B * N_SAMPLES * 4, "d2h_bytes_per_step": r["d2h_bytes"],
+                "note": "per step: pinned-host audio H2D (prefetched one step ahead on a copy stream), log-mel, "
+                        "model.generate, ids D2H, decode to text, WER/CER tally on the GPU (+ all-reduce); the "
+                        "transcript work of a step runs on a worker thread under the next step, the timed region ends "
+                        "when the last tally is back on the host"},
+        "gpu_launches": r["launches"], "clocks": clocks, "roofline": roofline,
+        "token_check": r.get("token_check"), "tally": r.get("tally"), "extra_configs": extra,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        c = cpu_reference_run(args.size, args.cpu_sample, T, steps=1, warmup=1)
+        line["cpu_baseline"] = {
+            "value": c["audio_s_per_s"], "unit": "audio-s/s", "cores": c["cores"], "kind": "reference",
+            "sample": f"{args.cpu_sample} x 30 s utterances of the same workload on the host: whisper-{args.size} "
+                      f"torch quantize_dynamic qint8 ({c['engine']}), greedy {T} new tokens, generate-only "
+                      f"timer, 1 warm-up + 1 timed pass ({c['ms_per_step'] / 1e3:.1f} s), {c['cores']} threads"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
