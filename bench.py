@@ -331,8 +331,13 @@ def decode_probe(model, eng, peaks, ms_step, T):
         avg = sum(a.elapsed_time(b) for a, b in ts) / len(ts) * 1e-3
         nbytes = 2.0 * B * S * d * elt
         launches_per_step = len(st.ckv) * T
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r02_xattn_traffic.json")
+        if os.path.exists(tp):      # DRAM bytes of one launch from the committed ncu --set full capture of this kernel
+            traffic = json.load(open(tp)).get("traffic_bytes_per_launch", {}).get(f"B{B}xH{H}xS{S}")
         out["cross_attention"] = {
-            "kernel": "k_cross_attn_decode (one pass over the cached encoder K/V per layer and token)",
+            "traffic": traffic,
+            "kernel": "k_cross_attn_decode_tma (one pass over the cached encoder K/V per layer and token)",
             "bound": "hbm", "algorithmic_bytes_per_launch": nbytes, "avg_launch_us": avg * 1e6,
             "achieved": nbytes / avg / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": nbytes / avg / 1e9 / peaks["hbm_gbs"], "launches_per_step": launches_per_step,
