@@ -219,6 +219,19 @@ int wq_quant_act_static(const void *x, int x_dtype, int64_t n, const float *scal
 int wq_gemm_w8a8(const int8_t *xq, const int8_t *wq, const float *out_scale, const float *bias, void *y,
                  int y_dtype, int64_t M, int64_t N, int64_t K, wq_stream_t stream);
 
+/* Decode-shaped forward (at most 32 rows) of the weight-only quantized linears -- bitsandbytes' own split: gemv_4bit
+ * for decode, dequantize + GEMM otherwise (Linear4bit.forward) -- for every weight-only scheme here:
+ *   mode 0  bnb NF4 / FP4 (quant_type), packed nibbles [N, K/2], s0 = absmax fp32 [N, K/64]
+ *   mode 1  quanto qint8, int8 [N, K], s0 = scale fp32 [N] (applied after the accumulation, as QLinear does)
+ *   mode 2  quanto qint4 / qint2, packed nibbles [N, K/2], s0 = scale, s1 = shift fp32 [N, K/group]
+ *   mode 3  quanto qfloat8 (e4m3fn codes) [N, K], s0 = scale fp32 [N]
+ * y[m, n] = sum_k x[m, k] * w[n, k] (+ scale) + bias[n]: the packed weights are streamed once, dequantized in registers
+ * to the value wq_gemm_w4a16 / w8a16 / u4a16 / wf8a16 feed the tensor core (rounded once to the activation dtype where
+ * the scheme rounds), fp32 accumulation on the CUDA cores, warp reduction in a fixed order.  x, y: F16 or BF16. */
+int wq_gemv_weightonly(const void *x, int x_dtype, int64_t M, int64_t K, int mode, const void *w,
+                       const float *s0, const float *s1, int group, int quant_type, const float *bias,
+                       void *y, int64_t N, wq_stream_t stream);
+
 /* torch.ao.nn.quantized.dynamic.Linear.forward GPU twin (quantized::linear_dynamic):
  *   y[m,n] = float(acc[m,n] - zp * wsum[n]) * (s_x * s_w) + bias[n], fp32
  * xq uint8 [M, K]; qparams device float[2] = {s_x, zp}; wq int8 [N, K]; w_scale device fp32[1];

@@ -57,6 +57,7 @@ _PROTOS = {
     "wq_quant_act_static": [c_ptr, c_int, c_i64, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "wq_gemm_w8a8": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],
     "wq_scatter_dense_f32": [c_ptr, c_ptr, c_int, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr],
+    "wq_gemv_weightonly": [c_ptr, c_int, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr, c_i64, c_ptr],
     "wq_gemm_f16": [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_ptr],
     "wq_argmax_finalize": [c_ptr, c_i64, c_ptr, c_ptr],
     "wq_logmel": [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_int, c_ptr, c_int, c_ptr, c_ptr],

@@ -90,6 +90,9 @@ class GraphedGreedy:
         # launch against ~50 us for the twelve PDL-chained launches it replaces; 146 vs 108 ms per bench step) -- eleven
         # grid barriers and eleven dependent L2 round trips cost more than programmatic dependent launch already hides
         self.mega = os.environ.get("WQ_DECODE_FUSED", "0") == "1"
+        # Opt-in: route <= 16-row int8 GEMMs of the step through the small-row dp4a kernel instead of the tensor-core
+        # tile.  Measured SLOWER on large-v3 (B=32, 2 row groups of 16: 485 vs 377 ms/step), so off by default.
+        self.small_int8 = os.environ.get("WQ_SMALL_INT8", "0") == "1"
         self.time_loop = False         # bench.py: CUDA events around the token loop of every generate call
         self.loop_events = []          # (start, end, replays)
         self.replays = 0
@@ -313,23 +316,29 @@ class GraphedGreedy:
 
         gemm = fused.gemm      # LLM.int8: consumes the producer's int8 rows; weight-only schemes: the fp16 / bf16 rows
 
+        # row groups of <= 16 rows: Linear8bitLt's single-launch small-row kernel (quantizes the few rows itself, dp4a)
+        # beats the tensor-core tile; the producer feeding such a GEMM then skips its own quantization (thr -> None)
+        def t_for(w):
+            return None if (thr is not None and self.small_int8 and fused.small_rows_ok(B, w)) else thr
+
         for li, (layer, fw) in enumerate(zip(dec.layers, st.fused)):
             ln = layer.self_attn_layer_norm
-            x, h, qt = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, thr)
+            x, h, qt = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, t_for(fw.qkv))
             qkv = gemm(qt, h, fw.qkv)
             a, qt = F.self_attn_decode(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], fw.scaling, v.k[li], v.v[li],
-                                       st.pos, H, thr)
+                                       st.pos, H, t_for(fw.o))
             delta = gemm(qt, a, fw.o)
             ln = layer.encoder_attn_layer_norm
-            x, h, qt = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, thr)
+            x, h, qt = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, t_for(fw.cq))
             q = gemm(qt, h, fw.cq)
+            tco = t_for(fw.co)
             if st.own_cross:
                 # q scaling, the pass over the 1500 cached encoder positions and out_proj's quantization: one launch
-                if self.cross_quant_inline or thr is None:
-                    a, qt = F.cross_attn_decode(q, v.ckv[li][:, :, :d], v.ckv[li][:, :, d:], fw.scaling, H, thr)
+                if self.cross_quant_inline or tco is None:
+                    a, qt = F.cross_attn_decode(q, v.ckv[li][:, :, :d], v.ckv[li][:, :, d:], fw.scaling, H, tco)
                 else:       # the row quantization as a launch of its own (no cross-CTA completion tail in the stream)
                     a, _ = F.cross_attn_decode(q, v.ckv[li][:, :, :d], v.ckv[li][:, :, d:], fw.scaling, H, None)
-                    qt = F.int8_vectorwise_quant(a, thr, finalize=False) if thr is not None else None
+                    qt = F.int8_vectorwise_quant(a, tco, finalize=False)
             else:
                 if fw.scaling_pow2:     # q * 2^-k is exact in fp16, so the scale can ride in the SDPA call
                     a = TF.scaled_dot_product_attention(q.view(B, 1, H, hd).transpose(1, 2),
@@ -339,11 +348,11 @@ class GraphedGreedy:
                     a = TF.scaled_dot_product_attention((q * fw.scaling).view(B, 1, H, hd).transpose(1, 2),
                                                         v.ck[li].transpose(1, 2), v.cv[li].transpose(1, 2), scale=1.0)
                 a = a.transpose(1, 2).reshape(B, d)
-                qt = F.int8_vectorwise_quant(a, thr, finalize=False) if thr is not None else None
+                qt = F.int8_vectorwise_quant(a, tco, finalize=False) if tco is not None else None
             delta = gemm(qt, a, fw.co)
             ln = layer.final_layer_norm
-            x, h, qt = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, thr)
-            g, qt = F.gelu_quant(gemm(qt, h, fw.fc1), thr)
+            x, h, qt = F.add_layernorm_quant(x, delta, ln.weight, ln.bias, ln.eps, t_for(fw.fc1))
+            g, qt = F.gelu_quant(gemm(qt, h, fw.fc1), t_for(fw.fc2))
             delta = gemm(qt, g, fw.fc2)
         ln = dec.layer_norm
         if not project:      # multi-stream step: the groups' final hidden rows meet in one buffer
@@ -506,7 +515,7 @@ class GraphedGreedy:
     def _get_state(self, B: int, t_max: int, dtype: torch.dtype, device, store_logits: bool = True) -> _State:
         fp = self._fingerprint()
         key = (B, t_max, dtype, torch.device(device).index, bool(store_logits), self.cross_attention, self.streams,
-               self.cross_quant_inline, self.mega, self.min_rows_per_stream)
+               self.cross_quant_inline, self.mega, self.min_rows_per_stream, self.small_int8)
         st = self._states.get(key)
         if st is not None and st.fingerprint == fp:
             return st

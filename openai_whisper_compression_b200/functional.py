@@ -160,6 +160,25 @@ def dequantize_absmax_double(q: torch.Tensor, absmax2: torch.Tensor, offset: tor
     return out
 
 
+# decode-shaped calls of the weight-only schemes with at most this many rows stream the packed weights through the
+# CUDA-core GEMV (gemv_wq.cu) instead of the tcgen05 pipeline (WQ_GEMV_ROWS=0 disables: A/B measurements)
+import os as _os
+GEMV_ROWS = int(_os.environ.get("WQ_GEMV_ROWS", "32"))
+
+
+def _gemv_weightonly(x2: torch.Tensor, mode: int, w: torch.Tensor, s0: torch.Tensor, s1, group: int, quant_type: int,
+                     bias, y: torch.Tensor, N: int, K: int) -> None:
+    with torch.cuda.device(x2.device):
+        _lib.check(_lib.load().wq_gemv_weightonly(_ptr(x2), _DT[x2.dtype], x2.shape[0], K, mode, _ptr(w), _ptr(s0), _ptr(s1),
+                                                  group, quant_type, _ptr(bias), _ptr(y), N, _stream()),
+                   "wq_gemv_weightonly")
+    STATS.launches += 1
+
+
+def _gemv_ok(x2: torch.Tensor, out_dtype) -> bool:
+    return 0 < x2.shape[0] <= GEMV_ROWS and out_dtype == x2.dtype and x2.dtype in (torch.float16, torch.bfloat16)
+
+
 def _dest(out: Optional[torch.Tensor], M: int, N: int, dtype, device, what: str) -> torch.Tensor:
     """[M, N] destination of a GEMM: a fresh tensor, or the caller's contiguous buffer of M*N elements."""
     if out is None:
@@ -177,6 +196,9 @@ def gemm_w4a16(x: torch.Tensor, packed: torch.Tensor, absmax: torch.Tensor, N: i
     _need_cuda(x2, packed, absmax, bias)
     out_dtype = out_dtype or x2.dtype
     y = _dest(out, x2.shape[0], N, out_dtype, x.device, "gemm_w4a16")
+    if _gemv_ok(x2, out_dtype):
+        _gemv_weightonly(x2, 0, packed, absmax, None, 0, _QT[quant_type], bias, y, N, K)
+        return y.reshape(*x.shape[:-1], N)
     with torch.cuda.device(x.device), _Timed("w4a16", x2.shape[0], N, K):
         _lib.check(_lib.load().wq_gemm_w4a16(_ptr(x2), _DT[x2.dtype], _ptr(packed), _ptr(absmax), _QT[quant_type],
                                              _ptr(bias), _ptr(y), _DT[out_dtype], x2.shape[0], N, K, _stream()),
@@ -566,6 +588,9 @@ def gemm_w8a16(x: torch.Tensor, wq: torch.Tensor, scale: torch.Tensor, bias: Opt
     _need_cuda(x2, wq, scale, bias)
     out_dtype = out_dtype or x2.dtype
     y = _dest(out, x2.shape[0], N, out_dtype, x.device, "gemm_w8a16")
+    if _gemv_ok(x2, out_dtype) and K % 8 == 0:
+        _gemv_weightonly(x2, 1, wq, scale, None, 0, 0, bias, y, N, K)
+        return y.reshape(*x.shape[:-1], N)
     with torch.cuda.device(x.device), _Timed("w8a16", x2.shape[0], N, K):
         _lib.check(_lib.load().wq_gemm_w8a16(_ptr(x2), _DT[x2.dtype], _ptr(wq), _ptr(scale), _ptr(bias), _ptr(y),
                                              _DT[out_dtype], x2.shape[0], N, K, _stream()), "wq_gemm_w8a16")
@@ -596,6 +621,9 @@ def gemm_wf8a16(x: torch.Tensor, wq: torch.Tensor, scale: torch.Tensor, bias: Op
     _need_cuda(x2, wq, scale, bias)
     out_dtype = out_dtype or x2.dtype
     y = _dest(out, x2.shape[0], N, out_dtype, x.device, "gemm_wf8a16")
+    if _gemv_ok(x2, out_dtype) and K % 8 == 0:
+        _gemv_weightonly(x2, 3, wq, scale, None, 0, 0, bias, y, N, K)
+        return y.reshape(*x.shape[:-1], N)
     with torch.cuda.device(x.device), _Timed("wf8a16", x2.shape[0], N, K):
         _lib.check(_lib.load().wq_gemm_wf8a16(_ptr(x2), _DT[x2.dtype], _ptr(wq), _ptr(scale), _ptr(bias), _ptr(y),
                                               _DT[out_dtype], x2.shape[0], N, K, _stream()), "wq_gemm_wf8a16")
@@ -680,6 +708,9 @@ def gemm_u4a16(x: torch.Tensor, packed: torch.Tensor, scale: torch.Tensor, shift
     _need_cuda(x2, packed, scale, shift, bias)
     out_dtype = out_dtype or x2.dtype
     y = _dest(out, x2.shape[0], N, out_dtype, x.device, "gemm_u4a16")
+    if _gemv_ok(x2, out_dtype):
+        _gemv_weightonly(x2, 2, packed, scale, shift, group, 0, bias, y, N, K)
+        return y.reshape(*x.shape[:-1], N)
     with torch.cuda.device(x.device), _Timed("u4a16", x2.shape[0], N, K):
         _lib.check(_lib.load().wq_gemm_u4a16(_ptr(x2), _DT[x2.dtype], _ptr(packed), _ptr(scale), _ptr(shift), group,
                                              _ptr(bias), _ptr(y), _DT[out_dtype], x2.shape[0], N, K, _stream()),

@@ -34,6 +34,12 @@ class Packed:
 PackedInt8 = Packed     # round-1 name
 
 
+def small_rows_ok(rows: int, w: "Packed") -> bool:
+    """True when Linear8bitLt's single-launch small-row kernel serves this call (functional.linear8bitlt's own rule)."""
+    K = w.in_features
+    return w.kind == "int8" and 0 < rows <= F.SMALL_M_ROWS and K % 16 == 0 and 64 * K + K + 272 <= 200 * 1024
+
+
 def is_pow2(x: float) -> bool:
     return x > 0 and math.frexp(x)[0] == 0.5
 
@@ -127,7 +133,13 @@ def pack(mods: Sequence[torch.nn.Module], dtype: torch.dtype) -> Optional[Packed
 def gemm_int8(quant, a: torch.Tensor, w: Packed, out: Optional[torch.Tensor] = None,
               keep_flags: bool = False, residual: Optional[torch.Tensor] = None, clamp_abs: float = 0.0) -> torch.Tensor:
     """Linear8bitLt's GEMM on rows that are already quantized: quant = (CA, SCA, outlier state) from a fused
-    producer, `a` the fp16 rows they were made from (read only for outlier columns)."""
+    producer, `a` the fp16 rows they were made from (read only for outlier columns).  quant None (decode-shaped calls
+    with <= 16 rows whose producer did not quantize): the single-launch kernel that quantizes the rows itself and
+    multiplies with dp4a (gemv_small.cu; bit-identical results)."""
+    if quant is None:
+        if residual is not None or out is not None:
+            raise RuntimeError("gemm_int8: the small-row kernel takes neither a residual nor a destination")
+        return F.linear8bitlt(a, w.cb, w.scb, w.bias, w.threshold)
     ca, sca, state = quant
     return F.gemm_llmint8(ca, sca, w.cb, w.scb, w.bias, a if state is not None else None, state, out=out,
                           keep_flags=keep_flags, residual=residual, clamp_abs=clamp_abs)

@@ -567,3 +567,67 @@ def test_gemm_w8a8_exact_vs_integer_matmul(out_dtype, M, N, K):
     acc = (xq.double() @ wq.double().t())
     ref = ((acc.float() * os_[None, :]) + bias[None, :]).to(out_dtype)
     assert torch.equal(y, ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: decode-shaped forward (<= 32 rows) of the weight-only schemes on the CUDA-core GEMV (gemv_wq.cu)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("M,N,K", [(1, 768, 768), (16, 768, 3072), (32, 3072, 768), (7, 130, 384), (32, 51, 1280), (9, 2304, 768)])
+@pytest.mark.parametrize("mode", ["nf4", "fp4", "w8", "u4", "u2", "f8"])
+def test_weight_only_gemv_matches_dequant_matmul_and_the_tensor_core_gemm(dtype, tol, M, N, K, mode):
+    """Same contract as the tcgen05 GEMMs it stands in for at <= 32 rows: y = x @ dequant(W)^T (* scale) + bias with
+    the dequantized weight rounded once to the activation dtype where the scheme rounds, fp32 accumulation, one output
+    rounding.  Checked against a float64 product of exactly those operand values, and against the tensor-core kernel
+    (WQ_GEMV_ROWS = 0 path) on the same inputs."""
+    g = torch.Generator(device="cuda").manual_seed(M * 31 + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05)
+    W[torch.rand(N, K, device="cuda", generator=g) < 0.3] = 0
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    if mode in ("nf4", "fp4"):
+        packed, absmax = F.quantize_4bit(W.to(dtype), 64, mode)
+        wd = F.dequantize_4bit(packed, absmax, (N, K), 64, mode, dtype).double()
+        call = lambda: F.gemm_w4a16(x, packed, absmax, N, K, bias, mode)
+        post = None
+    elif mode == "w8":
+        q, scale = F.quanto_quantize_qint8(W.to(dtype))
+        wd, post = q.double(), scale.view(1, -1).double()
+        call = lambda: F.gemm_w8a16(x, q, scale.view(-1), bias)
+    elif mode == "f8":
+        q, scale = F.quanto_quantize_qfloat8(W.to(dtype))
+        wd, post = q.view(torch.float8_e4m3fn).double(), scale.view(1, -1).double()
+        call = lambda: F.gemm_wf8a16(x, q, scale.view(-1), bias)
+    else:
+        bits = 4 if mode == "u4" else 2
+        packed, scale, shift, grp = F.quanto_quantize_qint4(W.to(dtype), bits=bits)
+        hi, lo = (packed >> 4).float(), (packed & 15).float()
+        codes = torch.stack([hi, lo], -1).reshape(N, K)
+        wd = (scale.repeat_interleave(grp, 1) * codes - shift.repeat_interleave(grp, 1)).to(dtype).double()
+        call = lambda: F.gemm_u4a16(x, packed, scale, shift, grp, bias)
+        post = None
+    assert F.GEMV_ROWS >= 32
+    y = call()
+    ref = x.double() @ wd.t()
+    if post is not None:
+        ref = ref * post
+    ref = ref + bias.double()
+    scale_ref = max(1.0, ref.abs().max().item())
+    assert y.dtype == dtype and y.shape == (M, N)
+    assert (y.double() - ref).abs().max().item() <= tol * scale_ref
+    old = F.GEMV_ROWS
+    F.GEMV_ROWS = 0
+    try:
+        y_tc = call()
+    finally:
+        F.GEMV_ROWS = old
+    assert (y.double() - y_tc.double()).abs().max().item() <= tol * scale_ref
+    if mode in ("nf4", "w8"):       # pruned weights: zero rows stay exactly bias
+        Wz = torch.zeros_like(W)
+        if mode == "nf4":
+            pz, az = F.quantize_4bit(Wz.to(dtype), 64, "nf4")
+            yz = F.gemm_w4a16(x, pz, az, N, K, bias, "nf4")
+        else:
+            qz, sz = F.quanto_quantize_qint8(Wz.to(dtype))
+            yz = F.gemm_w8a16(x, qz, sz.view(-1), bias)
+        assert torch.equal(yz, bias.to(dtype).expand(M, N))
