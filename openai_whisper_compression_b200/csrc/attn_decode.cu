@@ -313,6 +313,57 @@ __device__ __forceinline__ void quantize_row_if_last(const T *out, int b, int d,
     __threadfence();
     const bool sparse = threshold > 0.0f;
     const T *orow = out + (int64_t)b * d;
+    // The row comes from L2 (other CTAs wrote it): every 16-byte chunk of it is requested before the first one is
+    // used and stays in registers for the second pass.  (Element-wise loads in two dependent loops made this tail
+    // 40 + 10 serial L2 round trips at d = 1280: ~25 us at the end of every launch.)
+    constexpr int kRegChunks = 8;                    // 32 lanes x 8 chunks x 8 values: rows up to d = 2048
+    const int n8 = d >> 3;                           // d is a multiple of 64
+    if (n8 <= 32 * kRegChunks) {
+        uint4 buf[kRegChunks];
+#pragma unroll
+        for (int i = 0; i < kRegChunks; ++i) {
+            const int c8 = lane + 32 * i;
+            buf[i] = c8 < n8 ? __ldcg(reinterpret_cast<const uint4 *>(orow) + c8) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        float am = 0.0f;
+#pragma unroll
+        for (int i = 0; i < kRegChunks; ++i) {
+            const T *x8 = reinterpret_cast<const T *>(&buf[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float x = fabsf(to_f32(x8[j]));
+                if (!sparse || x < threshold) am = fmaxf(am, x);
+            }
+        }
+        am = warp_max(am);
+        if (lane == 0) {
+            row_stats[b] = am;
+            row_counters[b] = 0;
+        }
+        const float scale = bnb_row_scale(am);
+#pragma unroll
+        for (int i = 0; i < kRegChunks; ++i) {
+            const int c8 = lane + 32 * i;
+            if (c8 >= n8) break;
+            const T *x8 = reinterpret_cast<const T *>(&buf[i]);
+            uint32_t pk[2] = {0u, 0u};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float x = to_f32(x8[j]);
+                int qv;
+                if (sparse && !(fabsf(x) < threshold)) {
+                    qv = 0;
+                    col_flags[c8 * 8 + j] = 1;
+                    col_flags[d] = 1;
+                } else {
+                    qv = __float2int_rn(__fmul_rn(x, scale));
+                }
+                pk[j >> 2] |= (uint32_t)(qv & 0xff) << (8 * (j & 3));
+            }
+            *reinterpret_cast<uint2 *>(ca + (int64_t)b * d + c8 * 8) = make_uint2(pk[0], pk[1]);
+        }
+        return;
+    }
     float am = 0.0f;
     for (int c = lane; c < d; c += 32) {
         const float x = fabsf(to_f32(__ldcg(orow + c)));
@@ -475,7 +526,6 @@ k_cross_attn_decode(const T *__restrict__ q, int64_t ldq, float scaling, const T
 // HBM stream.  The ring is item-agnostic: the producer runs ahead across (utterance, head) boundaries.
 // ---------------------------------------------------------------------------------------------
 constexpr int kTMaxStages = 12;
-constexpr int kTStageBytes = 64 * 128;     // one operand (K or V) of one 64-position stage
 
 // kTCW consumer warps; a stage holds 16 * kTCW positions (one TMA box of K, one of V).  Warp kTCW is the TMA producer,
 // warp kTCW + 1 the finisher: the cross-CTA bookkeeping of the optional int8 row quantization (fence, counter, and

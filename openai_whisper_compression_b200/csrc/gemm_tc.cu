@@ -153,6 +153,14 @@ template <int BN, int BMODE, int LEAN = 0> constexpr int num_threads() { return 
 // LEAN = 1: the tile is 128 rows (ONE half) x BN columns with 4 epilogue warps -- decode-shaped calls with at most 128
 // rows.  Half the A bytes per stage, 192 threads and ~128 KB of shared memory instead of 320 / 226 KB, so that the CTA
 // fits on an SM next to a resident attention CTA of the other half-batch's stream (fastgen two-stream decode).
+//
+// LEAN = 2 / 3: the same tile for calls with at most 32 / 64 rows (decode row groups).  The MMA still spans 128 TMEM
+// lanes, but TMA fetches only a 32 / 64-row box of A per stage and the ring's A slots are packed at that pitch: the
+// instruction reads the following slots as rows 32.. / 64.. -- arbitrary bytes, accumulated into TMEM lanes whose rows
+// do not exist and are never stored.  A stage shrinks from 24 KB to 12 / 16 KB, so the same shared memory holds a ring
+// twice as deep: these launches are bound by the round trips of a shallow ring over a deep K (fc2), not by bytes.
+template <int LEAN> constexpr int lean_a_rows() { return LEAN == 2 ? 32 : (LEAN == 3 ? 64 : BMH); }
+
 template <int BN, int STAGES, int BMODE, int OUT_BUFS, int WS = 0, int COLS = 0, int LEAN = 0>
 struct SmemLayout {
     static_assert(LEAN == 0 || (WS == 0 && COLS == 0), "lean tiles: plain round-robin schedule");
@@ -160,8 +168,10 @@ struct SmemLayout {
     static_assert(COLS == 0 || (BMODE == B_DIRECT && BN == 128), "column-split tiles: int8 x int8 schemes, 2 x 128 columns");
     static constexpr int BMT = (COLS || LEAN) ? BMH : BM;      // tile rows
     static constexpr int BNT = COLS ? 2 * BN : BN;             // tile columns
-    static constexpr int A_BYTES = BMT * ROW_BYTES;
+    static constexpr int A_BYTES = (LEAN ? lean_a_rows<LEAN>() : BMT) * ROW_BYTES;
     static constexpr int B_BYTES = BNT * ROW_BYTES;
+    static_assert(LEAN < 2 || (BMODE == B_DIRECT && (STAGES - 1) * A_BYTES + BMH * ROW_BYTES <= STAGES * (A_BYTES + B_BYTES)),
+                  "packed A slots: the last slot's 128-row read must stay inside the ring");
     static constexpr int B_SLOTS = WS > 0 ? WS : STAGES;       // W buffers: one per ring stage, or the resident k-blocks
     static constexpr int P_ROW = is_byte<BMODE>() ? 64 : (is_nibble<BMODE>() ? 32 : 0);
     static constexpr int P_BYTES = BN * P_ROW;
@@ -542,33 +552,38 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    pdl_prologue_done();      // everything above touched only smem / TMEM / kernel parameters
+    pdl_prologue_done();
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
-        if (lane == 0) {
-            uint32_t it = 0;
-            int mt, nt;
-            if constexpr (WS > 0) {
-                if (tile_at<WS>(args, 0, mt, nt)) {      // the CTA's W tile, once: num_kb boxes of BN rows x 128 B
+        // The whole warp walks the loop and waits; one elected lane issues.  (Under `if (lane == 0)` the compiler
+        // cannot see that a single thread is active and wraps every UTMALDG / UTCIMMA / UTCBAR in an elect-broadcast-
+        // branch loop: ~55 cycles per instruction, ~500 cycles per k-block of pure issue overhead in each of the two
+        // warps -- more than the tensor time of an int8 k-block, and the whole cost of a decode-shaped call.)
+        uint32_t s = 0, ph = 0;      // ring slot and its parity
+        int mt, nt;
+        if constexpr (WS > 0) {
+            if (tile_at<WS>(args, 0, mt, nt)) {      // the CTA's W tile, once: num_kb boxes of BN rows x 128 B
+                if (elect_one()) {
                     mbar_arrive_expect_tx(bar_w, (uint32_t)num_kb * L::B_BYTES);
                     for (int kb = 0; kb < num_kb; ++kb)
                         tma_load_2d(smem + L::OFF_B + kb * L::B_BYTES, &map_b, bar_w, kb * 128, nt * BNT);
                 }
+                __syncwarp();
             }
-            for (int i = 0; tile_at<WS>(args, i, mt, nt); ++i) {
-                const int n0 = nt * BNT, m0 = mt * BMT;
-                // A streams from HBM with ~1.5 us of loaded latency and the ring holds < 1 tile: ask L2 for the row
-                // block this CTA reaches `prefetch` tiles from now (one of the tiles_n CTAs sharing it does)
-                int pf_m0 = -1;
-                if (args.prefetch > 0) {
-                    int pmt, pnt;
-                    if (tile_at<WS>(args, i + args.prefetch, pmt, pnt) && pmt % args.tiles_n == pnt) pf_m0 = pmt * BMT;
-                }
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&bar_empty[s], ph ^ 1);
+        }
+        for (int i = 0; tile_at<WS>(args, i, mt, nt); ++i) {
+            const int n0 = nt * BNT, m0 = mt * BMT;
+            // A streams from HBM with ~1.5 us of loaded latency and the ring holds < 1 tile: ask L2 for the row
+            // block this CTA reaches `prefetch` tiles from now (one of the tiles_n CTAs sharing it does)
+            int pf_m0 = -1;
+            if (args.prefetch > 0) {
+                int pmt, pnt;
+                if (tile_at<WS>(args, i + args.prefetch, pmt, pnt) && pmt % args.tiles_n == pnt) pf_m0 = pmt * BMT;
+            }
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&bar_empty[s], ph ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&bar_full[s], L::TX_BYTES);
                     tma_load_2d(smem + L::OFF_A + s * L::A_BYTES, &map_a, &bar_full[s], kb * A_ELEMS_PER_ROW, m0);
                     if (pf_m0 >= 0) tma_prefetch_2d(&map_a, kb * A_ELEMS_PER_ROW, pf_m0);
@@ -579,34 +594,36 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     else
                         tma_load_2d(smem + L::OFF_P + s * L::P_BYTES, &map_b, &bar_full[s], kb * L::P_ROW, n0);
                 }
+                __syncwarp();
+                if (++s == STAGES) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
-            constexpr uint32_t idesc =
-                kIntKind ? make_idesc(kAccS32, AKIND == A_S8 ? kFmtS8 : kFmtU8, kFmtS8, BMH, BNT)
-                         : make_idesc(kAccF32, AKIND == A_F16 ? kFmtF16 : kFmtBF16,
-                                      AKIND == A_F16 ? kFmtF16 : kFmtBF16, BMH, BN);
-            uint32_t it = 0, t = 0;
-            int mt, nt;
-            for (; tile_at<WS>(args, (int)t, mt, nt); ++t) {
-                const int m0 = mt * BMT;
-                const bool two_halves = COLS == 0 && LEAN == 0 && m0 + BMH < args.M;   // second 128 rows hold real data
-                if constexpr (WS > 0) {
-                    if (t == 0) mbar_wait(bar_w, 0);
-                }
-                const uint32_t as = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1;
-                mbar_wait(&bar_tmem_empty[as], aph ^ 1);      // epilogue has drained this accumulator
+        // ---------------- MMA issuer (whole warp in the loop, one elected lane issues) ----------------
+        constexpr uint32_t idesc =
+            kIntKind ? make_idesc(kAccS32, AKIND == A_S8 ? kFmtS8 : kFmtU8, kFmtS8, BMH, BNT)
+                     : make_idesc(kAccF32, AKIND == A_F16 ? kFmtF16 : kFmtBF16,
+                                  AKIND == A_F16 ? kFmtF16 : kFmtBF16, BMH, BN);
+        uint32_t s = 0, ph = 0, t = 0;
+        int mt, nt;
+        for (; tile_at<WS>(args, (int)t, mt, nt); ++t) {
+            const int m0 = mt * BMT;
+            const bool two_halves = COLS == 0 && LEAN == 0 && m0 + BMH < args.M;   // second 128 rows hold real data
+            if constexpr (WS > 0) {
+                if (t == 0) mbar_wait(bar_w, 0);
+            }
+            const uint32_t as = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1;
+            mbar_wait(&bar_tmem_empty[as], aph ^ 1);      // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + as * ACC_COLS;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&bar_full[s], ph);
+                if constexpr (BMODE != B_DIRECT) mbar_wait(&bar_bready[s], ph);
                 tc_fence_after();
-                const uint32_t tmem_acc = tmem_base + as * ACC_COLS;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&bar_full[s], ph);
-                    if constexpr (BMODE != B_DIRECT) mbar_wait(&bar_bready[s], ph);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint64_t adesc0 = make_smem_desc_sw128(smem + L::OFF_A + s * L::A_BYTES);
                     const uint64_t adesc1 = make_smem_desc_sw128(smem + L::OFF_A + s * L::A_BYTES + BMH * ROW_BYTES);
                     const uint64_t bdesc = make_smem_desc_sw128(smem + L::OFF_B + (WS > 0 ? kb : s) * L::B_BYTES);
@@ -623,10 +640,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     }
                     umma_commit(&bar_empty[s]);  // implicit tcgen05.fence::before_thread_sync
                 }
-                umma_commit(&bar_tmem_full[as]);
+                __syncwarp();
+                if (++s == STAGES) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
+            if (elect_one()) umma_commit(&bar_tmem_full[as]);
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp < 2 + EW) {
         // ---------------- epilogue: warps 2..9 ----------------
         uint8_t *boxes = smem + L::OFF_OUT + (warp - 2) * OUT_BUFS * BOX_BYTES;   // private staging of this warp
@@ -787,9 +809,9 @@ constexpr int pick_stages() {
     int best = 2;
     // lean tiles stop at 128 KB: they are meant to share an SM with another stream's resident CTAs
     const int budget = LEAN ? 131072 : 232448;
-    for (int st = 2; st <= 6; ++st) {
+    for (int st = 2; st <= (LEAN >= 2 ? 12 : 6); ++st) {
         const int bmt = (COLS || LEAN) ? BMH : BM, bnt = COLS ? 2 * BN : BN;
-        const int stage = bmt * ROW_BYTES + (WS > 0 ? 0 : bnt * ROW_BYTES) + BN * (is_byte<BMODE>() ? 64 : (is_nibble<BMODE>() ? 32 : 0));
+        const int stage = (LEAN ? lean_a_rows<LEAN>() : bmt) * ROW_BYTES + (WS > 0 ? 0 : bnt * ROW_BYTES) + BN * (is_byte<BMODE>() ? 64 : (is_nibble<BMODE>() ? 32 : 0));
         const int total = st * stage + WS * bnt * ROW_BYTES + epi_warps<BN, BMODE, LEAN>() * OUT_BUFS * BOX_BYTES +
                           (WS > 0 ? 1 : 2) * 3 * bnt * 4 + 64 + (3 * st + 2 * ACC_STAGES + 1) * 8 + 16 + 1024;
         if (total <= budget) best = st;
@@ -894,12 +916,20 @@ int launch_i8(const void *a, const void *b, GemmArgs args, cudaStream_t s) {
     const int64_t M = args.M, N = args.N, K = args.K;
     const bool narrow = use_narrow_tile(M, N), cols = use_cols(M, N, K);
     const bool lean = narrow && use_lean_tile(M);
+    static const bool slim_on = [] {        // WQ_GEMM_SLIM=0: 128-row A boxes for every lean call (A/B measurements)
+        const char *e = getenv("WQ_GEMM_SLIM");
+        return e == nullptr || e[0] != '0';
+    }();
+    const int slim = (lean && slim_on) ? (M <= 32 ? 2 : (M <= 64 ? 3 : 0)) : 0;
     CUtensorMap ma, mb;
-    int rc = make_map_2d(&ma, a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, (cols || lean) ? BMH : BM, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = make_map_2d(&ma, a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K,
+                         slim == 2 ? 32 : (slim == 3 ? 64 : ((cols || lean) ? BMH : BM)), 128, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
     rc = make_map_2d(&mb, b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, narrow ? 64 : (cols ? 256 : 128), 128,
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
+    if (slim == 2) return launch_gemm<64, AKIND, B_DIRECT, EPI, OutT, 0, 0, 2>(ma, mb, args, s);
+    if (slim == 3) return launch_gemm<64, AKIND, B_DIRECT, EPI, OutT, 0, 0, 3>(ma, mb, args, s);
     if (lean) return launch_gemm<64, AKIND, B_DIRECT, EPI, OutT, 0, 0, 1>(ma, mb, args, s);
     if (narrow) return launch_gemm<64, AKIND, B_DIRECT, EPI, OutT>(ma, mb, args, s);
     const bool ws = use_ws(M, N, K, cols);
@@ -925,6 +955,7 @@ int check_common(const char *fn, int64_t M, int64_t N, int64_t K) {
 }
 
 }  // namespace
+
 
 extern "C" int wq_gemm_llmint8(const int8_t *ca, const float *sca, const int8_t *cb, const float *scb,
                                const float *bias, void *y_f16, int64_t M, int64_t N, int64_t K, const void *a_f16,

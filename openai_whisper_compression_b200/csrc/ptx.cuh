@@ -58,6 +58,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// One lane of the (converged) warp: elect.sync.  Code under `if (elect_one())` is known to the compiler to run on a
+// single thread, so warp-level instructions inside it (TMA, tcgen05.mma / commit) are issued once, without the
+// per-active-lane serialisation loop that an `if (lane == 0)` region gets.  The same lane is chosen every time.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA
 // ---------------------------------------------------------------------------------------------
