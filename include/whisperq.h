@@ -161,11 +161,14 @@ int wq_gemm_llmint8_shared(const int8_t *ca, const float *sca, const int8_t *cb,
  * rank 3): y = clamp(fp16(linear) + residual, -clamp_abs, clamp_abs) -- HF's `hidden_states = residual +
  * hidden_states` and the fp16 overflow clamp that close WhisperEncoderLayer.forward (modeling_whisper.py:408-414),
  * evaluated as torch does (the projection rounded to fp16, one fp16 addition, clamp).  residual_f16: [M, N] fp16,
- * contiguous (may be NULL); clamp_abs 0 = no clamp. */
+ * contiguous (may be NULL); clamp_abs 0 = no clamp.
+ * a_pre_gelu != 0: the int8 rows were produced by wq_gelu_quant with h_out == NULL (fc2 after the layer's GELU,
+ * modeling_whisper.py:403-405) and a_f16 is the tensor BEFORE the activation (fc1's output); the outlier path
+ * evaluates the same fp16 GELU on the entries it needs, so the result is the one the stored activation would give. */
 int wq_gemm_llmint8_residual(const int8_t *ca, const float *sca, const int8_t *cb, const float *scb,
                              const float *bias, void *y_f16, int64_t M, int64_t N, int64_t K,
                              const void *a_f16, int32_t *col_flags, int keep_flags,
-                             const void *residual_f16, float clamp_abs, wq_stream_t stream);
+                             const void *residual_f16, float clamp_abs, int a_pre_gelu, wq_stream_t stream);
 
 /* The same Linear8bitLt forward for decode-shaped calls (M <= 64 rows, 64*K + K + 272 <= 200 KiB):
  * activation quantization (threshold rule), int8 products (dp4a), int8_mm_dequant and the outlier
@@ -268,7 +271,8 @@ int wq_add_layernorm_quant(const void *x, const void *delta, int dtype, const vo
                            void *h_out, float threshold, int8_t *ca, float *row_stats,
                            int32_t *col_flags, wq_stream_t stream);
 
-/* h_out = gelu(x) (erf form, torch approximate="none"), fp32 math.  cols % 8 == 0. */
+/* h_out = gelu(x) (erf form, torch approximate="none"), fp32 math.  cols % 8 == 0.  h_out may be NULL when `ca` is
+ * not: only the int8 rows (and row_stats / col_flags) are produced -- see wq_gemm_llmint8_residual, a_pre_gelu. */
 int wq_gelu_quant(const void *x, int dtype, int64_t rows, int64_t cols, void *h_out, float threshold,
                   int8_t *ca, float *row_stats, int32_t *col_flags, wq_stream_t stream);
 

@@ -37,7 +37,7 @@ _PROTOS = {
     "wq_gemm_llmint8_shared": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_int,
                                c_ptr],
     "wq_gemm_llmint8_residual": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_int,
-                                 c_ptr, c_f32, c_ptr],
+                                 c_ptr, c_f32, c_int, c_ptr],
     "wq_linear_llmint8_small": [c_ptr, c_i64, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     "wq_gemm_w8a16": [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],
     "wq_gemm_w4a16": [c_ptr, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_int, c_i64, c_i64, c_i64, c_ptr],

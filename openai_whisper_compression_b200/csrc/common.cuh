@@ -116,6 +116,13 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
     return __float2bfloat16_rn(v);
 }
 
+// gelu(x) as torch computes it for approximate='none': x * 0.5 * (1 + erf(x / sqrt(2))) in fp32, rounded to T.
+// One definition: the row kernels (rowops.cu), their lookup table, and the GEMM's outlier path that re-derives
+// gelu(fc1 output) when the fp16 activation was never stored must agree bit for bit.
+template <typename T> __device__ __forceinline__ T gelu_erf(float f) {
+    return from_f32<T>(f * 0.5f * (1.0f + erff(f * 0.70710678118654752440f)));
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -72,6 +72,8 @@ struct GemmArgs {
     // LLM.int8 mixed-precision decomposition (consumed only when flags != nullptr && flags[K] != 0)
     const int8_t *ca, *cb;
     const __half *a16;
+    int a_pre_gelu;          // 1: a16 holds the values BEFORE the GELU whose output was quantized (the fp16 GELU output was
+                             // never stored); the outlier path evaluates gelu_erf<__half> on the entries it needs
     int32_t *flags;          // [K + 2]: per-column flags, "any", completion counter
     int keep_flags;          // 1: leave the flags set (another GEMM consumes the same quantized rows next)
     int prefetch;            // > 0: the producer pulls the A row block it will load `prefetch` tiles later into L2
@@ -330,7 +332,11 @@ __device__ __noinline__ void llmint8_outlier_chunk(const GemmArgs &args, const f
     for (int c = 0; c < args.K; ++c) {
         if (args.flags[c] == 0) continue;
         const int a8 = row_ok ? (int)args.ca[(size_t)m * args.K + c] : 0;
-        const float af = row_ok ? __half2float(args.a16[(size_t)m * args.K + c]) : 0.0f;
+        float af = 0.0f;
+        if (row_ok) {
+            const __half raw = args.a16[(size_t)m * args.K + c];
+            af = __half2float(args.a_pre_gelu ? gelu_erf<__half>(__half2float(raw)) : raw);
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const int n = n_abs + j;
@@ -967,13 +973,14 @@ extern "C" int wq_gemm_llmint8_shared(const int8_t *ca, const float *sca, const 
                                       const float *bias, void *y_f16, int64_t M, int64_t N, int64_t K,
                                       const void *a_f16, int32_t *col_flags, int keep_flags, wq_stream_t stream) {
     return wq_gemm_llmint8_residual(ca, sca, cb, scb, bias, y_f16, M, N, K, a_f16, col_flags, keep_flags, nullptr, 0.0f,
-                                    stream);
+                                    0, stream);
 }
 
 extern "C" int wq_gemm_llmint8_residual(const int8_t *ca, const float *sca, const int8_t *cb, const float *scb,
                                         const float *bias, void *y_f16, int64_t M, int64_t N, int64_t K,
                                         const void *a_f16, int32_t *col_flags, int keep_flags,
-                                        const void *residual_f16, float clamp_abs, wq_stream_t stream) {
+                                        const void *residual_f16, float clamp_abs, int a_pre_gelu,
+                                        wq_stream_t stream) {
     int rc = check_common("wq_gemm_llmint8", M, N, K);
     if (rc != WQ_OK) return rc;
     if (M == 0 || N == 0) return WQ_OK;
@@ -988,6 +995,7 @@ extern "C" int wq_gemm_llmint8_residual(const int8_t *ca, const float *sca, cons
     args.row_scale = sca; args.col_scale = scb; args.bias = bias; args.out = y_f16;
     args.ca = ca; args.cb = cb; args.a16 = (const __half *)a_f16; args.flags = col_flags;
     args.keep_flags = keep_flags ? 1 : 0;
+    args.a_pre_gelu = a_pre_gelu ? 1 : 0;
     WQ_REQUIRE(residual_f16 == nullptr || (wq_aligned(residual_f16, 16) && N % 8 == 0),
                "wq_gemm_llmint8: the residual needs 16-byte aligned rows (N %% 8 == 0)");
     WQ_REQUIRE(clamp_abs >= 0.0f, "wq_gemm_llmint8: negative clamp");

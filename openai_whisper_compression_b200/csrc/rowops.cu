@@ -149,11 +149,6 @@ k_add_ln_quant(const T *x, const T *__restrict__ delta, const T *__restrict__ ga
     }
 }
 
-// gelu(x) as torch computes it for approximate='none': x * 0.5 * (1 + erf(x / sqrt(2))) in fp32, rounded to T.
-template <typename T> __device__ __forceinline__ T gelu_erf(float f) {
-    return from_f32<T>(f * 0.5f * (1.0f + erff(f * 0.70710678118654752440f)));
-}
-
 // ---------------------------------------------------------------------------------------------
 // h = gelu(x) (torch approximate='none': x * 0.5 * (1 + erf(x / sqrt(2))) in fp32); optional int8 row
 // quantization of h.  Two passes over the row (the second re-reads the lane's own stores); cols % 8 == 0.
@@ -181,7 +176,7 @@ k_gelu_quant(const T *__restrict__ x, int64_t rows, int64_t cols, T *__restrict_
                 h.set(j, r);
                 am = absmax_step(am, to_f32(r), sparse, threshold);
             }
-            *reinterpret_cast<uint4 *>(h_out + base + c) = h.raw;
+            if (h_out != nullptr) *reinterpret_cast<uint4 *>(h_out + base + c) = h.raw;
         }
     }
     if (ca == nullptr) return;
@@ -198,7 +193,14 @@ k_gelu_quant(const T *__restrict__ x, int64_t rows, int64_t cols, T *__restrict_
     const float scale = bnb_row_scale(am);
     for (int64_t c = (part * 32 + lane) * 8; c < cols; c += 256 * G) {
         Vec8<T> h;
-        h.raw = *reinterpret_cast<const uint4 *>(h_out + base + c);     // this lane's own store
+        if (h_out != nullptr) {
+            h.raw = *reinterpret_cast<const uint4 *>(h_out + base + c);     // this lane's own store
+        } else {                                                            // h not kept: evaluate it again
+            Vec8<T> a;
+            a.raw = *reinterpret_cast<const uint4 *>(x + base + c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h.set(j, gelu_erf<T>(to_f32(a.get(j))));
+        }
         uint32_t lo = 0, hi = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -215,7 +217,10 @@ k_gelu_quant(const T *__restrict__ x, int64_t rows, int64_t cols, T *__restrict_
 // every CTA of k_gelu_quant_lut copies it into shared memory and then replaces ~40 fp32 instructions per element
 // (erff) by one 2-byte shared-memory load -- bit-identical by construction, and the kernel goes from
 // instruction-bound (1.19 ms per 384000 x 2048 on B200) to the HBM stream it is (2 B read, 3 B written per element).
-// Persistent CTAs of 16 warps, one warp per row, the row's 8 x 16-byte chunks are loaded up front and converted in place.
+// Persistent CTAs of 16 warps, one warp per row, the row's NCH x 16-byte chunks per lane are loaded up front and
+// converted in place (NCH = 8 / 12 / 16 / 20: rows up to 2048 / 3072 / 4096 / 5120 columns -- every Whisper ffn width).
+// h_out may be NULL when only the int8 rows are wanted: the consumer GEMM re-derives the few fp16 values its outlier
+// path needs from x (wq_gemm_llmint8_residual, a_pre_gelu), and 2 of the 5 bytes per element never reach HBM.
 // ---------------------------------------------------------------------------------------------
 constexpr int kLutWarps = 16;
 constexpr int kLutEntries = 65536;
@@ -226,6 +231,7 @@ __global__ void k_gelu_table_fill() {
     if (i < (unsigned)kLutEntries) g_gelu_table[i] = gelu_erf<__half>(__half2float(__ushort_as_half((unsigned short)i)));
 }
 
+template <int NCH>
 __global__ void __launch_bounds__(kLutWarps * 32, 1)
 k_gelu_quant_lut(const __half *__restrict__ x, int64_t rows, int cols, __half *__restrict__ h_out, float threshold,
                  int8_t *__restrict__ ca, float *__restrict__ row_stats, int32_t *__restrict__ col_flags) {
@@ -241,15 +247,15 @@ k_gelu_quant_lut(const __half *__restrict__ x, int64_t rows, int cols, __half *_
     const bool sparse = threshold > 0.0f;
     for (int64_t row = (int64_t)blockIdx.x * kLutWarps + warp; row < rows; row += (int64_t)gridDim.x * kLutWarps) {
         const int64_t base = row * cols;
-        uint4 v[kMaxChunks];
+        uint4 v[NCH];
 #pragma unroll
-        for (int i = 0; i < kMaxChunks; ++i) {
+        for (int i = 0; i < NCH; ++i) {
             const int c = i * 256 + lane * 8;
             if (c < cols) v[i] = __ldcs(reinterpret_cast<const uint4 *>(x + base + c));     // streamed once
         }
         float am = 0.0f;
 #pragma unroll
-        for (int i = 0; i < kMaxChunks; ++i) {
+        for (int i = 0; i < NCH; ++i) {
             const int c = i * 256 + lane * 8;
             if (c < cols) {
                 uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
@@ -261,7 +267,7 @@ k_gelu_quant_lut(const __half *__restrict__ x, int64_t rows, int cols, __half *_
                     w[j] = lo | (hi << 16);
                 }
                 v[i] = make_uint4(w[0], w[1], w[2], w[3]);
-                *reinterpret_cast<uint4 *>(h_out + base + c) = v[i];
+                if (h_out != nullptr) *reinterpret_cast<uint4 *>(h_out + base + c) = v[i];
             }
         }
         if (ca == nullptr) continue;
@@ -269,7 +275,7 @@ k_gelu_quant_lut(const __half *__restrict__ x, int64_t rows, int cols, __half *_
         if (lane == 0) row_stats[row] = am;
         const float scale = bnb_row_scale(am);
 #pragma unroll
-        for (int i = 0; i < kMaxChunks; ++i) {
+        for (int i = 0; i < NCH; ++i) {
             const int c = i * 256 + lane * 8;
             if (c < cols) {
                 const __half *h8 = reinterpret_cast<const __half *>(&v[i]);
@@ -406,14 +412,14 @@ extern "C" int wq_gelu_quant(const void *x, int dtype, int64_t rows, int64_t col
     WQ_REQUIRE(dtype == WQ_F16 || dtype == WQ_BF16, "wq_gelu_quant: dtype must be f16 or bf16");
     WQ_REQUIRE(threshold >= 0.0f, "wq_gelu_quant: negative threshold");
     if (rows == 0) return WQ_OK;
-    WQ_REQUIRE(x && h_out, "wq_gelu_quant: null pointer");
+    WQ_REQUIRE(x && (h_out || ca), "wq_gelu_quant: null pointer (h_out may be NULL only when the int8 rows are asked for)");
     WQ_REQUIRE(ca == nullptr || (dtype == WQ_F16 && row_stats != nullptr),
                "wq_gelu_quant: the int8 outputs need fp16 rows and row_stats");
     WQ_REQUIRE(ca == nullptr || threshold == 0.0f || col_flags, "wq_gelu_quant: threshold needs col_flags");
-    WQ_REQUIRE(wq_aligned(x, 16) && wq_aligned(h_out, 16) && (ca == nullptr || wq_aligned(ca, 8)),
+    WQ_REQUIRE(wq_aligned(x, 16) && (h_out == nullptr || wq_aligned(h_out, 16)) && (ca == nullptr || wq_aligned(ca, 8)),
                "wq_gelu_quant: pointers must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == WQ_F16 && rows >= 4096 && cols <= 256 * kMaxChunks) {
+    if (dtype == WQ_F16 && rows >= 4096 && cols <= 256 * 20) {
         // table path (k_gelu_quant_lut).  The table of a device is filled on first use, synchronously; a first use
         // under stream capture (no synchronisation allowed) takes the erff kernel below instead.
         static bool ready[64] = {};
@@ -435,14 +441,22 @@ extern "C" int wq_gelu_quant(const void *x, int dtype, int64_t rows, int64_t col
         }
         if (ok) {
             if (!configured) {
-                WQ_CUDA(cudaFuncSetAttribute(k_gelu_quant_lut, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kLutEntries * 2));
+                WQ_CUDA(cudaFuncSetAttribute(k_gelu_quant_lut<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutEntries * 2));
+                WQ_CUDA(cudaFuncSetAttribute(k_gelu_quant_lut<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutEntries * 2));
+                WQ_CUDA(cudaFuncSetAttribute(k_gelu_quant_lut<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutEntries * 2));
+                WQ_CUDA(cudaFuncSetAttribute(k_gelu_quant_lut<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutEntries * 2));
                 configured = true;
             }
             const int64_t want = (rows + kLutWarps - 1) / kLutWarps;
             const unsigned grid = (unsigned)(want < wq_sm_count() ? want : wq_sm_count());
-            WQ_LAUNCH_PDL(k_gelu_quant_lut, dim3(grid), dim3(kLutWarps * 32), (size_t)kLutEntries * 2, s,
-                          (const __half *)x, rows, (int)cols, (__half *)h_out, threshold, ca, row_stats, col_flags);
+#define WQ_LUT_LAUNCH(NCH)                                                                                           \
+            WQ_LAUNCH_PDL(k_gelu_quant_lut<NCH>, dim3(grid), dim3(kLutWarps * 32), (size_t)kLutEntries * 2, s,           \
+                          (const __half *)x, rows, (int)cols, (__half *)h_out, threshold, ca, row_stats, col_flags)
+            if (cols <= 256 * 8) WQ_LUT_LAUNCH(8);
+            else if (cols <= 256 * 12) WQ_LUT_LAUNCH(12);
+            else if (cols <= 256 * 16) WQ_LUT_LAUNCH(16);
+            else WQ_LUT_LAUNCH(20);
+#undef WQ_LUT_LAUNCH
             return WQ_OK;
         }
     }

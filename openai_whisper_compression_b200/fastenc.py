@@ -98,12 +98,16 @@ def _layer_forward_int8(self, hidden_states, attention_mask=None, **kwargs):
     att = fused.gemm(F.int8_vectorwise_quant(a, thr, finalize=False) if thr is not None else None, a, plan.o)
     ln = self.final_layer_norm
     x, h, qt = F.add_layernorm_quant(x, att, ln.weight, ln.bias, ln.eps, thr)
-    g, qt = F.gelu_quant(fused.gemm(qt, h, plan.fc1), thr)
     clamp_value = torch.finfo(torch.float16).max - 1000
     if plan.qkv.kind == "int8":
-        # residual add + fp16 clamp in the fc2 GEMM's epilogue (bit-identical to the two torch kernels they replace)
-        out = fused.gemm_int8(qt, g, plan.fc2, residual=x, clamp_abs=float(clamp_value))
+        # The fp16 GELU output is only ever read for outlier columns: it is not stored; fc2 takes fc1's output and
+        # re-derives those entries (a_pre_gelu).  Residual add + fp16 clamp ride in fc2's epilogue (bit-identical to
+        # the two torch kernels they replace).
+        f1 = fused.gemm(qt, h, plan.fc1)
+        _, qt = F.gelu_quant(f1, thr, store_h=False)
+        out = fused.gemm_int8(qt, f1, plan.fc2, residual=x, clamp_abs=float(clamp_value), a_pre_gelu=True)
         return out.view(B, S, d)
+    g, qt = F.gelu_quant(fused.gemm(qt, h, plan.fc1), thr)
     out = x + fused.gemm(qt, g, plan.fc2)
     if out.dtype == torch.float16:      # HF clamps fp16 activations only
         out = torch.clamp(out, min=-clamp_value, max=clamp_value)

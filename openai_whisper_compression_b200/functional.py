@@ -293,12 +293,13 @@ def gemm_llmint8(ca: torch.Tensor, sca: torch.Tensor, cb: torch.Tensor, scb: tor
                  bias: Optional[torch.Tensor] = None, a_f16: Optional[torch.Tensor] = None,
                  state: Optional[OutlierState] = None, out: Optional[torch.Tensor] = None,
                  keep_flags: bool = False, residual: Optional[torch.Tensor] = None,
-                 clamp_abs: float = 0.0) -> torch.Tensor:
+                 clamp_abs: float = 0.0, a_pre_gelu: bool = False) -> torch.Tensor:
     """int8_linear_matmul + int8_mm_dequant (+ mixed-precision outlier decomposition when `state`
     carries raw flags from int8_vectorwise_quant(..., finalize=False)), one kernel; fp16 [M, N].
     out: optional contiguous fp16 [M, N] destination.  keep_flags: leave the outlier flags set because
     another GEMM consumes the same quantized rows next (the last consumer clears them).  residual / clamp_abs: the
-    layer's residual connection in the epilogue, y = clamp(fp16(linear) + residual) (fc2 of a Whisper layer)."""
+    layer's residual connection in the epilogue, y = clamp(fp16(linear) + residual) (fc2 of a Whisper layer).
+    a_pre_gelu: the int8 rows came from gelu_quant(..., store_h=False) and a_f16 is the tensor before the GELU."""
     ca2 = ca.reshape(-1, ca.shape[-1])
     _need_cuda(ca2, sca, cb, scb, bias, a_f16)
     M, K = ca2.shape
@@ -323,7 +324,7 @@ def gemm_llmint8(ca: torch.Tensor, sca: torch.Tensor, cb: torch.Tensor, scb: tor
             _ptr(ca2), _ptr(sca), _ptr(cb), _ptr(scb), _ptr(bias), _ptr(y), M, N, K,
             _ptr(a_f16) if state is not None else None,
             _ptr(state.col_flags) if state is not None else None, 1 if keep_flags else 0, _ptr(residual),
-            float(clamp_abs), _stream()), "wq_gemm_llmint8")
+            float(clamp_abs), 1 if a_pre_gelu else 0, _stream()), "wq_gemm_llmint8")
     STATS.launches += 1
     return y
 
@@ -395,14 +396,17 @@ def add_layernorm_quant(x: torch.Tensor, delta: Optional[torch.Tensor], weight: 
     return x_out.view(x.shape), h.view(x.shape), quant
 
 
-def gelu_quant(x: torch.Tensor, threshold: Optional[float] = None):
+def gelu_quant(x: torch.Tensor, threshold: Optional[float] = None, store_h: bool = True):
     """h = gelu(x) (erf form) and, with a threshold, the Linear8bitLt row quantization of h -- one launch.
-    Returns (h, (ca, sca, state) | None)."""
+    Returns (h, (ca, sca, state) | None).  store_h=False (needs a threshold): only the int8 rows are written and h is
+    None -- the consuming gemm_llmint8 takes x itself with a_pre_gelu=True (2 of 5 bytes per element less HBM traffic)."""
     cols = x.shape[-1]
     x2 = x.reshape(-1, cols)
     _need_cuda(x2)
     rows = x2.shape[0]
-    h = torch.empty_like(x2)
+    if not store_h and threshold is None:
+        raise RuntimeError("gelu_quant: store_h=False without a threshold would produce nothing")
+    h = torch.empty_like(x2) if store_h else None
     ca, sca, state = _quant_outputs(rows, cols, x.device, threshold)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().wq_gelu_quant(_ptr(x2), _DT[x2.dtype], rows, cols, _ptr(h), float(threshold or 0.0),
@@ -410,7 +414,7 @@ def gelu_quant(x: torch.Tensor, threshold: Optional[float] = None):
                                              _ptr(state.col_flags) if state is not None else None, _stream()),
                    "wq_gelu_quant")
     STATS.launches += 1
-    return h.view(x.shape), (None if threshold is None else (ca, sca, state))
+    return (h.view(x.shape) if h is not None else None), (None if threshold is None else (ca, sca, state))
 
 
 def self_attn_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scaling: float, k_cache: torch.Tensor,

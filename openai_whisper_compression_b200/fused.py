@@ -131,18 +131,20 @@ def pack(mods: Sequence[torch.nn.Module], dtype: torch.dtype) -> Optional[Packed
 
 
 def gemm_int8(quant, a: torch.Tensor, w: Packed, out: Optional[torch.Tensor] = None,
-              keep_flags: bool = False, residual: Optional[torch.Tensor] = None, clamp_abs: float = 0.0) -> torch.Tensor:
+              keep_flags: bool = False, residual: Optional[torch.Tensor] = None, clamp_abs: float = 0.0,
+              a_pre_gelu: bool = False) -> torch.Tensor:
     """Linear8bitLt's GEMM on rows that are already quantized: quant = (CA, SCA, outlier state) from a fused
-    producer, `a` the fp16 rows they were made from (read only for outlier columns).  quant None (decode-shaped calls
+    producer, `a` the fp16 rows they were made from (read only for outlier columns; with a_pre_gelu the rows BEFORE
+    the GELU whose output was quantized -- gelu_quant(store_h=False)).  quant None (decode-shaped calls
     with <= 16 rows whose producer did not quantize): the single-launch kernel that quantizes the rows itself and
     multiplies with dp4a (gemv_small.cu; bit-identical results)."""
     if quant is None:
-        if residual is not None or out is not None:
+        if residual is not None or out is not None or a_pre_gelu:
             raise RuntimeError("gemm_int8: the small-row kernel takes neither a residual nor a destination")
         return F.linear8bitlt(a, w.cb, w.scb, w.bias, w.threshold)
     ca, sca, state = quant
     return F.gemm_llmint8(ca, sca, w.cb, w.scb, w.bias, a if state is not None else None, state, out=out,
-                          keep_flags=keep_flags, residual=residual, clamp_abs=clamp_abs)
+                          keep_flags=keep_flags, residual=residual, clamp_abs=clamp_abs, a_pre_gelu=a_pre_gelu)
 
 
 def gemm(quant, a: torch.Tensor, w: Packed, out: Optional[torch.Tensor] = None, keep_flags: bool = False) -> torch.Tensor:

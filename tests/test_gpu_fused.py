@@ -124,10 +124,11 @@ def test_gelu_quant(rows, cols, threshold):
         _check_quant(quant, h, threshold)
 
 
-@pytest.mark.parametrize("rows,cols", [(4096, 2048), (5003, 1000), (6000, 384), (4100, 8)])
+@pytest.mark.parametrize("rows,cols", [(4096, 2048), (5003, 1000), (6000, 384), (4100, 8), (4097, 3072), (4200, 4096),
+                                       (4099, 5120), (4100, 2056)])
 @pytest.mark.parametrize("threshold", [None, 0.0, 6.0])
 def test_gelu_quant_table_path_is_bit_identical_to_erf_path(rows, cols, threshold):
-    """Encoder-sized fp16 calls (rows >= 4096, cols <= 2048) take the 65536-entry table kernel; the same rows in
+    """Encoder-sized fp16 calls (rows >= 4096, cols <= 5120) take the 65536-entry table kernel; the same rows in
     chunks of 1000 take the erff kernel.  Same values, codes, row statistics and outlier flags, bit for bit --
     including every special input (inf, nan, -0, subnormals)."""
     g = torch.Generator(device="cuda").manual_seed(rows + cols)
@@ -154,6 +155,33 @@ def test_gelu_quant_table_path_is_bit_identical_to_erf_path(rows, cols, threshol
         assert torch.equal(flags, st.col_flags[: cols + 1])
         st.col_flags.zero_()
         assert int(flags[cols].item()) == 1
+
+
+@pytest.mark.parametrize("rows,cols,N", [(4200, 2048, 512), (4100, 5120, 1280), (37, 3072, 768), (300, 1536, 384)])
+@pytest.mark.parametrize("threshold", [0.0, 6.0])
+def test_gelu_quant_without_the_fp16_store(rows, cols, N, threshold):
+    """gelu_quant(store_h=False) writes the same int8 rows, row statistics and outlier flags and no fp16 activation;
+    fc2 with a_pre_gelu=True on fc1's output then gives, bit for bit, what it gives on the stored activation --
+    outlier columns included (table kernel and erff kernel, every table width)."""
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    x = (torch.randn(rows, cols, device="cuda", generator=g) * 2.5).half()
+    cb = torch.randint(-127, 128, (N, cols), device="cuda", generator=g, dtype=torch.int8)
+    scb = torch.rand(N, device="cuda", generator=g) * 0.05 + 0.01
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(rows, N, device="cuda", generator=g).half()
+    h, q_ref = F.gelu_quant(x, threshold)
+    if threshold:
+        assert (h.float().abs() >= threshold).any()
+    y_ref = F.gemm_llmint8(q_ref[0], q_ref[1], cb, scb, bias, a_f16=h, state=q_ref[2], residual=res, clamp_abs=64000.0)
+    if q_ref[2] is not None:
+        assert int(q_ref[2].col_flags[: cols + 2].abs().sum().item()) == 0       # the GEMM cleared the flags
+    none, q = F.gelu_quant(x, threshold, store_h=False)
+    assert none is None
+    assert torch.equal(q[0], q_ref[0]) and torch.equal(q[1].view(torch.int32), q_ref[1].view(torch.int32))
+    y = F.gemm_llmint8(q[0], q[1], cb, scb, bias, a_f16=x, state=q[2], residual=res, clamp_abs=64000.0, a_pre_gelu=True)
+    assert torch.equal(y.view(torch.int16), y_ref.view(torch.int16))
+    with pytest.raises(RuntimeError, match="store_h"):
+        F.gelu_quant(x, None, store_h=False)
 
 
 @pytest.mark.parametrize("B,H,t_max,pos", [(3, 6, 64, 0), (5, 8, 128, 17), (2, 20, 448, 447), (64, 8, 128, 64),
