@@ -739,8 +739,19 @@ extern "C" int wq_cross_attn_decode(const void *q, int64_t ldq, int dtype, float
         rc = make_map_2d(&mv, v, dt, 2, (uint64_t)(B * S), (uint64_t)H * kHeadDim, box_rows, kHeadDim,
                          CU_TENSOR_MAP_SWIZZLE_NONE, (uint64_t)ld, promo);
         if (rc != WQ_OK) return rc;
-        const int cap = wq_sm_count();
-        const dim3 grid((unsigned)(n_items < cap ? n_items : cap));
+        // Grid: one CTA per SM walking the items.  With few items (<= 2.5 per SM) that walk ends in a ragged wave -- 320
+        // items on 148 CTAs: 24 CTAs carry a third item while 124 SMs idle -- so up to two resident CTAs per SM share
+        // them evenly instead (320 items as 160 x 2: 30.5 -> 27.9 us alone, large-v3 step 313 -> 309 ms; 192 items as
+        // 192 x 1: 21.6 -> 18.1 us).  Beyond that the even split measured no better inside the multi-stream step
+        // (whisper-base, 4 groups of 512 items: 256 x 2 109.3 ms, 128 x 4 107.1 ms, 148-CTA walk 106 ms per step).
+        // WQ_XATTN_TMA_CTAS=1 forces the one-per-SM walk.
+        static const bool even_split = [] { const char *e = getenv("WQ_XATTN_TMA_CTAS"); return !(e && atoi(e) == 1); }();
+        int n_ctas = n_items < wq_sm_count() ? n_items : wq_sm_count();
+        if (even_split && 2 * n_items <= 5 * wq_sm_count()) {
+            const int per_cta = (n_items + 2 * wq_sm_count() - 1) / (2 * wq_sm_count());
+            n_ctas = (n_items + per_cta - 1) / per_cta;
+        }
+        const dim3 grid((unsigned)n_ctas);
         static bool configured = false;
         if (!configured) {
             WQ_CUDA(cudaFuncSetAttribute(k_cross_attn_decode_tma<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));

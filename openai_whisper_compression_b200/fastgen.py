@@ -90,6 +90,10 @@ class GraphedGreedy:
         # launch against ~50 us for the twelve PDL-chained launches it replaces; 146 vs 108 ms per bench step) -- eleven
         # grid barriers and eleven dependent L2 round trips cost more than programmatic dependent launch already hides
         self.mega = os.environ.get("WQ_DECODE_FUSED", "0") == "1"
+        # Opt-in: vocabulary projection + greedy choice per row group on the group's own stream (no join before the
+        # projection) instead of one projection of the whole batch after the join.  Measured SLOWER (whisper-base, 4
+        # groups of 64: 1.131 vs 1.082 ms per token -- the 53 MB weight is then streamed once per group).
+        self.group_project = os.environ.get("WQ_GROUP_PROJECT", "0") == "1"
         # Opt-in: route <= 16-row int8 GEMMs of the step through the small-row dp4a kernel instead of the tensor-core
         # tile.  Measured SLOWER on large-v3 (B=32, 2 row groups of 16: 485 vs 377 ms/step), so off by default.
         self.small_int8 = os.environ.get("WQ_SMALL_INT8", "0") == "1"
@@ -235,13 +239,16 @@ class GraphedGreedy:
             cur = torch.cuda.current_stream()
             for v in st.views[1:]:
                 v.stream.wait_stream(cur)
+            gp = self.group_project
             with F.scratch_slot(st.views[0].slot):
-                step(st, st.views[0], project=False)
+                step(st, st.views[0], project=gp)
             for v in st.views[1:]:
                 with torch.cuda.stream(v.stream), F.scratch_slot(v.slot):
-                    step(st, v, project=False)
+                    step(st, v, project=gp)
             for v in st.views[1:]:
                 cur.wait_stream(v.stream)
+            if gp:
+                return None
             # one vocabulary projection for the whole batch (the 53 MB weight is streamed once per token)
             return self._project(st, st.whole, st.hfinal)
         model = self.model
@@ -515,7 +522,7 @@ class GraphedGreedy:
     def _get_state(self, B: int, t_max: int, dtype: torch.dtype, device, store_logits: bool = True) -> _State:
         fp = self._fingerprint()
         key = (B, t_max, dtype, torch.device(device).index, bool(store_logits), self.cross_attention, self.streams,
-               self.cross_quant_inline, self.mega, self.min_rows_per_stream, self.small_int8)
+               self.cross_quant_inline, self.mega, self.min_rows_per_stream, self.small_int8, self.group_project)
         st = self._states.get(key)
         if st is not None and st.fingerprint == fp:
             return st
