@@ -89,6 +89,37 @@ static inline cudaError_t wq_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// the same launch with a thread-block cluster of `cluster_x` consecutive CTAs (tcgen05 cta_group::2 pairs)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t wq_launch_pdl_cluster(unsigned cluster_x, void (*kern)(KArgs...), dim3 grid, dim3 block,
+                                                size_t smem, cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = cluster_x;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+#define WQ_LAUNCH_PDL_CLUSTER(...)                                                      \
+    do {                                                                                \
+        cudaError_t _e = wq_launch_pdl_cluster(__VA_ARGS__);                            \
+        if (_e != cudaSuccess) {                                                        \
+            wq_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,       \
+                         cudaGetErrorString(_e));                                       \
+            return WQ_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
 #define WQ_LAUNCH_PDL(...)                                                              \
     do {                                                                                \
         cudaError_t _e = wq_launch_pdl(__VA_ARGS__);                                    \

@@ -10,6 +10,9 @@
 //   round-robin                   tiles n-fastest over the grid: the CTAs sharing an A row-block run together (L2)
 //   weight-stationary             (WS) K <= 512, int8 x int8: the CTA's W tile stays in shared memory, the ring streams
 //                                 A alone and the producer prefetches the A row block of a later tile into L2
+//   CTA pair                      (PAIR) 256 x 256 on a cluster of two CTAs: ONE tcgen05.mma.cta_group::2 per k-step
+//                                 (M = 256, N = 256) issued by the leader; each CTA stages its 128 rows of A and HALF
+//                                 of the W tile, and drains its own 128 x 256 accumulator; int8 x int8 schemes
 // Warp roles:
 //   warp 0      TMA producer: A tile (and the W tile, or the PACKED W tile) -> shared memory ring
 //   warp 1      TMEM allocation + single-thread tcgen05.mma issue into a 2-deep TMEM accumulator ring
@@ -163,15 +166,24 @@ template <int BN, int BMODE, int LEAN = 0> constexpr int num_threads() { return 
 // twice as deep: these launches are bound by the round trips of a shallow ring over a deep K (fc2), not by bytes.
 template <int LEAN> constexpr int lean_a_rows() { return LEAN == 2 ? 32 : (LEAN == 3 ? 64 : BMH); }
 
-template <int BN, int STAGES, int BMODE, int OUT_BUFS, int WS = 0, int COLS = 0, int LEAN = 0>
+//
+// PAIR = 1 (with COLS): a cluster of two CTAs computes 256 rows x 256 columns with one cta_group::2 instruction per
+// k-step.  Per CTA and k-block the ring takes 16 KB of A (its 128 rows) + 16 KB of W (its 128 of the 256 W rows) for 512
+// tensor clocks -- against 16 + 32 KB for the single-CTA 128 x 256 tile -- and the tensor core reads 8 KB instead of
+// 12 KB of shared memory per instruction.  Weight-stationary pairs keep 64 KB of W per CTA and stream A alone
+// (16 KB per stage: a ring of 7 stages = 3 500 tensor clocks of work in flight, above the L2 round trip that starved
+// the 2-3-stage single-CTA rings).
+template <int BN, int STAGES, int BMODE, int OUT_BUFS, int WS = 0, int COLS = 0, int LEAN = 0, int PAIR = 0>
 struct SmemLayout {
+    static_assert(PAIR == 0 || (COLS == 1 && BMODE == B_DIRECT), "CTA pairs: column-split int8 x int8 tiles");
     static_assert(LEAN == 0 || (WS == 0 && COLS == 0), "lean tiles: plain round-robin schedule");
     static_assert(WS == 0 || BMODE == B_DIRECT, "weight-stationary tiles take W straight from TMA");
     static_assert(COLS == 0 || (BMODE == B_DIRECT && BN == 128), "column-split tiles: int8 x int8 schemes, 2 x 128 columns");
     static constexpr int BMT = (COLS || LEAN) ? BMH : BM;      // tile rows
     static constexpr int BNT = COLS ? 2 * BN : BN;             // tile columns
     static constexpr int A_BYTES = (LEAN ? lean_a_rows<LEAN>() : BMT) * ROW_BYTES;
-    static constexpr int B_BYTES = BNT * ROW_BYTES;
+    static constexpr int B_BYTES = (PAIR ? BNT / 2 : BNT) * ROW_BYTES;   // pair: this CTA's half of the W rows
+    static constexpr int TILE_M = PAIR ? 2 * BMT : BMT;                   // rows of one scheduled tile (pair: both CTAs)
     static_assert(LEAN < 2 || (BMODE == B_DIRECT && (STAGES - 1) * A_BYTES + BMH * ROW_BYTES <= STAGES * (A_BYTES + B_BYTES)),
                   "packed A slots: the last slot's 128-row read must stay inside the ring");
     static constexpr int B_SLOTS = WS > 0 ? WS : STAGES;       // W buffers: one per ring stage, or the resident k-blocks
@@ -196,14 +208,17 @@ struct SmemLayout {
 // i-th tile of this CTA -> (m tile, n tile); false past the CTA's last tile.  Default: tiles round-robin over the
 // grid, n fastest (the CTAs sharing an A row-block run together).  Weight-stationary: CTA c owns column block
 // c % tiles_n and every (gridDim / tiles_n)-th row block; the tiles_n CTAs of one row block still run together.
-template <int WS>
+// PAIR: the scheduling unit is the CTA pair (consecutive blockIdx.x), both CTAs walk the same tiles.
+template <int WS, int PAIR = 0>
 __device__ __forceinline__ bool tile_at(const GemmArgs &args, int i, int &mt, int &nt) {
+    const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     if constexpr (WS > 0) {
-        nt = (int)blockIdx.x % args.tiles_n;
-        mt = (int)blockIdx.x / args.tiles_n + i * ((int)gridDim.x / args.tiles_n);
+        nt = unit % args.tiles_n;
+        mt = unit / args.tiles_n + i * (units / args.tiles_n);
         return mt < args.tiles_m;
     } else {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int tile = unit + i * units;
         nt = tile % args.tiles_n;
         mt = tile / args.tiles_n;
         return tile < args.tiles_m * args.tiles_n;
@@ -358,10 +373,10 @@ __device__ __noinline__ void llmint8_outlier_chunk(const GemmArgs &args, const f
 }
 
 // Body of one epilogue warp: drains its 32-row slab of every tile this CTA owns.
-template <int BN, int EW, int EPI, typename OutT, int OUT_BUFS, bool TMA_STORE, int WS, int COLS, int LEAN>
+template <int BN, int EW, int EPI, typename OutT, int OUT_BUFS, bool TMA_STORE, int WS, int COLS, int LEAN, int PAIR>
 __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtensorMap *map_y, uint8_t *boxes,
                                               float *s_const, uint64_t *bar_tmem_full, uint64_t *bar_tmem_empty,
-                                              uint32_t tmem_base, int warp, int lane) {
+                                              uint32_t tmem_base, int warp, int lane, int rank) {
     constexpr int ACC_COLS = 2 * BN;
     constexpr int BMT = (COLS || LEAN) ? BMH : BM, BNT = COLS ? 2 * BN : BN;   // tile rows / columns
     constexpr int BOX_COLS = 128 / (int)sizeof(OutT);   // columns per TMA-store box (64 or 32)
@@ -382,8 +397,8 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
     }
     uint32_t t = 0, nstore = 0;
     int mt, nt;
-    for (; tile_at<WS>(args, (int)t, mt, nt); ++t) {
-        const int n0 = nt * BNT, m0 = mt * BMT;
+    for (; tile_at<WS, PAIR>(args, (int)t, mt, nt); ++t) {
+        const int n0 = nt * BNT, m0 = mt * (PAIR ? 2 * BMT : BMT) + rank * BMT;   // pair: this CTA's 128 of the 256 rows
         const uint32_t as = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1;
         const int mrow0 = m0 + (COLS ? 0 : h * BMH) + q * 32;  // first row of this warp's 32-row slab
         const int ch0 = COLS ? h * BN : 0;        // first tile column of this warp's half
@@ -493,7 +508,10 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
         // accumulator fully read: hand the TMEM stage back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_tmem_empty[as]);
+        if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tmem_empty[as]), 0));   // the leader's MMA warp waits
+            else mbar_arrive(&bar_tmem_empty[as]);
+        }
     }
     if constexpr (TMA_STORE) {
         if (lane == 0) tma_store_wait<0>();
@@ -501,11 +519,11 @@ __device__ __forceinline__ void epilogue_warp(const GemmArgs &args, const CUtens
     __syncwarp();
 }
 
-template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT, int OUT_BUFS, int WS, int COLS, int LEAN>
+template <int BN, int STAGES, int AKIND, int BMODE, int EPI, typename OutT, int OUT_BUFS, int WS, int COLS, int LEAN, int PAIR>
 __global__ void __launch_bounds__(num_threads<BN, BMODE, LEAN>(), (LEAN && BMODE == B_DIRECT) ? 2 : 1)   // lean int8: <= 168 registers
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ CUtensorMap map_y, const GemmArgs args) {
-    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS, COLS, LEAN>;
+    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS, COLS, LEAN, PAIR>;
     constexpr int BMT = L::BMT, BNT = L::BNT;
     static_assert(BN == 64 || BN == 128, "BN must be 64 or 128 (2 halves x 2 stages x BN <= 512 TMEM columns)");
     constexpr bool kIntKind = (AKIND == A_S8 || AKIND == A_U8);
@@ -529,6 +547,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = args.num_kb;
     const int total_tiles = args.tiles_m * args.tiles_n;
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;      // 0: the pair's leader (issues the MMAs, owns the barriers the
+                                                             // pair synchronises on: full[], tmem_empty[], bar_w)
 
     // ---------------- setup ----------------
     if (threadIdx.x == 0) {
@@ -536,26 +556,32 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         tma_prefetch_desc(&map_b);
         if (args.tma_store) tma_prefetch_desc(&map_y);
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_full[s], PAIR ? 2 : 1);      // pair: the leader's expect_tx arrive + the peer producer's arrive
             mbar_init(&bar_empty[s], 1);
             mbar_init(&bar_bready[s], DQ_WARPS > 0 ? DQ_WARPS : 1);
         }
         for (int a = 0; a < ACC_STAGES; ++a) {
             mbar_init(&bar_tmem_full[a], 1);
-            mbar_init(&bar_tmem_empty[a], EW);
+            mbar_init(&bar_tmem_empty[a], PAIR ? 2 * EW : EW);   // pair: both CTAs' epilogue warps
         }
-        mbar_init(bar_w, 1);
+        mbar_init(bar_w, PAIR ? 2 : 1);
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_holder, ACC_STAGES * ACC_COLS);
-        tmem_relinquish();
+        if constexpr (PAIR) {
+            tmem_alloc_pair(tmem_holder, ACC_STAGES * ACC_COLS);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_holder, ACC_STAGES * ACC_COLS);
+            tmem_relinquish();
+        }
     }
     if constexpr (BMODE == B_4BIT) {
         if (threadIdx.x < 16) s_lut[threadIdx.x] = args.quant_type ? kFP4Code[threadIdx.x] : kNF4Code[threadIdx.x];
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();     // the peer's barriers are initialised before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     pdl_prologue_done();
@@ -568,28 +594,50 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         // warps -- more than the tensor time of an int8 k-block, and the whole cost of a decode-shaped call.)
         uint32_t s = 0, ph = 0;      // ring slot and its parity
         int mt, nt;
+        // pair: every load lands in this CTA's shared memory and is counted on the LEADER's barrier, where the MMA
+        // warp waits for both halves (the leader expects the bytes of both CTAs, the peer only arrives)
+        const int b_row = PAIR ? rank * (BNT / 2) : 0;       // this CTA's rows inside the W tile
         if constexpr (WS > 0) {
-            if (tile_at<WS>(args, 0, mt, nt)) {      // the CTA's W tile, once: num_kb boxes of BN rows x 128 B
+            if (tile_at<WS, PAIR>(args, 0, mt, nt)) {      // the CTA's W tile, once: num_kb boxes of BN rows x 128 B
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(bar_w, (uint32_t)num_kb * L::B_BYTES);
-                    for (int kb = 0; kb < num_kb; ++kb)
-                        tma_load_2d(smem + L::OFF_B + kb * L::B_BYTES, &map_b, bar_w, kb * 128, nt * BNT);
+                    if constexpr (PAIR) {
+                        const uint32_t lw = mapa_u32(smem_u32(bar_w), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(bar_w, 2u * (uint32_t)num_kb * L::B_BYTES);
+                        else mbar_arrive_cluster(lw);
+                        for (int kb = 0; kb < num_kb; ++kb)
+                            tma_load_2d_pair(smem + L::OFF_B + kb * L::B_BYTES, &map_b, lw, kb * 128, nt * BNT + b_row);
+                    } else {
+                        mbar_arrive_expect_tx(bar_w, (uint32_t)num_kb * L::B_BYTES);
+                        for (int kb = 0; kb < num_kb; ++kb)
+                            tma_load_2d(smem + L::OFF_B + kb * L::B_BYTES, &map_b, bar_w, kb * 128, nt * BNT);
+                    }
                 }
                 __syncwarp();
             }
         }
-        for (int i = 0; tile_at<WS>(args, i, mt, nt); ++i) {
-            const int n0 = nt * BNT, m0 = mt * BMT;
+        for (int i = 0; tile_at<WS, PAIR>(args, i, mt, nt); ++i) {
+            const int n0 = nt * BNT, m0 = mt * L::TILE_M + rank * BMT;
             // A streams from HBM with ~1.5 us of loaded latency and the ring holds < 1 tile: ask L2 for the row
             // block this CTA reaches `prefetch` tiles from now (one of the tiles_n CTAs sharing it does)
             int pf_m0 = -1;
             if (args.prefetch > 0) {
                 int pmt, pnt;
-                if (tile_at<WS>(args, i + args.prefetch, pmt, pnt) && pmt % args.tiles_n == pnt) pf_m0 = pmt * BMT;
+                if (tile_at<WS, PAIR>(args, i + args.prefetch, pmt, pnt) && pmt % args.tiles_n == pnt)
+                    pf_m0 = pmt * L::TILE_M + rank * BMT;
             }
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&bar_empty[s], ph ^ 1);
-                if (elect_one()) {
+                if constexpr (PAIR) {
+                    if (elect_one()) {
+                        const uint32_t lf = mapa_u32(smem_u32(&bar_full[s]), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(&bar_full[s], 2u * L::TX_BYTES);
+                        else mbar_arrive_cluster(lf);
+                        tma_load_2d_pair(smem + L::OFF_A + s * L::A_BYTES, &map_a, lf, kb * A_ELEMS_PER_ROW, m0);
+                        if (pf_m0 >= 0) tma_prefetch_2d(&map_a, kb * A_ELEMS_PER_ROW, pf_m0);
+                        if constexpr (WS == 0)
+                            tma_load_2d_pair(smem + L::OFF_B + s * L::B_BYTES, &map_b, lf, kb * A_ELEMS_PER_ROW, n0 + b_row);
+                    }
+                } else if (elect_one()) {
                     mbar_arrive_expect_tx(&bar_full[s], L::TX_BYTES);
                     tma_load_2d(smem + L::OFF_A + s * L::A_BYTES, &map_a, &bar_full[s], kb * A_ELEMS_PER_ROW, m0);
                     if (pf_m0 >= 0) tma_prefetch_2d(&map_a, kb * A_ELEMS_PER_ROW, pf_m0);
@@ -607,15 +655,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 }
             }
         }
-    } else if (warp == 1) {
-        // ---------------- MMA issuer (whole warp in the loop, one elected lane issues) ----------------
+    } else if (warp == 1 && rank == 0) {
+        // ---------------- MMA issuer (whole warp in the loop, one elected lane issues; pair: the leader CTA's) ----------------
         constexpr uint32_t idesc =
-            kIntKind ? make_idesc(kAccS32, AKIND == A_S8 ? kFmtS8 : kFmtU8, kFmtS8, BMH, BNT)
+            kIntKind ? make_idesc(kAccS32, AKIND == A_S8 ? kFmtS8 : kFmtU8, kFmtS8, PAIR ? 2 * BMH : BMH, BNT)
                      : make_idesc(kAccF32, AKIND == A_F16 ? kFmtF16 : kFmtBF16,
                                   AKIND == A_F16 ? kFmtF16 : kFmtBF16, BMH, BN);
         uint32_t s = 0, ph = 0, t = 0;
         int mt, nt;
-        for (; tile_at<WS>(args, (int)t, mt, nt); ++t) {
+        for (; tile_at<WS, PAIR>(args, (int)t, mt, nt); ++t) {
             const int m0 = mt * BMT;
             const bool two_halves = COLS == 0 && LEAN == 0 && m0 + BMH < args.M;   // second 128 rows hold real data
             if constexpr (WS > 0) {
@@ -636,7 +684,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
                     for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
                         const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-                        if constexpr (kIntKind) {
+                        if constexpr (PAIR) {
+                            umma_i8_pair(tmem_acc, adesc0 + 2 * k, bdesc + 2 * k, idesc, acc);
+                        } else if constexpr (kIntKind) {
                             umma_i8(tmem_acc, adesc0 + 2 * k, bdesc + 2 * k, idesc, acc);
                             if (two_halves) umma_i8(tmem_acc + BN, adesc1 + 2 * k, bdesc + 2 * k, idesc, acc);
                         } else {
@@ -644,7 +694,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                             if (two_halves) umma_f16(tmem_acc + BN, adesc1 + 2 * k, bdesc + 2 * k, idesc, acc);
                         }
                     }
-                    umma_commit(&bar_empty[s]);  // implicit tcgen05.fence::before_thread_sync
+                    if constexpr (PAIR) umma_commit_pair(&bar_empty[s]);   // frees the slot in both CTAs
+                    else umma_commit(&bar_empty[s]);  // implicit tcgen05.fence::before_thread_sync
                 }
                 __syncwarp();
                 if (++s == STAGES) {
@@ -652,17 +703,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     ph ^= 1;
                 }
             }
-            if (elect_one()) umma_commit(&bar_tmem_full[as]);
+            if (elect_one()) {
+                if constexpr (PAIR) umma_commit_pair(&bar_tmem_full[as]);
+                else umma_commit(&bar_tmem_full[as]);
+            }
             __syncwarp();
         }
+    } else if (warp == 1) {
+        // the peer CTA's warp 1 only owns its half of the pair's TMEM allocation
     } else if (warp < 2 + EW) {
         // ---------------- epilogue: warps 2..9 ----------------
         uint8_t *boxes = smem + L::OFF_OUT + (warp - 2) * OUT_BUFS * BOX_BYTES;   // private staging of this warp
         float *s_const = reinterpret_cast<float *>(smem + L::OFF_CONST);
         if (args.tma_store)
-            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, true, WS, COLS, LEAN>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane);
+            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, true, WS, COLS, LEAN, PAIR>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane, rank);
         else
-            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, false, WS, COLS, LEAN>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane);
+            epilogue_warp<BN, EW, EPI, OutT, OUT_BUFS, false, WS, COLS, LEAN, PAIR>(args, &map_y, boxes, s_const, bar_tmem_full, bar_tmem_empty, tmem_base, warp, lane, rank);
     } else {
         // ---------------- weight expansion (W8A16 / W4A16): warps 10.. ----------------
         const int t = threadIdx.x - 32 * (2 + EW);
@@ -777,8 +833,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
     // ---------------- teardown ----------------
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, ACC_STAGES * ACC_COLS);
+    if constexpr (PAIR) {
+        // neither CTA may leave while the other still reads its shared memory through the tensor core or arrives on
+        // its barriers
+        cluster_sync_all();
+        if (warp == 1) tmem_dealloc_pair(tmem_base, ACC_STAGES * ACC_COLS);
+    } else {
+        __syncthreads();
+        if (warp == 1) tmem_dealloc(tmem_base, ACC_STAGES * ACC_COLS);
+    }
     if constexpr (EPI == EPI_LLMINT8) {
         // outlier flags are self-cleaning: the last CTA to finish clears them for the next call
         if (args.flags != nullptr && !args.keep_flags && args.flags[args.K] != 0) {
@@ -810,15 +873,16 @@ template <int BN, int BMODE> constexpr int pick_out_bufs() {
 }
 
 // deepest smem ring that fits next to the epilogue staging boxes
-template <int BN, int BMODE, int OUT_BUFS, int WS, int COLS, int LEAN>
+template <int BN, int BMODE, int OUT_BUFS, int WS, int COLS, int LEAN, int PAIR = 0>
 constexpr int pick_stages() {
     int best = 2;
     // lean tiles stop at 128 KB: they are meant to share an SM with another stream's resident CTAs
     const int budget = LEAN ? 131072 : 232448;
-    for (int st = 2; st <= (LEAN >= 2 ? 12 : 6); ++st) {
+    for (int st = 2; st <= (LEAN >= 2 ? 12 : (PAIR ? 8 : 6)); ++st) {
         const int bmt = (COLS || LEAN) ? BMH : BM, bnt = COLS ? 2 * BN : BN;
-        const int stage = (LEAN ? lean_a_rows<LEAN>() : bmt) * ROW_BYTES + (WS > 0 ? 0 : bnt * ROW_BYTES) + BN * (is_byte<BMODE>() ? 64 : (is_nibble<BMODE>() ? 32 : 0));
-        const int total = st * stage + WS * bnt * ROW_BYTES + epi_warps<BN, BMODE, LEAN>() * OUT_BUFS * BOX_BYTES +
+        const int brows = PAIR ? bnt / 2 : bnt;     // W rows this CTA stages
+        const int stage = (LEAN ? lean_a_rows<LEAN>() : bmt) * ROW_BYTES + (WS > 0 ? 0 : brows * ROW_BYTES) + BN * (is_byte<BMODE>() ? 64 : (is_nibble<BMODE>() ? 32 : 0));
+        const int total = st * stage + WS * brows * ROW_BYTES + epi_warps<BN, BMODE, LEAN>() * OUT_BUFS * BOX_BYTES +
                           (WS > 0 ? 1 : 2) * 3 * bnt * 4 + 64 + (3 * st + 2 * ACC_STAGES + 1) * 8 + 16 + 1024;
         if (total <= budget) best = st;
     }
@@ -830,22 +894,42 @@ template <> CUtensorMapDataType out_dtype_enum<float>() { return CU_TENSOR_MAP_D
 template <> CUtensorMapDataType out_dtype_enum<__half>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT16; }
 template <> CUtensorMapDataType out_dtype_enum<__nv_bfloat16>() { return CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
 
-template <int BN, int AKIND, int BMODE, int EPI, typename OutT, int WS = 0, int COLS = 0, int LEAN = 0>
+template <int BN, int AKIND, int BMODE, int EPI, typename OutT, int WS = 0, int COLS = 0, int LEAN = 0, int PAIR = 0>
 int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cudaStream_t stream) {
     // a resident 256-row W tile (128 KB) leaves room for single store buffers only
 #ifndef WQ_LEAN_OUT_BUFS
 #define WQ_LEAN_OUT_BUFS 1     /* measured: 109.6 vs 110.7 ms per bench step with double buffers (smaller CTA beside the attention stream) */
 #endif
-    constexpr int OUT_BUFS = (WS > 0 && COLS) ? 1 : (LEAN ? WQ_LEAN_OUT_BUFS : pick_out_bufs<BN, BMODE>());
-    constexpr int STAGES = pick_stages<BN, BMODE, OUT_BUFS, WS, COLS, LEAN>();
-    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS, COLS, LEAN>;
-    auto kfn = k_gemm_tc<BN, STAGES, AKIND, BMODE, EPI, OutT, OUT_BUFS, WS, COLS, LEAN>;
+#ifndef WQ_PAIR_OUT_BUFS
+#define WQ_PAIR_OUT_BUFS 1
+#endif
+    constexpr int OUT_BUFS = PAIR ? WQ_PAIR_OUT_BUFS : ((WS > 0 && COLS) ? 1 : (LEAN ? WQ_LEAN_OUT_BUFS : pick_out_bufs<BN, BMODE>()));
+    constexpr int STAGES = pick_stages<BN, BMODE, OUT_BUFS, WS, COLS, LEAN, PAIR>();
+    using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS, COLS, LEAN, PAIR>;
+    auto kfn = k_gemm_tc<BN, STAGES, AKIND, BMODE, EPI, OutT, OUT_BUFS, WS, COLS, LEAN, PAIR>;
     static bool configured = false;
+    static int max_pairs = 0;           // CTA pairs the device holds at once (persistent grid of the pair schedule)
     if (!configured) {
         WQ_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        if (PAIR) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * wq_sm_count());
+            cfg.blockDim = dim3(num_threads<BN, BMODE, LEAN>());
+            cfg.dynamicSmemBytes = (size_t)L::TOTAL;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kfn, &cfg) != cudaSuccess || n < 1) {
+                (void)cudaGetLastError();
+                n = wq_sm_count() / 2;
+            }
+            max_pairs = n < wq_sm_count() / 2 ? n : wq_sm_count() / 2;
+        }
         configured = true;
     }
-    args.tiles_m = (args.M + L::BMT - 1) / L::BMT;
+    args.tiles_m = (args.M + L::TILE_M - 1) / L::TILE_M;
     args.tiles_n = (args.N + L::BNT - 1) / L::BNT;
     if (args.ldy == 0) args.ldy = args.N;
     // TMA store needs a 16-byte-aligned row pitch; otherwise the epilogue stores directly
@@ -859,6 +943,14 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cud
         my = ma;  // unused
     }
     const int total = args.tiles_m * args.tiles_n;
+    if (PAIR) {
+        int pairs = total < max_pairs ? total : max_pairs;
+        if (WS > 0) pairs = (max_pairs / args.tiles_n) * args.tiles_n;      // whole groups of tiles_n pairs (use_ws())
+        WQ_REQUIRE(pairs >= 1, "wq gemm: no CTA pair fits the device");
+        WQ_LAUNCH_PDL_CLUSTER(2, kfn, dim3(2 * pairs), dim3(num_threads<BN, BMODE, LEAN>()), (size_t)L::TOTAL, stream, ma, mb,
+                              my, args);
+        return WQ_OK;
+    }
     int grid = total < wq_sm_count() ? total : wq_sm_count();
     if (WS > 0) grid = (wq_sm_count() / args.tiles_n) * args.tiles_n;   // whole groups of tiles_n CTAs (use_ws())
 
@@ -916,10 +1008,40 @@ bool use_cols(int64_t M, int64_t N, int64_t K) {
     return !(use_ws(M, N, K, false) && N < 1536);
 }
 
+// CTA pairs (256 x 256 per cluster of two, one cta_group::2 instruction per k-step) for the int8 x int8 schemes: every
+// call that is not decode-shaped and whose 256-wide column blocks add no padding over 128-wide ones.  WQ_GEMM_PAIR=0
+// falls back to the single-CTA tiles (A/B measurements, scripts/gemm_ws_bench.py).
+bool use_pair(int64_t M, int64_t N) {
+    static const bool on = [] {
+        const char *e = getenv("WQ_GEMM_PAIR");
+        return e == nullptr || e[0] != '0';
+    }();
+    return on && !use_narrow_tile(M, N) && ((N + 127) / 128) % 2 == 0;
+}
+// weight-stationary pairs: K fits the resident half tiles (kWS k-blocks x 128 W rows = 64 KB per CTA), the column
+// blocks divide the pairs into whole groups and every group has several row blocks to walk
+bool use_ws_pair(int64_t M, int64_t N, int64_t K) {
+    const int64_t tiles_n = (N + 255) / 256, tiles_m = (M + 255) / 256, kb = (K + 127) / 128;
+    const int64_t pairs = wq_sm_count() / 2;
+    return ws_enabled() && kb <= kWS && tiles_n <= pairs && tiles_m >= 4 * (pairs / tiles_n);
+}
+
 // tensor maps + launch of the int8 x int8 schemes (LLM.int8, torch dynamic): tile shape and schedule by shape
 template <int AKIND, int EPI, typename OutT>
 int launch_i8(const void *a, const void *b, GemmArgs args, cudaStream_t s) {
     const int64_t M = args.M, N = args.N, K = args.K;
+    if (use_pair(M, N)) {
+        CUtensorMap ma, mb;
+        int rc = make_map_2d(&ma, a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, BMH, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc != WQ_OK) return rc;
+        rc = make_map_2d(&mb, b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, 128, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc != WQ_OK) return rc;
+        if (use_ws_pair(M, N, K)) {
+            args.prefetch = kWSPrefetch;
+            return launch_gemm<128, AKIND, B_DIRECT, EPI, OutT, kWS, 1, 0, 1>(ma, mb, args, s);
+        }
+        return launch_gemm<128, AKIND, B_DIRECT, EPI, OutT, 0, 1, 0, 1>(ma, mb, args, s);
+    }
     const bool narrow = use_narrow_tile(M, N), cols = use_cols(M, N, K);
     const bool lean = narrow && use_lean_tile(M);
     static const bool slim_on = [] {        // WQ_GEMM_SLIM=0: 128-row A boxes for every lean call (A/B measurements)

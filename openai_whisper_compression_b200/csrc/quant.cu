@@ -141,9 +141,7 @@ k_quant_i8_rowwise_bnb(const __half *__restrict__ a, int64_t rows, int64_t cols,
     }
     am = warp_max(am);
     if (lane == 0) row_stats[row] = am;
-    // bitsandbytes uses __fdividef(127, absmax); the IEEE quotient is used here so that the CPU
-    // oracle can be bit-exact (DESIGN.md "Known deviations").
-    const float scale = bnb_row_scale(am);
+    const float scale = bnb_row_scale(am);      // __fdividef(127, absmax), as bitsandbytes ships it (common.cuh)
 
     if (vec_ok) {
         for (int64_t c = lane * 8; c < cols; c += 256) {

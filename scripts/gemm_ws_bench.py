@@ -1,5 +1,6 @@
 """A/B timing of the int8 x int8 GEMM's tile shape and schedule on the bench's encoder shapes (M = 384000): run as is
-(128 x 256 tiles, one N = 256 MMA per k-step, weight-stationary when K <= 512), with WQ_GEMM_WS=0 (round-robin tiles)
+(CTA pairs: 256 x 256 per cluster of two, one cta_group::2 MMA per k-step, weight-stationary when K <= 512), with
+WQ_GEMM_PAIR=0 (single-CTA 128 x 256 tiles, one N = 256 MMA per k-step), and then WQ_GEMM_WS=0 (round-robin tiles)
 and/or WQ_GEMM_COLS=0 (256 x 128 tiles, two N = 128 MMAs).  CUDA events, L2 flushed between iterations."""
 import json
 import os
@@ -16,7 +17,8 @@ peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_P
 dev = torch.device("cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 torch.manual_seed(0)
-print("WQ_GEMM_WS =", os.environ.get("WQ_GEMM_WS", "(default: on)"), " WQ_GEMM_COLS =", os.environ.get("WQ_GEMM_COLS", "(default: on)"))
+print("WQ_GEMM_PAIR =", os.environ.get("WQ_GEMM_PAIR", "(default: on)"), " WQ_GEMM_WS =", os.environ.get("WQ_GEMM_WS", "(default: on)"),
+      " WQ_GEMM_COLS =", os.environ.get("WQ_GEMM_COLS", "(default: on)"))
 SHAPES = ((512, 512), (1024, 512), (1536, 512), (2048, 512), (512, 2048), (384, 384), (1152, 384))
 if len(sys.argv) > 4:
     SHAPES = ((int(sys.argv[3]), int(sys.argv[4])),)

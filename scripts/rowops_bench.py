@@ -40,6 +40,8 @@ torch.manual_seed(0)
 x = (torch.randn(rows, 2048, device=dev) * 1.5).half()
 t = timed(lambda: F.gelu_quant(x, 6.0))
 report(f"gelu_quant {rows}x2048 (table)", t, rows * 2048 * 5 + 4 * rows)
+t = timed(lambda: F.gelu_quant(x, 6.0, store_h=False))
+report(f"gelu_quant {rows}x2048 (table, int8 rows only)", t, rows * 2048 * 3 + 4 * rows)
 xs = x[:4095].contiguous()
 t = timed(lambda: F.gelu_quant(xs, 6.0))
 report("gelu_quant 4095x2048 (erff)", t, 4095 * 2048 * 5)
