@@ -17,12 +17,42 @@ namespace {
 
 constexpr int kHeadDim = 64;
 
+// 8 consecutive elements of a head row: 16 bytes of fp16 / bf16, 32 bytes of fp32 (the reference's quanto flow keeps
+// fp32 activations, model_utils.py:139-142: the fp32 caches go through the same kernels, two 16-byte loads per lane)
+template <typename T> struct Chunk8 {
+    uint4 r[sizeof(T) / 2];
+};
+template <typename T> __device__ __forceinline__ Chunk8<T> chunk_zero() {
+    Chunk8<T> c;
+#pragma unroll
+    for (int i = 0; i < (int)sizeof(T) / 2; ++i) c.r[i] = make_uint4(0u, 0u, 0u, 0u);
+    return c;
+}
+template <typename T> __device__ __forceinline__ Chunk8<T> chunk_ld(const T *p) {
+    Chunk8<T> c;
+#pragma unroll
+    for (int i = 0; i < (int)sizeof(T) / 2; ++i) c.r[i] = reinterpret_cast<const uint4 *>(p)[i];
+    return c;
+}
+template <typename T> __device__ __forceinline__ Chunk8<T> chunk_ldg(const T *p) {
+    Chunk8<T> c;
+#pragma unroll
+    for (int i = 0; i < (int)sizeof(T) / 2; ++i) c.r[i] = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+    return c;
+}
+template <typename T> __device__ __forceinline__ void chunk_st(T *p, const Chunk8<T> &c) {
+#pragma unroll
+    for (int i = 0; i < (int)sizeof(T) / 2; ++i) reinterpret_cast<uint4 *>(p)[i] = c.r[i];
+}
+template <typename T> __device__ __forceinline__ float chunk_at(const Chunk8<T> &c, int j) {
+    return to_f32(reinterpret_cast<const T *>(&c)[j]);
+}
+
 template <typename T>
 __device__ __forceinline__ void load8(const T *p, float (&f)[8]) {
-    const uint4 raw = *reinterpret_cast<const uint4 *>(p);
-    const T *h = reinterpret_cast<const T *>(&raw);
+    const Chunk8<T> raw = chunk_ld(p);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = to_f32(h[j]);
+    for (int j = 0; j < 8; ++j) f[j] = chunk_at(raw, j);
 }
 
 template <typename T>
@@ -59,11 +89,9 @@ k_self_attn_decode(const T *__restrict__ q, const T *__restrict__ k, const T *__
 
     // append this step's k / v rows (lanes 0-7: k, lanes 8-15: v)
     if (lane < 8) {
-        *reinterpret_cast<uint4 *>(kc_b + (int64_t)pos * d + sub * 8) =
-            *reinterpret_cast<const uint4 *>(k + (int64_t)b * ld + h * kHeadDim + sub * 8);
+        chunk_st(kc_b + (int64_t)pos * d + sub * 8, chunk_ld(k + (int64_t)b * ld + h * kHeadDim + sub * 8));
     } else if (lane < 16) {
-        *reinterpret_cast<uint4 *>(vc_b + (int64_t)pos * d + sub * 8) =
-            *reinterpret_cast<const uint4 *>(v + (int64_t)b * ld + h * kHeadDim + sub * 8);
+        chunk_st(vc_b + (int64_t)pos * d + sub * 8, chunk_ld(v + (int64_t)b * ld + h * kHeadDim + sub * 8));
     }
     __syncwarp();
 
@@ -71,20 +99,19 @@ k_self_attn_decode(const T *__restrict__ q, const T *__restrict__ k, const T *__
     // L2 round trips, not bandwidth)
     float mx = -INFINITY;
     for (int t0 = 0; t0 <= pos; t0 += 16) {
-        uint4 kr[4];
+        Chunk8<T> kr[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int t = t0 + u * 4 + g;
-            kr[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (t <= pos) kr[u] = *reinterpret_cast<const uint4 *>(kc_b + (int64_t)t * d + sub * 8);
+            kr[u] = chunk_zero<T>();
+            if (t <= pos) kr[u] = chunk_ld(kc_b + (int64_t)t * d + sub * 8);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int t = t0 + u * 4 + g;
-            const T *k8 = reinterpret_cast<const T *>(&kr[u]);
             float s = 0.0f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s = fmaf(q8[j], to_f32(k8[j]), s);
+            for (int j = 0; j < 8; ++j) s = fmaf(q8[j], chunk_at(kr[u], j), s);
             s += __shfl_xor_sync(0xffffffffu, s, 4);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -110,21 +137,20 @@ k_self_attn_decode(const T *__restrict__ q, const T *__restrict__ k, const T *__
     // P V
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int t0 = 0; t0 <= pos; t0 += 16) {
-        uint4 vr[4];
+        Chunk8<T> vr[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int t = t0 + u * 4 + g;
-            vr[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (t <= pos) vr[u] = *reinterpret_cast<const uint4 *>(vc_b + (int64_t)t * d + sub * 8);
+            vr[u] = chunk_zero<T>();
+            if (t <= pos) vr[u] = chunk_ld(vc_b + (int64_t)t * d + sub * 8);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int t = t0 + u * 4 + g;
             if (t <= pos) {
-                const T *v8 = reinterpret_cast<const T *>(&vr[u]);
                 const float p = sc[t];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(p, to_f32(v8[j]), acc[j]);
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(p, chunk_at(vr[u], j), acc[j]);
             }
         }
     }
@@ -135,14 +161,14 @@ k_self_attn_decode(const T *__restrict__ q, const T *__restrict__ k, const T *__
         acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
     }
     if (g == 0) {
-        uint4 raw;
+        Chunk8<T> raw;
         T *o8 = reinterpret_cast<T *>(&raw);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             o8[j] = from_f32<T>(acc[j] * inv);
             if (ca != nullptr) orow[h * kHeadDim + sub * 8 + j] = to_f32(o8[j]);
         }
-        *reinterpret_cast<uint4 *>(out + (int64_t)b * d + h * kHeadDim + sub * 8) = raw;
+        chunk_st(out + (int64_t)b * d + h * kHeadDim + sub * 8, raw);
     }
     if (ca == nullptr) return;
 
@@ -183,7 +209,7 @@ extern "C" int wq_self_attn_decode(const void *q, const void *k, const void *v, 
                                    void *out, float threshold, int8_t *ca, float *row_stats, int32_t *col_flags,
                                    wq_stream_t stream) {
     WQ_REQUIRE(B >= 0 && H >= 1 && H <= 32 && t_max >= 1, "wq_self_attn_decode: bad shape (H must be 1..32)");
-    WQ_REQUIRE(dtype == WQ_F16 || dtype == WQ_BF16, "wq_self_attn_decode: dtype must be f16 or bf16");
+    WQ_REQUIRE(dtype == WQ_F16 || dtype == WQ_BF16 || dtype == WQ_F32, "wq_self_attn_decode: dtype must be f16, bf16 or f32");
     WQ_REQUIRE(threshold >= 0.0f, "wq_self_attn_decode: negative threshold");
     if (B == 0) return WQ_OK;
     WQ_REQUIRE(q && k && v && k_cache && v_cache && pos && out, "wq_self_attn_decode: null pointer");
@@ -197,7 +223,13 @@ extern "C" int wq_self_attn_decode(const void *q, const void *k, const void *v, 
     const size_t smem = ((size_t)H * t_max + (size_t)H * kHeadDim) * sizeof(float);
     WQ_REQUIRE(smem <= 200 * 1024, "wq_self_attn_decode: H * t_max too large for shared memory");
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == WQ_F16) {
+    if (dtype == WQ_F32) {
+        auto kern = k_self_attn_decode<float>;
+        if (smem > 48 * 1024) WQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        WQ_LAUNCH_PDL(kern, dim3((unsigned)B), dim3(H * 32), smem, s, (const float *)q, (const float *)k, (const float *)v, ld,
+                      scaling, (float *)k_cache, (float *)v_cache, t_max, pos, H, (float *)out, threshold, (int8_t *)nullptr,
+                      (float *)nullptr, (int32_t *)nullptr);
+    } else if (dtype == WQ_F16) {
         auto kern = k_self_attn_decode<__half>;
         if (smem > 48 * 1024) WQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         WQ_LAUNCH_PDL(kern, dim3((unsigned)B), dim3(H * 32), smem, s, (const __half *)q, (const __half *)k,
@@ -253,16 +285,15 @@ __device__ __forceinline__ void partial_merge(Partial &a, float om, float ol, co
 // max / rescale and four independent exponentials.  Row by row the update is a serial chain of ~250 cycles per row
 // (max -> exp2 -> rescale), which left a warp latency-bound; block-wise it is ~200 cycles per FOUR rows.  valid[u]:
 // the row exists (positions past S are masked).
-template <typename T>
-__device__ __forceinline__ void fold_rows(Partial &p, const float (&q8)[8], const uint4 (&kr)[kXUnroll],
-                                          const uint4 (&vr)[kXUnroll], const bool (&valid)[kXUnroll]) {
+template <typename T, int kXUnroll>
+__device__ __forceinline__ void fold_rows(Partial &p, const float (&q8)[8], const Chunk8<T> (&kr)[kXUnroll],
+                                          const Chunk8<T> (&vr)[kXUnroll], const bool (&valid)[kXUnroll]) {
     float sc[kXUnroll];
 #pragma unroll
     for (int u = 0; u < kXUnroll; ++u) {
-        const T *k8 = reinterpret_cast<const T *>(&kr[u]);
         float s = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s = fmaf(q8[j], to_f32(k8[j]), s);
+        for (int j = 0; j < 8; ++j) s = fmaf(q8[j], chunk_at(kr[u], j), s);
         sc[u] = s;
     }
 #pragma unroll
@@ -288,7 +319,7 @@ __device__ __forceinline__ void fold_rows(Partial &p, const float (&q8)[8], cons
     for (int j = 0; j < 8; ++j) {
         float a = p.acc[j] * corr;
 #pragma unroll
-        for (int u = 0; u < kXUnroll; ++u) a = fmaf(e[u], to_f32(reinterpret_cast<const T *>(&vr[u])[j]), a);
+        for (int u = 0; u < kXUnroll; ++u) a = fmaf(e[u], chunk_at(vr[u], j), a);
         p.acc[j] = a;
     }
     p.l = l;
@@ -394,7 +425,9 @@ __device__ __forceinline__ void quantize_row_if_last(const T *out, int b, int d,
     }
 }
 
-template <typename T, int kXWarps>
+// fp32 rows are twice as wide: half the rows per block (kXU = 2) keep the same bytes in flight per lane and the same
+// register budget
+template <typename T, int kXWarps, int kXU = kXUnroll>
 __global__ void __launch_bounds__(kXWarps * 32, 2)
 k_cross_attn_decode(const T *__restrict__ q, int64_t ldq, float scaling, const T *__restrict__ kmat,
                     const T *__restrict__ vmat, int64_t ld, int S, int H, int n_items, T *out, float threshold,
@@ -407,22 +440,22 @@ k_cross_attn_decode(const T *__restrict__ q, int64_t ldq, float scaling, const T
     const int d = H * kHeadDim;
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr int ROWS_PER_IT = kXWarps * 4;
-    constexpr int STEP = ROWS_PER_IT * kXUnroll;
+    constexpr int STEP = ROWS_PER_IT * kXU;
     const int t_first = warp * 4 + g;
 
     int item = (int)blockIdx.x;
     if (item >= n_items) return;
 
-    uint4 kr[kXUnroll], vr[kXUnroll], kn[kXUnroll], vn[kXUnroll];
-    auto fetch = [&](const T *kb, const T *vb, int t0, uint4 (&kk)[kXUnroll], uint4 (&vv)[kXUnroll]) {
+    Chunk8<T> kr[kXU], vr[kXU], kn[kXU], vn[kXU];
+    auto fetch = [&](const T *kb, const T *vb, int t0, Chunk8<T> (&kk)[kXU], Chunk8<T> (&vv)[kXU]) {
 #pragma unroll
-        for (int u = 0; u < kXUnroll; ++u) {
+        for (int u = 0; u < kXU; ++u) {
             const int t = t0 + u * ROWS_PER_IT;
-            kk[u] = make_uint4(0u, 0u, 0u, 0u);
-            vv[u] = make_uint4(0u, 0u, 0u, 0u);
+            kk[u] = chunk_zero<T>();
+            vv[u] = chunk_zero<T>();
             if (t < S) {
-                kk[u] = __ldg(reinterpret_cast<const uint4 *>(kb + (int64_t)t * ld));
-                vv[u] = __ldg(reinterpret_cast<const uint4 *>(vb + (int64_t)t * ld));
+                kk[u] = chunk_ldg(kb + (int64_t)t * ld);
+                vv[u] = chunk_ldg(vb + (int64_t)t * ld);
             }
         }
     };
@@ -459,12 +492,12 @@ k_cross_attn_decode(const T *__restrict__ q, int64_t ldq, float scaling, const T
         for (int tb = 0; tb < S; tb += STEP, t0 += STEP) {
             if (tb + STEP < S) fetch(kb, vb, t0 + STEP, kn, vn);          // next block of this item ...
             else if (has_next) fetch(kbn, vbn, t_first, kn, vn);          // ... or the first block of the next item
-            bool valid[kXUnroll];
+            bool valid[kXU];
 #pragma unroll
-            for (int u = 0; u < kXUnroll; ++u) valid[u] = t0 + u * ROWS_PER_IT < S;
-            fold_rows<T>(p, q8, kr, vr, valid);
+            for (int u = 0; u < kXU; ++u) valid[u] = t0 + u * ROWS_PER_IT < S;
+            fold_rows<T, kXU>(p, q8, kr, vr, valid);
 #pragma unroll
-            for (int u = 0; u < kXUnroll; ++u) {
+            for (int u = 0; u < kXU; ++u) {
                 kr[u] = kn[u];
                 vr[u] = vn[u];
             }
@@ -497,14 +530,16 @@ k_cross_attn_decode(const T *__restrict__ q, int64_t ldq, float scaling, const T
                 partial_merge(p, s_part[par][w][sub][0], s_part[par][w][sub][1], oacc);
             }
             const float inv = 1.0f / p.l;
-            uint4 raw;
+            Chunk8<T> raw;
             T *o8 = reinterpret_cast<T *>(&raw);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o8[j] = from_f32<T>(p.acc[j] * inv);
-            *reinterpret_cast<uint4 *>(out + (int64_t)b * d + h * kHeadDim + sub * 8) = raw;
+            chunk_st(out + (int64_t)b * d + h * kHeadDim + sub * 8, raw);
         }
-        if (ca != nullptr && warp == 0)
-            quantize_row_if_last(out, b, d, H, lane, g, threshold, ca, row_stats, col_flags, row_counters);
+        if constexpr (sizeof(T) == 2) {     // the int8 outputs exist for 16-bit rows only
+            if (ca != nullptr && warp == 0)
+                quantize_row_if_last(out, b, d, H, lane, g, threshold, ca, row_stats, col_flags, row_counters);
+        }
         if (!has_next) break;
         kb = kbn;
         vb = vbn;
@@ -617,11 +652,11 @@ k_cross_attn_decode_tma(const __grid_constant__ CUtensorMap map_k, const __grid_
             const uint8_t *pk = sK + s * kOpBytes + (warp * 16 + g) * 128 + sub * 16;
             const uint8_t *pv = sV + s * kOpBytes + (warp * 16 + g) * 128 + sub * 16;
             static_assert(kXUnroll == 4, "a consumer warp takes 16 positions of a stage: 4 lane groups x 4 rows");
-            uint4 kr[kXUnroll], vr[kXUnroll];
+            Chunk8<T> kr[kXUnroll], vr[kXUnroll];
 #pragma unroll
             for (int u = 0; u < kXUnroll; ++u) {
-                kr[u] = *reinterpret_cast<const uint4 *>(pk + u * 4 * 128);
-                vr[u] = *reinterpret_cast<const uint4 *>(pv + u * 4 * 128);
+                kr[u].r[0] = *reinterpret_cast<const uint4 *>(pk + u * 4 * 128);
+                vr[u].r[0] = *reinterpret_cast<const uint4 *>(pv + u * 4 * 128);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[s]);      // this warp's rows of the stage are in registers
@@ -629,7 +664,7 @@ k_cross_attn_decode_tma(const __grid_constant__ CUtensorMap map_k, const __grid_
             bool valid[kXUnroll];
 #pragma unroll
             for (int u = 0; u < kXUnroll; ++u) valid[u] = t_base + u * 4 < S;
-            fold_rows<T>(p, q8, kr, vr, valid);
+            fold_rows<T, kXUnroll>(p, q8, kr, vr, valid);
         }
         if (item + (int)gridDim.x >= n_items) pdl_trigger();
         // merge the 4 lane groups of the warp (same dims, different rows)
@@ -691,7 +726,7 @@ extern "C" int wq_cross_attn_decode(const void *q, int64_t ldq, int dtype, float
                                     wq_stream_t stream) {
     WQ_REQUIRE(B >= 0 && S >= 1 && S < (1 << 30) && H >= 1 && H <= 65535 && B * H < (1ll << 30),
                "wq_cross_attn_decode: bad shape");
-    WQ_REQUIRE(dtype == WQ_F16 || dtype == WQ_BF16, "wq_cross_attn_decode: dtype must be f16 or bf16");
+    WQ_REQUIRE(dtype == WQ_F16 || dtype == WQ_BF16 || dtype == WQ_F32, "wq_cross_attn_decode: dtype must be f16, bf16 or f32");
     if (B == 0) return WQ_OK;
     WQ_REQUIRE(q && k && v && out, "wq_cross_attn_decode: null pointer");
     WQ_REQUIRE(ld % 8 == 0 && ld >= (int64_t)H * kHeadDim && ldq % 8 == 0 && ldq >= (int64_t)H * kHeadDim,
@@ -708,6 +743,15 @@ extern "C" int wq_cross_attn_decode(const void *q, int64_t ldq, int dtype, float
         const char *e = getenv("WQ_XATTN");
         return e == nullptr || e[0] != 'r';
     }();
+    if (dtype == WQ_F32) {
+        // the reference's fp32 flows (quanto, bnb *_32): register-fed walk, two 16-byte loads per lane and row
+        const int cap = wq_sm_count() * 2;
+        const dim3 grid((unsigned)(n_items < cap ? n_items : cap));
+        WQ_LAUNCH_PDL((k_cross_attn_decode<float, 8, 2>), grid, dim3(256), 0, s, (const float *)q, ldq, scaling,
+                      (const float *)k, (const float *)v, ld, (int)S, H, n_items, (float *)out, 0.0f, (int8_t *)nullptr,
+                      (float *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr);
+        return WQ_OK;
+    }
     if (use_tma && B * S < (1ll << 31)) {
         // K and V as [B*S, H*64] matrices with a row pitch of ld elements; one box = 16 * CW positions of one head
         static const int cw = [] { const char *e = getenv("WQ_XATTN_CW"); return (e && atoi(e) == 4) ? 4 : 8; }();

@@ -543,7 +543,8 @@ class GraphedGreedy:
         st.arange = torch.arange(t_max, device=device)
         st.mask = torch.zeros((t_max,), dtype=torch.bool, device=device)
         st.fused, st.threshold = self._plan_int8(dtype) if self.fuse_int8 else (None, 0.0)
-        st.own_attn = self.own_attention and st.hd == 64 and dtype in (torch.float16, torch.bfloat16)
+        # (fp32: the reference's quanto / bnb *_32 flows; torch's fp32 SDPA was 77 % of a whisper-medium step)
+        st.own_attn = self.own_attention and st.hd == 64 and dtype in (torch.float16, torch.bfloat16, torch.float32)
         # decode-time cross-attention: the persistent item-walking kernel of attn_decode.cu for every batch size
         # ("cudnn" keeps torch SDPA for A/B measurements only)
         st.own_cross = self.cross_attention != "cudnn"

@@ -316,3 +316,53 @@ def test_cross_attn_decode_matches_torch_sdpa_bf16_and_errors():
         F.cross_attn_decode(q, k, v, 0.125, H, threshold=6.0)
     with pytest.raises(RuntimeError, match="strides"):
         F.cross_attn_decode(q, k.transpose(1, 2).contiguous().transpose(1, 2), v, 0.125, H)
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32 caches: the reference's quanto / bnb *_32 flows keep fp32 activations (model_utils.py:139-142), HF then runs
+# torch SDPA in fp32 (modeling_whisper.py:338-352); the same decode kernels serve it with 32-byte row chunks
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,S,fused", [(3, 6, 1500, False), (5, 16, 1500, True), (2, 20, 777, True), (300, 8, 96, False)])
+def test_cross_attn_decode_fp32_matches_float64_attention(B, H, S, fused):
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(B + H + S)
+    q = torch.randn(B, d, device="cuda", generator=g)
+    if fused:                        # K and V as the two column blocks of one [B, S, 2d] buffer (fastgen's layout)
+        kv = torch.randn(B, S, 2 * d, device="cuda", generator=g)
+        k, v = kv[:, :, :d], kv[:, :, d:]
+    else:
+        k = torch.randn(B, S, d, device="cuda", generator=g)
+        v = torch.randn(B, S, d, device="cuda", generator=g)
+    out, quant = F.cross_attn_decode(q, k, v, 0.125, H)
+    assert quant is None and out.dtype == torch.float32
+    qh = (q * 0.125).double().view(B, 1, H, 64).transpose(1, 2)
+    kh = k.double().reshape(B, S, H, 64).transpose(1, 2)
+    vh = v.double().reshape(B, S, H, 64).transpose(1, 2)
+    w = torch.softmax(qh @ kh.transpose(-1, -2), dim=-1)
+    ref = (w @ vh).transpose(1, 2).reshape(B, d)
+    assert (out.double() - ref).abs().max().item() <= 2e-5
+    # the torch fp32 SDPA HF would call agrees to the same bar
+    sd = TF.scaled_dot_product_attention(qh.float(), kh.float(), vh.float(), scale=1.0).transpose(1, 2).reshape(B, d)
+    assert (out - sd).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("B,H,t_max,pos", [(4, 16, 64, 20), (2, 20, 128, 0), (64, 6, 72, 71)])
+def test_self_attn_decode_fp32_matches_float64_attention_and_appends(B, H, t_max, pos):
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(B + H + pos)
+    qkv = torch.randn(B, 3 * d, device="cuda", generator=g)           # one fused projection: common row stride
+    q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+    kc = torch.randn(B, t_max, d, device="cuda", generator=g)
+    vc = torch.randn(B, t_max, d, device="cuda", generator=g)
+    kc0, vc0 = kc.clone(), vc.clone()
+    pos_t = torch.tensor([pos], dtype=torch.int64, device="cuda")
+    out, _ = F.self_attn_decode(q, k, v, 0.125, kc, vc, pos_t, H)
+    assert torch.equal(kc[:, pos], k) and torch.equal(vc[:, pos], v)            # appended in place
+    keep = torch.ones(t_max, dtype=torch.bool, device="cuda")
+    keep[pos] = False
+    assert torch.equal(kc[:, keep], kc0[:, keep]) and torch.equal(vc[:, keep], vc0[:, keep])
+    qh = (q * 0.125).double().view(B, 1, H, 64).transpose(1, 2)
+    kh = kc[:, : pos + 1].double().view(B, pos + 1, H, 64).transpose(1, 2)
+    vh = vc[:, : pos + 1].double().view(B, pos + 1, H, 64).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2), dim=-1) @ vh).transpose(1, 2).reshape(B, d)
+    assert (out.double() - ref).abs().max().item() <= 2e-5
