@@ -337,7 +337,8 @@ def decode_probe(model, eng, peaks, ms_step, T):
             traffic = json.load(open(tp)).get("traffic_bytes_per_launch", {}).get(f"B{B}xH{H}xS{S}")
         out["cross_attention"] = {
             "traffic": traffic,
-            "kernel": "k_cross_attn_decode_tma (one pass over the cached encoder K/V per layer and token)",
+            "kernel": ("k_cross_attn_decode<float> (register-fed walk, fp32 K/V of the reference's fp32 flow; "
+                       if elt == 4 else "k_cross_attn_decode_tma (") + "one pass over the cached encoder K/V per layer and token)",
             "bound": "hbm", "algorithmic_bytes_per_launch": nbytes, "avg_launch_us": avg * 1e6,
             "achieved": nbytes / avg / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": nbytes / avg / 1e9 / peaks["hbm_gbs"], "launches_per_step": launches_per_step,

@@ -1016,7 +1016,9 @@ bool use_pair(int64_t M, int64_t N) {
         const char *e = getenv("WQ_GEMM_PAIR");
         return e == nullptr || e[0] != '0';
     }();
-    return on && !use_narrow_tile(M, N) && ((N + 127) / 128) % 2 == 0;
+    // (at most 128 rows: the peer CTA of every pair would hold no rows at all -- wide decode-shaped calls such as a
+    // quantized vocabulary projection keep the single-CTA tiles)
+    return on && M > BMH && !use_narrow_tile(M, N) && ((N + 127) / 128) % 2 == 0;
 }
 // weight-stationary pairs: K fits the resident half tiles (kWS k-blocks x 128 W rows = 64 KB per CTA), the column
 // blocks divide the pairs into whole groups and every group has several row blocks to walk
