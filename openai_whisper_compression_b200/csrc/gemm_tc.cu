@@ -175,10 +175,11 @@ template <int LEAN> constexpr int lean_a_rows() { return LEAN == 2 ? 32 : (LEAN 
 // the 2-3-stage single-CTA rings).
 template <int BN, int STAGES, int BMODE, int OUT_BUFS, int WS = 0, int COLS = 0, int LEAN = 0, int PAIR = 0>
 struct SmemLayout {
-    static_assert(PAIR == 0 || (COLS == 1 && BMODE == B_DIRECT), "CTA pairs: column-split int8 x int8 tiles");
+    static_assert(PAIR == 0 || COLS == 1, "CTA pairs: column-split tiles (128 rows x 256 columns per CTA)");
     static_assert(LEAN == 0 || (WS == 0 && COLS == 0), "lean tiles: plain round-robin schedule");
     static_assert(WS == 0 || BMODE == B_DIRECT, "weight-stationary tiles take W straight from TMA");
-    static_assert(COLS == 0 || (BMODE == B_DIRECT && BN == 128), "column-split tiles: int8 x int8 schemes, 2 x 128 columns");
+    static_assert(COLS == 0 || ((BMODE == B_DIRECT || PAIR) && BN == 128),
+                  "column-split tiles: W straight from TMA, or a CTA pair whose CTAs each expand BN = 128 rows of W");
     static constexpr int BMT = (COLS || LEAN) ? BMH : BM;      // tile rows
     static constexpr int BNT = COLS ? 2 * BN : BN;             // tile columns
     static constexpr int A_BYTES = (LEAN ? lean_a_rows<LEAN>() : BMT) * ROW_BYTES;
@@ -198,10 +199,10 @@ struct SmemLayout {
     static constexpr int OFF_CONST = OFF_OUT + EW * OUT_BUFS * BOX_BYTES;  // float [CONST_BUFS][3][BNT] per-tile constants
     static constexpr int OFF_LUT = OFF_CONST + CONST_BUFS * 3 * BNT * 4;          // float lut[16]
     static constexpr int OFF_BAR = OFF_LUT + 64;               // uint64 barriers
-    static constexpr int NUM_BARS = 3 * STAGES + 2 * ACC_STAGES + 1;
+    static constexpr int NUM_BARS = 4 * STAGES + 2 * ACC_STAGES + 1;   // full | empty | bready | pfull (pairs: packed W landed)
     static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
     static constexpr int TOTAL = OFF_TMEM + 16 + 1024;         // + slack for manual 1024-B alignment
-    static constexpr int TX_BYTES = A_BYTES + (WS > 0 ? 0 : (BMODE == B_DIRECT ? B_BYTES : P_BYTES));
+    [[maybe_unused]] static constexpr int TX_BYTES = A_BYTES + (WS > 0 ? 0 : (BMODE == B_DIRECT ? B_BYTES : P_BYTES));
     static_assert(TOTAL <= 232448, "shared memory budget exceeded");
 };
 
@@ -538,15 +539,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     uint64_t *bar_full = bars;
     uint64_t *bar_empty = bars + STAGES;
     uint64_t *bar_bready = bars + 2 * STAGES;
-    uint64_t *bar_tmem_full = bars + 3 * STAGES;
-    uint64_t *bar_tmem_empty = bars + 3 * STAGES + ACC_STAGES;
-    uint64_t *bar_w = bars + 3 * STAGES + 2 * ACC_STAGES;     // weight-stationary: the resident W tile has landed
+    uint64_t *bar_pfull = bars + 3 * STAGES;                   // pairs with packed weights: this CTA's packed tile landed
+    uint64_t *bar_tmem_full = bars + 4 * STAGES;
+    uint64_t *bar_tmem_empty = bars + 4 * STAGES + ACC_STAGES;
+    uint64_t *bar_w = bars + 4 * STAGES + 2 * ACC_STAGES;     // weight-stationary: the resident W tile has landed
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(smem + L::OFF_TMEM);
     float *s_lut = reinterpret_cast<float *>(smem + L::OFF_LUT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = args.num_kb;
-    const int total_tiles = args.tiles_m * args.tiles_n;
     const int rank = PAIR ? (int)cluster_ctarank() : 0;      // 0: the pair's leader (issues the MMAs, owns the barriers the
                                                              // pair synchronises on: full[], tmem_empty[], bar_w)
 
@@ -558,7 +559,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&bar_full[s], PAIR ? 2 : 1);      // pair: the leader's expect_tx arrive + the peer producer's arrive
             mbar_init(&bar_empty[s], 1);
-            mbar_init(&bar_bready[s], DQ_WARPS > 0 ? DQ_WARPS : 1);
+            mbar_init(&bar_bready[s], DQ_WARPS > 0 ? (PAIR ? 2 * DQ_WARPS : DQ_WARPS) : 1);   // pair: both CTAs' expansion warps
+            mbar_init(&bar_pfull[s], 1);
         }
         for (int a = 0; a < ACC_STAGES; ++a) {
             mbar_init(&bar_tmem_full[a], 1);
@@ -630,12 +632,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 if constexpr (PAIR) {
                     if (elect_one()) {
                         const uint32_t lf = mapa_u32(smem_u32(&bar_full[s]), 0);
-                        if (rank == 0) mbar_arrive_expect_tx(&bar_full[s], 2u * L::TX_BYTES);
+                        // bytes the leader's MMA warp waits for: A of both CTAs, and W when it comes straight from TMA
+                        constexpr uint32_t kPairTx = L::A_BYTES + ((WS == 0 && BMODE == B_DIRECT) ? L::B_BYTES : 0);
+                        if (rank == 0) mbar_arrive_expect_tx(&bar_full[s], 2u * kPairTx);
                         else mbar_arrive_cluster(lf);
                         tma_load_2d_pair(smem + L::OFF_A + s * L::A_BYTES, &map_a, lf, kb * A_ELEMS_PER_ROW, m0);
                         if (pf_m0 >= 0) tma_prefetch_2d(&map_a, kb * A_ELEMS_PER_ROW, pf_m0);
-                        if constexpr (WS == 0)
+                        if constexpr (BMODE != B_DIRECT) {
+                            // packed weights: this CTA's expansion warps wait for them on a barrier of their own
+                            mbar_arrive_expect_tx(&bar_pfull[s], L::P_BYTES);
+                            tma_load_2d(smem + L::OFF_P + s * L::P_BYTES, &map_b, &bar_pfull[s], kb * L::P_ROW, n0 + b_row);
+                        } else if constexpr (WS == 0) {
                             tma_load_2d_pair(smem + L::OFF_B + s * L::B_BYTES, &map_b, lf, kb * A_ELEMS_PER_ROW, n0 + b_row);
+                        }
                     }
                 } else if (elect_one()) {
                     mbar_arrive_expect_tx(&bar_full[s], L::TX_BYTES);
@@ -660,7 +669,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         constexpr uint32_t idesc =
             kIntKind ? make_idesc(kAccS32, AKIND == A_S8 ? kFmtS8 : kFmtU8, kFmtS8, PAIR ? 2 * BMH : BMH, BNT)
                      : make_idesc(kAccF32, AKIND == A_F16 ? kFmtF16 : kFmtBF16,
-                                  AKIND == A_F16 ? kFmtF16 : kFmtBF16, BMH, BN);
+                                  AKIND == A_F16 ? kFmtF16 : kFmtBF16, PAIR ? 2 * BMH : BMH, PAIR ? BNT : BN);
         uint32_t s = 0, ph = 0, t = 0;
         int mt, nt;
         for (; tile_at<WS, PAIR>(args, (int)t, mt, nt); ++t) {
@@ -685,7 +694,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
                         const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
                         if constexpr (PAIR) {
-                            umma_i8_pair(tmem_acc, adesc0 + 2 * k, bdesc + 2 * k, idesc, acc);
+                            if constexpr (kIntKind) umma_i8_pair(tmem_acc, adesc0 + 2 * k, bdesc + 2 * k, idesc, acc);
+                            else umma_f16_pair(tmem_acc, adesc0 + 2 * k, bdesc + 2 * k, idesc, acc);
                         } else if constexpr (kIntKind) {
                             umma_i8(tmem_acc, adesc0 + 2 * k, bdesc + 2 * k, idesc, acc);
                             if (two_halves) umma_i8(tmem_acc + BN, adesc1 + 2 * k, bdesc + 2 * k, idesc, acc);
@@ -725,11 +735,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         if constexpr (is_byte<BMODE>()) {
             const int qd = t & 3, row0 = t >> 2;      // 128 threads: 4 per row, 32 rows per pass
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int mt, nt;
+            for (int ti = 0; tile_at<WS, PAIR>(args, ti, mt, nt); ++ti) {
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&bar_full[s], ph);
+                    mbar_wait(PAIR ? &bar_pfull[s] : &bar_full[s], ph);
                     const uint8_t *P = smem + L::OFF_P + s * L::P_BYTES;
                     uint8_t *B = smem + L::OFF_B + s * L::B_BYTES;
 #pragma unroll
@@ -776,15 +787,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_bready[s]);
+                    if (lane == 0) {
+                        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_bready[s]), 0));   // the leader's MMA warp waits
+                        else mbar_arrive(&bar_bready[s]);
+                    }
                 }
             }
         } else if constexpr (is_nibble<BMODE>()) {
             const int hf = t & 1, r = t >> 1;         // 256 threads: 2 per row; rows >= BN idle
             const bool active = r < BN;
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n = (tile % args.tiles_n) * BN + r;
+            int mt, nt;
+            for (int ti = 0; tile_at<WS, PAIR>(args, ti, mt, nt); ++ti) {
+                const int n = nt * BNT + (PAIR ? rank * BN : 0) + r;      // pair: this CTA expands its 128 of the 256 W rows
                 const float *am_row = args.absmax + (size_t)(n < args.N ? n : 0) * args.absmax_ld;
                 const float *sh_row = (BMODE == B_U4) ? args.shift + (size_t)(n < args.N ? n : 0) * args.absmax_ld : nullptr;
                 const bool n_ok = active && n < args.N;
@@ -797,7 +812,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     const float am = n_ok ? __ldg(am_row + gi) : 0.0f;
                     float sh = 0.0f;
                     if constexpr (BMODE == B_U4) sh = n_ok ? __ldg(sh_row + gi) : 0.0f;
-                    mbar_wait(&bar_full[s], ph);
+                    mbar_wait(PAIR ? &bar_pfull[s] : &bar_full[s], ph);
                     if (active) {
                         const uint8_t *P = smem + L::OFF_P + s * L::P_BYTES;
                         uint8_t *B = smem + L::OFF_B + s * L::B_BYTES;
@@ -825,7 +840,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_bready[s]);
+                    if (lane == 0) {
+                        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_bready[s]), 0));
+                        else mbar_arrive(&bar_bready[s]);
+                    }
                 }
             }
         }
@@ -883,7 +901,7 @@ constexpr int pick_stages() {
         const int brows = PAIR ? bnt / 2 : bnt;     // W rows this CTA stages
         const int stage = (LEAN ? lean_a_rows<LEAN>() : bmt) * ROW_BYTES + (WS > 0 ? 0 : brows * ROW_BYTES) + BN * (is_byte<BMODE>() ? 64 : (is_nibble<BMODE>() ? 32 : 0));
         const int total = st * stage + WS * brows * ROW_BYTES + epi_warps<BN, BMODE, LEAN>() * OUT_BUFS * BOX_BYTES +
-                          (WS > 0 ? 1 : 2) * 3 * bnt * 4 + 64 + (3 * st + 2 * ACC_STAGES + 1) * 8 + 16 + 1024;
+                          (WS > 0 ? 1 : 2) * 3 * bnt * 4 + 64 + (4 * st + 2 * ACC_STAGES + 1) * 8 + 16 + 1024;
         if (total <= budget) best = st;
     }
     return best;
@@ -1011,11 +1029,14 @@ bool use_cols(int64_t M, int64_t N, int64_t K) {
 // CTA pairs (256 x 256 per cluster of two, one cta_group::2 instruction per k-step) for the int8 x int8 schemes: every
 // call that is not decode-shaped and whose 256-wide column blocks add no padding over 128-wide ones.  WQ_GEMM_PAIR=0
 // falls back to the single-CTA tiles (A/B measurements, scripts/gemm_ws_bench.py).
-bool use_pair(int64_t M, int64_t N) {
-    static const bool on = [] {
+// WQ_GEMM_PAIR: 0 = no pairs, 1 = int8 x int8 schemes only, 2 = + the weight-expanding schemes (W8A16, W4A16, u4, e4m3),
+// 3 (default) = + the unquantized fp16 / bf16 projection.
+bool use_pair(int64_t M, int64_t N, int level = 1) {
+    static const int max_level = [] {
         const char *e = getenv("WQ_GEMM_PAIR");
-        return e == nullptr || e[0] != '0';
+        return e == nullptr ? 3 : atoi(e);
     }();
+    const bool on = level <= max_level;
     // (at most 128 rows: the peer CTA of every pair would hold no rows at all -- wide decode-shaped calls such as a
     // quantized vocabulary projection keep the single-CTA tiles)
     return on && M > BMH && !use_narrow_tile(M, N) && ((N + 127) / 128) % 2 == 0;
@@ -1146,20 +1167,23 @@ extern "C" int wq_gemm_dyn_i8(const uint8_t *xq, const float *qparams, const int
 
 namespace {
 
+// pair: the CTA-pair schedule (use_pair(); the A map then has 128-row boxes, the W map 128-row boxes as before)
 template <int BMODE, int EPI>
 int dispatch_a16(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &args, int x_dtype, int y_dtype,
-                 bool narrow, cudaStream_t s, bool lean = false) {
+                 bool narrow, cudaStream_t s, bool lean = false, bool pair = false) {
 #define WQ_CASE(BN, AK, OT) return launch_gemm<BN, AK, BMODE, EPI, OT>(ma, mb, args, s)
 #define WQ_LEAN(AK, OT) return launch_gemm<64, AK, BMODE, EPI, OT, 0, 0, 1>(ma, mb, args, s)
+#define WQ_PAIR(AK, OT) return launch_gemm<128, AK, BMODE, EPI, OT, 0, 1, 0, 1>(ma, mb, args, s)
     if (x_dtype == WQ_F16) {
-        if (y_dtype == WQ_F16) { if (lean) WQ_LEAN(A_F16, __half); if (narrow) WQ_CASE(64, A_F16, __half); else WQ_CASE(128, A_F16, __half); }
-        if (y_dtype == WQ_F32) { if (narrow) WQ_CASE(64, A_F16, float); else WQ_CASE(128, A_F16, float); }
+        if (y_dtype == WQ_F16) { if (pair) WQ_PAIR(A_F16, __half); if (lean) WQ_LEAN(A_F16, __half); if (narrow) WQ_CASE(64, A_F16, __half); else WQ_CASE(128, A_F16, __half); }
+        if (y_dtype == WQ_F32) { if (pair) WQ_PAIR(A_F16, float); if (narrow) WQ_CASE(64, A_F16, float); else WQ_CASE(128, A_F16, float); }
     } else if (x_dtype == WQ_BF16) {
-        if (y_dtype == WQ_BF16) { if (lean) WQ_LEAN(A_BF16, __nv_bfloat16); if (narrow) WQ_CASE(64, A_BF16, __nv_bfloat16); else WQ_CASE(128, A_BF16, __nv_bfloat16); }
-        if (y_dtype == WQ_F32) { if (narrow) WQ_CASE(64, A_BF16, float); else WQ_CASE(128, A_BF16, float); }
+        if (y_dtype == WQ_BF16) { if (pair) WQ_PAIR(A_BF16, __nv_bfloat16); if (lean) WQ_LEAN(A_BF16, __nv_bfloat16); if (narrow) WQ_CASE(64, A_BF16, __nv_bfloat16); else WQ_CASE(128, A_BF16, __nv_bfloat16); }
+        if (y_dtype == WQ_F32) { if (pair) WQ_PAIR(A_BF16, float); if (narrow) WQ_CASE(64, A_BF16, float); else WQ_CASE(128, A_BF16, float); }
     }
 #undef WQ_CASE
 #undef WQ_LEAN
+#undef WQ_PAIR
     wq_set_error("unsupported dtype combination x=%d y=%d (x: F16/BF16, y: same as x or F32)", x_dtype, y_dtype);
     return WQ_ERR_INVALID;
 }
@@ -1178,16 +1202,16 @@ extern "C" int wq_gemm_w8a16(const void *x, int x_dtype, const int8_t *wq, const
     args.M = (int)M; args.N = (int)N; args.K = (int)K;
     args.num_kb = (int)((K + 63) / 64);
     args.col_scale = scale; args.bias = bias; args.out = y;
-    const bool narrow = use_narrow_tile(M, N);
+    const bool narrow = use_narrow_tile(M, N), pair = use_pair(M, N, 2);
     const bool lean = narrow && use_lean_tile(M) && y_dtype == x_dtype;    // decode-shaped calls, <= 128 rows
     CUtensorMap ma, mb;
     rc = make_map_2d(&ma, x, x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                     M, K, lean ? BMH : BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+                     M, K, (lean || pair) ? BMH : BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
     rc = make_map_2d(&mb, wq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, narrow ? 64 : 128, 64,
                      CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc != WQ_OK) return rc;
-    return dispatch_a16<B_I8, EPI_W8A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream, lean);
+    return dispatch_a16<B_I8, EPI_W8A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream, lean, pair);
 }
 
 extern "C" int wq_gemm_w4a16(const void *x, int x_dtype, const uint8_t *packed, const float *absmax, int quant_type,
@@ -1205,16 +1229,16 @@ extern "C" int wq_gemm_w4a16(const void *x, int x_dtype, const uint8_t *packed, 
     args.num_kb = (int)(K / 64);
     args.absmax = absmax; args.absmax_ld = (int)(K / 64);
     args.bias = bias; args.out = y; args.quant_type = quant_type;
-    const bool narrow = use_narrow_tile(M, N);
+    const bool narrow = use_narrow_tile(M, N), pair = use_pair(M, N, 2);
     const bool lean = narrow && use_lean_tile(M) && y_dtype == x_dtype;    // decode-shaped calls, <= 128 rows
     CUtensorMap ma, mb;
     rc = make_map_2d(&ma, x, x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                     M, K, lean ? BMH : BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+                     M, K, (lean || pair) ? BMH : BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
     rc = make_map_2d(&mb, packed, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K / 2, narrow ? 64 : 128, 32,
                      CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc != WQ_OK) return rc;
-    return dispatch_a16<B_4BIT, EPI_W4A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream, lean);
+    return dispatch_a16<B_4BIT, EPI_W4A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream, lean, pair);
 }
 
 /* quanto QLinear.forward with weights=qint4 (group-wise affine uint4, MaxOptimizer):
@@ -1234,16 +1258,16 @@ extern "C" int wq_gemm_u4a16(const void *x, int x_dtype, const uint8_t *packed, 
     args.num_kb = (int)(K / 64);
     args.absmax = scale; args.shift = shift; args.group = group; args.absmax_ld = (int)(K / group);
     args.bias = bias; args.out = y;
-    const bool narrow = use_narrow_tile(M, N);
+    const bool narrow = use_narrow_tile(M, N), pair = use_pair(M, N, 2);
     const bool lean = narrow && use_lean_tile(M) && y_dtype == x_dtype;    // decode-shaped calls, <= 128 rows
     CUtensorMap ma, mb;
     rc = make_map_2d(&ma, x, x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                     M, K, lean ? BMH : BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+                     M, K, (lean || pair) ? BMH : BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
     rc = make_map_2d(&mb, packed, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K / 2, narrow ? 64 : 128, 32,
                      CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc != WQ_OK) return rc;
-    return dispatch_a16<B_U4, EPI_W4A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream, lean);
+    return dispatch_a16<B_U4, EPI_W4A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream, lean, pair);
 }
 
 /* Unquantized linear on the same tcgen05 pipeline: y = x @ W^T + bias with W [N, K] in the activation dtype, taken
@@ -1276,12 +1300,13 @@ extern "C" int wq_gemm_f16(const void *x, int x_dtype, const void *w, const floa
     }
     const CUtensorMapDataType dt = x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     CUtensorMap ma, mb;
-    rc = make_map_2d(&ma, x, dt, 2, M, K, BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    const bool pair = use_pair(M, N, 3);
+    rc = make_map_2d(&ma, x, dt, 2, M, K, pair ? BMH : BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
     rc = make_map_2d(&mb, w, dt, 2, N, K, narrow ? 64 : 128, 64, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
     return dispatch_a16<B_DIRECT, EPI_PLAIN>(ma, mb, args, x_dtype, y == nullptr ? x_dtype : y_dtype, narrow,
-                                             (cudaStream_t)stream);
+                                             (cudaStream_t)stream, false, pair);
 }
 
 namespace {
@@ -1320,14 +1345,14 @@ extern "C" int wq_gemm_wf8a16(const void *x, int x_dtype, const uint8_t *wq, con
     args.M = (int)M; args.N = (int)N; args.K = (int)K;
     args.num_kb = (int)((K + 63) / 64);
     args.col_scale = scale; args.bias = bias; args.out = y;
-    const bool narrow = use_narrow_tile(M, N);
+    const bool narrow = use_narrow_tile(M, N), pair = use_pair(M, N, 2);
     CUtensorMap ma, mb;
     rc = make_map_2d(&ma, x, x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                     M, K, BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+                     M, K, pair ? BMH : BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != WQ_OK) return rc;
     rc = make_map_2d(&mb, wq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, narrow ? 64 : 128, 64, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc != WQ_OK) return rc;
-    return dispatch_a16<B_F8, EPI_W8A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream);
+    return dispatch_a16<B_F8, EPI_W8A16>(ma, mb, args, x_dtype, y_dtype, narrow, (cudaStream_t)stream, false, pair);
 }
 
 /* quanto QLinear.forward with qint8 weights AND statically quantized qint8 activations (quantize(model, weights=qint8,

@@ -125,3 +125,92 @@ def test_pair_fused_residual_epilogue_matches_separate_add():
     want = (y + res).clamp(-clamp, clamp)
     got = F.gemm_llmint8(ca, sca, cb, scb, bias, residual=res, clamp_abs=clamp)
     assert torch.equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------------
+# weight-expanding schemes on CTA pairs: each CTA expands its 128 of the tile's 256 W rows (bready barrier of the
+# leader counts both CTAs' expansion warps); fp32 output against a float64 matmul of the dequantized weights
+# ------------------------------------------------------------------------------------------------
+A16_SHAPES = [(9800, 768, 768), (4900, 1024, 4096), (12077, 1280, 1280), (2600, 3072, 768)]
+
+
+# fp32 accumulation over K products: the error against float64 grows ~ sqrt(K) * 2^-24 * sum|x w|; 5e-5 of max(|y|, 1)
+# covers K = 4096 with 2x headroom (the K <= 1280 oracle tests of test_gpu_kernels.py use 2e-5)
+def _check_a16(y32, x, wd, bias, tol32=5e-5):
+    ref = x.double() @ wd.double().t() + bias.double()[None, :]
+    err = (y32.double() - ref).abs() / ref.abs().clamp_min(1.0)
+    assert err.max().item() <= tol32
+    return ref
+
+
+@pytest.mark.parametrize("M,N,K", A16_SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_pair_w8a16_matches_dequant_matmul(M, N, K, dtype):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    w[torch.rand(N, K, device="cuda", generator=g) < 0.5] = 0
+    x = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    q, scale = F.quanto_quantize_qint8(w)
+    y32 = F.gemm_w8a16(x, q, scale, bias, out_dtype=torch.float32)
+    ref = x.double() @ q.double().t() * scale.double().view(1, -1) + bias.double()[None, :]
+    err = (y32.double() - ref).abs() / ref.abs().clamp_min(1.0)
+    assert err.max().item() <= 5e-5
+    y = F.gemm_w8a16(x, q, scale, bias)
+    assert y.dtype == dtype
+    tol = 2e-3 if dtype == torch.float16 else 1.6e-2
+    assert ((y.double() - ref).abs() / ref.abs().clamp_min(1.0)).max().item() <= tol
+    # every row block of both CTAs of a pair equals the rounded fp32 result
+    assert torch.equal(y, y32.to(dtype))
+
+
+@pytest.mark.parametrize("M,N,K", A16_SHAPES)
+@pytest.mark.parametrize("quant_type", ["nf4", "fp4"])
+def test_pair_w4a16_matches_dequant_matmul(M, N, K, quant_type):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + 1)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+    x = torch.randn(M, K, device="cuda", generator=g).half()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    packed, absmax = F.quantize_4bit(w, 64, quant_type)
+    wd = F.dequantize_4bit(packed, absmax, (N, K), 64, quant_type, torch.float16)
+    y32 = F.gemm_w4a16(x, packed, absmax, N, K, bias, quant_type, out_dtype=torch.float32)
+    _check_a16(y32, x, wd, bias)
+    y = F.gemm_w4a16(x, packed, absmax, N, K, bias, quant_type)
+    assert torch.equal(y, y32.half())
+
+
+@pytest.mark.parametrize("M,N,K", [(9800, 768, 768), (4900, 1024, 4096)])
+def test_pair_u4a16_and_f8_match_dequant_matmul(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + 2)
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    x = torch.randn(M, K, device="cuda", generator=g).half()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    p, s, sh, grp = F.quanto_quantize_qint4(w)
+    y32 = F.gemm_u4a16(x, p, s, sh, grp, bias, torch.float32)
+    codes = torch.stack([p >> 4, p & 15], -1).reshape(N, K).float()
+    wd = (s.repeat_interleave(grp, 1) * codes - sh.repeat_interleave(grp, 1)).half()
+    _check_a16(y32, x, wd, bias)
+    q8, s8 = F.quanto_quantize_qfloat8(w)
+    y32 = F.gemm_wf8a16(x, q8, s8.view(-1), bias, torch.float32)
+    ref = x.double() @ q8.view(torch.float8_e4m3fn).float().double().t() * s8.double().view(1, -1) + bias.double()[None, :]
+    assert ((y32.double() - ref).abs() / ref.abs().clamp_min(1.0)).max().item() <= 5e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(256, 51865, 512), (3000, 2048, 384)])
+def test_pair_gemm_f16_projection_and_argmax(dtype, M, N, K):
+    """Unquantized projection (proj_out of the HF bitsandbytes flows) on pairs, with the masked arg-max epilogue."""
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(dtype)
+    y = F.gemm_f16(x, w)
+    ref = (x.double() @ w.double().t())
+    tol = 2e-3 if dtype == torch.float16 else 1.6e-2
+    assert ((y.double() - ref).abs() / ref.abs().clamp_min(1.0)).max().item() <= tol
+    mask = torch.zeros(-(-N // 256) * 256, dtype=torch.bool, device="cuda")
+    mask[torch.randint(0, N, (N // 3,), device="cuda", generator=g)] = True
+    keys = torch.zeros(M, dtype=torch.long, device="cuda")
+    F.gemm_f16(x, w, mask=mask, argmax_keys=keys, store=False)
+    ids = F.argmax_finalize(keys)
+    want = y.float().masked_fill(mask[:N][None, :], float("-inf")).argmax(-1)
+    assert torch.equal(ids, want)
