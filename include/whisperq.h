@@ -230,7 +230,9 @@ int wq_gemm_w8a8(const int8_t *xq, const int8_t *wq, const float *out_scale, con
  *   mode 3  quanto qfloat8 (e4m3fn codes) [N, K], s0 = scale fp32 [N]
  * y[m, n] = sum_k x[m, k] * w[n, k] (+ scale) + bias[n]: the packed weights are streamed once, dequantized in registers
  * to the value wq_gemm_w4a16 / w8a16 / u4a16 / wf8a16 feed the tensor core (rounded once to the activation dtype where
- * the scheme rounds), fp32 accumulation on the CUDA cores, warp reduction in a fixed order.  x, y: F16 or BF16. */
+ * the scheme rounds), fp32 accumulation on the CUDA cores, warp reduction in a fixed order.  x, y: F16 or BF16; or
+ * x_dtype WQ_F32 (the reference's fp32 flows, model_utils.py:139-142): x and y are fp32, the rows are rounded to fp16 as
+ * they are staged -- the operand the tensor-core GEMMs of the same flow multiply -- and the sums are stored unrounded. */
 int wq_gemv_weightonly(const void *x, int x_dtype, int64_t M, int64_t K, int mode, const void *w,
                        const float *s0, const float *s1, int group, int quant_type, const float *bias,
                        void *y, int64_t N, wq_stream_t stream);

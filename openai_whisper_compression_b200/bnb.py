@@ -149,7 +149,7 @@ def matmul_4bit(A: torch.Tensor, B: torch.Tensor, quant_state: QuantState, out=N
     if x.dtype == torch.float32:
         # fp32 compute flow (bnb_implementation.py:1216-1218): tensor cores take fp16 operands,
         # accumulate fp32 and write fp32 (DESIGN.md "Numerics")
-        return F.gemm_w4a16(x.to(torch.float16), B, quant_state.effective_absmax(), N, K,
+        return F.gemm_w4a16(x, B, quant_state.effective_absmax(), N, K,
                             None if bias is None else bias.float(), quant_state.quant_type, torch.float32)
     return F.gemm_w4a16(x, B, quant_state.effective_absmax(), N, K, None if bias is None else bias.float(),
                         quant_state.quant_type)

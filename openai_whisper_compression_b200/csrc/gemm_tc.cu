@@ -921,7 +921,10 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cud
 #ifndef WQ_PAIR_OUT_BUFS
 #define WQ_PAIR_OUT_BUFS 1
 #endif
-    constexpr int OUT_BUFS = PAIR ? WQ_PAIR_OUT_BUFS : ((WS > 0 && COLS) ? 1 : (LEAN ? WQ_LEAN_OUT_BUFS : pick_out_bufs<BN, BMODE>()));
+#ifndef WQ_PAIR_WS_OUT_BUFS
+#define WQ_PAIR_WS_OUT_BUFS 2     /* weight-stationary pairs are bound by the epilogue's stores (K <= 512: 2 048 tensor clocks per tile) */
+#endif
+    constexpr int OUT_BUFS = PAIR ? ((WS > 0 && BMODE == B_DIRECT) ? WQ_PAIR_WS_OUT_BUFS : WQ_PAIR_OUT_BUFS) : ((WS > 0 && COLS) ? 1 : (LEAN ? WQ_LEAN_OUT_BUFS : pick_out_bufs<BN, BMODE>()));
     constexpr int STAGES = pick_stages<BN, BMODE, OUT_BUFS, WS, COLS, LEAN, PAIR>();
     using L = SmemLayout<BN, STAGES, BMODE, OUT_BUFS, WS, COLS, LEAN, PAIR>;
     auto kfn = k_gemm_tc<BN, STAGES, AKIND, BMODE, EPI, OutT, OUT_BUFS, WS, COLS, LEAN, PAIR>;

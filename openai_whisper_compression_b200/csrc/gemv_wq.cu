@@ -110,7 +110,10 @@ __device__ __forceinline__ void decode_w8(const WRaw &r, const float *lut, float
     }
 }
 
-template <typename T, int MODE, int MT>     // MT: rows rounded up to 8 / 16 / 32
+// F32IO: the reference's fp32 flows (quanto on a model that was never .half()-ed, model_utils.py:139-142).  The rows
+// arrive as fp32, are rounded to T while they are staged -- the operand the tensor-core GEMM of the same flow sees
+// after its cast pass -- and the fp32 accumulators are stored as fp32.
+template <typename T, int MODE, int MT, bool F32IO = false>     // MT: rows rounded up to 8 / 16 / 32
 __global__ void __launch_bounds__(GV_THREADS)
 k_gemv_wq(const GvArgs a) {
     extern __shared__ __align__(16) uint8_t gv_smem[];
@@ -155,7 +158,18 @@ k_gemv_wq(const GvArgs a) {
             for (int j = 0; j < XV; ++j) {
                 const int i = tid + j * GV_THREADS, m = i / VPR, c = i - m * VPR;
                 xr[j] = make_uint4(0u, 0u, 0u, 0u);
-                if (m < a.M && c * 8 < kc) xr[j] = *reinterpret_cast<const uint4 *>(x + (size_t)m * a.K + k0 + c * 8);
+                if (m < a.M && c * 8 < kc) {
+                    if constexpr (F32IO) {
+                        const float4 *xf = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(a.x) +
+                                                                            (size_t)m * a.K + k0 + c * 8);
+                        const float4 lo = xf[0], hi = xf[1];
+                        T *t8 = reinterpret_cast<T *>(&xr[j]);
+                        t8[0] = from_f32<T>(lo.x); t8[1] = from_f32<T>(lo.y); t8[2] = from_f32<T>(lo.z); t8[3] = from_f32<T>(lo.w);
+                        t8[4] = from_f32<T>(hi.x); t8[5] = from_f32<T>(hi.y); t8[6] = from_f32<T>(hi.z); t8[7] = from_f32<T>(hi.w);
+                    } else {
+                        xr[j] = *reinterpret_cast<const uint4 *>(x + (size_t)m * a.K + k0 + c * 8);
+                    }
+                }
             }
 #pragma unroll
             for (int j = 0; j < XV; ++j) {
@@ -197,7 +211,8 @@ k_gemv_wq(const GvArgs a) {
             float r = tot;
             if constexpr (MODE == W_I8 || MODE == W_F8) r = __fmul_rn(r, __ldg(a.s0 + n));   // quanto: scale after the matmul
             if (a.bias != nullptr) r = __fadd_rn(r, __ldg(a.bias + n));
-            y[(size_t)m * a.N + n] = from_f32<T>(r);
+            if constexpr (F32IO) reinterpret_cast<float *>(a.y)[(size_t)m * a.N + n] = r;
+            else y[(size_t)m * a.N + n] = from_f32<T>(r);
         }
     }
     if constexpr (MT * GV_COLS < 32) {      // MT = 8: a single pass over 16 quantities padded to 32
@@ -210,12 +225,13 @@ k_gemv_wq(const GvArgs a) {
             float r = tot;
             if constexpr (MODE == W_I8 || MODE == W_F8) r = __fmul_rn(r, __ldg(a.s0 + n));
             if (a.bias != nullptr) r = __fadd_rn(r, __ldg(a.bias + n));
-            y[(size_t)m * a.N + n] = from_f32<T>(r);
+            if constexpr (F32IO) reinterpret_cast<float *>(a.y)[(size_t)m * a.N + n] = r;
+            else y[(size_t)m * a.N + n] = from_f32<T>(r);
         }
     }
 }
 
-template <typename T, int MODE>
+template <typename T, int MODE, bool F32IO = false>
 int launch_gemv(const GvArgs &a, cudaStream_t s) {
     const unsigned grid = (unsigned)((a.N + GV_TILE - 1) / GV_TILE);
 #define WQ_GV(MT)                                                                                              \
@@ -223,10 +239,10 @@ int launch_gemv(const GvArgs &a, cudaStream_t s) {
         const size_t smem = (size_t)MT * GV_KCH * sizeof(T);                                                   \
         static bool configured = false;                                                                        \
         if (!configured && smem > 48 * 1024) {                                                                 \
-            WQ_CUDA(cudaFuncSetAttribute(k_gemv_wq<T, MODE, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            WQ_CUDA(cudaFuncSetAttribute(k_gemv_wq<T, MODE, MT, F32IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             configured = true;                                                                                 \
         }                                                                                                      \
-        WQ_LAUNCH_PDL((k_gemv_wq<T, MODE, MT>), dim3(grid), dim3(GV_THREADS), smem, s, a);                     \
+        WQ_LAUNCH_PDL((k_gemv_wq<T, MODE, MT, F32IO>), dim3(grid), dim3(GV_THREADS), smem, s, a);              \
         return WQ_OK;                                                                                          \
     }
     if (a.M <= 8) WQ_GV(8)
@@ -243,7 +259,7 @@ extern "C" int wq_gemv_weightonly(const void *x, int x_dtype, int64_t M, int64_t
     WQ_REQUIRE(M >= 0 && N >= 0 && K > 0 && N < (1ll << 31) && K < (1ll << 31), "wq_gemv_weightonly: bad shape");
     if (M == 0 || N == 0) return WQ_OK;
     WQ_REQUIRE(M <= 32, "wq_gemv_weightonly: at most 32 rows (got %lld)", (long long)M);
-    WQ_REQUIRE(x_dtype == WQ_F16 || x_dtype == WQ_BF16, "wq_gemv_weightonly: activations must be f16 or bf16");
+    WQ_REQUIRE(x_dtype == WQ_F16 || x_dtype == WQ_BF16 || x_dtype == WQ_F32, "wq_gemv_weightonly: activations must be f16, bf16 or f32");
     WQ_REQUIRE(mode >= W_NF4 && mode <= W_F8, "wq_gemv_weightonly: bad mode %d", mode);
     WQ_REQUIRE(x && w && s0 && y, "wq_gemv_weightonly: null pointer");
     WQ_REQUIRE(K % 8 == 0, "wq_gemv_weightonly: K=%lld must be a multiple of 8", (long long)K);
@@ -257,6 +273,7 @@ extern "C" int wq_gemv_weightonly(const void *x, int x_dtype, int64_t M, int64_t
     cudaStream_t s = (cudaStream_t)stream;
 #define WQ_GV_MODE(MODE)                                                            \
     if (mode == MODE) {                                                             \
+        if (x_dtype == WQ_F32) return launch_gemv<__half, MODE, true>(a, s);        \
         if (x_dtype == WQ_F16) return launch_gemv<__half, MODE>(a, s);              \
         return launch_gemv<__nv_bfloat16, MODE>(a, s);                              \
     }

@@ -179,6 +179,23 @@ def _gemv_ok(x2: torch.Tensor, out_dtype) -> bool:
     return 0 < x2.shape[0] <= GEMV_ROWS and out_dtype == x2.dtype and x2.dtype in (torch.float16, torch.bfloat16)
 
 
+def _gemv_f32_ok(x2: torch.Tensor, out_dtype) -> bool:
+    """fp32 rows of the reference's fp32 flows (the reference evaluates in batches of 16, quantization.py:33): one GEMV
+    launch replaces the fp32 -> fp16 cast pass + tensor-core tile.  Only up to GEMV_ROWS rows: splitting 64 rows into
+    two launches measured SLOWER than cast + GEMM (whisper-medium quanto, 64 utterances: 8.9 vs 7.1 ms per token --
+    at 32 rows the CUDA-core FMAs, not the weight bytes, bound the GEMV)."""
+    return 0 < x2.shape[0] <= GEMV_ROWS and out_dtype == torch.float32 and x2.dtype == torch.float32
+
+
+def _gemv_f32(x2: torch.Tensor, mode: int, w, s0, s1, group: int, quant_type: int, bias, y: torch.Tensor, N: int, K: int):
+    _gemv_weightonly(x2, mode, w, s0, s1, group, quant_type, bias, y, N, K)
+
+
+def _operand(x2: torch.Tensor) -> torch.Tensor:
+    """fp32 activations go to the tensor cores as fp16 (DESIGN.md "Numerics"): the one cast pass of the fp32 flows."""
+    return x2.to(torch.float16) if x2.dtype == torch.float32 else x2
+
+
 def _dest(out: Optional[torch.Tensor], M: int, N: int, dtype, device, what: str) -> torch.Tensor:
     """[M, N] destination of a GEMM: a fresh tensor, or the caller's contiguous buffer of M*N elements."""
     if out is None:
@@ -199,6 +216,10 @@ def gemm_w4a16(x: torch.Tensor, packed: torch.Tensor, absmax: torch.Tensor, N: i
     if _gemv_ok(x2, out_dtype):
         _gemv_weightonly(x2, 0, packed, absmax, None, 0, _QT[quant_type], bias, y, N, K)
         return y.reshape(*x.shape[:-1], N)
+    if _gemv_f32_ok(x2, out_dtype):
+        _gemv_f32(x2, 0, packed, absmax, None, 0, _QT[quant_type], bias, y, N, K)
+        return y.reshape(*x.shape[:-1], N)
+    x2 = _operand(x2)
     with torch.cuda.device(x.device), _Timed("w4a16", x2.shape[0], N, K):
         _lib.check(_lib.load().wq_gemm_w4a16(_ptr(x2), _DT[x2.dtype], _ptr(packed), _ptr(absmax), _QT[quant_type],
                                              _ptr(bias), _ptr(y), _DT[out_dtype], x2.shape[0], N, K, _stream()),
@@ -595,6 +616,10 @@ def gemm_w8a16(x: torch.Tensor, wq: torch.Tensor, scale: torch.Tensor, bias: Opt
     if _gemv_ok(x2, out_dtype) and K % 8 == 0:
         _gemv_weightonly(x2, 1, wq, scale, None, 0, 0, bias, y, N, K)
         return y.reshape(*x.shape[:-1], N)
+    if _gemv_f32_ok(x2, out_dtype) and K % 8 == 0:
+        _gemv_f32(x2, 1, wq, scale, None, 0, 0, bias, y, N, K)
+        return y.reshape(*x.shape[:-1], N)
+    x2 = _operand(x2)
     with torch.cuda.device(x.device), _Timed("w8a16", x2.shape[0], N, K):
         _lib.check(_lib.load().wq_gemm_w8a16(_ptr(x2), _DT[x2.dtype], _ptr(wq), _ptr(scale), _ptr(bias), _ptr(y),
                                              _DT[out_dtype], x2.shape[0], N, K, _stream()), "wq_gemm_w8a16")
@@ -628,6 +653,10 @@ def gemm_wf8a16(x: torch.Tensor, wq: torch.Tensor, scale: torch.Tensor, bias: Op
     if _gemv_ok(x2, out_dtype) and K % 8 == 0:
         _gemv_weightonly(x2, 3, wq, scale, None, 0, 0, bias, y, N, K)
         return y.reshape(*x.shape[:-1], N)
+    if _gemv_f32_ok(x2, out_dtype) and K % 8 == 0:
+        _gemv_f32(x2, 3, wq, scale, None, 0, 0, bias, y, N, K)
+        return y.reshape(*x.shape[:-1], N)
+    x2 = _operand(x2)
     with torch.cuda.device(x.device), _Timed("wf8a16", x2.shape[0], N, K):
         _lib.check(_lib.load().wq_gemm_wf8a16(_ptr(x2), _DT[x2.dtype], _ptr(wq), _ptr(scale), _ptr(bias), _ptr(y),
                                               _DT[out_dtype], x2.shape[0], N, K, _stream()), "wq_gemm_wf8a16")
@@ -715,6 +744,10 @@ def gemm_u4a16(x: torch.Tensor, packed: torch.Tensor, scale: torch.Tensor, shift
     if _gemv_ok(x2, out_dtype):
         _gemv_weightonly(x2, 2, packed, scale, shift, group, 0, bias, y, N, K)
         return y.reshape(*x.shape[:-1], N)
+    if _gemv_f32_ok(x2, out_dtype):
+        _gemv_f32(x2, 2, packed, scale, shift, group, 0, bias, y, N, K)
+        return y.reshape(*x.shape[:-1], N)
+    x2 = _operand(x2)
     with torch.cuda.device(x.device), _Timed("u4a16", x2.shape[0], N, K):
         _lib.check(_lib.load().wq_gemm_u4a16(_ptr(x2), _DT[x2.dtype], _ptr(packed), _ptr(scale), _ptr(shift), group,
                                              _ptr(bias), _ptr(y), _DT[out_dtype], x2.shape[0], N, K, _stream()),

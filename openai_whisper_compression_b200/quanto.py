@@ -257,17 +257,17 @@ class QLinear(nn.Linear):
             return self._forward_quantized_activations(x, bias)
         if self.weight_qtype.is_floating_point:      # qfloat8 weights, float activations
             if x.dtype == torch.float32:
-                return F.gemm_wf8a16(x.to(torch.float16), self._wq, self._wscale.view(-1), bias, torch.float32)
+                return F.gemm_wf8a16(x, self._wq, self._wscale.view(-1), bias, torch.float32)
             return F.gemm_wf8a16(x, self._wq, self._wscale.view(-1), bias)
         if self._wshift is not None:      # qint4
             if x.dtype == torch.float32:
-                return F.gemm_u4a16(x.to(torch.float16), self._wq, self._wscale, self._wshift, self._group, bias,
-                                    torch.float32)
+                return F.gemm_u4a16(x, self._wq, self._wscale, self._wshift, self._group, bias, torch.float32)
             return F.gemm_u4a16(x, self._wq, self._wscale, self._wshift, self._group, bias)
         if x.dtype == torch.float32:
             # fp32 flow of the reference (model never .half()-ed, model_utils.py:139-142): operands go
             # to the tensor cores as fp16, accumulate fp32, result written fp32 (DESIGN.md "Numerics")
-            return F.gemm_w8a16(x.to(torch.float16), self._wq, self._wscale, bias, torch.float32)
+            # (functional casts once for the tensor-core GEMM; decode-shaped calls take the fp32-in GEMV instead)
+            return F.gemm_w8a16(x, self._wq, self._wscale, bias, torch.float32)
         return F.gemm_w8a16(x, self._wq, self._wscale, bias)
 
 

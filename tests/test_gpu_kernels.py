@@ -631,3 +631,52 @@ def test_weight_only_gemv_matches_dequant_matmul_and_the_tensor_core_gemm(dtype,
             qz, sz = F.quanto_quantize_qint8(Wz.to(dtype))
             yz = F.gemm_w8a16(x, qz, sz.view(-1), bias)
         assert torch.equal(yz, bias.to(dtype).expand(M, N))
+
+
+@pytest.mark.parametrize("M,N,K", [(16, 1024, 1024), (32, 4096, 1024), (16, 1024, 4096), (7, 130, 384), (32, 51, 1280),
+                                   (48, 768, 768)])
+@pytest.mark.parametrize("mode", ["nf4", "w8", "u4", "f8"])
+def test_weight_only_gemv_fp32_flow(M, N, K, mode):
+    """The reference's fp32 flows (quanto / bnb compute_dtype fp32 on a model that was never .half()-ed,
+    model_utils.py:139-142) at decode shapes: fp32 rows in, rounded to fp16 as the tensor-core GEMM of the same flow
+    rounds them, fp32 sums out; up to 32 rows (more rows: cast pass + tensor-core GEMM, 48-row case).  Against a float64 product of exactly those operands
+    (2e-5 of max(|y|, 1): fp32 accumulation) and against the tensor-core path (cast pass + GEMM) on the same inputs."""
+    g = torch.Generator(device="cuda").manual_seed(M * 31 + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    W[torch.rand(N, K, device="cuda", generator=g) < 0.3] = 0
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    post = None
+    if mode == "nf4":
+        packed, absmax = F.quantize_4bit(W, 64, "nf4")
+        wd = F.dequantize_4bit(packed, absmax, (N, K), 64, "nf4", torch.float16).double()
+        call = lambda: F.gemm_w4a16(x, packed, absmax, N, K, bias, "nf4", out_dtype=torch.float32)
+    elif mode == "w8":
+        q, scale = F.quanto_quantize_qint8(W)
+        wd, post = q.double(), scale.view(1, -1).double()
+        call = lambda: F.gemm_w8a16(x, q, scale.view(-1), bias, torch.float32)
+    elif mode == "f8":
+        q, scale = F.quanto_quantize_qfloat8(W)
+        wd, post = q.view(torch.float8_e4m3fn).float().double(), scale.view(1, -1).double()
+        call = lambda: F.gemm_wf8a16(x, q, scale.view(-1), bias, torch.float32)
+    else:
+        packed, scale, shift, grp = F.quanto_quantize_qint4(W)
+        codes = torch.stack([(packed >> 4).float(), (packed & 15).float()], -1).reshape(N, K)
+        wd = (scale.repeat_interleave(grp, 1) * codes - shift.repeat_interleave(grp, 1)).half().double()
+        call = lambda: F.gemm_u4a16(x, packed, scale, shift, grp, bias, torch.float32)
+    before = F.STATS.launches
+    y = call()
+    assert F.STATS.launches - before == 1
+    assert y.dtype == torch.float32 and y.shape == (M, N)
+    ref = x.half().double() @ wd.t()
+    if post is not None:
+        ref = ref * post
+    ref = ref + bias.double()
+    assert ((y.double() - ref).abs() / ref.abs().clamp_min(1.0)).max().item() <= 5e-5
+    old = F.GEMV_ROWS
+    F.GEMV_ROWS = 0
+    try:
+        y_tc = call()
+    finally:
+        F.GEMV_ROWS = old
+    assert ((y - y_tc).abs() / ref.abs().clamp_min(1.0).float()).max().item() <= 5e-5
