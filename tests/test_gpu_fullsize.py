@@ -18,7 +18,10 @@ def F():
     return functional
 
 
-@pytest.mark.parametrize("M,N,K", [(96000, 512, 512), (24000, 2048, 512), (24000, 512, 2048), (12000, 1280, 5120)])
+# whisper-tiny widths (384, 1152, 1536 x 384) have an odd number of 128-column blocks: they keep the single-CTA tiles
+# (weight-stationary 256 x 128 / round-robin), every other shape here runs on CTA pairs (tests/test_gpu_pair.py)
+@pytest.mark.parametrize("M,N,K", [(96000, 512, 512), (24000, 2048, 512), (24000, 512, 2048), (12000, 1280, 5120),
+                                   (48000, 384, 384), (24000, 1152, 384), (24000, 384, 1536)])
 def test_llmint8_full_size_bit_exact_vs_integer_matmul(F, M, N, K):
     """configs[1] encoder shapes (64 x 1500 rows): the fused tcgen05 path equals the reference
     formula evaluated with exact integer sums (torch._int_mm) on every element."""
