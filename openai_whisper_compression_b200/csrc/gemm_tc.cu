@@ -1179,7 +1179,7 @@ int dispatch_a16(const CUtensorMap &ma, const CUtensorMap &mb, const GemmArgs &a
 #define WQ_PAIR(AK, OT) return launch_gemm<128, AK, BMODE, EPI, OT, 0, 1, 0, 1>(ma, mb, args, s)
     if (x_dtype == WQ_F16) {
         if (y_dtype == WQ_F16) { if (pair) WQ_PAIR(A_F16, __half); if (lean) WQ_LEAN(A_F16, __half); if (narrow) WQ_CASE(64, A_F16, __half); else WQ_CASE(128, A_F16, __half); }
-        if (y_dtype == WQ_F32) { if (pair) WQ_PAIR(A_F16, float); if (narrow) WQ_CASE(64, A_F16, float); else WQ_CASE(128, A_F16, float); }
+        if (y_dtype == WQ_F32) { if (pair) WQ_PAIR(A_F16, float); if (lean) WQ_LEAN(A_F16, float); if (narrow) WQ_CASE(64, A_F16, float); else WQ_CASE(128, A_F16, float); }
     } else if (x_dtype == WQ_BF16) {
         if (y_dtype == WQ_BF16) { if (pair) WQ_PAIR(A_BF16, __nv_bfloat16); if (lean) WQ_LEAN(A_BF16, __nv_bfloat16); if (narrow) WQ_CASE(64, A_BF16, __nv_bfloat16); else WQ_CASE(128, A_BF16, __nv_bfloat16); }
         if (y_dtype == WQ_F32) { if (pair) WQ_PAIR(A_BF16, float); if (narrow) WQ_CASE(64, A_BF16, float); else WQ_CASE(128, A_BF16, float); }
@@ -1206,7 +1206,8 @@ extern "C" int wq_gemm_w8a16(const void *x, int x_dtype, const int8_t *wq, const
     args.num_kb = (int)((K + 63) / 64);
     args.col_scale = scale; args.bias = bias; args.out = y;
     const bool narrow = use_narrow_tile(M, N), pair = use_pair(M, N, 2);
-    const bool lean = narrow && use_lean_tile(M) && y_dtype == x_dtype;    // decode-shaped calls, <= 128 rows
+    // decode-shaped calls, <= 128 rows (fp32 output of fp16 operands: the decode steps of the reference's fp32 flows)
+    const bool lean = narrow && use_lean_tile(M) && (y_dtype == x_dtype || (x_dtype == WQ_F16 && y_dtype == WQ_F32));
     CUtensorMap ma, mb;
     rc = make_map_2d(&ma, x, x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                      M, K, (lean || pair) ? BMH : BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -1233,7 +1234,8 @@ extern "C" int wq_gemm_w4a16(const void *x, int x_dtype, const uint8_t *packed, 
     args.absmax = absmax; args.absmax_ld = (int)(K / 64);
     args.bias = bias; args.out = y; args.quant_type = quant_type;
     const bool narrow = use_narrow_tile(M, N), pair = use_pair(M, N, 2);
-    const bool lean = narrow && use_lean_tile(M) && y_dtype == x_dtype;    // decode-shaped calls, <= 128 rows
+    // decode-shaped calls, <= 128 rows (fp32 output of fp16 operands: the decode steps of the reference's fp32 flows)
+    const bool lean = narrow && use_lean_tile(M) && (y_dtype == x_dtype || (x_dtype == WQ_F16 && y_dtype == WQ_F32));
     CUtensorMap ma, mb;
     rc = make_map_2d(&ma, x, x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                      M, K, (lean || pair) ? BMH : BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -1262,7 +1264,8 @@ extern "C" int wq_gemm_u4a16(const void *x, int x_dtype, const uint8_t *packed, 
     args.absmax = scale; args.shift = shift; args.group = group; args.absmax_ld = (int)(K / group);
     args.bias = bias; args.out = y;
     const bool narrow = use_narrow_tile(M, N), pair = use_pair(M, N, 2);
-    const bool lean = narrow && use_lean_tile(M) && y_dtype == x_dtype;    // decode-shaped calls, <= 128 rows
+    // decode-shaped calls, <= 128 rows (fp32 output of fp16 operands: the decode steps of the reference's fp32 flows)
+    const bool lean = narrow && use_lean_tile(M) && (y_dtype == x_dtype || (x_dtype == WQ_F16 && y_dtype == WQ_F32));
     CUtensorMap ma, mb;
     rc = make_map_2d(&ma, x, x_dtype == WQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                      M, K, (lean || pair) ? BMH : BM, 64, CU_TENSOR_MAP_SWIZZLE_128B);
