@@ -243,7 +243,7 @@ def encoder_gemm_roofline(records, peaks, ms_dev):
         tot_time += sum(ts)
         n_launch += len(ts)
     traffic = None
-    for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+    for name in ("r02z_gemm_traffic.json", "r02_gemm_traffic.json", "r01_gemm_traffic.json"):
         tpath = os.path.join(ROOT, "profiles", name)
         if os.path.exists(tpath):
             # DRAM bytes per launch from the committed ncu --set full capture of this command's kernel

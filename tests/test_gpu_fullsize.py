@@ -26,7 +26,9 @@ def test_llmint8_full_size_bit_exact_vs_integer_matmul(F, M, N, K):
     """configs[1] encoder shapes (64 x 1500 rows): the fused tcgen05 path equals the reference
     formula evaluated with exact integer sums (torch._int_mm) on every element."""
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
-    x = torch.randn(M, K, device="cuda", generator=g).half()
+    # no entry reaches the outlier threshold (among 3.7e7 normal samples one or two do: the decomposition then takes
+    # those columns out of the int8 product, which the threshold-free reference below does not model)
+    x = torch.randn(M, K, device="cuda", generator=g).clamp_(-5.5, 5.5).half()
     W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
     bias = (torch.randn(N, device="cuda", generator=g) * 0.1).half()
     cb, scb, _ = F.int8_vectorwise_quant(W, 0.0)

@@ -71,9 +71,10 @@ def test_linear4bit_module_surface_and_parity(pkg):
     y_ref = oracle.linear4bit_forward(x.numpy(), p_ref, a_ref, (96, 128), lin.bias.detach().numpy(),
                                       compute_dtype=np.float16)
     assert np.abs(y.cpu().numpy() - y_ref).max() / max(1.0, np.abs(y_ref).max()) < 2e-3
-    # decode-shaped call (one token, batch 1) goes through the same fused kernel
+    # decode-shaped call (one token, batch 1): the weight-only GEMV (as bitsandbytes switches to gemv_4bit) --
+    # same operands, fp32 accumulation in another order
     y1 = m(x[:1, :1].cuda())
-    np.testing.assert_array_equal(y1.cpu().numpy(), y[:1, :1].cpu().numpy())
+    np.testing.assert_allclose(y1.cpu().numpy(), y[:1, :1].cpu().numpy(), rtol=0, atol=2e-6)
 
 
 def test_linear8bitlt_module_surface_and_parity(pkg):

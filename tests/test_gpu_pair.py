@@ -39,7 +39,7 @@ def _llmint8_reference(x, cb, scb, bias):
 @pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
 def test_pair_llmint8_equals_integer_matmul(M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
-    x = torch.randn(M, K, device="cuda", generator=g).half()
+    x = torch.randn(M, K, device="cuda", generator=g).clamp_(-5.5, 5.5).half()     # below the outlier threshold
     W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
     bias = (torch.randn(N, device="cuda", generator=g) * 0.1).half()
     cb, scb, _ = F.int8_vectorwise_quant(W, 0.0)
