@@ -283,7 +283,9 @@ int wq_gelu_quant(const void *x, int dtype, int64_t rows, int64_t cols, void *h_
  * the three can be column blocks of one fused [B, 3*H*64] projection).  q is multiplied by `scaling`
  * and rounded to `dtype` first, as HF does.  k_cache / v_cache: [B, t_max, H*64]; the new k/v rows are
  * written at position *pos (device scalar), then softmax(q K^T) V over positions 0..*pos in fp32.
- * out: [B, H*64].  Optional int8 row quantization of out as above.  head_dim is 64 (all Whisper sizes). */
+ * out: [B, H*64].  Optional int8 row quantization of out as above.  head_dim is 64 (all Whisper sizes).
+ * dtype: WQ_F16 / WQ_BF16, or WQ_F32 for the reference's fp32 flows (quanto / bnb *_32 on a model that was never
+ * .half()-ed, model_utils.py:139-142, where HF runs torch's fp32 SDPA); the int8 outputs exist for WQ_F16 only. */
 int wq_self_attn_decode(const void *q, const void *k, const void *v, int64_t ld, int dtype, float scaling,
                         void *k_cache, void *v_cache, int64_t B, int H, int t_max, const int64_t *pos,
                         void *out, float threshold, int8_t *ca, float *row_stats, int32_t *col_flags,
@@ -295,7 +297,9 @@ int wq_self_attn_decode(const void *q, const void *k, const void *v, int64_t ld,
  * first (as HF does).  k, v: [B, S, H*64] with rows `ld` elements apart (a layer's K and V may be the two column
  * blocks of one [B, S, 2*H*64] projection).  out: [B, H*64] contiguous.  HBM-bound: 2*S*H*64*sizeof(dtype) bytes
  * per utterance.  head_dim is 64.  Optional int8 row quantization of out (ca != NULL, as above); it then needs
- * row_counters: device int32[B], zero before the first call (the kernel leaves it zero). */
+ * row_counters: device int32[B], zero before the first call (the kernel leaves it zero).
+ * dtype: WQ_F16 / WQ_BF16 (TMA-fed walk), or WQ_F32 for the reference's fp32 flows (register-fed walk, 32-byte row
+ * chunks; no int8 outputs). */
 int wq_cross_attn_decode(const void *q, int64_t ldq, int dtype, float scaling, const void *k, const void *v,
                          int64_t ld, int64_t B, int64_t S, int H, void *out, float threshold, int8_t *ca,
                          float *row_stats, int32_t *col_flags, int32_t *row_counters, wq_stream_t stream);
