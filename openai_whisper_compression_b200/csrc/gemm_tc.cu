@@ -966,7 +966,9 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmArgs args, cud
     const int total = args.tiles_m * args.tiles_n;
     if (PAIR) {
         int pairs = total < max_pairs ? total : max_pairs;
-        if (WS > 0) pairs = (max_pairs / args.tiles_n) * args.tiles_n;      // whole groups of tiles_n pairs (use_ws())
+        // whole groups of tiles_n pairs (use_ws_pair()); if fewer pairs than one group can be resident at once (SMs
+        // withheld from this context) the surplus pairs simply queue: no pair waits on another
+        if (WS > 0) pairs = (max_pairs / args.tiles_n > 0 ? max_pairs / args.tiles_n : 1) * args.tiles_n;
         WQ_REQUIRE(pairs >= 1, "wq gemm: no CTA pair fits the device");
         WQ_LAUNCH_PDL_CLUSTER(2, kfn, dim3(2 * pairs), dim3(num_threads<BN, BMODE, LEAN>()), (size_t)L::TOTAL, stream, ma, mb,
                               my, args);
