@@ -223,14 +223,34 @@ def gemm_algorithmic(kind, M, N, K):
             2.0 * M * N * K)
 
 
-def encoder_gemm_roofline(records, peaks, ms_dev):
+def measure_write_peak(dev):
+    """Write-only HBM bandwidth of this device, measured live (memset of 1 GiB, CUDA events, median of 7).  The copy
+    bandwidth of MEASURED_PEAKS.json is half reads, half writes; on B200 a pure store stream tops out at ~3.9 TB/s,
+    which is what bounds a GEMM launch whose traffic is mostly its output (whisper-base fc1: 0.2 GB read, 1.5 GB
+    written)."""
+    import torch
+    buf = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        buf.zero_()
+    ts = []
+    for _ in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        buf.zero_()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    return buf.numel() / sorted(ts)[len(ts) // 2] / 1e9
+
+
+def encoder_gemm_roofline(records, peaks, ms_dev, write_peak=None):
     """Encoder-shaped GEMM launches (M >= 1024) timed live with CUDA events inside the device-timed steps."""
     by_shape = {}
     for kind, M, N, Kd, s, e in records:
         by_shape.setdefault((kind, M, N, Kd), []).append(s.elapsed_time(e) * 1e-3)
     if not by_shape:
         return None
-    tot_bytes = tot_flops = tot_time = 0.0
+    tot_bytes = tot_flops = tot_time = tot_floor = 0.0
     n_launch = 0
     shapes = []
     for (kind, M, N, Kd), ts in sorted(by_shape.items()):
@@ -238,6 +258,13 @@ def encoder_gemm_roofline(records, peaks, ms_dev):
         avg = sum(ts) / len(ts)
         shapes.append({"kind": kind, "M": M, "N": N, "K": Kd, "launches": len(ts), "avg_us": avg * 1e6,
                        "GBps": nbytes / avg / 1e9, "TFLOPs": flops / avg / 1e12})
+        if write_peak:
+            # time floor of the launch: its stores at the write-only rate, or all its bytes at the copy rate
+            wbytes = M * N * (4 if kind.replace("+res", "") == "dyn_i8" else 2)
+            floor = max(wbytes / (write_peak * 1e9), nbytes / (peaks["hbm_gbs"] * 1e9))
+            shapes[-1].update({"write_GBps": wbytes / avg / 1e9, "frac_of_hbm_floor": floor / avg,
+                               "floor": "stores" if wbytes / write_peak > nbytes / peaks["hbm_gbs"] else "copy rate"})
+            tot_floor = tot_floor + floor * len(ts)
         tot_bytes += nbytes * len(ts)
         tot_flops += flops * len(ts)
         tot_time += sum(ts)
@@ -277,6 +304,12 @@ def encoder_gemm_roofline(records, peaks, ms_dev):
            "hbm_GBps": gbs, "hbm_frac": gbs / peaks["hbm_gbs"],
            "tensor_TFLOPs": tfs, "tensor_frac_of_bf16_peak": tfs / peaks["bf16_tflops"],
            "share_of_step": tot_time * 1e3 / ms_dev, "shapes": shapes}
+    if write_peak:
+        out["hbm_write_peak_GBps"] = write_peak
+        out["frac_of_hbm_floor"] = tot_floor / tot_time
+        out["hbm_floor_how"] = ("per launch max(output bytes / write-only bandwidth measured live by a 1 GiB memset, algorithmic "
+                                "bytes / copy bandwidth of MEASURED_PEAKS.json): a store-dominated launch cannot reach the "
+                                "copy rate, which is half reads")
     if intensity <= ridge:
         out.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": gbs / peaks["hbm_gbs"],
@@ -593,7 +626,7 @@ def run_config(wl: Workload, K: int, W: int, world: int, rank: int, peaks, with_
         res["tally"] = {"WER": tally.rates(t)["WER"], "CER": tally.rates(t)["CER"], "ref_words": int(t[1])}
         res["d2h_bytes"] = int(ids.shape[1]) * B * 8 + 32
     if rank == 0:
-        res["encoder_gemm"] = encoder_gemm_roofline(records, peaks, ms_dev)
+        res["encoder_gemm"] = encoder_gemm_roofline(records, peaks, ms_dev, measure_write_peak(dev))
         if wl.eng is not None:
             res["decode"] = decode_probe(wl.model, wl.eng, peaks, ms_dev / K, T)
     if do_token_check:
