@@ -202,7 +202,7 @@ struct SmemLayout {
     static constexpr int NUM_BARS = 4 * STAGES + 2 * ACC_STAGES + 1;   // full | empty | bready | pfull (pairs: packed W landed)
     static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
     static constexpr int TOTAL = OFF_TMEM + 16 + 1024;         // + slack for manual 1024-B alignment
-    [[maybe_unused]] static constexpr int TX_BYTES = A_BYTES + (WS > 0 ? 0 : (BMODE == B_DIRECT ? B_BYTES : P_BYTES));
+    static constexpr int TX_BYTES = A_BYTES + (WS > 0 ? 0 : (BMODE == B_DIRECT ? B_BYTES : P_BYTES));
     static_assert(TOTAL <= 232448, "shared memory budget exceeded");
 };
 
@@ -633,7 +633,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     if (elect_one()) {
                         const uint32_t lf = mapa_u32(smem_u32(&bar_full[s]), 0);
                         // bytes the leader's MMA warp waits for: A of both CTAs, and W when it comes straight from TMA
-                        constexpr uint32_t kPairTx = L::A_BYTES + ((WS == 0 && BMODE == B_DIRECT) ? L::B_BYTES : 0);
+                        // (packed weights of the expanding schemes are counted on pfull[s] instead)
+                        constexpr uint32_t kPairTx = L::TX_BYTES - (BMODE != B_DIRECT ? L::P_BYTES : 0);
                         if (rank == 0) mbar_arrive_expect_tx(&bar_full[s], 2u * kPairTx);
                         else mbar_arrive_cluster(lf);
                         tma_load_2d_pair(smem + L::OFF_A + s * L::A_BYTES, &map_a, lf, kb * A_ELEMS_PER_ROW, m0);
