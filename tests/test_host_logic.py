@@ -41,6 +41,9 @@ def test_sass_has_blackwell_tensor_and_tma_instructions(lib_path):
     out = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
     for mnem in ("UTCIMMA", "UTCHMMA", "UTMALDG", "LDTM"):
         assert mnem in out, f"{mnem} missing from SASS"
+    # CTA-pair schedule (tcgen05 cta_group::2): pair MMAs of both kinds, pair TMA loads, multicast commits, cluster barrier
+    for mnem in ("UTCIMMA.2CTA", "UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA.MULTICAST", "UCGABAR_ARV"):
+        assert mnem in out, f"{mnem} missing from SASS"
     assert "HMMA.16816" not in out      # no legacy mma.sync path
 
 
