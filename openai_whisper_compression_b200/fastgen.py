@@ -75,6 +75,7 @@ class GraphedGreedy:
         # transcribe_batch makes (data_utils.py:152) that walk only strips trailing pad/eos tokens and re-pads:
         # done here in a few batched ops, same result (tests/test_host_logic.py)
         self.fast_post = os.environ.get("WQ_FAST_POST", "1") != "0"
+        self.before_readback = None      # optional callable, see _sample: runs after a batch is queued, before the host blocks
         self._unwind = False
         self.keep_logits = False       # True: the captured step always writes the [B, V] logits (tests, debugging)
         # fused LLM.int8 step: row groups of the batch decoded on as many streams (1 = off).  Per token and layer the
@@ -793,6 +794,11 @@ class GraphedGreedy:
             self.loop_events.append((ev0, ev1, self.replays - replays0))
         if not self.host_postprocess:
             return input_ids
+        # everything of this batch is queued and the host is about to block on the read-back: a caller's host work on
+        # the PREVIOUS batch (ids -> text, metric tallies: ~4 ms per 256 utterances) fits here, under this batch's GPU
+        # time -- an evaluation loop pipelined one batch deep (bench.py's end-to-end arm sets it)
+        if self.before_readback is not None:
+            self.before_readback()
         ids = input_ids.cpu()
         self._maybe_unwind(ids, P, generation_config)
         return ids

@@ -69,9 +69,19 @@ def _host_pack(references: Sequence[str], predictions: Sequence[str]):
     return ids, off, n_rw + n_rc, n_rw, n_rc
 
 
-def tally_on_device(references: Sequence[str], predictions: Sequence[str], device) -> torch.Tensor:
+def _to_device(a: np.ndarray, dev, non_blocking: bool) -> torch.Tensor:
+    t = torch.from_numpy(a)
+    if non_blocking:
+        # pinned staging + asynchronous copy: the host does not wait for the stream's earlier work (the caching host
+        # allocator keeps the staging block alive until the copy has run)
+        return t.pin_memory().to(dev, non_blocking=True)
+    return t.to(dev)
+
+
+def tally_on_device(references: Sequence[str], predictions: Sequence[str], device, non_blocking: bool = False) -> torch.Tensor:
     """int64[4] tally on `device`; word ids are per-batch vocab indices, chars are code points.  One edit-distance
-    launch over the 2P pairs, two host->device copies."""
+    launch over the 2P pairs, two host->device copies.  non_blocking: nothing here waits for the device (a caller that
+    overlaps the tally with other GPU work reads the result later)."""
     if len(references) != len(predictions):
         raise ValueError("references and predictions differ in length")
     dev = torch.device(device)
@@ -79,11 +89,11 @@ def tally_on_device(references: Sequence[str], predictions: Sequence[str], devic
     if P == 0:
         return torch.zeros(4, dtype=torch.int64, device=dev)
     ids, off, n_ref, n_rw, n_rc = _host_pack(references, predictions)
-    ids_d = torch.from_numpy(ids).to(dev)
-    off_d = torch.from_numpy(off).to(dev)
+    ids_d = _to_device(ids, dev, non_blocking)
+    off_d = _to_device(off, dev, non_blocking)
     d = F.edit_distance(ids_d[:n_ref], off_d[:2 * P + 1], ids_d[n_ref:], off_d[2 * P + 1:])
     errs = d.view(2, P).sum(1)       # (the kernel's -1 sentinel for over-long pairs cannot occur: _host_pack refuses them)
-    out = torch.tensor([0, n_rw, 0, n_rc], dtype=torch.int64).to(dev)
+    out = _to_device(np.array([0, n_rw, 0, n_rc], dtype=np.int64), dev, non_blocking)
     out[0::2] = errs
     return out
 
