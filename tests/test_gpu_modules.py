@@ -594,3 +594,34 @@ def test_persistent_decoder_layer_kernel_is_bit_identical_to_the_launch_chain(pk
     for a, b in zip(outs[True][2] + outs[True][3], outs[False][2] + outs[False][3]):
         assert torch.equal(a[:, :T], b[:, :T])
     assert (outs[True][1].float().abs() > 0).any()
+
+
+def test_before_readback_hook_runs_once_per_generate_and_changes_nothing(pkg):
+    """fastgen's `before_readback` hook (bench.py's end-to-end arm: the previous batch's transcript + tally run on the
+    host while this batch executes): called exactly once per plain generate call, after the batch's replays are
+    queued; the returned ids are the ids without the hook; work the hook queues on the stream is ordered after the
+    batch (its result is right once the stream is drained)."""
+    from openai_whisper_compression_b200 import fastgen, harness
+    model = harness.apply_scheme(harness.build_model("tiny", **REAL2), "llm_int8", "cuda")
+    feats = _feats(n=4, frames=3000).half().cuda()
+    T = 8
+    eng = fastgen.enable(model)
+    want = harness.greedy_generate(model, feats, T)
+    calls = []
+    probe = torch.zeros(1, device="cuda")
+
+    def hook():
+        calls.append(eng.replays)          # every replay of this call has been queued by now
+        probe.add_(1.0)                    # stream-ordered work from inside the hook
+
+    eng.before_readback = hook
+    r0 = eng.replays
+    got = harness.greedy_generate(model, feats, T)
+    eng.before_readback = None
+    assert torch.equal(got, want)
+    assert len(calls) == 1 and calls[0] - r0 >= T
+    torch.cuda.synchronize()
+    assert probe.item() == 1.0
+    again = harness.greedy_generate(model, feats, T)       # hook removed: not called again
+    assert torch.equal(again, want) and len(calls) == 1
+    eng.uninstall()
