@@ -239,3 +239,22 @@ def test_stub_processor_decode_forms_agree():
     assert [p.decode(r) for r in ids] == want
     assert p.batch_decode(torch.zeros((0, 4), dtype=torch.long)) == []
     assert p.batch_decode([[1, 2], [3]]) == ["t1 t2", "t3"]
+
+
+def test_decode_shape_dispatch_rules_are_host_side_and_dtype_exact():
+    """Which decode-shaped calls of the weight-only schemes take the GEMV (functional._gemv_ok / _gemv_f32_ok): at most
+    GEMV_ROWS rows; 16-bit rows with the same output dtype, or fp32 rows with fp32 output (the reference's fp32 flows,
+    model_utils.py:139-142) -- never a mixed pair, never more rows (two launches for 64 rows measured slower)."""
+    import torch
+    from openai_whisper_compression_b200 import functional as F
+    rows = F.GEMV_ROWS
+    assert rows == 32
+    h = torch.zeros(rows, 64, dtype=torch.float16)
+    f = torch.zeros(rows, 64, dtype=torch.float32)
+    assert F._gemv_ok(h, torch.float16) and not F._gemv_ok(h, torch.float32) and not F._gemv_ok(f, torch.float32)
+    assert F._gemv_f32_ok(f, torch.float32) and not F._gemv_f32_ok(f, torch.float16) and not F._gemv_f32_ok(h, torch.float32)
+    assert not F._gemv_ok(torch.zeros(rows + 1, 64, dtype=torch.float16), torch.float16)
+    assert not F._gemv_f32_ok(torch.zeros(rows + 1, 64), torch.float32)
+    assert not F._gemv_ok(torch.zeros(0, 64, dtype=torch.float16), torch.float16)
+    # the one cast pass of the fp32 flows in front of the tensor-core GEMM
+    assert F._operand(f).dtype == torch.float16 and F._operand(h) is h
